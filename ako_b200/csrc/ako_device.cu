@@ -1,0 +1,615 @@
+// ako_device.cu -- the CUDA translation unit of libako_b200: context management, kernel launchers
+// and the container kernels, exported through the internal C-ABI of ako_device.h.
+// Compiled for sm_100a only (no other architecture is built; see Makefile).
+
+#include <stdlib.h>
+
+#include "common.cuh"
+#include "format.cuh"
+#include "kagari_dec.cuh"
+#include "kagari_enc.cuh"
+#include "lift.cuh"
+
+// ------------------------------------------------------------------------------------------------
+// context
+
+extern "C" int akod_context_create(int device, akodContext** out)
+{
+	*out = nullptr;
+	int count = 0;
+	AKOD_TRY(cudaGetDeviceCount(&count));
+	if (device < 0 || device >= count)
+		return AKOD_ERROR;
+	AKOD_TRY(cudaSetDevice(device));
+
+	akodContext* c = new akodContext();
+	c->device = device;
+	c->profiling = false;
+	c->launch_count = 0;
+	c->mailbox = nullptr;
+	for (int i = 0; i < AKOD_WS_COUNT; i++)
+	{
+		c->ws[i] = nullptr;
+		c->ws_size[i] = 0;
+	}
+	cudaDeviceProp prop;
+	if (cudaGetDeviceProperties(&prop, device) != cudaSuccess)
+	{
+		delete c;
+		return AKOD_ERROR;
+	}
+	c->sm_count = prop.multiProcessorCount;
+	if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess ||
+	    cudaHostAlloc(&c->mailbox, 1 << 16, cudaHostAllocDefault) != cudaSuccess)
+	{
+		delete c;
+		return AKOD_ERROR;
+	}
+	*out = c;
+	return AKOD_OK;
+}
+
+static void akod_collect_pending(akodContext* c)
+{
+	if (c->pending.empty())
+		return;
+	cudaStreamSynchronize(c->stream);
+	for (akodPending& p : c->pending)
+	{
+		float ms = 0.f;
+		if (cudaEventElapsedTime(&ms, p.a, p.b) == cudaSuccess)
+			c->prof[p.entry].ms += ms;
+		c->event_pool.push_back(p.a);
+		c->event_pool.push_back(p.b);
+	}
+	c->pending.clear();
+}
+
+extern "C" void akod_context_destroy(akodContext* c)
+{
+	if (!c)
+		return;
+	cudaSetDevice(c->device);
+	cudaStreamSynchronize(c->stream);
+	akod_collect_pending(c);
+	for (cudaEvent_t e : c->event_pool)
+		cudaEventDestroy(e);
+	for (int i = 0; i < AKOD_WS_COUNT; i++)
+		if (c->ws[i])
+			cudaFree(c->ws[i]);
+	if (c->mailbox)
+		cudaFreeHost(c->mailbox);
+	cudaStreamDestroy(c->stream);
+	delete c;
+}
+
+extern "C" int akod_device_index(akodContext* c)
+{
+	return c->device;
+}
+
+extern "C" void* akod_stream(akodContext* c)
+{
+	return (void*)c->stream;
+}
+
+extern "C" int akod_sync(akodContext* c)
+{
+	AKOD_TRY(cudaStreamSynchronize(c->stream));
+	return AKOD_OK;
+}
+
+extern "C" void* akod_alloc(akodContext* c, size_t bytes)
+{
+	void* p = nullptr;
+	cudaSetDevice(c->device);
+	if (cudaMalloc(&p, bytes ? bytes : 1) != cudaSuccess)
+	{
+		cudaGetLastError();
+		return nullptr;
+	}
+	return p;
+}
+
+extern "C" void akod_free(akodContext* c, void* p)
+{
+	if (p)
+	{
+		cudaSetDevice(c->device);
+		cudaFree(p);
+	}
+}
+
+extern "C" void* akod_pinned_alloc(size_t bytes)
+{
+	void* p = nullptr;
+	if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocDefault) != cudaSuccess)
+	{
+		cudaGetLastError();
+		return nullptr;
+	}
+	return p;
+}
+
+extern "C" void akod_pinned_free(void* p)
+{
+	if (p)
+		cudaFreeHost(p);
+}
+
+extern "C" int akod_h2d(akodContext* c, void* d, const void* s, size_t n)
+{
+	AKOD_TRY(cudaMemcpyAsync(d, s, n, cudaMemcpyHostToDevice, c->stream));
+	return AKOD_OK;
+}
+
+extern "C" int akod_d2h(akodContext* c, void* d, const void* s, size_t n)
+{
+	AKOD_TRY(cudaMemcpyAsync(d, s, n, cudaMemcpyDeviceToHost, c->stream));
+	return AKOD_OK;
+}
+
+extern "C" int akod_d2d(akodContext* c, void* d, const void* s, size_t n)
+{
+	AKOD_TRY(cudaMemcpyAsync(d, s, n, cudaMemcpyDeviceToDevice, c->stream));
+	return AKOD_OK;
+}
+
+extern "C" int akod_memset(akodContext* c, void* d, int v, size_t n)
+{
+	AKOD_TRY(cudaMemsetAsync(d, v, n, c->stream));
+	return AKOD_OK;
+}
+
+__global__ void k_fill_words(uint64_t* dst, uint64_t value, size_t count)
+{
+	const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (i < count)
+		dst[i] = value;
+}
+
+extern "C" int akod_fill_words(akodContext* c, uint64_t* d, uint64_t value, size_t count)
+{
+	AKOD_LAUNCH(c, "fill_words", k_fill_words, (unsigned)((count + 255) / 256), 256, 0, d, value, count);
+	return AKOD_OK;
+}
+
+extern "C" int akod_workspace(akodContext* c, int slot, size_t bytes, void** out)
+{
+	*out = nullptr;
+	if (slot < 0 || slot >= AKOD_WS_COUNT)
+		return AKOD_ERROR;
+	if (c->ws_size[slot] < bytes)
+	{
+		cudaSetDevice(c->device);
+		// earlier work may still be using the old buffer
+		AKOD_TRY(cudaStreamSynchronize(c->stream));
+		if (c->ws[slot])
+			cudaFree(c->ws[slot]);
+		c->ws[slot] = nullptr;
+		c->ws_size[slot] = 0;
+		const size_t rounded = (bytes + ((size_t)1 << 20)) & ~(((size_t)1 << 20) - 1);
+		AKOD_TRY(cudaMalloc(&c->ws[slot], rounded));
+		c->ws_size[slot] = rounded;
+	}
+	*out = c->ws[slot];
+	return AKOD_OK;
+}
+
+extern "C" void* akod_mailbox(akodContext* c)
+{
+	return c->mailbox;
+}
+
+extern "C" void akod_profile_enable(akodContext* c, int enable)
+{
+	akod_collect_pending(c);
+	c->profiling = enable != 0;
+}
+
+extern "C" void akod_profile_reset(akodContext* c)
+{
+	akod_collect_pending(c);
+	c->prof.clear();
+	c->launch_count = 0;
+}
+
+extern "C" size_t akod_profile_get(akodContext* c, size_t cap, const char** names, uint64_t* launches, double* ms)
+{
+	akod_collect_pending(c);
+	for (size_t i = 0; i < c->prof.size() && i < cap; i++)
+	{
+		names[i] = c->prof[i].name;
+		launches[i] = c->prof[i].launches;
+		ms[i] = c->prof[i].ms;
+	}
+	return c->prof.size();
+}
+
+extern "C" uint64_t akod_launch_count(akodContext* c)
+{
+	return c->launch_count;
+}
+
+// grid for grid-stride streaming kernels: a whole number of waves of the SM count
+static inline unsigned akod_stream_grid(akodContext* c, uint64_t items, unsigned block, unsigned ctas_per_sm)
+{
+	const uint64_t need = (items + block - 1) / block;
+	const uint64_t cap = (uint64_t)c->sm_count * ctas_per_sm;
+	return (unsigned)(need < cap ? (need ? need : 1) : cap);
+}
+
+// ------------------------------------------------------------------------------------------------
+// format
+
+extern "C" int akod_format_forward(akodContext* c, int discard, int color, uint32_t channels, uint32_t w, uint32_t h,
+                                   uint64_t in_stride_px, const uint8_t* d_in, int16_t* d_planes, const akodBatch* b)
+{
+	const uint32_t n = b ? b->n : 1;
+	const uint64_t in_is = b ? b->in_stride : 0, pl_is = b ? b->planes_stride : 0;
+	const bool fast = channels == 4 && (w % 8) == 0 && (in_stride_px % 4) == 0 && ((uintptr_t)d_in % 16) == 0 &&
+	                  ((uintptr_t)d_planes % 16) == 0 && (in_is % 16) == 0 && (pl_is % 8) == 0;
+	if (fast)
+	{
+		const dim3 grid(akod_stream_grid(c, (uint64_t)(w / 8) * h, 256, 8), n);
+		AKOD_LAUNCH(c, "format_fwd_rgba8x8", k_format_fwd_rgba8x8, grid, 256, 0, d_in, d_planes, w, h, in_stride_px, color,
+		            discard, in_is, pl_is);
+	}
+	else
+	{
+		const dim3 grid(akod_stream_grid(c, (uint64_t)w * h, 256, 8), n);
+		AKOD_LAUNCH(c, "format_fwd_generic", k_format_fwd_generic, grid, 256, 0, d_in, d_planes, channels, w, h,
+		            in_stride_px, color, discard, in_is, pl_is);
+	}
+	return AKOD_OK;
+}
+
+extern "C" int akod_format_inverse(akodContext* c, int color, uint32_t channels, uint32_t w, uint32_t h,
+                                   uint64_t out_stride_px, const int16_t* d_planes, uint8_t* d_out, const akodBatch* b)
+{
+	const uint32_t n = b ? b->n : 1;
+	const uint64_t out_is = b ? b->in_stride : 0, pl_is = b ? b->planes_stride : 0;
+	const bool fast = channels == 4 && (w % 8) == 0 && (out_stride_px % 4) == 0 && ((uintptr_t)d_out % 16) == 0 &&
+	                  ((uintptr_t)d_planes % 16) == 0 && (out_is % 16) == 0 && (pl_is % 8) == 0;
+	if (fast)
+	{
+		const dim3 grid(akod_stream_grid(c, (uint64_t)(w / 8) * h, 256, 8), n);
+		AKOD_LAUNCH(c, "format_inv_rgba8x8", k_format_inv_rgba8x8, grid, 256, 0, d_planes, d_out, w, h, out_stride_px, color,
+		            pl_is, out_is);
+	}
+	else
+	{
+		const dim3 grid(akod_stream_grid(c, (uint64_t)w * h, 256, 8), n);
+		AKOD_LAUNCH(c, "format_inv_generic", k_format_inv_generic, grid, 256, 0, d_planes, d_out, channels, w, h,
+		            out_stride_px, color, pl_is, out_is);
+	}
+	return AKOD_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// lifting
+
+template <int WL>
+static int launch_lift_level(akodContext* c, const LiftParams& p, uint32_t n_images)
+{
+	const dim3 grid((p.tw + LIFT_TW - 1) / LIFT_TW, (p.th + LIFT_TH - 1) / LIFT_TH, p.channels * n_images);
+	static const char* const names[3] = {"lift_dd137", "lift_cdf53", "lift_haar"};
+	AKOD_LAUNCH(c, names[WL], k_lift_level<WL>, grid, LIFT_THREADS, lift_smem_bytes<WL>(), p);
+	return AKOD_OK;
+}
+
+template <int WL>
+static int launch_unlift_level(akodContext* c, const UnliftParams& p, uint32_t n_images)
+{
+	const dim3 grid((p.hw + LIFT_TW - 1) / LIFT_TW, (p.hh + LIFT_TH - 1) / LIFT_TH, p.channels * n_images);
+	static const char* const names[3] = {"unlift_dd137", "unlift_cdf53", "unlift_haar"};
+	AKOD_LAUNCH(c, names[WL], k_unlift_level<WL>, grid, LIFT_THREADS, unlift_smem_bytes<WL>(), p);
+	return AKOD_OK;
+}
+
+extern "C" int akod_lift(akodContext* c, const akodPlan* plan, int16_t* d_planes, int16_t* d_scratch, int16_t* d_stream,
+                         const akodBatch* b)
+{
+	const uint32_t n = b ? b->n : 1;
+	const uint64_t planes_is = b ? b->planes_stride : 0, scratch_is = b ? b->scratch_stride : 0;
+	const uint64_t stream_is = b ? b->stream_stride : 0;
+
+	// ping-pong: level l reads 'src' (dense cw x ch planes) and writes the next LL densely into 'dst'
+	int16_t* src = d_planes;
+	int16_t* dst = d_scratch;
+	uint64_t src_is = planes_is, dst_is = scratch_is;
+	uint64_t src_ps = (uint64_t)plan->w * plan->h; // level 0 planes keep the full-image plane stride
+
+	for (uint32_t l = 0; l < plan->levels; l++)
+	{
+		const akodLevel* L = &plan->level[l];
+		LiftParams p;
+		memset(&p, 0, sizeof(p));
+		p.in = src;
+		p.in_rs = L->cw;
+		p.in_ps = src_ps;
+		p.in_is = src_is;
+		p.cw = L->cw;
+		p.ch = L->ch;
+		p.tw = L->tw;
+		p.th = L->th;
+		p.wrap = plan->wrap;
+		p.channels = plan->channels;
+		p.stream = d_stream;
+		p.stream_is = stream_is;
+		if (l + 1 == plan->levels)
+		{
+			// coarsest level: its lowpass IS the stream's LP section (lifting.c:280-291)
+			p.ll = d_stream + plan->off_lp[0];
+			p.ll_rs = L->tw;
+			p.ll_ps = (uint64_t)plan->lp_w * plan->lp_h;
+			p.ll_is = stream_is;
+		}
+		else
+		{
+			p.ll = dst;
+			p.ll_rs = L->tw;
+			p.ll_ps = (uint64_t)L->tw * L->th;
+			p.ll_is = dst_is;
+		}
+		for (uint32_t ch = 0; ch < plan->channels; ch++)
+		{
+			p.off_c[ch] = L->off_c[ch];
+			p.q[ch] = L->q[ch] < 1 ? 1 : L->q[ch];
+			p.g[ch] = L->g[ch];
+			p.qmagic[ch] = (p.q[ch] > 1) ? (uint32_t)((((uint64_t)1 << 32) + p.q[ch] - 1) / (uint64_t)p.q[ch]) : 0;
+		}
+		int rc;
+		if (L->wavelet == AKOD_DD137)
+			rc = launch_lift_level<AKOD_DD137>(c, p, n);
+		else if (L->wavelet == AKOD_CDF53)
+			rc = launch_lift_level<AKOD_CDF53>(c, p, n);
+		else
+			rc = launch_lift_level<AKOD_HAAR>(c, p, n);
+		if (rc != AKOD_OK)
+			return rc;
+
+		// swap
+		int16_t* t = src;
+		src = dst;
+		dst = t;
+		const uint64_t ti = src_is;
+		src_is = dst_is;
+		dst_is = ti;
+		src_ps = (uint64_t)L->tw * L->th;
+	}
+
+	if (plan->levels == 0)
+	{
+		// w <= 2 or h <= 2: no lift at all; the planes are the LP section. (Outside the reference's own
+		// well-defined domain; we define it as the dense copy.)
+		for (uint32_t i = 0; i < n; i++)
+			AKOD_TRY(cudaMemcpyAsync(d_stream + stream_is * i, d_planes + planes_is * i,
+			                         sizeof(int16_t) * plan->stream_len, cudaMemcpyDeviceToDevice, c->stream));
+	}
+	return AKOD_OK;
+}
+
+extern "C" int akod_unlift(akodContext* c, const akodPlan* plan, const int16_t* d_stream, int16_t* d_planes,
+                           int16_t* d_scratch, const akodBatch* b)
+{
+	const uint32_t n = b ? b->n : 1;
+	const uint64_t planes_is = b ? b->planes_stride : 0, scratch_is = b ? b->scratch_stride : 0;
+	const uint64_t stream_is = b ? b->stream_stride : 0;
+
+	if (plan->levels == 0)
+	{
+		for (uint32_t i = 0; i < n; i++)
+			AKOD_TRY(cudaMemcpyAsync(d_planes + planes_is * i, d_stream + stream_is * i,
+			                         sizeof(int16_t) * plan->stream_len, cudaMemcpyDeviceToDevice, c->stream));
+		return AKOD_OK;
+	}
+
+	// The finest level must land in d_planes; alternate buffers backwards from there.
+	// level index l (0 = finest) writes to planes if l is even, scratch if odd.
+	for (uint32_t l = plan->levels; l-- > 0;)
+	{
+		const akodLevel* L = &plan->level[l];
+		UnliftParams p;
+		memset(&p, 0, sizeof(p));
+		p.hw = L->tw;
+		p.hh = L->th;
+		p.tw = L->cw;
+		p.th = L->ch;
+		p.wrap = plan->wrap;
+		p.channels = plan->channels;
+		p.stream = d_stream;
+		p.stream_is = stream_is;
+		if (l + 1 == plan->levels)
+		{
+			p.ll = d_stream + plan->off_lp[0];
+			p.ll_rs = plan->lp_w;
+			p.ll_ps = (uint64_t)plan->lp_w * plan->lp_h;
+			p.ll_is = stream_is;
+		}
+		else
+		{
+			const bool from_planes = ((l + 1) % 2) == 0;
+			p.ll = from_planes ? d_planes : d_scratch;
+			p.ll_rs = L->tw;
+			p.ll_ps = (uint64_t)L->tw * L->th;
+			p.ll_is = from_planes ? planes_is : scratch_is;
+		}
+		const bool to_planes = (l % 2) == 0;
+		p.out = to_planes ? d_planes : d_scratch;
+		p.out_rs = L->cw;
+		p.out_ps = (uint64_t)L->cw * L->ch;
+		p.out_is = to_planes ? planes_is : scratch_is;
+		for (uint32_t ch = 0; ch < plan->channels; ch++)
+		{
+			p.off_c[ch] = L->off_c[ch];
+			p.q[ch] = L->q[ch];
+		}
+		int rc;
+		if (L->wavelet == AKOD_DD137)
+			rc = launch_unlift_level<AKOD_DD137>(c, p, n);
+		else if (L->wavelet == AKOD_CDF53)
+			rc = launch_unlift_level<AKOD_CDF53>(c, p, n);
+		else
+			rc = launch_unlift_level<AKOD_HAAR>(c, p, n);
+		if (rc != AKOD_OK)
+			return rc;
+	}
+	return AKOD_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Kagari
+
+extern "C" int akod_kagari_encode(akodContext* c, uint64_t n_values, const int16_t* d_in, uint64_t in_stride,
+                                  uint8_t* d_out, uint64_t out_stride, uint64_t out_cap, uint64_t* d_bits,
+                                  uint32_t n_images)
+{
+	if (n_values == 0 || n_values >= ((uint64_t)1 << 32))
+		return AKOD_ERROR;
+	const uint32_t nblocks = (uint32_t)((n_values + KG_BLOCK - 1) / KG_BLOCK);
+	const uint64_t per_img = nblocks;
+
+	void* ws;
+	const size_t need = (size_t)per_img * n_images * (sizeof(long long) + sizeof(uint32_t) + sizeof(uint64_t));
+	int rc = akod_workspace(c, AKOD_WS_KAGARI, need, &ws);
+	if (rc != AKOD_OK)
+		return rc;
+	long long* blk_start = (long long*)ws;
+	uint64_t* blk_off = (uint64_t*)(blk_start + per_img * n_images);
+	uint32_t* blk_bits = (uint32_t*)(blk_off + per_img * n_images);
+
+	const dim3 grid(nblocks, n_images);
+	AKOD_LAUNCH(c, "kagari_starts", k_kg_starts, grid, KG_THREADS, 0, d_in, in_stride, n_values, blk_start, nblocks);
+	AKOD_LAUNCH(c, "kagari_scan_max", k_kg_scan_max, n_images, 1024, 0, blk_start, nblocks);
+	AKOD_LAUNCH(c, "kagari_lengths", k_kg_lengths, grid, KG_THREADS, 0, d_in, in_stride, n_values, blk_start, blk_bits,
+	            nblocks);
+	AKOD_LAUNCH(c, "kagari_scan_sum", k_kg_scan_sum, n_images, 1024, 0, blk_bits, blk_off, nblocks, d_bits);
+	const dim3 zgrid((nblocks + 255) / 256, n_images);
+	AKOD_LAUNCH(c, "kagari_zero_edges", k_kg_zero_edges, zgrid, 256, 0, blk_off, blk_bits, nblocks, d_out, out_stride,
+	            out_cap * 8);
+	AKOD_LAUNCH(c, "kagari_pack", k_kg_pack, grid, KG_THREADS, 0, d_in, in_stride, n_values, blk_start, blk_off, nblocks,
+	            d_out, out_stride, out_cap * 8);
+	return AKOD_OK;
+}
+
+extern "C" int akod_kagari_decode(akodContext* c, uint64_t n_values, const uint8_t* d_in, const uint64_t* d_off,
+                                  const uint64_t* d_size, int16_t* d_out, uint64_t out_stride, uint64_t* d_result,
+                                  uint32_t n_images)
+{
+	if (n_values == 0 || n_images == 0)
+		return AKOD_ERROR;
+	AKOD_LAUNCH(c, "kagari_decode_seq", k_kd_sequential, n_images, 32, 0, d_in, d_off, d_size, n_values, d_out, out_stride,
+	            d_result);
+	return AKOD_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// container
+
+// one thread per image: byte offset of every tile block inside the blob, and the blob size.
+// bits is [tiles][n_images]. A tile that did not fit its capacity voids the image (total = 0).
+__global__ void k_tile_offsets(const uint64_t* __restrict__ bits, const uint64_t* __restrict__ cap, uint32_t n_tiles,
+                               uint32_t n_images, int with_heads, uint64_t* __restrict__ off,
+                               uint64_t* __restrict__ total)
+{
+	const uint32_t img = blockIdx.x * blockDim.x + threadIdx.x;
+	if (img >= n_images)
+		return;
+	uint64_t o = 16;
+	bool ok = true;
+	for (uint32_t t = 0; t < n_tiles; t++)
+	{
+		const uint64_t bytes = (bits[(uint64_t)t * n_images + img] + 7) >> 3;
+		ok = ok && bytes <= cap[t];
+		off[(uint64_t)t * n_images + img] = o;
+		o += bytes + (with_heads ? 4 : 0);
+	}
+	total[img] = ok ? o : 0;
+}
+
+struct HeadWords
+{
+	uint32_t w[4];
+};
+
+// grid (chunks, tiles, images)
+__global__ void __launch_bounds__(256)
+    k_assemble(const HeadWords head, const uint8_t* __restrict__ blocks, uint64_t blocks_stride,
+               const uint64_t* __restrict__ block_off, const uint64_t* __restrict__ bits,
+               const uint64_t* __restrict__ tile_off, const uint64_t* __restrict__ total, int with_heads,
+               uint8_t* __restrict__ out, uint64_t out_stride)
+{
+	const uint32_t t = blockIdx.y, img = blockIdx.z, n_images = gridDim.z;
+	if (total[img] == 0)
+		return;
+	const uint64_t size = (bits[(uint64_t)t * n_images + img] + 7) >> 3;
+	out += out_stride * img;
+	uint8_t* dst = out + tile_off[(uint64_t)t * n_images + img];
+	if (t == 0 && blockIdx.x == 0 && threadIdx.x < 16)
+		out[threadIdx.x] = (uint8_t)(head.w[threadIdx.x >> 2] >> (8 * (threadIdx.x & 3)));
+	if (with_heads)
+	{
+		if (blockIdx.x == 0 && threadIdx.x < 4)
+			dst[threadIdx.x] = (uint8_t)((uint32_t)size >> (8 * threadIdx.x)); // akoBlockHead, compression.c:30-33
+		dst += 4;
+	}
+	const uint8_t* src = blocks + blocks_stride * img + block_off[t];
+	for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < size; i += (uint64_t)gridDim.x * blockDim.x)
+		dst[i] = src[i];
+}
+
+extern "C" int akod_assemble(akodContext* c, const uint8_t head16[16], uint32_t n_tiles, uint32_t n_images,
+                             const uint8_t* d_blocks, uint64_t blocks_stride, const uint64_t* d_block_off,
+                             const uint64_t* d_block_cap, const uint64_t* d_bits, int with_heads, uint8_t* d_out,
+                             uint64_t out_stride, uint64_t* d_total)
+{
+	void* ws;
+	int rc = akod_workspace(c, AKOD_WS_KAGARI2, sizeof(uint64_t) * (size_t)n_tiles * n_images, &ws);
+	if (rc != AKOD_OK)
+		return rc;
+	uint64_t* d_tile_off = (uint64_t*)ws;
+	HeadWords hw;
+	memcpy(hw.w, head16, 16);
+	AKOD_LAUNCH(c, "tile_offsets", k_tile_offsets, (n_images + 63) / 64, 64, 0, d_bits, d_block_cap, n_tiles, n_images,
+	            with_heads, d_tile_off, d_total);
+	unsigned chunks = (unsigned)c->sm_count;
+	if ((uint64_t)n_tiles * n_images >= 64)
+		chunks = 4;
+	const dim3 grid(chunks, n_tiles, n_images);
+	AKOD_LAUNCH(c, "assemble", k_assemble, grid, 256, 0, hw, d_blocks, blocks_stride, d_block_off, d_bits, d_tile_off,
+	            d_total, with_heads, d_out, out_stride);
+	return AKOD_OK;
+}
+
+__global__ void k_walk_blocks(const uint8_t* __restrict__ blob, uint64_t input_size, uint32_t n_tiles,
+                              uint64_t* __restrict__ off, uint64_t* __restrict__ size)
+{
+	if (threadIdx.x != 0 || blockIdx.x != 0)
+		return;
+	uint64_t pos = 16;
+	bool ok = true;
+	for (uint32_t t = 0; t < n_tiles; t++)
+	{
+		uint64_t s = 0;
+		if (ok && pos + 4 <= input_size)
+		{
+			s = (uint64_t)blob[pos] | ((uint64_t)blob[pos + 1] << 8) | ((uint64_t)blob[pos + 2] << 16) |
+			    ((uint64_t)blob[pos + 3] << 24);
+			if (s == 0 || pos + 4 + s > input_size)
+				s = 0;
+		}
+		if (s == 0)
+			ok = false;
+		off[t] = pos + 4;
+		size[t] = s;
+		pos += 4 + s;
+	}
+}
+
+extern "C" int akod_walk_blocks(akodContext* c, const uint8_t* d_blob, uint64_t input_size, uint32_t n_tiles,
+                                uint64_t* d_off, uint64_t* d_size)
+{
+	AKOD_LAUNCH(c, "walk_blocks", k_walk_blocks, 1, 32, 0, d_blob, input_size, n_tiles, d_off, d_size);
+	return AKOD_OK;
+}

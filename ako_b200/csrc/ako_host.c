@@ -1,0 +1,1450 @@
+/*
+ * ako_host.c -- host side of libako_b200, in C like the reference.
+ *
+ * Holds everything that is not per-pixel work: defaults and status strings (reference misc.c:30-95),
+ * version getters (version.c), the 16-byte container header (head.c), tile geometry (misc.c:98-203), the
+ * float quantiser schedule (quantization.c:43-98, evaluated on the host only, same expression order, no
+ * fast-math) and the orchestration of akoEncodeExt / akoDecodeExt (encode.c, decode.c). The per-pixel
+ * work is issued to the CUDA layer through ako_device.h. There is no CPU implementation of any stage:
+ * if the CUDA layer cannot run, every entry point fails with AKO_ERROR / AKO_NO_ENOUGH_MEMORY.
+ */
+#include <math.h>
+#include <pthread.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "ako_b200.h"
+#include "ako_device.h"
+
+#define AKO_API __attribute__((visibility("default")))
+
+struct akoB200Context
+{
+	akodContext* dev;
+	/* small plan cache: full tile, right edge, bottom edge, corner */
+	akodPlan plan[4];
+	struct akoSettings plan_settings[4];
+	int plan_valid[4];
+	int plan_next;
+};
+
+/* ------------------------------------------------------------------------------------------------ */
+/* defaults, strings, versions                                                                       */
+
+AKO_API struct akoSettings akoDefaultSettings(void)
+{
+	struct akoSettings s;
+	memset(&s, 0, sizeof(s));
+	s.wavelet = AKO_WAVELET_DD137;
+	s.color = AKO_COLOR_YCOCG;
+	s.wrap = AKO_WRAP_CLAMP;
+	s.compression = AKO_COMPRESSION_KAGARI;
+	s.tiles_dimension = 0;
+	s.quantization = 16;
+	s.gate = 0;
+	s.chroma_loss = 1;
+	s.discard_non_visible = 0;
+	return s;
+}
+
+AKO_API struct akoCallbacks akoDefaultCallbacks(void)
+{
+	struct akoCallbacks c;
+	memset(&c, 0, sizeof(c));
+	c.malloc = malloc;
+	c.realloc = realloc;
+	c.free = free;
+	return c;
+}
+
+AKO_API void akoDefaultFree(void* p)
+{
+	free(p);
+}
+
+AKO_API const char* akoStatusString(enum akoStatus status)
+{
+	static const char* const text[] = {
+	    "Everything Ok!",
+	    "Something went wrong",
+	    "Invalid channels number",
+	    "Invalid dimensions",
+	    "Invalid tiles dimensions",
+	    "Invalid wrap mode",
+	    "Invalid wavelet transformation",
+	    "Invalid color transformation",
+	    "Invalid compression method",
+	    "Invalid input",
+	    "Invalid callbacks",
+	    "Invalid magic (not an Ako file)",
+	    "Unsupported version",
+	    "No enough memory",
+	    "Invalid flags",
+	    "Broken input/premature end",
+	};
+	if ((int)status < 0 || (size_t)status >= sizeof(text) / sizeof(text[0]))
+		return "Unknown status code";
+	return text[status];
+}
+
+AKO_API int akoVersionMajor(void)
+{
+	return AKO_VERSION_MAJOR;
+}
+AKO_API int akoVersionMinor(void)
+{
+	return AKO_VERSION_MINOR;
+}
+AKO_API int akoVersionPatch(void)
+{
+	return AKO_VERSION_PATCH;
+}
+AKO_API int akoFormatVersion(void)
+{
+	return AKO_FORMAT_VERSION;
+}
+
+/* ------------------------------------------------------------------------------------------------ */
+/* container header, head.c                                                                          */
+
+static enum akoStatus validate(size_t channels, size_t w, size_t h, size_t tiles, int wrap, int wavelet, int color,
+                               int compression)
+{
+	/* same order as head.c:38-63: the first failing property decides the status */
+	if (channels > AKO_MAX_CHANNELS)
+		return AKO_INVALID_CHANNELS_NO;
+	if (w == 0 || h == 0 || w > AKO_MAX_WIDTH || h > AKO_MAX_HEIGHT)
+		return AKO_INVALID_DIMENSIONS;
+	if (tiles != 0 && (tiles < AKO_MIN_TILES_DIMENSION || tiles > AKO_MAX_TILES_DIMENSION))
+		return AKO_INVALID_TILES_DIMENSIONS;
+	if (wrap < AKO_WRAP_CLAMP || wrap > AKO_WRAP_ZERO)
+		return AKO_INVALID_WRAP_MODE;
+	if (wavelet < AKO_WAVELET_DD137 || wavelet > AKO_WAVELET_NONE)
+		return AKO_INVALID_WAVELET_TRANSFORMATION;
+	if (color < AKO_COLOR_YCOCG || color > AKO_COLOR_YCOCG_Q)
+		return AKO_INVALID_COLOR_TRANSFORMATION;
+	if (compression < AKO_COMPRESSION_KAGARI || compression > AKO_COMPRESSION_NONE)
+		return AKO_INVALID_COMPRESSION_METHOD;
+	return AKO_OK;
+}
+
+static void store_le32(uint8_t* p, uint32_t v)
+{
+	p[0] = (uint8_t)(v);
+	p[1] = (uint8_t)(v >> 8);
+	p[2] = (uint8_t)(v >> 16);
+	p[3] = (uint8_t)(v >> 24);
+}
+
+static uint32_t load_le32(const uint8_t* p)
+{
+	return (uint32_t)p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16) | ((uint32_t)p[3] << 24);
+}
+
+/* head.c:67-109. Written byte by byte, so it is endian-neutral. */
+static enum akoStatus head_write(size_t channels, size_t w, size_t h, const struct akoSettings* s, uint8_t out[16])
+{
+	uint32_t tiles_code = 0;
+	if (s->tiles_dimension != 0)
+	{
+		size_t log2 = 0;
+		for (size_t b = s->tiles_dimension; b > 1; b >>= 1)
+			log2++;
+		if (((size_t)1 << log2) != s->tiles_dimension)
+			return AKO_INVALID_TILES_DIMENSIONS;
+		tiles_code = (uint32_t)(log2 - 2); /* 8 -> 1 */
+	}
+
+	const enum akoStatus st = validate(channels, w, h, s->tiles_dimension, (int)s->wrap, (int)s->wavelet,
+	                                   (int)s->color, (int)s->compression);
+	if (st != AKO_OK)
+		return st;
+
+	out[0] = 'A';
+	out[1] = 'k';
+	out[2] = 'o';
+	out[3] = AKO_FORMAT_VERSION;
+	store_le32(out + 4, (uint32_t)w);
+	store_le32(out + 8, (uint32_t)h);
+	store_le32(out + 12, (uint32_t)(channels - 1) | ((uint32_t)s->wrap << 4) | ((uint32_t)s->wavelet << 6) |
+	                         ((uint32_t)s->color << 8) | ((uint32_t)s->compression << 10) | (tiles_code << 12));
+	return AKO_OK;
+}
+
+/* head.c:112-169 */
+static enum akoStatus head_read(const uint8_t in[16], size_t* channels, size_t* w, size_t* h, struct akoSettings* s)
+{
+	if (in[0] != 'A' || in[1] != 'k' || in[2] != 'o')
+		return AKO_INVALID_MAGIC;
+	if (in[3] != AKO_FORMAT_VERSION)
+		return AKO_UNSUPPORTED_VERSION;
+
+	const uint32_t flags = load_le32(in + 12);
+	if ((flags >> 15) != 0)
+		return AKO_INVALID_FLAGS;
+
+	const size_t ch = (size_t)(flags & 15u) + 1;
+	const int wrap = (int)((flags >> 4) & 3u);
+	const int wavelet = (int)((flags >> 6) & 3u);
+	const int color = (int)((flags >> 8) & 3u);
+	const int compression = (int)((flags >> 10) & 3u);
+	size_t tiles = (flags >> 12) & 31u;
+	if (tiles != 0)
+		tiles = (size_t)1 << (tiles + 2);
+
+	const enum akoStatus st = validate(ch, load_le32(in + 4), load_le32(in + 8), tiles, wrap, wavelet, color, compression);
+	if (st != AKO_OK)
+		return st;
+
+	*channels = ch;
+	*w = load_le32(in + 4);
+	*h = load_le32(in + 8);
+	s->wrap = (enum akoWrap)wrap;
+	s->wavelet = (enum akoWavelet)wavelet;
+	s->color = (enum akoColor)color;
+	s->compression = (enum akoCompression)compression;
+	s->tiles_dimension = tiles;
+	return AKO_OK;
+}
+
+/* ------------------------------------------------------------------------------------------------ */
+/* geometry, misc.c:98-203                                                                           */
+
+static size_t half_up(size_t v) /* akoDividePlusOneRule, misc.c:98-101 */
+{
+	return (v >> 1) + (v & 1);
+}
+
+static size_t tile_data_size(size_t w, size_t h) /* akoTileDataSize, misc.c:117-149; bytes per channel */
+{
+	size_t bytes = 0;
+	while (w > 2 && h > 2)
+	{
+		w = half_up(w);
+		h = half_up(h);
+		bytes += w * h * 3 * sizeof(int16_t) + sizeof(int16_t);
+	}
+	return bytes + w * h * sizeof(int16_t);
+}
+
+static size_t tile_dimension(size_t pos, size_t image_d, size_t tiles) /* akoTileDimension, misc.c:152-161 */
+{
+	if (tiles == 0)
+		return image_d;
+	if (pos + tiles > image_d)
+		return image_d % tiles;
+	return tiles;
+}
+
+static size_t tiles_count(size_t w, size_t h, size_t tiles) /* akoImageTilesNo, misc.c:192-203 */
+{
+	if (tiles == 0)
+		return 1;
+	return ((w / tiles) + (w % tiles != 0)) * ((h / tiles) + (h % tiles != 0));
+}
+
+AKO_API size_t akoB200StreamSize(size_t channels, size_t tile_w, size_t tile_h)
+{
+	return tile_data_size(tile_w, tile_h) * channels;
+}
+
+/* ------------------------------------------------------------------------------------------------ */
+/* quantiser schedule, quantization.c:43-98 -- float32, host only                        */
+
+static float schedule(float factor, float tile_w, float tile_h, float current_w, float current_h)
+{
+	const float side0 = sqrtf(tile_w * tile_h);
+	const float side = sqrtf(current_w * current_h);
+	const float lifts_total = log2f(side0) - 1.0F;
+	const float lift_now = log2f(side) - 1.0F;
+	const float ramp = lift_now / lifts_total;
+	const float highs = powf(ramp + 1.0F, 6.0F) / powf(2.0F, 6.0F);
+	const float step = powf(2.0F, lift_now - 1.0F) * highs;
+	return roundf(step * (factor / (512.0F * 0.73F)));
+}
+
+static int16_t level_quantization(int factor, int mul, size_t tw, size_t th, size_t cw, size_t ch)
+{
+	if (factor <= 0)
+		return 1;
+	float q = schedule((float)factor * (float)mul, (float)tw, (float)th, (float)cw, (float)ch);
+	q = (q < 1.0F) ? 1.0F : q;
+	q = (q > 32765.0F) ? 32765.0F : q;
+	return (int16_t)q;
+}
+
+static int16_t level_gate(int factor, int mul, size_t tw, size_t th, size_t cw, size_t ch)
+{
+	if (factor <= 0)
+		return 0;
+	float g = schedule((float)factor * (float)mul, (float)tw, (float)th, (float)cw, (float)ch);
+	g = (g < 0.0F) ? 0.0F : g;
+	g = (g > 32765.0F) ? 32765.0F : g;
+	return (int16_t)g;
+}
+
+/* Builds the integer description of one tile: level dimensions, the wavelet each level really uses
+ * (lifting.c:49-75), q and gate per level and channel (lifting.c:197-211) and the offset of every
+ * subband in the coefficient stream (lifting.c:179, :251-267, :280-285 / misc.c:229-285). */
+static void build_plan(akodPlan* p, const struct akoSettings* s, size_t channels, size_t w, size_t h)
+{
+	memset(p, 0, sizeof(*p));
+	p->w = (uint32_t)w;
+	p->h = (uint32_t)h;
+	p->channels = (uint32_t)channels;
+	p->wrap = (int32_t)s->wrap;
+
+	size_t cw = w, ch = h;
+	uint32_t levels = 0;
+	while (cw > 2 && ch > 2)
+	{
+		akodLevel* L = &p->level[levels];
+		L->cw = (uint32_t)cw;
+		L->ch = (uint32_t)ch;
+		L->tw = (uint32_t)half_up(cw);
+		L->th = (uint32_t)half_up(ch);
+		if (s->wavelet == AKO_WAVELET_HAAR)
+			L->wavelet = AKOD_HAAR;
+		else if (s->wavelet == AKO_WAVELET_CDF53 || L->tw < 8 || L->th < 8)
+			L->wavelet = AKOD_CDF53;
+		else
+			L->wavelet = AKOD_DD137;
+		for (size_t c = 0; c < channels; c++)
+		{
+			const int mul = (c == 0) ? 1 : s->chroma_loss + 1;
+			L->q[c] = level_quantization(s->quantization, mul, w, h, cw, ch);
+			L->g[c] = level_gate(s->gate, mul, w, h, cw, ch);
+		}
+		cw = L->tw;
+		ch = L->th;
+		levels++;
+	}
+	p->levels = levels;
+	p->lp_w = (uint32_t)cw;
+	p->lp_h = (uint32_t)ch;
+
+	/* stream order: lowpasses, then coarsest..finest level, channels ascending inside a level */
+	uint64_t cursor = 0;
+	for (size_t c = 0; c < channels; c++)
+	{
+		p->off_lp[c] = cursor;
+		cursor += (uint64_t)cw * ch;
+	}
+	for (uint32_t l = levels; l-- > 0;)
+	{
+		akodLevel* L = &p->level[l];
+		for (size_t c = 0; c < channels; c++)
+		{
+			cursor += 1; /* akoLiftHead */
+			L->off_c[c] = cursor;
+			cursor += 3 * (uint64_t)L->tw * L->th;
+		}
+	}
+	p->stream_len = cursor;
+}
+
+static int same_settings_for_plan(const struct akoSettings* a, const struct akoSettings* b)
+{
+	return a->wavelet == b->wavelet && a->wrap == b->wrap && a->quantization == b->quantization &&
+	       a->gate == b->gate && a->chroma_loss == b->chroma_loss;
+}
+
+static const akodPlan* get_plan(akoB200Context* ctx, const struct akoSettings* s, size_t channels, size_t w, size_t h)
+{
+	for (int i = 0; i < 4; i++)
+		if (ctx->plan_valid[i] && ctx->plan[i].w == w && ctx->plan[i].h == h && ctx->plan[i].channels == channels &&
+		    same_settings_for_plan(&ctx->plan_settings[i], s))
+			return &ctx->plan[i];
+	const int slot = ctx->plan_next;
+	ctx->plan_next = (ctx->plan_next + 1) & 3;
+	build_plan(&ctx->plan[slot], s, channels, w, h);
+	ctx->plan_settings[slot] = *s;
+	ctx->plan_valid[slot] = 1;
+	return &ctx->plan[slot];
+}
+
+/* ------------------------------------------------------------------------------------------------ */
+/* contexts                                                                                          */
+
+static enum akoStatus from_dev(int rc)
+{
+	if (rc == AKOD_OK)
+		return AKO_OK;
+	return (rc == AKOD_NOMEM) ? AKO_NO_ENOUGH_MEMORY : AKO_ERROR;
+}
+
+static int env_device(void)
+{
+	const char* e = getenv("AKO_CUDA_DEVICE");
+	return (e != NULL && *e != '\0') ? atoi(e) : 0;
+}
+
+AKO_API akoB200Context* akoB200ContextCreate(int device, enum akoStatus* out_status)
+{
+	akoB200Context* ctx = calloc(1, sizeof(*ctx));
+	enum akoStatus st = AKO_OK;
+	if (ctx == NULL)
+		st = AKO_NO_ENOUGH_MEMORY;
+	else
+	{
+		st = from_dev(akod_context_create(device < 0 ? env_device() : device, &ctx->dev));
+		if (st != AKO_OK)
+		{
+			free(ctx);
+			ctx = NULL;
+		}
+	}
+	if (out_status != NULL)
+		*out_status = st;
+	return ctx;
+}
+
+AKO_API void akoB200ContextDestroy(akoB200Context* ctx)
+{
+	if (ctx == NULL)
+		return;
+	akod_context_destroy(ctx->dev);
+	free(ctx);
+}
+
+AKO_API void* akoB200ContextStream(akoB200Context* ctx)
+{
+	return akod_stream(ctx->dev);
+}
+
+AKO_API enum akoStatus akoB200Synchronize(akoB200Context* ctx)
+{
+	return from_dev(akod_sync(ctx->dev));
+}
+
+AKO_API void* akoB200DeviceAlloc(akoB200Context* ctx, size_t bytes)
+{
+	return akod_alloc(ctx->dev, bytes);
+}
+
+AKO_API void akoB200DeviceFree(akoB200Context* ctx, void* p)
+{
+	akod_free(ctx->dev, p);
+}
+
+AKO_API void* akoB200PinnedAlloc(size_t bytes)
+{
+	return akod_pinned_alloc(bytes);
+}
+
+AKO_API void akoB200PinnedFree(void* p)
+{
+	akod_pinned_free(p);
+}
+
+AKO_API enum akoStatus akoB200CopyToDevice(akoB200Context* ctx, void* d_dst, const void* src, size_t bytes)
+{
+	return from_dev(akod_h2d(ctx->dev, d_dst, src, bytes));
+}
+
+AKO_API enum akoStatus akoB200CopyToHost(akoB200Context* ctx, void* dst, const void* d_src, size_t bytes)
+{
+	return from_dev(akod_d2h(ctx->dev, dst, d_src, bytes));
+}
+
+/* Pinned realloc needs the old size: keep it in a 64-byte prefix (keeps 64-byte alignment). */
+#define PIN_PREFIX 64
+
+static void* pinned_malloc(size_t bytes)
+{
+	uint8_t* raw = akod_pinned_alloc(bytes + PIN_PREFIX);
+	if (raw == NULL)
+		return NULL;
+	*(size_t*)raw = bytes;
+	return raw + PIN_PREFIX;
+}
+
+static void pinned_free(void* p)
+{
+	if (p != NULL)
+		akod_pinned_free((uint8_t*)p - PIN_PREFIX);
+}
+
+static void* pinned_realloc(void* p, size_t bytes)
+{
+	if (p == NULL)
+		return pinned_malloc(bytes);
+	const size_t old = *(size_t*)((uint8_t*)p - PIN_PREFIX);
+	void* n = pinned_malloc(bytes);
+	if (n == NULL)
+		return NULL;
+	memcpy(n, p, old < bytes ? old : bytes);
+	pinned_free(p);
+	return n;
+}
+
+AKO_API struct akoCallbacks akoB200PinnedCallbacks(void)
+{
+	struct akoCallbacks c;
+	memset(&c, 0, sizeof(c));
+	c.malloc = pinned_malloc;
+	c.realloc = pinned_realloc;
+	c.free = pinned_free;
+	return c;
+}
+
+AKO_API void akoB200ProfileEnable(akoB200Context* ctx, int enable)
+{
+	akod_profile_enable(ctx->dev, enable);
+}
+
+AKO_API void akoB200ProfileReset(akoB200Context* ctx)
+{
+	akod_profile_reset(ctx->dev);
+}
+
+AKO_API size_t akoB200ProfileGet(akoB200Context* ctx, size_t cap, const char** names, uint64_t* launches,
+                                 double* total_ms)
+{
+	return akod_profile_get(ctx->dev, cap, names, launches, total_ms);
+}
+
+AKO_API uint64_t akoB200LaunchCount(akoB200Context* ctx)
+{
+	return akod_launch_count(ctx->dev);
+}
+
+/* Contexts used by the host-pointer API: created lazily, one per concurrent caller, recycled. */
+#define POOL_MAX 64
+static pthread_mutex_t g_pool_lock = PTHREAD_MUTEX_INITIALIZER;
+static akoB200Context* g_pool[POOL_MAX];
+static int g_pool_len = 0;
+
+static akoB200Context* pool_acquire(enum akoStatus* st)
+{
+	const int device = env_device();
+	akoB200Context* ctx = NULL;
+	pthread_mutex_lock(&g_pool_lock);
+	for (int i = 0; i < g_pool_len; i++)
+		if (akod_device_index(g_pool[i]->dev) == device)
+		{
+			ctx = g_pool[i];
+			g_pool[i] = g_pool[--g_pool_len];
+			break;
+		}
+	pthread_mutex_unlock(&g_pool_lock);
+	if (ctx == NULL)
+		ctx = akoB200ContextCreate(device, st);
+	return ctx;
+}
+
+static void pool_release(akoB200Context* ctx)
+{
+	pthread_mutex_lock(&g_pool_lock);
+	if (g_pool_len < POOL_MAX)
+	{
+		g_pool[g_pool_len++] = ctx;
+		ctx = NULL;
+	}
+	pthread_mutex_unlock(&g_pool_lock);
+	if (ctx != NULL)
+		akoB200ContextDestroy(ctx);
+}
+
+/* Small uint64 arrays to/from the device through the context's pinned mailbox (64 KiB): truly
+ * asynchronous uploads, and read-backs that do not stage through pageable memory. */
+#define MAILBOX_WORDS 8192
+
+static enum akoStatus upload_words(akoB200Context* ctx, uint64_t* d_dst, const uint64_t* src, size_t words)
+{
+	enum akoStatus st = AKO_OK;
+	uint64_t* mail = akod_mailbox(ctx->dev);
+	for (size_t o = 0; o < words && st == AKO_OK; o += MAILBOX_WORDS)
+	{
+		const size_t m = (words - o < MAILBOX_WORDS) ? words - o : MAILBOX_WORDS;
+		if (o != 0)
+			st = from_dev(akod_sync(ctx->dev)); /* previous chunk still in flight */
+		if (st == AKO_OK)
+		{
+			memcpy(mail, src + o, sizeof(uint64_t) * m);
+			st = from_dev(akod_h2d(ctx->dev, d_dst + o, mail, sizeof(uint64_t) * m));
+		}
+	}
+	return st;
+}
+
+static enum akoStatus download_words(akoB200Context* ctx, uint64_t* dst, const uint64_t* d_src, size_t words)
+{
+	enum akoStatus st = AKO_OK;
+	uint64_t* mail = akod_mailbox(ctx->dev);
+	for (size_t o = 0; o < words && st == AKO_OK; o += MAILBOX_WORDS)
+	{
+		const size_t m = (words - o < MAILBOX_WORDS) ? words - o : MAILBOX_WORDS;
+		st = from_dev(akod_d2h(ctx->dev, mail, d_src + o, sizeof(uint64_t) * m));
+		if (st == AKO_OK)
+			st = from_dev(akod_sync(ctx->dev));
+		if (st == AKO_OK)
+			memcpy(dst + o, mail, sizeof(uint64_t) * m);
+	}
+	return st;
+}
+
+/* ------------------------------------------------------------------------------------------------ */
+/* single stages                                                                                     */
+
+static size_t align_up(size_t v, size_t a)
+{
+	return (v + a - 1) / a * a;
+}
+
+static enum akoStatus scratch_for(akoB200Context* ctx, size_t channels, size_t w, size_t h, size_t n, int16_t** out,
+                                  size_t* stride)
+{
+	void* p = NULL;
+	*stride = align_up(half_up(w) * half_up(h) * channels, 8);
+	const enum akoStatus st = from_dev(akod_workspace(ctx->dev, AKOD_WS_SCRATCH, *stride * n * sizeof(int16_t) + 64, &p));
+	*out = p;
+	return st;
+}
+
+AKO_API enum akoStatus akoB200FormatForward(akoB200Context* ctx, const struct akoSettings* s, size_t channels, size_t w,
+                                            size_t h, size_t in_stride_px, const void* d_in, int16_t* d_planes)
+{
+	return from_dev(akod_format_forward(ctx->dev, s->discard_non_visible, (int)s->color, (uint32_t)channels, (uint32_t)w,
+	                                    (uint32_t)h, in_stride_px, d_in, d_planes, NULL));
+}
+
+AKO_API enum akoStatus akoB200FormatInverse(akoB200Context* ctx, enum akoColor color, size_t channels, size_t w,
+                                            size_t h, size_t out_stride_px, const int16_t* d_planes, void* d_out)
+{
+	return from_dev(akod_format_inverse(ctx->dev, (int)color, (uint32_t)channels, (uint32_t)w, (uint32_t)h,
+	                                    out_stride_px, d_planes, d_out, NULL));
+}
+
+AKO_API enum akoStatus akoB200Lift(akoB200Context* ctx, const struct akoSettings* s, size_t channels, size_t w, size_t h,
+                                   int16_t* d_planes, int16_t* d_stream)
+{
+	if (s->wavelet == AKO_WAVELET_NONE || channels == 0 || channels > AKO_MAX_CHANNELS)
+		return AKO_ERROR;
+	int16_t* scratch;
+	size_t stride;
+	const enum akoStatus st = scratch_for(ctx, channels, w, h, 1, &scratch, &stride);
+	if (st != AKO_OK)
+		return st;
+	return from_dev(akod_lift(ctx->dev, get_plan(ctx, s, channels, w, h), d_planes, scratch, d_stream, NULL));
+}
+
+AKO_API enum akoStatus akoB200Unlift(akoB200Context* ctx, const struct akoSettings* s, size_t channels, size_t w,
+                                     size_t h, const int16_t* d_stream, int16_t* d_planes)
+{
+	if (s->wavelet == AKO_WAVELET_NONE || channels == 0 || channels > AKO_MAX_CHANNELS)
+		return AKO_ERROR;
+	int16_t* scratch;
+	size_t stride;
+	const enum akoStatus st = scratch_for(ctx, channels, w, h, 1, &scratch, &stride);
+	if (st != AKO_OK)
+		return st;
+	return from_dev(akod_unlift(ctx->dev, get_plan(ctx, s, channels, w, h), d_stream, d_planes, scratch, NULL));
+}
+
+AKO_API size_t akoB200KagariEncode(akoB200Context* ctx, size_t n_values, const int16_t* d_in, void* d_out,
+                                   size_t out_capacity, enum akoStatus* out_status)
+{
+	enum akoStatus st = AKO_OK;
+	size_t result = 0;
+	void* small = NULL;
+	uint64_t* mail = akod_mailbox(ctx->dev);
+
+	if (n_values == 0 || out_capacity < 4)
+		st = AKO_ERROR;
+	if (st == AKO_OK)
+		st = from_dev(akod_workspace(ctx->dev, AKOD_WS_SMALL, 4096, &small));
+	if (st == AKO_OK)
+		st = from_dev(akod_kagari_encode(ctx->dev, n_values, d_in, 0, d_out, 0, out_capacity & ~(size_t)3, small, 1));
+	if (st == AKO_OK)
+		st = from_dev(akod_d2h(ctx->dev, mail, small, sizeof(uint64_t)));
+	if (st == AKO_OK)
+		st = from_dev(akod_sync(ctx->dev));
+	if (st == AKO_OK)
+	{
+		const uint64_t bytes = (mail[0] + 7) / 8;
+		/* the reference's "fits" rule: kagari.c:65-68, :93-107 */
+		if (bytes < out_capacity && bytes <= (out_capacity & ~(size_t)3))
+			result = (size_t)bytes;
+	}
+	if (out_status != NULL)
+		*out_status = st;
+	return result;
+}
+
+AKO_API size_t akoB200KagariDecode(akoB200Context* ctx, size_t n_values, size_t in_size, const void* d_in,
+                                   int16_t* d_out, enum akoStatus* out_status)
+{
+	enum akoStatus st = AKO_OK;
+	size_t result = 0;
+	void* small = NULL;
+	uint64_t words[2] = {0, in_size};
+	uint64_t answer = 0;
+
+	if (n_values == 0 || in_size == 0)
+		st = AKO_ERROR;
+	if (st == AKO_OK)
+		st = from_dev(akod_workspace(ctx->dev, AKOD_WS_SMALL, 4096, &small));
+	uint64_t* d_words = small;
+	if (st == AKO_OK)
+		st = upload_words(ctx, d_words, words, 2);
+	if (st == AKO_OK)
+		st = from_dev(akod_kagari_decode(ctx->dev, n_values, d_in, d_words, d_words + 1, d_out, 0, d_words + 2, 1));
+	if (st == AKO_OK)
+		st = download_words(ctx, &answer, d_words + 2, 1);
+	if (st == AKO_OK)
+		result = (size_t)answer;
+	if (out_status != NULL)
+		*out_status = st;
+	return result;
+}
+
+/* ------------------------------------------------------------------------------------------------ */
+/* whole codec                                                                                       */
+
+static void fire(const struct akoCallbacks* c, akoB200Context* ctx, size_t tile, size_t tiles, enum akoEvent e)
+{
+	/* Events bracket GPU work, so the stream is drained first: the caller's stopwatch
+	 * (tools/benchmark.hpp:73-90 in the reference) then measures the stage it names. */
+	if (c != NULL && c->events != NULL)
+	{
+		akod_sync(ctx->dev);
+		c->events(tile, tiles, e, c->events_data);
+	}
+}
+
+AKO_API size_t akoB200EncodeBound(const struct akoSettings* s_in, size_t channels, size_t w, size_t h)
+{
+	const struct akoSettings s = (s_in != NULL) ? *s_in : akoDefaultSettings();
+	const size_t td = s.tiles_dimension;
+	size_t bound = 16;
+	size_t tx = 0, ty = 0;
+	const size_t tiles = tiles_count(w, h, td);
+	for (size_t t = 0; t < tiles; t++)
+	{
+		const size_t tw = tile_dimension(tx, w, td), th = tile_dimension(ty, h, td);
+		const size_t data = (s.wavelet != AKO_WAVELET_NONE) ? tile_data_size(tw, th) * channels : tw * th * channels * 2;
+		bound += align_up(data, 4) + 4;
+		tx += td;
+		if (tx >= w)
+		{
+			tx = 0;
+			ty += td;
+		}
+	}
+	return bound;
+}
+
+/* Same-shape batch core. n images at d_in + i*in_stride -> n blobs at d_out + i*out_stride.
+ * 'cb' only for events (may be NULL). */
+static size_t encode_core(akoB200Context* ctx, const struct akoCallbacks* cb, const struct akoSettings* s_in,
+                          size_t channels, size_t w, size_t h, size_t n, const uint8_t* d_in, size_t in_stride,
+                          uint8_t* d_out, size_t out_stride, size_t out_capacity, size_t* out_sizes,
+                          enum akoStatus* out_status)
+{
+	enum akoStatus st = AKO_OK;
+	struct akoSettings s = (s_in != NULL) ? *s_in : akoDefaultSettings();
+	size_t done = 0;
+	uint64_t* host_off = NULL;
+
+	/* encode.c:59-64 */
+	if (s.color == AKO_COLOR_YCOCG && (s.quantization > 0 || s.gate > 0))
+		s.color = AKO_COLOR_YCOCG_Q;
+	else if (s.color == AKO_COLOR_YCOCG_Q && (s.quantization <= 0 && s.gate <= 0))
+		s.color = AKO_COLOR_YCOCG;
+
+	if (d_in == NULL)
+	{
+		st = AKO_INVALID_INPUT;
+		goto done;
+	}
+
+	uint8_t head[16];
+	if ((st = head_write(channels, w, h, &s, head)) != AKO_OK)
+		goto done;
+	if (channels == 0)
+	{
+		st = AKO_INVALID_CHANNELS_NO; /* the reference would write flags 0xFFFFFFFF; refuse instead */
+		goto done;
+	}
+	if (s.wavelet == AKO_WAVELET_NONE && s.compression != AKO_COMPRESSION_NONE)
+	{
+		/* The reference compresses akoTileDataSize() bytes of a buffer it only formatted w*h*2 bytes of
+		 * (compression.c:40 vs encode.c:127): its output depends on uninitialised memory. */
+		st = AKO_ERROR;
+		goto done;
+	}
+	if (out_capacity < akoB200EncodeBound(&s, channels, w, h))
+	{
+		st = AKO_NO_ENOUGH_MEMORY;
+		goto done;
+	}
+
+	const size_t td = s.tiles_dimension;
+	const size_t tiles = tiles_count(w, h, td);
+	const size_t max_w = tile_dimension(0, w, td), max_h = tile_dimension(0, h, td);
+	const size_t planes_stride = align_up(max_w * max_h * channels, 8);
+	const size_t stream_cap = align_up(
+	    (s.wavelet != AKO_WAVELET_NONE ? tile_data_size(max_w, max_h) * channels : max_w * max_h * channels * 2) / 2, 8);
+
+	void *planes, *scratch, *stream, *blocks, *small;
+	size_t scratch_stride;
+	if ((st = from_dev(akod_workspace(ctx->dev, AKOD_WS_PLANES, planes_stride * n * 2 + 64, &planes))) != AKO_OK ||
+	    (st = scratch_for(ctx, channels, max_w, max_h, n, (int16_t**)&scratch, &scratch_stride)) != AKO_OK ||
+	    (st = from_dev(akod_workspace(ctx->dev, AKOD_WS_STREAM, stream_cap * n * 2 + 64, &stream))) != AKO_OK)
+		goto done;
+
+	/* every tile's compressed block gets its own 16-byte aligned region, image-major */
+	host_off = malloc(sizeof(uint64_t) * tiles * 3); /* [off | cap | data] : off and cap are uploaded together */
+	if (host_off == NULL)
+	{
+		st = AKO_NO_ENOUGH_MEMORY;
+		goto done;
+	}
+	uint64_t* host_cap = host_off + tiles;
+	uint64_t* host_data = host_cap + tiles;
+	size_t blocks_per_image = 0;
+	{
+		size_t tx = 0, ty = 0;
+		for (size_t t = 0; t < tiles; t++)
+		{
+			const size_t tw = tile_dimension(tx, w, td), th = tile_dimension(ty, h, td);
+			const size_t data = (s.wavelet != AKO_WAVELET_NONE) ? tile_data_size(tw, th) * channels : tw * th * channels * 2;
+			host_off[t] = blocks_per_image;
+			host_data[t] = data;
+			host_cap[t] = (data >= 4) ? ((data - 4) & ~(uint64_t)3) : 0; /* what the packer may write */
+			blocks_per_image += align_up(data, 16);
+			tx += td;
+			if (tx >= w)
+			{
+				tx = 0;
+				ty += td;
+			}
+		}
+	}
+	if ((st = from_dev(akod_workspace(ctx->dev, AKOD_WS_BLOCKS, blocks_per_image * n + 64, &blocks))) != AKO_OK ||
+	    (st = from_dev(akod_workspace(ctx->dev, AKOD_WS_SMALL, sizeof(uint64_t) * ((tiles + 1) * n + 2 * tiles) + 64,
+	                                  &small))) != AKO_OK)
+		goto done;
+	uint64_t* d_bits = small;                    /* [tiles][n] */
+	uint64_t* d_total = d_bits + tiles * n;      /* [n] */
+	uint64_t* d_block_off = d_total + n;         /* [tiles] */
+	uint64_t* d_block_cap = d_block_off + tiles; /* [tiles] */
+	if ((st = upload_words(ctx, d_block_off, host_off, tiles * 2)) != AKO_OK)
+		goto done;
+
+	akodBatch batch;
+	batch.n = (uint32_t)n;
+	batch.in_stride = in_stride;
+	batch.planes_stride = planes_stride;
+	batch.scratch_stride = scratch_stride;
+	batch.stream_stride = stream_cap;
+
+	size_t tx = 0, ty = 0;
+	for (size_t t = 0; t < tiles && st == AKO_OK; t++)
+	{
+		const size_t tw = tile_dimension(tx, w, td), th = tile_dimension(ty, h, td);
+		const uint8_t* tile_in = d_in + (w * ty + tx) * channels;
+
+		fire(cb, ctx, t, tiles, AKO_EVENT_FORMAT_START);
+		st = from_dev(akod_format_forward(ctx->dev, s.discard_non_visible, (int)s.color, (uint32_t)channels, (uint32_t)tw,
+		                                  (uint32_t)th, w, tile_in, planes, &batch));
+		fire(cb, ctx, t, tiles, AKO_EVENT_FORMAT_END);
+
+		const int16_t* data = planes;
+		uint64_t data_stride = planes_stride;
+		if (st == AKO_OK && s.wavelet != AKO_WAVELET_NONE)
+		{
+			fire(cb, ctx, t, tiles, AKO_EVENT_WAVELET_START);
+			st = from_dev(akod_lift(ctx->dev, get_plan(ctx, &s, channels, tw, th), planes, scratch, stream, &batch));
+			fire(cb, ctx, t, tiles, AKO_EVENT_WAVELET_END);
+			data = stream;
+			data_stride = stream_cap;
+		}
+
+		fire(cb, ctx, t, tiles, AKO_EVENT_COMPRESSION_START);
+		if (st == AKO_OK && s.compression != AKO_COMPRESSION_NONE)
+		{
+			/* capacity = what the reference hands to akoKagariEncode (compression.c:40-45), rounded down to words */
+			st = from_dev(akod_kagari_encode(ctx->dev, host_data[t] / 2, data, data_stride, (uint8_t*)blocks + host_off[t],
+			                                 blocks_per_image, host_cap[t], d_bits + t * n, (uint32_t)n));
+		}
+		else if (st == AKO_OK)
+		{
+			/* no compression: the block is the raw int16 data (encode.c:151-153) */
+			for (size_t i = 0; i < n && st == AKO_OK; i++)
+				st = from_dev(akod_d2d(ctx->dev, (uint8_t*)blocks + blocks_per_image * i + host_off[t],
+				                       data + data_stride * i, host_data[t]));
+			if (st == AKO_OK)
+				st = from_dev(akod_fill_words(ctx->dev, d_bits + t * n, (uint64_t)host_data[t] * 8, n));
+		}
+		fire(cb, ctx, t, tiles, AKO_EVENT_COMPRESSION_END);
+
+		tx += td;
+		if (tx >= w)
+		{
+			tx = 0;
+			ty += td;
+		}
+	}
+	if (st != AKO_OK)
+		goto done;
+
+	/* container assembly on the device, then one small read-back of sizes */
+	if ((st = from_dev(akod_assemble(ctx->dev, head, (uint32_t)tiles, (uint32_t)n, blocks, blocks_per_image, d_block_off,
+	                                 d_block_cap, d_bits, s.compression != AKO_COMPRESSION_NONE, d_out, out_stride,
+	                                 d_total))) != AKO_OK)
+		goto done;
+
+	{
+		const size_t words = (tiles + 1) * n;
+		uint64_t* all = malloc(sizeof(uint64_t) * words);
+		if (all == NULL)
+		{
+			st = AKO_NO_ENOUGH_MEMORY;
+			goto done;
+		}
+		st = download_words(ctx, all, small, words);
+		for (size_t i = 0; i < n && st == AKO_OK; i++)
+		{
+			if (s.compression != AKO_COMPRESSION_NONE)
+				for (size_t t = 0; t < tiles; t++)
+				{
+					/* akoKagariEncode succeeds iff its bytes are < the capacity it was given, which is the tile's
+					 * stream size minus the block head (compression.c:40-49; kagari.c:65-68, :93-107). A failure
+					 * makes akoEncodeExt return AKO_ERROR (encode.c:159-164). */
+					const uint64_t bytes = (all[t * n + i] + 7) / 8;
+					if (bytes == 0 || bytes >= host_data[t] - 4)
+						st = AKO_ERROR;
+				}
+			if (st == AKO_OK && all[tiles * n + i] == 0)
+				st = AKO_ERROR;
+			if (st == AKO_OK)
+			{
+				if (out_sizes != NULL)
+					out_sizes[i] = (size_t)all[tiles * n + i];
+				done = i + 1;
+			}
+		}
+		free(all);
+	}
+
+done:
+	free(host_off);
+	if (out_status != NULL)
+		*out_status = st;
+	return done;
+}
+
+AKO_API size_t akoB200EncodeBatchDevice(akoB200Context* ctx, const struct akoSettings* s, size_t channels, size_t w,
+                                        size_t h, size_t n_images, const void* d_in, size_t in_stride, void* d_out,
+                                        size_t out_stride, size_t* out_sizes, enum akoStatus* out_status)
+{
+	if (n_images == 0)
+	{
+		if (out_status != NULL)
+			*out_status = AKO_OK;
+		return 0;
+	}
+	return encode_core(ctx, NULL, s, channels, w, h, n_images, d_in, in_stride, d_out, out_stride, out_stride, out_sizes,
+	                   out_status);
+}
+
+AKO_API size_t akoB200EncodeDevice(akoB200Context* ctx, const struct akoSettings* s, size_t channels, size_t w, size_t h,
+                                   const void* d_in, void* d_out, size_t out_capacity, enum akoStatus* out_status)
+{
+	size_t size = 0;
+	const size_t ok = encode_core(ctx, NULL, s, channels, w, h, 1, d_in, 0, d_out, 0, out_capacity, &size, out_status);
+	return ok ? size : 0;
+}
+
+AKO_API size_t akoEncodeExt(const struct akoCallbacks* c, const struct akoSettings* s, size_t channels, size_t w,
+                            size_t h, const void* in, void** out, enum akoStatus* out_status)
+{
+	enum akoStatus st = AKO_OK;
+	const struct akoCallbacks cb = (c != NULL) ? *c : akoDefaultCallbacks();
+	struct akoSettings checked = (s != NULL) ? *s : akoDefaultSettings();
+	akoB200Context* ctx = NULL;
+	uint8_t* blob = NULL;
+	size_t size = 0;
+
+	/* check order of encode.c:53-82: callbacks, input, (allocation), header validation */
+	if (cb.malloc == NULL || cb.realloc == NULL || cb.free == NULL)
+	{
+		st = AKO_INVALID_CALLBACKS;
+		goto done;
+	}
+	if (in == NULL)
+	{
+		st = AKO_INVALID_INPUT;
+		goto done;
+	}
+	{
+		/* validate before touching the device so that bad arguments never cost a context */
+		struct akoSettings v = checked;
+		uint8_t head[16];
+		if (v.color == AKO_COLOR_YCOCG && (v.quantization > 0 || v.gate > 0))
+			v.color = AKO_COLOR_YCOCG_Q;
+		if ((st = head_write(channels, w, h, &v, head)) != AKO_OK)
+			goto done;
+	}
+	if ((ctx = pool_acquire(&st)) == NULL)
+		goto done;
+
+	{
+		const size_t image_bytes = w * h * channels;
+		const size_t bound = akoB200EncodeBound(&checked, channels, w, h);
+		void *d_in, *d_out;
+		if ((st = from_dev(akod_workspace(ctx->dev, AKOD_WS_INPUT, image_bytes + 64, &d_in))) != AKO_OK ||
+		    (st = from_dev(akod_workspace(ctx->dev, AKOD_WS_OUTPUT, bound + 64, &d_out))) != AKO_OK ||
+		    (st = from_dev(akod_h2d(ctx->dev, d_in, in, image_bytes))) != AKO_OK)
+			goto done;
+
+		if (encode_core(ctx, &cb, &checked, channels, w, h, 1, d_in, 0, d_out, 0, bound, &size, &st) != 1)
+		{
+			size = 0;
+			goto done;
+		}
+		if ((blob = cb.malloc(size)) == NULL)
+		{
+			st = AKO_NO_ENOUGH_MEMORY;
+			size = 0;
+			goto done;
+		}
+		if ((st = from_dev(akod_d2h(ctx->dev, blob, d_out, size))) != AKO_OK || (st = from_dev(akod_sync(ctx->dev))) != AKO_OK)
+		{
+			cb.free(blob);
+			blob = NULL;
+			size = 0;
+			goto done;
+		}
+	}
+
+	if (out != NULL)
+		*out = blob;
+	else
+		cb.free(blob); /* size query only, as in encode.c:214-217 */
+
+done:
+	if (ctx != NULL)
+		pool_release(ctx);
+	if (out_status != NULL)
+		*out_status = st;
+	return size;
+}
+
+/* ---- decode ---- */
+
+/* n same-shape blobs. Block offsets/sizes per image and tile are host arrays [n][tiles]. */
+static enum akoStatus decode_core(akoB200Context* ctx, const struct akoCallbacks* cb, const struct akoSettings* s,
+                                  size_t channels, size_t w, size_t h, size_t n, const uint8_t* d_in, size_t in_stride,
+                                  const uint64_t* blk_off, const uint64_t* blk_size, uint8_t* d_out, size_t out_stride,
+                                  size_t* done_out)
+{
+	enum akoStatus st = AKO_OK;
+	const size_t td = s->tiles_dimension;
+	const size_t tiles = tiles_count(w, h, td);
+	const size_t max_w = tile_dimension(0, w, td), max_h = tile_dimension(0, h, td);
+	const size_t planes_stride = align_up(max_w * max_h * channels, 8);
+	const size_t stream_cap = align_up(
+	    (s->wavelet != AKO_WAVELET_NONE ? tile_data_size(max_w, max_h) * channels : max_w * max_h * channels * 2) / 2, 8);
+	uint64_t* off_abs = NULL;
+	*done_out = 0;
+
+	void *planes, *scratch, *stream, *small;
+	size_t scratch_stride;
+	if ((st = from_dev(akod_workspace(ctx->dev, AKOD_WS_PLANES, planes_stride * n * 2 + 64, &planes))) != AKO_OK ||
+	    (st = scratch_for(ctx, channels, max_w, max_h, n, (int16_t**)&scratch, &scratch_stride)) != AKO_OK ||
+	    (st = from_dev(akod_workspace(ctx->dev, AKOD_WS_STREAM, stream_cap * n * 2 + 64, &stream))) != AKO_OK ||
+	    (st = from_dev(akod_workspace(ctx->dev, AKOD_WS_SMALL, sizeof(uint64_t) * tiles * n * 3 + 64, &small))) != AKO_OK)
+		return st;
+	uint64_t* d_result = small;            /* [tiles][n] */
+	uint64_t* d_off = d_result + tiles * n; /* [tiles][n] absolute byte offsets into d_in */
+	uint64_t* d_size = d_off + tiles * n;   /* [tiles][n] */
+
+	off_abs = malloc(sizeof(uint64_t) * tiles * n * 3);
+	if (off_abs == NULL)
+		return AKO_NO_ENOUGH_MEMORY;
+	uint64_t* size_abs = off_abs + tiles * n;
+	uint64_t* results = size_abs + tiles * n;
+	for (size_t t = 0; t < tiles; t++)
+		for (size_t i = 0; i < n; i++)
+		{
+			off_abs[t * n + i] = in_stride * i + blk_off[tiles * i + t];
+			size_abs[t * n + i] = blk_size[tiles * i + t];
+		}
+	if ((st = upload_words(ctx, d_off, off_abs, tiles * n * 2)) != AKO_OK)
+	{
+		free(off_abs);
+		return st;
+	}
+
+	akodBatch batch;
+	batch.n = (uint32_t)n;
+	batch.in_stride = out_stride; /* format_inverse uses in_stride as the u8 image stride */
+	batch.planes_stride = planes_stride;
+	batch.scratch_stride = scratch_stride;
+	batch.stream_stride = stream_cap;
+
+	size_t tx = 0, ty = 0;
+	for (size_t t = 0; t < tiles && st == AKO_OK; t++)
+	{
+		const size_t tw = tile_dimension(tx, w, td), th = tile_dimension(ty, h, td);
+		const size_t data = (s->wavelet != AKO_WAVELET_NONE) ? tile_data_size(tw, th) * channels : tw * th * channels * 2;
+		int16_t* target = (s->wavelet != AKO_WAVELET_NONE) ? stream : planes;
+		const uint64_t target_stride = (s->wavelet != AKO_WAVELET_NONE) ? stream_cap : planes_stride;
+
+		fire(cb, ctx, t, tiles, AKO_EVENT_COMPRESSION_START);
+		if (s->compression != AKO_COMPRESSION_NONE)
+			st = from_dev(akod_kagari_decode(ctx->dev, data / 2, d_in, d_off + t * n, d_size + t * n, target,
+			                                 target_stride, d_result + t * n, (uint32_t)n));
+		else
+			for (size_t i = 0; i < n && st == AKO_OK; i++)
+				st = from_dev(akod_d2d(ctx->dev, target + target_stride * i, d_in + off_abs[t * n + i], data));
+		fire(cb, ctx, t, tiles, AKO_EVENT_COMPRESSION_END);
+
+		if (st == AKO_OK && s->wavelet != AKO_WAVELET_NONE)
+		{
+			fire(cb, ctx, t, tiles, AKO_EVENT_WAVELET_START);
+			st = from_dev(akod_unlift(ctx->dev, get_plan(ctx, s, channels, tw, th), stream, planes, scratch, &batch));
+			fire(cb, ctx, t, tiles, AKO_EVENT_WAVELET_END);
+		}
+		if (st == AKO_OK)
+		{
+			fire(cb, ctx, t, tiles, AKO_EVENT_FORMAT_START);
+			st = from_dev(akod_format_inverse(ctx->dev, (int)s->color, (uint32_t)channels, (uint32_t)tw, (uint32_t)th, w,
+			                                  planes, d_out + (w * ty + tx) * channels, &batch));
+			fire(cb, ctx, t, tiles, AKO_EVENT_FORMAT_END);
+		}
+
+		tx += td;
+		if (tx >= w)
+		{
+			tx = 0;
+			ty += td;
+		}
+	}
+
+	if (st == AKO_OK && s->compression != AKO_COMPRESSION_NONE)
+	{
+		/* compression.c:69-70, decode.c:152-156: every block must have been consumed exactly */
+		size_t first_bad = n;
+		st = download_words(ctx, results, d_result, tiles * n);
+		for (size_t k = 0; k < tiles * n && st == AKO_OK; k++)
+			if (results[k] == 0 || results[k] != size_abs[k])
+				if (k % n < first_bad)
+					first_bad = k % n;
+		if (st == AKO_OK)
+		{
+			*done_out = first_bad;
+			if (first_bad != n)
+				st = AKO_BROKEN_INPUT;
+		}
+	}
+	else if (st == AKO_OK)
+	{
+		st = from_dev(akod_sync(ctx->dev));
+		if (st == AKO_OK)
+			*done_out = n;
+	}
+	free(off_abs);
+	return st;
+}
+
+/* walks the block heads of one blob on the host; returns AKO_BROKEN_INPUT if it runs past the end */
+static enum akoStatus walk_blocks_host(const uint8_t* blob, size_t input_size, const struct akoSettings* s,
+                                       size_t channels, size_t w, size_t h, uint64_t* off, uint64_t* size)
+{
+	const size_t td = s->tiles_dimension;
+	const size_t tiles = tiles_count(w, h, td);
+	size_t pos = 16, tx = 0, ty = 0;
+	for (size_t t = 0; t < tiles; t++)
+	{
+		const size_t tw = tile_dimension(tx, w, td), th = tile_dimension(ty, h, td);
+		if (s->compression != AKO_COMPRESSION_NONE)
+		{
+			if (pos + 4 > input_size)
+				return AKO_BROKEN_INPUT;
+			const size_t block = load_le32(blob + pos);
+			if (block == 0 || pos + 4 + block > input_size)
+				return AKO_BROKEN_INPUT;
+			off[t] = pos + 4;
+			size[t] = block;
+			pos += 4 + block;
+		}
+		else
+		{
+			const size_t data = (s->wavelet != AKO_WAVELET_NONE) ? tile_data_size(tw, th) * channels : tw * th * channels * 2;
+			if (pos + data > input_size) /* decode.c:163-167 */
+				return AKO_BROKEN_INPUT;
+			off[t] = pos;
+			size[t] = data;
+			pos += data;
+		}
+		tx += td;
+		if (tx >= w)
+		{
+			tx = 0;
+			ty += td;
+		}
+	}
+	return AKO_OK;
+}
+
+AKO_API uint8_t* akoDecodeExt(const struct akoCallbacks* c, size_t input_size, const void* in, struct akoSettings* out_s,
+                              size_t* out_channels, size_t* out_w, size_t* out_h, enum akoStatus* out_status)
+{
+	enum akoStatus st = AKO_OK;
+	const struct akoCallbacks cb = (c != NULL) ? *c : akoDefaultCallbacks();
+	struct akoSettings s;
+	size_t channels = 0, w = 0, h = 0;
+	akoB200Context* ctx = NULL;
+	uint8_t* image = NULL;
+	uint64_t* blk = NULL;
+	memset(&s, 0, sizeof(s));
+
+	if (cb.malloc == NULL || cb.realloc == NULL || cb.free == NULL)
+	{
+		st = AKO_INVALID_CALLBACKS;
+		goto done;
+	}
+	if (in == NULL)
+	{
+		st = AKO_INVALID_INPUT;
+		goto done;
+	}
+	if (input_size < 16) /* the reference's own check is a tautology (decode.c:71); this one is real */
+	{
+		st = AKO_BROKEN_INPUT;
+		goto done;
+	}
+	if ((st = head_read(in, &channels, &w, &h, &s)) != AKO_OK)
+		goto done;
+	if (s.wavelet == AKO_WAVELET_NONE && s.compression != AKO_COMPRESSION_NONE)
+	{
+		st = AKO_ERROR; /* see encode_core */
+		goto done;
+	}
+
+	const size_t tiles = tiles_count(w, h, s.tiles_dimension);
+	if ((blk = malloc(sizeof(uint64_t) * tiles * 2)) == NULL)
+	{
+		st = AKO_NO_ENOUGH_MEMORY;
+		goto done;
+	}
+	if ((st = walk_blocks_host(in, input_size, &s, channels, w, h, blk, blk + tiles)) != AKO_OK)
+		goto done;
+	if ((ctx = pool_acquire(&st)) == NULL)
+		goto done;
+
+	{
+		const size_t image_bytes = w * h * channels;
+		void *d_in, *d_out;
+		size_t ok = 0;
+		if ((st = from_dev(akod_workspace(ctx->dev, AKOD_WS_INPUT, input_size + 64, &d_in))) != AKO_OK ||
+		    (st = from_dev(akod_workspace(ctx->dev, AKOD_WS_OUTPUT, image_bytes + 64, &d_out))) != AKO_OK ||
+		    (st = from_dev(akod_h2d(ctx->dev, d_in, in, input_size))) != AKO_OK)
+			goto done;
+		if ((st = decode_core(ctx, &cb, &s, channels, w, h, 1, d_in, 0, blk, blk + tiles, d_out, 0, &ok)) != AKO_OK)
+			goto done;
+		if ((image = cb.malloc(image_bytes)) == NULL)
+		{
+			st = AKO_NO_ENOUGH_MEMORY;
+			goto done;
+		}
+		if ((st = from_dev(akod_d2h(ctx->dev, image, d_out, image_bytes))) != AKO_OK ||
+		    (st = from_dev(akod_sync(ctx->dev))) != AKO_OK)
+		{
+			cb.free(image);
+			image = NULL;
+			goto done;
+		}
+	}
+
+	if (out_s != NULL)
+		*out_s = s;
+	if (out_channels != NULL)
+		*out_channels = channels;
+	if (out_w != NULL)
+		*out_w = w;
+	if (out_h != NULL)
+		*out_h = h;
+
+done:
+	free(blk);
+	if (ctx != NULL)
+		pool_release(ctx);
+	if (out_status != NULL)
+		*out_status = st;
+	return image;
+}
+
+/* device-resident blobs: the block heads are walked on the device, then read back */
+static enum akoStatus walk_blocks_device(akoB200Context* ctx, const uint8_t* d_blob, size_t input_size,
+                                         const struct akoSettings* s, size_t channels, size_t w, size_t h, uint64_t* off,
+                                         uint64_t* size)
+{
+	const size_t tiles = tiles_count(w, h, s->tiles_dimension);
+	if (s->compression == AKO_COMPRESSION_NONE)
+	{
+		/* sizes are pure geometry */
+		uint8_t fake[4] = {0, 0, 0, 0};
+		(void)fake;
+		size_t pos = 16, tx = 0, ty = 0;
+		const size_t td = s->tiles_dimension;
+		for (size_t t = 0; t < tiles; t++)
+		{
+			const size_t tw = tile_dimension(tx, w, td), th = tile_dimension(ty, h, td);
+			const size_t data = (s->wavelet != AKO_WAVELET_NONE) ? tile_data_size(tw, th) * channels : tw * th * channels * 2;
+			if (pos + data > input_size)
+				return AKO_BROKEN_INPUT;
+			off[t] = pos;
+			size[t] = data;
+			pos += data;
+			tx += td;
+			if (tx >= w)
+			{
+				tx = 0;
+				ty += td;
+			}
+		}
+		return AKO_OK;
+	}
+
+	enum akoStatus st;
+	void* small;
+	uint64_t* mail = akod_mailbox(ctx->dev);
+	if (tiles * 2 * sizeof(uint64_t) > (1 << 16))
+		return AKO_ERROR; /* more than 4096 tiles per device-resident blob: use the host-pointer API */
+	if ((st = from_dev(akod_workspace(ctx->dev, AKOD_WS_SMALL, sizeof(uint64_t) * tiles * 2 + 64, &small))) != AKO_OK)
+		return st;
+	uint64_t* d_off = small;
+	if ((st = from_dev(akod_walk_blocks(ctx->dev, d_blob, input_size, (uint32_t)tiles, d_off, d_off + tiles))) != AKO_OK ||
+	    (st = from_dev(akod_d2h(ctx->dev, mail, d_off, sizeof(uint64_t) * tiles * 2))) != AKO_OK ||
+	    (st = from_dev(akod_sync(ctx->dev))) != AKO_OK)
+		return st;
+	for (size_t t = 0; t < tiles; t++)
+	{
+		off[t] = mail[t];
+		size[t] = mail[tiles + t];
+		if (size[t] == 0)
+			return AKO_BROKEN_INPUT;
+	}
+	return AKO_OK;
+}
+
+AKO_API enum akoStatus akoB200DecodeDevice(akoB200Context* ctx, size_t input_size, const void* d_in, const void* head16,
+                                           void* d_out, size_t out_capacity, struct akoSettings* out_s,
+                                           size_t* out_channels, size_t* out_w, size_t* out_h)
+{
+	enum akoStatus st;
+	struct akoSettings s;
+	size_t channels = 0, w = 0, h = 0, ok = 0;
+	uint8_t head[16];
+	uint64_t* blk = NULL;
+	memset(&s, 0, sizeof(s));
+
+	if (d_in == NULL || d_out == NULL)
+		return AKO_INVALID_INPUT;
+	if (input_size < 16)
+		return AKO_BROKEN_INPUT;
+	if (head16 != NULL)
+		memcpy(head, head16, 16);
+	else
+	{
+		uint8_t* mail = akod_mailbox(ctx->dev);
+		if ((st = from_dev(akod_d2h(ctx->dev, mail, d_in, 16))) != AKO_OK || (st = from_dev(akod_sync(ctx->dev))) != AKO_OK)
+			return st;
+		memcpy(head, mail, 16);
+	}
+	if ((st = head_read(head, &channels, &w, &h, &s)) != AKO_OK)
+		return st;
+	if (s.wavelet == AKO_WAVELET_NONE && s.compression != AKO_COMPRESSION_NONE)
+		return AKO_ERROR;
+	if (out_capacity < w * h * channels)
+		return AKO_NO_ENOUGH_MEMORY;
+
+	const size_t tiles = tiles_count(w, h, s.tiles_dimension);
+	if ((blk = malloc(sizeof(uint64_t) * tiles * 2)) == NULL)
+		return AKO_NO_ENOUGH_MEMORY;
+	st = walk_blocks_device(ctx, d_in, input_size, &s, channels, w, h, blk, blk + tiles);
+	if (st == AKO_OK)
+		st = decode_core(ctx, NULL, &s, channels, w, h, 1, d_in, 0, blk, blk + tiles, d_out, 0, &ok);
+	free(blk);
+	if (st != AKO_OK)
+		return st;
+
+	if (out_s != NULL)
+		*out_s = s;
+	if (out_channels != NULL)
+		*out_channels = channels;
+	if (out_w != NULL)
+		*out_w = w;
+	if (out_h != NULL)
+		*out_h = h;
+	return AKO_OK;
+}
+
+AKO_API size_t akoB200DecodeBatchDevice(akoB200Context* ctx, size_t n_images, const void* d_in, size_t in_stride,
+                                        const size_t* in_sizes, void* d_out, size_t out_stride,
+                                        enum akoStatus* out_status)
+{
+	enum akoStatus st = AKO_OK;
+	struct akoSettings s;
+	size_t channels = 0, w = 0, h = 0, ok = 0;
+	uint64_t* blk = NULL;
+	memset(&s, 0, sizeof(s));
+
+	if (n_images == 0)
+		goto done;
+	if (d_in == NULL || d_out == NULL || in_sizes == NULL)
+	{
+		st = AKO_INVALID_INPUT;
+		goto done;
+	}
+	{
+		/* header of blob 0 defines the batch's shape */
+		uint8_t* mail = akod_mailbox(ctx->dev);
+		if (in_sizes[0] < 16)
+		{
+			st = AKO_BROKEN_INPUT;
+			goto done;
+		}
+		if ((st = from_dev(akod_d2h(ctx->dev, mail, d_in, 16))) != AKO_OK || (st = from_dev(akod_sync(ctx->dev))) != AKO_OK)
+			goto done;
+		uint8_t head[16];
+		memcpy(head, mail, 16);
+		if ((st = head_read(head, &channels, &w, &h, &s)) != AKO_OK)
+			goto done;
+	}
+	if (s.wavelet == AKO_WAVELET_NONE && s.compression != AKO_COMPRESSION_NONE)
+	{
+		st = AKO_ERROR;
+		goto done;
+	}
+	if (out_stride < w * h * channels)
+	{
+		st = AKO_NO_ENOUGH_MEMORY;
+		goto done;
+	}
+
+	const size_t tiles = tiles_count(w, h, s.tiles_dimension);
+	if ((blk = malloc(sizeof(uint64_t) * tiles * 2 * n_images)) == NULL)
+	{
+		st = AKO_NO_ENOUGH_MEMORY;
+		goto done;
+	}
+	uint64_t* off = blk;
+	uint64_t* size = blk + tiles * n_images;
+	for (size_t i = 0; i < n_images && st == AKO_OK; i++)
+		st = walk_blocks_device(ctx, (const uint8_t*)d_in + in_stride * i, in_sizes[i], &s, channels, w, h,
+		                        off + tiles * i, size + tiles * i);
+	if (st == AKO_OK)
+		st = decode_core(ctx, NULL, &s, channels, w, h, n_images, d_in, in_stride, off, size, d_out, out_stride, &ok);
+
+done:
+	free(blk);
+	if (out_status != NULL)
+		*out_status = st;
+	return ok;
+}

@@ -1,0 +1,196 @@
+// common.cuh -- context, launch accounting and block-level scan helpers shared by all kernels.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <vector>
+
+#include "ako_device.h"
+
+struct akodProfEntry
+{
+	const char* name;
+	uint64_t launches;
+	double ms;
+};
+
+struct akodPending
+{
+	int entry;
+	cudaEvent_t a, b;
+};
+
+struct akodContext
+{
+	int device;
+	int sm_count;
+	cudaStream_t stream;
+	void* ws[AKOD_WS_COUNT];
+	size_t ws_size[AKOD_WS_COUNT];
+	void* mailbox; // pinned host, 64 KiB
+	// accounting
+	bool profiling;
+	uint64_t launch_count;
+	std::vector<akodProfEntry> prof;
+	std::vector<akodPending> pending;
+	std::vector<cudaEvent_t> event_pool;
+};
+
+static inline int akod_cuda_status(cudaError_t e)
+{
+	if (e == cudaSuccess)
+		return AKOD_OK;
+	if (getenv("AKO_B200_DEBUG"))
+		fprintf(stderr, "[ako_b200] CUDA error: %s\n", cudaGetErrorString(e));
+	return (e == cudaErrorMemoryAllocation) ? AKOD_NOMEM : AKOD_ERROR;
+}
+
+#define AKOD_TRY(expr)                                   \
+	do                                                   \
+	{                                                    \
+		const int akod_try_rc = akod_cuda_status(expr);  \
+		if (akod_try_rc != AKOD_OK)                      \
+			return akod_try_rc;                          \
+	} while (0)
+
+static inline int akod_prof_entry(akodContext* c, const char* name)
+{
+	for (size_t i = 0; i < c->prof.size(); i++)
+		if (c->prof[i].name == name || strcmp(c->prof[i].name, name) == 0)
+			return (int)i;
+	c->prof.push_back(akodProfEntry{name, 0, 0.0});
+	return (int)c->prof.size() - 1;
+}
+
+static inline cudaEvent_t akod_event_get(akodContext* c)
+{
+	if (!c->event_pool.empty())
+	{
+		cudaEvent_t e = c->event_pool.back();
+		c->event_pool.pop_back();
+		return e;
+	}
+	cudaEvent_t e;
+	cudaEventCreate(&e);
+	return e;
+}
+
+// Every kernel of the library is launched through this macro: it counts the launch (always) and,
+// when profiling is enabled, brackets it with CUDA events on the context's stream.
+#define AKOD_LAUNCH(ctx, label, kernel, grid, block, smem, ...)                              \
+	do                                                                                       \
+	{                                                                                        \
+		akodContext* akod_l_c = (ctx);                                                       \
+		const int akod_l_e = akod_prof_entry(akod_l_c, label);                               \
+		akod_l_c->prof[akod_l_e].launches++;                                                 \
+		akod_l_c->launch_count++;                                                            \
+		akodPending akod_l_p;                                                                \
+		if (akod_l_c->profiling)                                                             \
+		{                                                                                    \
+			akod_l_p.entry = akod_l_e;                                                       \
+			akod_l_p.a = akod_event_get(akod_l_c);                                           \
+			akod_l_p.b = akod_event_get(akod_l_c);                                           \
+			cudaEventRecord(akod_l_p.a, akod_l_c->stream);                                   \
+		}                                                                                    \
+		kernel<<<(grid), (block), (smem), akod_l_c->stream>>>(__VA_ARGS__);                  \
+		if (akod_l_c->profiling)                                                             \
+		{                                                                                    \
+			cudaEventRecord(akod_l_p.b, akod_l_c->stream);                                   \
+			akod_l_c->pending.push_back(akod_l_p);                                           \
+		}                                                                                    \
+		AKOD_TRY(cudaGetLastError());                                                        \
+	} while (0)
+
+// ---------------------------------------------------------------- device helpers
+
+#define AKOD_FULL_MASK 0xffffffffu
+
+template <typename T>
+__device__ __forceinline__ T akod_max(T a, T b)
+{
+	return a > b ? a : b;
+}
+
+// Inclusive warp scans
+__device__ __forceinline__ uint32_t warp_incl_sum(uint32_t v)
+{
+	const int lane = threadIdx.x & 31;
+#pragma unroll
+	for (int d = 1; d < 32; d <<= 1)
+	{
+		const uint32_t o = __shfl_up_sync(AKOD_FULL_MASK, v, d);
+		if (lane >= d)
+			v += o;
+	}
+	return v;
+}
+
+__device__ __forceinline__ long long warp_incl_max(long long v)
+{
+	const int lane = threadIdx.x & 31;
+#pragma unroll
+	for (int d = 1; d < 32; d <<= 1)
+	{
+		const long long o = __shfl_up_sync(AKOD_FULL_MASK, v, d);
+		if (lane >= d)
+			v = akod_max(v, o);
+	}
+	return v;
+}
+
+// Block-wide exclusive sum of one uint32 per thread; returns the exclusive prefix, *total gets the block sum.
+// sm must hold 33 uint32. blockDim.x must be a multiple of 32, <= 1024.
+__device__ __forceinline__ uint32_t block_excl_sum(uint32_t v, uint32_t* sm, uint32_t* total)
+{
+	const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+	const uint32_t incl = warp_incl_sum(v);
+	if (lane == 31)
+		sm[wid] = incl;
+	__syncthreads();
+	if (wid == 0)
+	{
+		uint32_t w = (lane < nw) ? sm[lane] : 0;
+		const uint32_t wi = warp_incl_sum(w);
+		sm[lane] = wi - w;
+		if (lane == 31)
+			sm[32] = wi;
+	}
+	__syncthreads();
+	const uint32_t r = sm[wid] + incl - v;
+	*total = sm[32];
+	__syncthreads();
+	return r;
+}
+
+// Block-wide exclusive max of one int64 per thread (identity = -1); *total gets the block max.
+// sm must hold 33 long long.
+__device__ __forceinline__ long long block_excl_max(long long v, long long* sm, long long* total)
+{
+	const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+	const long long incl = warp_incl_max(v);
+	long long excl = __shfl_up_sync(AKOD_FULL_MASK, incl, 1);
+	if (lane == 0)
+		excl = -1;
+	if (lane == 31)
+		sm[wid] = incl;
+	__syncthreads();
+	if (wid == 0)
+	{
+		long long w = (lane < nw) ? sm[lane] : -1;
+		const long long wi = warp_incl_max(w);
+		long long we = __shfl_up_sync(AKOD_FULL_MASK, wi, 1);
+		if (lane == 0)
+			we = -1;
+		sm[lane] = we;
+		if (lane == 31)
+			sm[32] = wi;
+	}
+	__syncthreads();
+	const long long r = akod_max(sm[wid], excl);
+	*total = sm[32];
+	__syncthreads();
+	return r;
+}

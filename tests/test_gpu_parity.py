@@ -1,0 +1,334 @@
+"""GPU parity: the CUDA path (through the C-ABI of libako_b200.so) against the oracle, the committed golden
+vectors and the survey's known answers. Bit-exact everywhere (integer / byte work)."""
+import base64
+import ctypes as C
+import hashlib
+import itertools
+import json
+import os
+
+import numpy as np
+import pytest
+
+import ako_b200
+import oracle_lib as ol
+from cases import *
+from golden.make_golden import make_input
+
+pytestmark = pytest.mark.gpu
+P, u8p, i16p = ol._p, ol.u8p, ol.i16p
+
+
+def sha(b):
+    return hashlib.sha256(b).hexdigest()
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    c = ako_b200.Context()
+    yield c
+    c.close()
+
+
+def S(**kw):
+    return ako_b200.default_settings(**kw)
+
+
+def OS(**kw):
+    return ol.make_settings(ol.OrcSettings, **kw)
+
+
+# ------------------------------------------------------------------ stages
+
+@pytest.mark.parametrize("color", [C_YCOCG, C_SUBG, C_NONE, C_YCOCG_Q])
+def test_format_stage(orc, ctx, color):
+    rs = np.random.RandomState(color)
+    for (w, h, ch) in [(16, 9, 4), (64, 33, 4), (7, 5, 3), (9, 4, 1), (8, 8, 2), (5, 5, 6), (24, 3, 16)]:
+        for discard in (0, 1):
+            img = noise_image(w, h, ch, 3 + w)
+            img[rs.rand(h, w) < 0.3, ch - 1] = 0
+            want = np.zeros((ch, h, w), np.int16)
+            orc.orc_format_forward(discard, color, ch, w, h, w, P(img, u8p), P(want, i16p))
+            got = ctx.format_forward(img, S(color=color, discard=discard))
+            assert np.array_equal(want, got), (w, h, ch, discard)
+            pl = rs.randint(-600, 900, size=(ch, h, w)).astype(np.int16)
+            a = pl.copy()
+            want_px = np.zeros((h, w, ch), np.uint8)
+            orc.orc_format_inverse(color, ch, w, h, w, P(a, i16p), P(want_px, u8p))
+            assert np.array_equal(want_px, ctx.format_inverse(pl, color)), (w, h, ch)
+
+
+LIFT_SHAPES = [(64, 64, 4), (65, 63, 3), (33, 47, 1), (16, 17, 2), (3, 3, 4), (5, 9, 3), (100, 7, 4), (129, 70, 4),
+               (200, 131, 2), (257, 66, 1), (128, 128, 1), (15, 300, 1)]
+
+
+@pytest.mark.parametrize("wrap", [0, 1, 2, 3])
+@pytest.mark.parametrize("wavelet", [W_DD137, W_CDF53, W_HAAR])
+def test_lift_unlift_stage(orc, ctx, wavelet, wrap):
+    rs = np.random.RandomState(100 + wavelet * 4 + wrap)
+    for (w, h, ch) in LIFT_SHAPES:
+        for q, g in [(0, 0), (16, 0), (7, 9)]:
+            amp = 30000 if (q == 0 and w == 64) else 600
+            planes = rs.randint(-amp // 2, amp, size=(ch, h, w)).astype(np.int16)
+            n = orc.orc_tile_data_size(w, h) * ch // 2
+            want = np.zeros(n, np.int16)
+            tmp = planes.copy()
+            os_ = OS(wavelet=wavelet, wrap=wrap, q=q, g=g)
+            orc.orc_lift(C.byref(os_), ch, w, h, P(tmp, i16p), P(want, i16p))
+            s = S(wavelet=wavelet, wrap=wrap, q=q, g=g)
+            got = ctx.lift(planes, s)
+            assert np.array_equal(want, got), (w, h, ch, q, g, int(np.argmax(want != got)))
+
+            back_want = np.zeros((ch, h, w), np.int16)
+            st = want.copy()
+            orc.orc_unlift(C.byref(os_), ch, w, h, P(st, i16p), P(back_want, i16p))
+            back = ctx.unlift(want, s, ch, w, h)
+            assert np.array_equal(back_want, back), (w, h, ch, q, g)
+            if q == 0 and g == 0:
+                assert np.array_equal(back, planes)
+
+
+def _runs_vector(rs, n, zero_heavy):
+    out = []
+    while len(out) < n:
+        v = 0 if (zero_heavy and rs.rand() < 0.6) else int(rs.randint(-40, 41))
+        if rs.rand() < 0.02:
+            v = int(rs.randint(-32767, 32768))
+        out += [v] * int(rs.choice([1, 1, 1, 2, 3, 4, 7, 50, 400, 5000]))
+    return np.array(out[:n], np.int16)
+
+
+def test_kagari_stage(orc, ctx):
+    rs = np.random.RandomState(5)
+    vectors = [np.array([5], np.int16), np.array([0, 0], np.int16), np.array([0, 0, 0], np.int16),
+               np.array([3, 3, 3, 3], np.int16), np.arange(1, 9).astype(np.int16),
+               np.array([32767, -32767, 32767, -32767], np.int16),
+               rs.randint(-32767, 32768, size=5000).astype(np.int16)]
+    vectors += [_runs_vector(rs, n, z) for n in (10, 100, 2047, 2048, 2049, 5000, 70000, 300001) for z in (False, True)]
+    for n in (65534, 65535, 65536, 65537, 65538, 2 * 65534 + 10, 3 * 65535 + 7):
+        vectors.append(np.zeros(n, np.int16))
+        vectors.append(np.concatenate([np.array([9], np.int16), np.full(n, -2, np.int16), np.array([9, 9], np.int16)]))
+    for v in vectors:
+        n = len(v)
+        cap = n * 4 + 64
+        want = np.zeros(cap, np.uint8)
+        wn = orc.orc_kagari_encode(n, P(v, i16p), cap, P(want, u8p))
+        got = ctx.kagari_encode(v, cap)
+        assert got is not None and len(got) == wn and np.array_equal(want[:wn], got), n
+        used, back = ctx.kagari_decode(got, n)
+        assert used == wn and np.array_equal(back, v), n
+
+
+def test_kagari_capacity_rule(orc, ctx):
+    rs = np.random.RandomState(11)
+    for n in (7, 64, 300, 3000):
+        v = rs.randint(-3000, 3000, size=n).astype(np.int16)
+        need = (orc.orc_kagari_bits(n, P(v, i16p)) + 7) // 8
+        for cap in (need - 5, need - 1, need, need + 1, need + 4, need + 9):
+            got = ctx.kagari_encode(v, cap)
+            # the C-ABI packs whole words, so besides "bytes < cap" (the reference's rule) it needs bytes <= cap&~3
+            if need < cap and need <= (cap & ~3):
+                assert got is not None and len(got) == need
+            elif need >= cap:
+                assert got is None
+
+
+def test_kagari_decode_rejects_broken(ctx):
+    v = np.arange(-100, 100).astype(np.int16)
+    good = ctx.kagari_encode(v)
+    used, _ = ctx.kagari_decode(good[:-3], len(v))
+    assert used == 0
+    used, _ = ctx.kagari_decode(np.zeros(40, np.uint8), 16)
+    assert used == 0
+
+
+# ------------------------------------------------------------------ whole codec through akoEncodeExt / akoDecodeExt
+
+def _e2e(orc, img, **kw):
+    want, wst = ol.orc_encode(orc, img, **kw)
+    got, gst = ako_b200.encode(img, S(**kw))
+    assert wst == gst, (kw, wst, gst)
+    assert want == got, kw
+    if want is None:
+        return None
+    want_px, _ = ol.orc_decode(orc, want)
+    got_px, st, s = ako_b200.decode(want)
+    assert st == 0 and np.array_equal(want_px, got_px), kw
+    return want
+
+
+@pytest.mark.parametrize("shape", SHAPES, ids=lambda s: "x".join(map(str, s)))
+def test_end_to_end_shapes(orc, shape):
+    w, h, ch = shape
+    for wavelet, wrap in itertools.product([W_DD137, W_CDF53, W_HAAR], [0, 1, 2, 3]):
+        for q, g in [(0, 0), (16, 0), (5, 12)]:
+            img = smooth_image(w, h, ch, 1 + w * 3 + h)
+            blob = _e2e(orc, img, wavelet=wavelet, wrap=wrap, q=q, g=g)
+            if q == 0 and g == 0 and blob is not None:
+                out, st, _ = ako_b200.decode(blob)
+                assert np.array_equal(out, img)
+
+
+def test_end_to_end_options(orc):
+    img = ol.synth(orc, 200, 150, 9)
+    for color in (C_YCOCG, C_SUBG, C_NONE):
+        for discard in (0, 1):
+            for cl in (0, 1, 3):
+                _e2e(orc, img, wavelet=W_CDF53, color=color, discard=discard, chroma_loss=cl, q=10, g=3)
+    for comp in (0, 1, 2):
+        _e2e(orc, img, wavelet=W_DD137, compression=comp, q=16)
+        _e2e(orc, img, wavelet=W_DD137, compression=comp, q=0)
+    _e2e(orc, noise_image(96, 96, 4, 2), wavelet=W_CDF53, q=0)
+    _e2e(orc, img, wavelet=W_NONE, compression=2, q=0)
+
+
+@pytest.mark.parametrize("tiles", [8, 32, 64, 256])
+def test_end_to_end_tiles(orc, tiles):
+    for (w, h) in [(200, 150), (256, 256), (67, 131)]:
+        if 0 < w % tiles < 3 or 0 < h % tiles < 3:
+            continue
+        img = ol.synth(orc, w, h, tiles + w)
+        for wavelet in (W_DD137, W_CDF53, W_HAAR):
+            _e2e(orc, img, wavelet=wavelet, tiles=tiles, q=0)
+            _e2e(orc, img, wavelet=wavelet, tiles=tiles, q=16, g=4)
+
+
+with open(os.path.join(os.path.dirname(__file__), "golden", "golden.json")) as f:
+    GOLDEN = json.load(f)
+
+
+def test_golden_vectors():
+    """Committed outputs of the unmodified reference (tests/golden/make_golden.py)."""
+    orc = ol.load_oracle()
+    for c in GOLDEN:
+        img = make_input(orc, c)
+        blob, st = ako_b200.encode(img, S(wavelet=c["wavelet"], wrap=c["wrap"], q=c["q"], g=c["g"], tiles=c["tiles"],
+                                          color=c["color"], discard=c["discard"], chroma_loss=c["chroma_loss"]))
+        assert st == 0 and len(blob) == c["blob_len"] and sha(blob) == c["blob_sha256"], c
+        if "blob_b64" in c:
+            assert blob == base64.b64decode(c["blob_b64"])
+        dec, st, _ = ako_b200.decode(blob)
+        assert st == 0 and sha(dec.tobytes()) == c["decoded_sha256"], c
+
+
+@pytest.mark.parametrize("kat", KATS, ids=lambda k: f"{k[0]}x{k[1]}-w{k[2]}-q{k[3]}-g{k[4]}")
+def test_known_answers(orc, kat):
+    """SHA-256 of the reference's blobs and decoded pixels at the BASELINE shapes."""
+    w, h, wavelet, q, g, seed, size, blob_sha, dec_sha = kat
+    img = ol.synth(orc, w, h, seed)
+    blob, st = ako_b200.encode(img, S(wavelet=wavelet, q=q, g=g))
+    assert st == 0 and len(blob) == size and sha(blob) == blob_sha
+    out, st, s = ako_b200.decode(blob)
+    assert st == 0
+    if dec_sha:
+        assert sha(out.tobytes()) == dec_sha
+    if q == 0:
+        assert np.array_equal(out, img)
+    assert (s.wavelet, s.wrap, s.compression) == (wavelet, 0, 0)
+
+
+def test_reference_decodes_our_blobs_and_we_decode_its(orc, ref):
+    """Cross-decoding with the real reference library (oracle/_ref)."""
+    img = ol.synth(orc, 333, 222, 12)
+    for wavelet in (W_DD137, W_CDF53, W_HAAR):
+        ours, st = ako_b200.encode(img, S(wavelet=wavelet, q=8, g=2))
+        theirs, _ = ol.ref_encode(ref, img, wavelet=wavelet, q=8, g=2)
+        assert ours == theirs
+        a, _ = ol.ref_decode(ref, ours)
+        b, st, _ = ako_b200.decode(theirs)
+        assert np.array_equal(a, b)
+
+
+def test_status_codes(orc):
+    img = ol.synth(orc, 40, 40, 1)
+    good, _ = ol.orc_encode(orc, img, wavelet=W_CDF53)
+    for mutate in (lambda b: b[:-5], lambda b: b[:16] + b"\x10\0\0\0" + b[20:], lambda b: b[:20],
+                   lambda b: b[:16] + b"\0\0\0\0" + b[20:]):
+        bad = mutate(good)
+        od, ost = ol.orc_decode(orc, bad)
+        gd, gst, _ = ako_b200.decode(bad)
+        assert od is None and gd is None and gst == ost == 15
+    # incompressible edge tiles: the block would not be smaller than its stream -> AKO_ERROR (encode.c:159-164)
+    noise = noise_image(9, 9, 4, 1)
+    want, wst = ol.orc_encode(orc, noise, wavelet=W_CDF53, q=0, tiles=8)
+    got, gst = ako_b200.encode(noise, S(wavelet=W_CDF53, q=0, tiles=8))
+    assert (want is None) == (got is None) and wst == gst
+
+
+def test_events_order():
+    """ako.h:75-84: per tile FORMAT, WAVELET, COMPRESSION on encode; the reverse stage order on decode."""
+    from ako_b200 import lib as akolib
+    L = ako_b200.load()
+    seen = []
+    fn = akolib.EVENTS_FN(lambda t, n, e, d: seen.append((t, n, e)))
+    cb = L.akoDefaultCallbacks()
+    cb.events = C.cast(fn, C.c_void_p)
+    img = noise_image(40, 24, 4, 3)
+    blob, st = ako_b200.encode(img, S(wavelet=W_CDF53, tiles=16, q=4), C.byref(cb))
+    assert st == 0
+    tiles = 3 * 2
+    assert seen == [(t, tiles, e) for t in range(tiles) for e in (1, 2, 3, 4, 5, 6)]
+    seen.clear()
+    out, st, _ = ako_b200.decode(blob, C.byref(cb))
+    assert st == 0
+    assert seen == [(t, tiles, e) for t in range(tiles) for e in (5, 6, 3, 4, 1, 2)]
+
+
+# ------------------------------------------------------------------ device-resident and batched API
+
+def test_device_resident_and_batch(orc, ctx):
+    w, h, ch, n = 320, 200, 4, 5
+    imgs = np.stack([ol.synth(orc, w, h, 1000 + i) for i in range(n)])
+    s = S(wavelet=W_DD137, q=16, g=16)
+    want = [ol.orc_encode(orc, imgs[i], wavelet=W_DD137, q=16, g=16)[0] for i in range(n)]
+
+    bound = ctx.encode_bound(s, ch, w, h)
+    stride = (bound + 255) // 256 * 256
+    d_in = ctx.to_device(imgs)
+    d_out = ctx.alloc(stride * n)
+    # single image, device resident
+    size, st = ctx.encode_device(s, ch, w, h, d_in, d_out, stride)
+    assert st == 0 and size == len(want[0])
+    assert ctx.to_host(d_out, (size,), np.uint8).tobytes() == want[0]
+    # batch
+    done, st, sizes = ctx.encode_batch_device(s, ch, w, h, n, d_in, w * h * ch, d_out, stride)
+    assert done == n and st == 0 and sizes == [len(b) for b in want]
+    blobs = ctx.to_host(d_out, (n, stride), np.uint8)
+    for i in range(n):
+        assert blobs[i, :sizes[i]].tobytes() == want[i]
+    # batch decode of those blobs
+    d_px = ctx.alloc(w * h * ch * n)
+    done, st = ctx.decode_batch_device(n, d_out, stride, sizes, d_px, w * h * ch)
+    assert done == n and st == 0
+    px = ctx.to_host(d_px, (n, h, w, ch), np.uint8)
+    for i in range(n):
+        assert np.array_equal(px[i], ol.orc_decode(orc, want[i])[0])
+    # single decode, device resident
+    st, dims, s2 = ctx.decode_device(sizes[2], d_out + 2 * stride, d_px, w * h * ch)
+    assert st == 0 and dims == (ch, w, h)
+    assert np.array_equal(ctx.to_host(d_px, (h, w, ch), np.uint8), px[2])
+    assert ctx.launch_count() > 0
+    for p in (d_in, d_out, d_px):
+        ctx.free(p)
+
+
+# ------------------------------------------------------------------ BASELINE full sizes: size-independent properties
+
+@pytest.mark.parametrize("kat", KATS_BIG[:3], ids=lambda k: f"{k[0]}x{k[1]}-w{k[2]}")
+def test_big_known_answers(kat):
+    orc = ol.load_oracle()
+    w, h, wavelet, q, g, seed, size, blob_sha, _ = kat
+    img = ol.synth(orc, w, h, seed)
+    blob, st = ako_b200.encode(img, S(wavelet=wavelet, q=q, g=g))
+    assert st == 0 and len(blob) == size and sha(blob) == blob_sha
+
+
+@pytest.mark.parametrize("wavelet", [W_DD137, W_CDF53, W_HAAR])
+def test_big_lossless_roundtrip_property(wavelet):
+    """8192x8192 RGBA8, q=0: decode(encode(x)) == x, through the public API."""
+    orc = ol.load_oracle()
+    img = ol.synth(orc, 8192, 8192, 4)
+    blob, st = ako_b200.encode(img, S(wavelet=wavelet, q=0))
+    assert st == 0
+    out, st, _ = ako_b200.decode(blob)
+    assert st == 0 and np.array_equal(out, img)
