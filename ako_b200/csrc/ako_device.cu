@@ -441,10 +441,7 @@ extern "C" int akod_unlift(akodContext* c, const akodPlan* plan, const int16_t* 
 		p.out_ps = (uint64_t)L->cw * L->ch;
 		p.out_is = to_planes ? planes_is : scratch_is;
 		for (uint32_t ch = 0; ch < plan->channels; ch++)
-		{
 			p.off_c[ch] = L->off_c[ch];
-			p.q[ch] = L->q[ch];
-		}
 		int rc;
 		if (L->wavelet == AKOD_DD137)
 			rc = launch_unlift_level<AKOD_DD137>(c, p, n);

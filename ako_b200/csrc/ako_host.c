@@ -812,7 +812,10 @@ static size_t encode_core(akoB200Context* ctx, const struct akoCallbacks* cb, co
 			const size_t data = (s.wavelet != AKO_WAVELET_NONE) ? tile_data_size(tw, th) * channels : tw * th * channels * 2;
 			host_off[t] = blocks_per_image;
 			host_data[t] = data;
-			host_cap[t] = (data >= 4) ? ((data - 4) & ~(uint64_t)3) : 0; /* what the packer may write */
+			if (s.compression == AKO_COMPRESSION_NONE)
+				host_cap[t] = data; /* raw copy */
+			else
+				host_cap[t] = (data >= 4) ? ((data - 4) & ~(uint64_t)3) : 0; /* what the packer may write */
 			blocks_per_image += align_up(data, 16);
 			tx += td;
 			if (tx >= w)

@@ -333,7 +333,6 @@ struct UnliftParams
 	int wrap;
 	uint32_t channels;
 	uint64_t off_c[AKOD_MAX_CHANNELS];
-	int16_t q[AKOD_MAX_CHANNELS];
 };
 
 template <int WL>
@@ -358,7 +357,8 @@ __global__ void __launch_bounds__(LIFT_THREADS) k_unlift_level(const UnliftParam
 	const uint64_t band = (uint64_t)p.hw * p.hh;
 	const int16_t* in_ll = p.ll + p.ll_is * img + p.ll_ps * chn;
 	const int16_t* in_c = p.stream + p.stream_is * img + p.off_c[chn];
-	const int q = p.q[chn];
+	// the decoder knows q only from the lift head stored right before C (misc.c:262-268, lifting.c:114-116)
+	const int q = __ldg(in_c - 1);
 
 	// ---- stage the four subband tiles (+halo), inverse quantisation fused (lifting.c:30-40)
 	for (int i = threadIdx.x; i < MS * NS; i += LIFT_THREADS)

@@ -145,13 +145,15 @@ def status_string(status):
 
 
 def encode(image, settings=None, callbacks=None):
-    """akoEncodeExt on a host array of shape (h, w, channels) uint8. Returns (blob bytes | None, status)."""
+    """akoEncodeExt on a host array of shape (h, w, channels) uint8. Returns (blob bytes | None, status).
+    ``callbacks`` is an AkoCallbacks structure (or None for the defaults)."""
     L = load()
     image = np.ascontiguousarray(image, dtype=np.uint8)
     h, w, ch = image.shape
     out = c_void_p()
     st = c_int(0)
-    n = L.akoEncodeExt(callbacks, C.byref(settings) if settings is not None else None, ch, w, h,
+    n = L.akoEncodeExt(C.byref(callbacks) if callbacks is not None else None,
+                       C.byref(settings) if settings is not None else None, ch, w, h,
                        image.ctypes.data, C.byref(out), C.byref(st))
     if n == 0:
         return None, st.value
@@ -168,8 +170,8 @@ def decode(blob, callbacks=None):
     s = AkoSettings()
     ch, w, h = c_size_t(), c_size_t(), c_size_t()
     st = c_int(0)
-    p = L.akoDecodeExt(callbacks, len(blob), buf.ctypes.data, C.byref(s), C.byref(ch), C.byref(w), C.byref(h),
-                       C.byref(st))
+    p = L.akoDecodeExt(C.byref(callbacks) if callbacks is not None else None, len(blob), buf.ctypes.data, C.byref(s),
+                       C.byref(ch), C.byref(w), C.byref(h), C.byref(st))
     if not p:
         return None, st.value, None
     n = ch.value * w.value * h.value

@@ -264,12 +264,12 @@ def test_events_order():
     cb = L.akoDefaultCallbacks()
     cb.events = C.cast(fn, C.c_void_p)
     img = noise_image(40, 24, 4, 3)
-    blob, st = ako_b200.encode(img, S(wavelet=W_CDF53, tiles=16, q=4), C.byref(cb))
+    blob, st = ako_b200.encode(img, S(wavelet=W_CDF53, tiles=16, q=4), cb)
     assert st == 0
     tiles = 3 * 2
     assert seen == [(t, tiles, e) for t in range(tiles) for e in (1, 2, 3, 4, 5, 6)]
     seen.clear()
-    out, st, _ = ako_b200.decode(blob, C.byref(cb))
+    out, st, _ = ako_b200.decode(blob, cb)
     assert st == 0
     assert seen == [(t, tiles, e) for t in range(tiles) for e in (5, 6, 3, 4, 1, 2)]
 
