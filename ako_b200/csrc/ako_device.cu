@@ -491,13 +491,83 @@ extern "C" int akod_kagari_encode(akodContext* c, uint64_t n_values, const int16
 }
 
 extern "C" int akod_kagari_decode(akodContext* c, uint64_t n_values, const uint8_t* d_in, const uint64_t* d_off,
-                                  const uint64_t* d_size, int16_t* d_out, uint64_t out_stride, uint64_t* d_result,
-                                  uint32_t n_images)
+                                  const uint64_t* d_size, uint64_t max_in_size, int16_t* d_out, uint64_t out_stride,
+                                  uint64_t* d_result, uint32_t n_images)
 {
-	if (n_values == 0 || n_images == 0)
+	if (n_values == 0 || n_images == 0 || n_values >= ((uint64_t)1 << 32))
 		return AKOD_ERROR;
-	AKOD_LAUNCH(c, "kagari_decode_seq", k_kd_sequential, n_images, 32, 0, d_in, d_off, d_size, n_values, d_out, out_stride,
-	            d_result);
+	static const bool force_sequential = getenv("AKO_B200_SEQ_DECODE") != nullptr;
+	if (force_sequential)
+	{
+		AKOD_LAUNCH(c, "kagari_decode_seq", k_kd_sequential, n_images, 32, 0, d_in, d_off, d_size, n_values, d_out,
+		            out_stride, d_result, (const KdImage*)nullptr, 0);
+		return AKOD_OK;
+	}
+
+	// geometry shared by all images of the batch (sized for the largest block)
+	const uint64_t max_bits = max_in_size * 8;
+	const uint32_t nblk1 = (uint32_t)(max_bits / KD_CTA_BITS) + 1;
+	uint64_t token_cap = n_values + n_values / 2 + 64; // a well-formed block never has more codewords (2 values per count)
+	if (token_cap > max_bits)
+		token_cap = max_bits;
+	token_cap = (token_cap + 15) & ~(uint64_t)15;
+	const uint32_t nblk2 = (uint32_t)((token_cap + KT_BLOCK - 1) / KT_BLOCK);
+
+	// workspace carve-up
+	size_t bytes = 0;
+	auto carve = [&bytes](size_t n) {
+		const size_t at = bytes;
+		bytes += (n + 255) & ~(size_t)255;
+		return at;
+	};
+	const size_t o_info = carve(sizeof(KdImage) * n_images);
+	const size_t o_ends_a = carve(sizeof(uint64_t) * nblk1 * n_images);
+	const size_t o_ends_b = carve(sizeof(uint64_t) * nblk1 * n_images);
+	const size_t o_sub = carve(sizeof(KdSubState) * (size_t)nblk1 * KD_THREADS * n_images);
+	const size_t o_cnt = carve(sizeof(uint32_t) * nblk1 * n_images);
+	const size_t o_base = carve(sizeof(uint64_t) * nblk1 * n_images);
+	const size_t o_tok = carve(sizeof(uint16_t) * token_cap * n_images);
+	const size_t o_span = carve(sizeof(KtSpan) * nblk2 * n_images);
+	const size_t o_state = carve(sizeof(uint32_t) * nblk2 * n_images);
+	const size_t o_out = carve(sizeof(uint64_t) * nblk2 * n_images);
+	void* ws;
+	int rc = akod_workspace(c, AKOD_WS_KAGARI, bytes, &ws);
+	if (rc != AKOD_OK)
+		return rc;
+	uint8_t* w8 = (uint8_t*)ws;
+	KdImage* info = (KdImage*)(w8 + o_info);
+	uint64_t* ends_a = (uint64_t*)(w8 + o_ends_a);
+	uint64_t* ends_b = (uint64_t*)(w8 + o_ends_b);
+	KdSubState* sub = (KdSubState*)(w8 + o_sub);
+	uint32_t* blk_count = (uint32_t*)(w8 + o_cnt);
+	uint64_t* blk_base = (uint64_t*)(w8 + o_base);
+	uint16_t* tokens = (uint16_t*)(w8 + o_tok);
+	KtSpan* blk_span = (KtSpan*)(w8 + o_span);
+	uint32_t* blk_state = (uint32_t*)(w8 + o_state);
+	uint64_t* blk_out = (uint64_t*)(w8 + o_out);
+
+	AKOD_LAUNCH(c, "kagari_dec_init", k_kd_init, (n_images + 63) / 64, 64, 0, info, n_images);
+	const dim3 grid1(nblk1, n_images);
+	for (int run = 0; run < KD_MAX_RUNS; run++)
+	{
+		uint64_t* prev = (run & 1) ? ends_a : ends_b;
+		uint64_t* next = (run & 1) ? ends_b : ends_a;
+		AKOD_LAUNCH(c, "kagari_dec_sync", k_kd_sync, grid1, KD_THREADS, 0, d_in, d_off, d_size, nblk1, run, prev, next, sub,
+		            blk_count, info);
+	}
+	AKOD_LAUNCH(c, "kagari_dec_scan", k_kd_scan_counts, n_images, 1024, 0, blk_count, blk_base, nblk1, info);
+	AKOD_LAUNCH(c, "kagari_dec_extract", k_kd_extract, grid1, KD_THREADS, 0, d_in, d_off, d_size, nblk1, sub, blk_base, tokens,
+	            token_cap, token_cap);
+	const dim3 grid2(nblk2, n_images);
+	AKOD_LAUNCH(c, "kagari_dec_spans", k_kt_spans, grid2, KT_THREADS, 0, tokens, token_cap, token_cap, info, blk_span, nblk2);
+	AKOD_LAUNCH(c, "kagari_dec_resolve", k_kt_resolve, n_images, 32, 0, blk_span, nblk2, blk_state, blk_out, info, n_values,
+	            token_cap, d_result);
+	AKOD_LAUNCH(c, "kagari_dec_expand", k_kt_expand, grid2, KT_THREADS, 0, tokens, token_cap, token_cap, info, blk_state,
+	            blk_out, nblk2, d_out, out_stride, n_values);
+	// Streams that did not self-synchronise within KD_MAX_RUNS (adversarial input) are decoded by one thread
+	// on the device; a no-op for every other image.
+	AKOD_LAUNCH(c, "kagari_dec_rescue", k_kd_sequential, n_images, 32, 0, d_in, d_off, d_size, n_values, d_out, out_stride,
+	            d_result, (const KdImage*)info, 1);
 	return AKOD_OK;
 }
 

@@ -129,8 +129,8 @@ int akod_kagari_encode(akodContext*, uint64_t n_values, const int16_t* d_in, uin
 /* Kagari decode of n_images blocks. Block i: d_size[i] bytes at d_in + d_off[i] (DEVICE arrays).
  * d_result[i] (uint64, device): bytes consumed, or 0 when the block is malformed. */
 int akod_kagari_decode(akodContext*, uint64_t n_values, const uint8_t* d_in, const uint64_t* d_off,
-                       const uint64_t* d_size, int16_t* d_out, uint64_t out_stride, uint64_t* d_result,
-                       uint32_t n_images);
+                       const uint64_t* d_size, uint64_t max_in_size /* host copy of max(d_size) */, int16_t* d_out,
+                       uint64_t out_stride, uint64_t* d_result, uint32_t n_images);
 
 /* Container assembly on the device (encode.c:170-182 without the CPU pass), for n_images same-shape images:
  * out_i = head16 | for each tile t: [u32 size][bytes of tile t]. Sizes come from d_bits ([tiles][n_images] bit

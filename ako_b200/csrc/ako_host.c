@@ -689,7 +689,7 @@ AKO_API size_t akoB200KagariDecode(akoB200Context* ctx, size_t n_values, size_t 
 	if (st == AKO_OK)
 		st = upload_words(ctx, d_words, words, 2);
 	if (st == AKO_OK)
-		st = from_dev(akod_kagari_decode(ctx->dev, n_values, d_in, d_words, d_words + 1, d_out, 0, d_words + 2, 1));
+		st = from_dev(akod_kagari_decode(ctx->dev, n_values, d_in, d_words, d_words + 1, in_size, d_out, 0, d_words + 2, 1));
 	if (st == AKO_OK)
 		st = download_words(ctx, &answer, d_words + 2, 1);
 	if (st == AKO_OK)
@@ -1099,8 +1099,13 @@ static enum akoStatus decode_core(akoB200Context* ctx, const struct akoCallbacks
 
 		fire(cb, ctx, t, tiles, AKO_EVENT_COMPRESSION_START);
 		if (s->compression != AKO_COMPRESSION_NONE)
-			st = from_dev(akod_kagari_decode(ctx->dev, data / 2, d_in, d_off + t * n, d_size + t * n, target,
+		{
+			uint64_t largest = 0;
+			for (size_t i = 0; i < n; i++)
+				largest = (size_abs[t * n + i] > largest) ? size_abs[t * n + i] : largest;
+			st = from_dev(akod_kagari_decode(ctx->dev, data / 2, d_in, d_off + t * n, d_size + t * n, largest, target,
 			                                 target_stride, d_result + t * n, (uint32_t)n));
+		}
 		else
 			for (size_t i = 0; i < n && st == AKO_OK; i++)
 				st = from_dev(akod_d2d(ctx->dev, target + target_stride * i, d_in + off_abs[t * n + i], data));

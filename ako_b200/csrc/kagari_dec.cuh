@@ -1,11 +1,40 @@
-// kagari_dec.cuh -- Kagari decoder. Replaces akoKagariDecode / akoEliasDecodeStep
-// (reference library/kagari.c:119-163, :301-366).
+// kagari_dec.cuh -- parallel Kagari decoder. Replaces akoKagariDecode / akoEliasDecodeStep
+// (reference library/kagari.c:119-163, :301-366), which parse one monolithic bit stream sequentially.
+//
+// Two sequential dependencies are broken up:
+//
+// (1) Codeword boundaries. next(p) = p + 2*clz(bits at p) + 1. The stream is cut into 256-bit subsequences,
+//     one thread each. Every thread first decodes from its subsequence start as if it were a boundary, then
+//     threads repeatedly restart from their predecessor's real end until nothing changes: Elias gamma codes
+//     self-synchronise after a few codewords, so this takes 2-3 rounds; it is correct for any input because
+//     it only stops at the fixed point. The same is done between CTAs (64 Kibit each) by re-running the
+//     kernel with the previous run's CTA ends; a run that changes nothing proves the chain consistent.
+//
+// (2) Which codeword is a value and which an RLE count (kagari.c:337-355). Written over the raw codeword
+//     values u[j], the reference's (previous_value, consecutive_no) state is a 4-state machine whose
+//     transitions only look at u[j] == u[j-1] and u[j] == u[j-2]:
+//         V  : last token was a value, 0 repeats  : u[j]==u[j-1] ? S : V
+//         A  : last token was an RLE count        : u[j]==u[j-2] ? S : V     (previous_value predates the count)
+//         S  : 1 repeat so far                    : u[j]==u[j-1] ? R : V
+//         R  : this token IS the RLE count        : -> A
+//     Functions on 4 states compose associatively, so a scan classifies every token; carrying, per entry
+//     state, the number of values a span of tokens expands to gives every token its output position too.
+//
+// A token expands to one value, or to (u-1) copies of the value before it. Long runs are filled
+// cooperatively by the whole CTA with 128-bit stores.
+//
+// Result per block: bytes consumed = ceil(end of last codeword / 8) when exactly n values came out, else 0.
+// (The reference reports what its 64-bit accumulator happened to have fetched, kagari.c:365; for every
+// well-formed block both equal block_size. Blocks with trailing garbage are rejected here.)
 #pragma once
 
 #include "common.cuh"
 
-// 32 bits of the MSB-first stream starting at bit 'pos' (zero beyond 'size' bytes)
-__device__ __forceinline__ uint32_t kd_peek32(const uint8_t* __restrict__ in, uint64_t size, uint64_t pos)
+// ------------------------------------------------------------------------------------------------
+// sequential decoder, one thread per block: the simple device implementation the parallel decoder is
+// validated against (AKO_B200_SEQ_DECODE=1 selects it)
+
+__device__ __forceinline__ uint32_t kd_peek32_bytes(const uint8_t* __restrict__ in, uint64_t size, uint64_t pos)
 {
 	const uint64_t byte = pos >> 3;
 	uint64_t acc = 0;
@@ -18,14 +47,17 @@ __device__ __forceinline__ uint32_t kd_peek32(const uint8_t* __restrict__ in, ui
 	return (uint32_t)(acc >> (8 - (pos & 7)));
 }
 
-// Reference-shaped sequential decoder: one thread per block. Kept as the simple, obviously-right device
-// implementation the parallel decoder is validated against (AKO_B200_SEQ_DECODE=1 selects it).
+struct KdImage;
+__device__ __forceinline__ bool kd_needs_rescue(const KdImage* info, uint32_t img);
+
 __global__ void k_kd_sequential(const uint8_t* __restrict__ in_base, const uint64_t* __restrict__ in_off,
                                 const uint64_t* __restrict__ in_size, uint64_t n, int16_t* __restrict__ out_base,
-                                uint64_t out_stride, uint64_t* __restrict__ result)
+                                uint64_t out_stride, uint64_t* __restrict__ result, const KdImage* info, int rescue)
 {
 	const uint32_t img = blockIdx.x;
 	if (threadIdx.x != 0)
+		return;
+	if (rescue && !kd_needs_rescue(info, img))
 		return;
 	const uint8_t* in = in_base + in_off[img];
 	const uint64_t size = in_size[img];
@@ -39,7 +71,7 @@ __global__ void k_kd_sequential(const uint8_t* __restrict__ in_base, const uint6
 
 	while (ok && produced < n)
 	{
-		uint32_t w = kd_peek32(in, size, pos);
+		uint32_t w = kd_peek32_bytes(in, size, pos);
 		int z = w ? __clz(w) : 32;
 		if (z > 15 || pos + 2 * z + 1 > total_bits)
 		{
@@ -54,7 +86,7 @@ __global__ void k_kd_sequential(const uint8_t* __restrict__ in_base, const uint6
 		{
 			if (++cn == 2)
 			{
-				w = kd_peek32(in, size, pos);
+				w = kd_peek32_bytes(in, size, pos);
 				z = w ? __clz(w) : 32;
 				if (z > 15 || pos + 2 * z + 1 > total_bits)
 				{
@@ -80,4 +112,607 @@ __global__ void k_kd_sequential(const uint8_t* __restrict__ in_base, const uint6
 		}
 	}
 	result[img] = ok ? ((pos + 7) >> 3) : 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// phase 1: codeword boundaries
+
+constexpr int KD_SUB_BITS = 256;                           // bits per thread
+constexpr int KD_THREADS = 256;
+constexpr int KD_CTA_BITS = KD_SUB_BITS * KD_THREADS;      // 65536 bits = 8 KiB of stream per CTA
+constexpr int KD_CTA_WORDS = KD_CTA_BITS / 32;
+constexpr uint32_t KD_STOP = 0xFFFFFFFFu;                  // "the chain ended before this point"
+constexpr uint64_t KD_STOP64 = ~(uint64_t)0;
+constexpr int KD_MAX_RUNS = 6;                             // CTA-level synchronisation runs (later ones are no-ops once stable)
+
+// per-image bookkeeping, device resident
+struct KdImage
+{
+	uint64_t changed[8];   // per sync run: number of CTAs whose end moved
+	uint64_t stop_pos;     // bit position right after the last codeword
+	uint64_t tokens;       // number of codewords
+	uint64_t outputs;      // values they expand to
+	uint64_t overflow;     // token buffer too small / inconsistent
+};
+
+__device__ __forceinline__ bool kd_needs_rescue(const KdImage* info, uint32_t img)
+{
+	return info[img].changed[KD_MAX_RUNS - 1] != 0;
+}
+
+__global__ void k_kd_init(KdImage* info, uint32_t n)
+{
+	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n)
+		return;
+	for (int r = 0; r < 8; r++)
+		info[i].changed[r] = 0;
+	info[i].stop_pos = KD_STOP64;
+	info[i].tokens = 0;
+	info[i].outputs = 0;
+	info[i].overflow = 0;
+}
+
+struct KdSubState
+{
+	uint32_t start; // first codeword boundary of the subsequence, relative to its CTA (KD_STOP: none)
+	uint32_t count; // codewords that start in it
+};
+
+// stages 8 KiB (+ 2 words look-ahead) of the stream as big-endian words; bytes past 'size' read as zero
+__device__ __forceinline__ void kd_stage_bits(uint32_t* sm, const uint8_t* __restrict__ in, uint64_t size,
+                                              uint64_t first_byte)
+{
+	for (int i = threadIdx.x; i < KD_CTA_WORDS + 2; i += KD_THREADS)
+	{
+		const uint64_t b = first_byte + (uint64_t)i * 4;
+		uint32_t w = 0;
+		if (b + 4 <= size)
+			w = ((uint32_t)in[b] << 24) | ((uint32_t)in[b + 1] << 16) | ((uint32_t)in[b + 2] << 8) | (uint32_t)in[b + 3];
+		else
+		{
+#pragma unroll
+			for (int k = 0; k < 4; k++)
+				w = (w << 8) | (uint32_t)((b + k < size) ? in[b + k] : 0);
+		}
+		sm[i] = w;
+	}
+}
+
+__device__ __forceinline__ uint32_t kd_peek(const uint32_t* sm, uint32_t pos)
+{
+	return __funnelshift_l(sm[(pos >> 5) + 1], sm[pos >> 5], pos & 31);
+}
+
+// walks codewords from 'start' (relative to the CTA) until the first boundary >= limit.
+// Returns that boundary (or KD_STOP if the chain ends), counts codewords starting before 'limit'.
+// If stop_at != nullptr and the chain ends, *stop_at receives the relative position where it ended.
+template <bool EMIT>
+__device__ __forceinline__ uint32_t kd_walk(const uint32_t* sm, uint32_t start, uint32_t limit, uint64_t bits_left,
+                                            uint32_t& count, uint32_t* stop_at, uint16_t* __restrict__ tokens,
+                                            uint64_t token_base, uint64_t token_cap)
+{
+	count = 0;
+	if (start == KD_STOP)
+		return KD_STOP;
+	uint32_t p = start;
+	while (p < limit)
+	{
+		const uint32_t w = kd_peek(sm, p);
+		const int z = __clz(w); // 32 for w == 0
+		const uint32_t len = 2 * z + 1;
+		if (z > 15 || (uint64_t)p + len > bits_left)
+		{
+			if (stop_at)
+				*stop_at = p;
+			return KD_STOP;
+		}
+		if (EMIT)
+		{
+			const uint64_t t = token_base + count;
+			if (t < token_cap)
+				tokens[t] = (uint16_t)(w >> (31 - 2 * z));
+		}
+		count++;
+		p += len;
+	}
+	return p;
+}
+
+// One synchronisation run. run == 0: every CTA assumes it starts on a boundary.
+// run > 0: CTA b starts where CTA b-1 ended in the previous run (ends_prev).
+__global__ void __launch_bounds__(KD_THREADS)
+    k_kd_sync(const uint8_t* __restrict__ in_base, const uint64_t* __restrict__ in_off,
+              const uint64_t* __restrict__ in_size, uint32_t nblk, int run, const uint64_t* __restrict__ ends_prev,
+              uint64_t* __restrict__ ends_new, KdSubState* __restrict__ sub, uint32_t* __restrict__ blk_count,
+              KdImage* __restrict__ info)
+{
+	__shared__ uint32_t sm[KD_CTA_WORDS + 2];
+	__shared__ uint32_t sm_end[KD_THREADS];
+	__shared__ uint32_t sm_sum[33];
+
+	const uint32_t img = blockIdx.y, b = blockIdx.x, t = threadIdx.x;
+	const uint64_t size = in_size[img];
+	const uint64_t total_bits = size * 8;
+	const uint64_t cta_bit0 = (uint64_t)b * KD_CTA_BITS;
+	ends_prev += (uint64_t)nblk * img;
+	ends_new += (uint64_t)nblk * img;
+	sub += (uint64_t)nblk * KD_THREADS * img;
+	blk_count += (uint64_t)nblk * img;
+
+	if (run >= 2 && info[img].changed[run - 1] == 0)
+	{
+		// the previous run changed nothing: the chain is consistent, keep its results
+		if (t == 0)
+			ends_new[b] = ends_prev[b];
+		return;
+	}
+	if (cta_bit0 > total_bits)
+	{
+		// past the end of this image's stream (the CTA starting exactly AT the end still runs: it is the one
+		// that records where a chain that fills its last CTA completely stops)
+		if (t == 0)
+		{
+			if (run > 0 && ends_prev[b] != KD_STOP64)
+				atomicAdd((unsigned long long*)&info[img].changed[run], 1ull);
+			ends_new[b] = KD_STOP64;
+			blk_count[b] = 0;
+		}
+		sub[(uint64_t)b * KD_THREADS + t] = KdSubState{KD_STOP, 0};
+		return;
+	}
+	kd_stage_bits(sm, in_base + in_off[img], size, cta_bit0 >> 3);
+	__syncthreads();
+
+	const uint64_t bits_left = total_bits - cta_bit0; // codewords may not cross this (relative) position
+	uint32_t start;
+	if (t == 0)
+	{
+		if (run == 0 || b == 0)
+			start = 0;
+		else
+		{
+			const uint64_t e = ends_prev[b - 1];
+			start = (e == KD_STOP64) ? KD_STOP : (uint32_t)(e - cta_bit0);
+		}
+	}
+	else
+		start = t * KD_SUB_BITS;
+	const uint32_t limit = (t + 1) * KD_SUB_BITS;
+
+	uint32_t count, stop_rel = KD_STOP;
+	uint32_t end = kd_walk<false>(sm, start, limit, bits_left, count, &stop_rel, nullptr, 0, 0);
+	for (;;)
+	{
+		sm_end[t] = end;
+		__syncthreads();
+		bool moved = false;
+		if (t > 0)
+		{
+			const uint32_t real_start = sm_end[t - 1];
+			if (real_start != start)
+			{
+				start = real_start;
+				stop_rel = KD_STOP;
+				end = kd_walk<false>(sm, start, limit, bits_left, count, &stop_rel, nullptr, 0, 0);
+				moved = true;
+			}
+		}
+		if (!__syncthreads_or(moved))
+			break;
+	}
+
+	sub[(uint64_t)b * KD_THREADS + t] = KdSubState{start, count};
+	// the one thread of the consistent chain that ran into the end of the stream records where
+	if (start != KD_STOP && end == KD_STOP)
+		info[img].stop_pos = cta_bit0 + stop_rel;
+
+	uint32_t total;
+	block_excl_sum(count, sm_sum, &total);
+	if (t == KD_THREADS - 1)
+	{
+		const uint64_t e = (end == KD_STOP) ? KD_STOP64 : cta_bit0 + end;
+		if (run > 0 && ends_prev[b] != e)
+			atomicAdd((unsigned long long*)&info[img].changed[run], 1ull);
+		ends_new[b] = e;
+	}
+	if (t == 0)
+		blk_count[b] = total;
+}
+
+// exclusive sum over CTAs of codeword counts (one CTA per image) -> first token index of every CTA
+__global__ void __launch_bounds__(1024)
+    k_kd_scan_counts(const uint32_t* __restrict__ blk_count, uint64_t* __restrict__ blk_base, uint32_t nblk,
+                     KdImage* __restrict__ info)
+{
+	__shared__ uint32_t sm[33];
+	blk_count += (uint64_t)nblk * blockIdx.x;
+	blk_base += (uint64_t)nblk * blockIdx.x;
+	uint64_t carry = 0;
+	for (uint32_t b0 = 0; b0 < nblk; b0 += 1024)
+	{
+		const uint32_t b = b0 + threadIdx.x;
+		const uint32_t v = (b < nblk) ? blk_count[b] : 0; // <= 65536 each
+		uint32_t tot;
+		const uint32_t ex = block_excl_sum(v, sm, &tot);
+		if (b < nblk)
+			blk_base[b] = carry + ex;
+		carry += tot;
+	}
+	if (threadIdx.x == 0)
+		info[blockIdx.x].tokens = carry;
+}
+
+// re-walks every subsequence from its final start and stores the raw codeword values
+__global__ void __launch_bounds__(KD_THREADS)
+    k_kd_extract(const uint8_t* __restrict__ in_base, const uint64_t* __restrict__ in_off,
+                 const uint64_t* __restrict__ in_size, uint32_t nblk, const KdSubState* __restrict__ sub,
+                 const uint64_t* __restrict__ blk_base, uint16_t* __restrict__ tokens, uint64_t token_stride,
+                 uint64_t token_cap)
+{
+	__shared__ uint32_t sm[KD_CTA_WORDS + 2];
+	__shared__ uint32_t sm_sum[33];
+	const uint32_t img = blockIdx.y, b = blockIdx.x, t = threadIdx.x;
+	const uint64_t size = in_size[img];
+	const uint64_t total_bits = size * 8;
+	const uint64_t cta_bit0 = (uint64_t)b * KD_CTA_BITS;
+	if (cta_bit0 > total_bits)
+		return;
+	kd_stage_bits(sm, in_base + in_off[img], size, cta_bit0 >> 3);
+	const KdSubState s = sub[((uint64_t)nblk * img + b) * KD_THREADS + t];
+	uint32_t total;
+	const uint32_t excl = block_excl_sum(s.count, sm_sum, &total); // syncs: sm is staged after it
+	uint32_t count;
+	kd_walk<true>(sm, s.start, (t + 1) * KD_SUB_BITS, total_bits - cta_bit0, count, nullptr,
+	              tokens + token_stride * img, blk_base[(uint64_t)nblk * img + b] + excl, token_cap);
+}
+
+// ------------------------------------------------------------------------------------------------
+// phase 2: classification + expansion
+
+constexpr int KT_THREADS = 256;
+constexpr int KT_ITEMS = 16;
+constexpr int KT_BLOCK = KT_THREADS * KT_ITEMS; // tokens per CTA
+constexpr int KT_LONG = 48;                     // runs at least this long are filled by the whole CTA
+
+enum : uint32_t
+{
+	ST_V = 0, // last token was a value, no repeat pending
+	ST_A = 1, // last token was an RLE count
+	ST_S = 2, // one repeat seen
+	ST_R = 3  // this token is an RLE count
+};
+
+// A span of tokens as a function of the state it is entered in: exit state (2 bits each, packed) and the
+// number of values it expands to.
+struct KtSpan
+{
+	uint32_t map;
+	uint32_t out[4];
+};
+
+__device__ __forceinline__ KtSpan kt_identity()
+{
+	KtSpan s;
+	s.map = (ST_V) | (ST_A << 2) | (ST_S << 4) | (ST_R << 6);
+	s.out[0] = s.out[1] = s.out[2] = s.out[3] = 0;
+	return s;
+}
+
+__device__ __forceinline__ uint32_t kt_next(uint32_t state, bool e1, bool e2)
+{
+	switch (state)
+	{
+	case ST_V: return e1 ? ST_S : ST_V;
+	case ST_A: return e2 ? ST_S : ST_V;
+	case ST_S: return e1 ? ST_R : ST_V;
+	default: return ST_A;
+	}
+}
+
+// a then b
+__device__ __forceinline__ KtSpan kt_compose(const KtSpan& a, const KtSpan& b)
+{
+	KtSpan r;
+	r.map = 0;
+#pragma unroll
+	for (int s = 0; s < 4; s++)
+	{
+		const uint32_t mid = (a.map >> (2 * s)) & 3u;
+		r.map |= ((b.map >> (2 * mid)) & 3u) << (2 * s);
+		r.out[s] = a.out[s] + b.out[mid];
+	}
+	return r;
+}
+
+__device__ __forceinline__ KtSpan kt_shfl_up(const KtSpan& v, int d)
+{
+	KtSpan r;
+	r.map = __shfl_up_sync(AKOD_FULL_MASK, v.map, d);
+#pragma unroll
+	for (int s = 0; s < 4; s++)
+		r.out[s] = __shfl_up_sync(AKOD_FULL_MASK, v.out[s], d);
+	return r;
+}
+
+// loads this thread's KT_ITEMS tokens plus the two before them
+__device__ __forceinline__ int kt_load(const uint16_t* __restrict__ tok, uint64_t m, uint64_t base, uint32_t u[KT_ITEMS + 2])
+{
+	int valid = 0;
+	u[0] = (base >= 2 && base - 2 < m) ? tok[base - 2] : 0x10000u; // sentinels never compare equal
+	u[1] = (base >= 1 && base - 1 < m) ? tok[base - 1] : 0x20000u;
+	if (base + KT_ITEMS <= m)
+	{
+		uint16_t tmp[KT_ITEMS];
+		*reinterpret_cast<uint4*>(tmp) = __ldg(reinterpret_cast<const uint4*>(tok + base));
+		*reinterpret_cast<uint4*>(tmp + 8) = __ldg(reinterpret_cast<const uint4*>(tok + base + 8));
+#pragma unroll
+		for (int j = 0; j < KT_ITEMS; j++)
+			u[j + 2] = tmp[j];
+		valid = KT_ITEMS;
+	}
+	else
+	{
+#pragma unroll
+		for (int j = 0; j < KT_ITEMS; j++)
+		{
+			u[j + 2] = 0x30000u;
+			if (base + j < m)
+			{
+				u[j + 2] = tok[base + j];
+				valid = j + 1;
+			}
+		}
+	}
+	return valid;
+}
+
+__device__ __forceinline__ KtSpan kt_thread_span(const uint32_t u[KT_ITEMS + 2], int valid)
+{
+	// simulate the four entry states side by side
+	uint32_t st[4] = {ST_V, ST_A, ST_S, ST_R};
+	uint32_t out[4] = {0, 0, 0, 0};
+#pragma unroll
+	for (int j = 0; j < KT_ITEMS; j++)
+	{
+		if (j < valid)
+		{
+			const bool e1 = u[j + 2] == u[j + 1], e2 = u[j + 2] == u[j];
+#pragma unroll
+			for (int s = 0; s < 4; s++)
+			{
+				out[s] += (st[s] == ST_R) ? (u[j + 2] - 1u) : 1u;
+				st[s] = kt_next(st[s], e1, e2);
+			}
+		}
+	}
+	KtSpan r;
+	r.map = st[0] | (st[1] << 2) | (st[2] << 4) | (st[3] << 6);
+#pragma unroll
+	for (int s = 0; s < 4; s++)
+		r.out[s] = out[s];
+	return r;
+}
+
+// Block-wide exclusive scan of spans. sm must hold 33 KtSpan. Returns the span of everything before this thread;
+// *total = span of the whole CTA.
+__device__ __forceinline__ KtSpan kt_block_excl_scan(KtSpan v, KtSpan* sm, KtSpan* total)
+{
+	const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+	KtSpan incl = v;
+#pragma unroll
+	for (int d = 1; d < 32; d <<= 1)
+	{
+		const KtSpan o = kt_shfl_up(incl, d);
+		if (lane >= d)
+			incl = kt_compose(o, incl);
+	}
+	KtSpan excl = kt_shfl_up(incl, 1);
+	if (lane == 0)
+		excl = kt_identity();
+	if (lane == 31)
+		sm[wid] = incl;
+	__syncthreads();
+	if (wid == 0)
+	{
+		KtSpan w = (lane < nw) ? sm[lane] : kt_identity();
+		KtSpan wi = w;
+#pragma unroll
+		for (int d = 1; d < 32; d <<= 1)
+		{
+			const KtSpan o = kt_shfl_up(wi, d);
+			if (lane >= d)
+				wi = kt_compose(o, wi);
+		}
+		KtSpan we = kt_shfl_up(wi, 1);
+		if (lane == 0)
+			we = kt_identity();
+		sm[lane] = we;
+		if (lane == 31)
+			sm[32] = wi;
+	}
+	__syncthreads();
+	const KtSpan r = kt_compose(sm[wid], excl);
+	*total = sm[32];
+	__syncthreads();
+	return r;
+}
+
+// pass A: the span of every CTA's tokens
+__global__ void __launch_bounds__(KT_THREADS)
+    k_kt_spans(const uint16_t* __restrict__ tokens, uint64_t token_stride, uint64_t token_cap,
+               const KdImage* __restrict__ info, KtSpan* __restrict__ blk_span, uint32_t nblk)
+{
+	__shared__ KtSpan sm[33];
+	const uint32_t img = blockIdx.y;
+	const uint64_t m = min(info[img].tokens, token_cap);
+	const uint64_t base = (uint64_t)blockIdx.x * KT_BLOCK + (uint64_t)threadIdx.x * KT_ITEMS;
+	uint32_t u[KT_ITEMS + 2];
+	const int valid = (base < m) ? kt_load(tokens + token_stride * img, m, base, u) : 0;
+	KtSpan total;
+	kt_block_excl_scan(kt_thread_span(u, valid), sm, &total);
+	if (threadIdx.x == 0)
+		blk_span[(uint64_t)nblk * img + blockIdx.x] = total;
+}
+
+// pass B: one warp per image resolves every CTA's entry state and output base; validates the block
+__global__ void __launch_bounds__(32)
+    k_kt_resolve(const KtSpan* __restrict__ blk_span, uint32_t nblk, uint32_t* __restrict__ blk_state,
+                 uint64_t* __restrict__ blk_out, KdImage* __restrict__ info, uint64_t n_values, uint64_t token_cap,
+                 uint64_t* __restrict__ result)
+{
+	const uint32_t img = blockIdx.x, lane = threadIdx.x;
+	blk_span += (uint64_t)nblk * img;
+	blk_state += (uint64_t)nblk * img;
+	blk_out += (uint64_t)nblk * img;
+	const uint64_t m = min(info[img].tokens, token_cap);
+	const uint32_t used = (uint32_t)((m + KT_BLOCK - 1) / KT_BLOCK);
+	const uint32_t chunk = (used + 31) / 32;
+	const uint32_t b0 = min(lane * chunk, used), b1 = min(b0 + chunk, used);
+
+	// spans carry 32-bit output counts; the running base is 64-bit, so lanes first reduce (state map only
+	// matters across lanes) and the 64-bit sums are rebuilt in the second walk
+	KtSpan mine = kt_identity();
+	for (uint32_t b = b0; b < b1; b++)
+		mine = kt_compose(mine, blk_span[b]);
+	// entry state of each lane: sequential over 32 lanes (maps only)
+	uint32_t state = ST_V;
+	uint64_t base = 0;
+	for (int l = 0; l < 32; l++)
+	{
+		const uint32_t map_l = __shfl_sync(AKOD_FULL_MASK, mine.map, l);
+		const uint32_t o0 = __shfl_sync(AKOD_FULL_MASK, mine.out[0], l), o1 = __shfl_sync(AKOD_FULL_MASK, mine.out[1], l);
+		const uint32_t o2 = __shfl_sync(AKOD_FULL_MASK, mine.out[2], l), o3 = __shfl_sync(AKOD_FULL_MASK, mine.out[3], l);
+		if ((int)lane > l)
+		{
+			const uint32_t o = state == 0 ? o0 : state == 1 ? o1 : state == 2 ? o2 : o3;
+			base += o;
+			state = (map_l >> (2 * state)) & 3u;
+		}
+	}
+	// note: a lane's chunk can expand to more than 2^32 values only for n_values >= 2^32, which the host refuses
+	for (uint32_t b = b0; b < b1; b++)
+	{
+		blk_state[b] = state;
+		blk_out[b] = base;
+		const KtSpan s = blk_span[b];
+		base += s.out[state];
+		state = (s.map >> (2 * state)) & 3u;
+	}
+	// lane 31 (or the last lane with work) holds the grand total
+	const uint64_t grand = __shfl_sync(AKOD_FULL_MASK, base, 31);
+	if (lane == 0)
+	{
+		info[img].outputs = grand;
+		const bool ok = grand == n_values && info[img].tokens <= token_cap && !kd_needs_rescue(info, img) &&
+		                info[img].stop_pos != KD_STOP64;
+		result[img] = ok ? ((info[img].stop_pos + 7) >> 3) : 0;
+	}
+}
+
+__device__ __forceinline__ int16_t kt_value(uint32_t u)
+{
+	const uint32_t z = (u - 1u) & 0xFFFFu;
+	return (int16_t)((z >> 1) ^ (0u - (z & 1u))); // kagari.c:175-178
+}
+
+// fills out[pos, pos+count) with v; called by all threads of the CTA
+__device__ __forceinline__ void kt_fill_cooperative(int16_t* __restrict__ out, uint64_t pos, uint32_t count, int16_t v)
+{
+	const uint64_t end = pos + count;
+	const uint64_t a0 = (pos + 7) & ~(uint64_t)7, a1 = end & ~(uint64_t)7; // 16-byte aligned body
+	if (a0 >= a1)
+	{
+		for (uint64_t i = pos + threadIdx.x; i < end; i += blockDim.x)
+			out[i] = v;
+		return;
+	}
+	for (uint64_t i = pos + threadIdx.x; i < a0; i += blockDim.x)
+		out[i] = v;
+	const uint32_t vv = (uint32_t)(uint16_t)v * 0x10001u;
+	const uint4 q = make_uint4(vv, vv, vv, vv);
+	uint4* body = reinterpret_cast<uint4*>(out + a0);
+	const uint64_t nq = (a1 - a0) >> 3;
+	for (uint64_t i = threadIdx.x; i < nq; i += blockDim.x)
+		body[i] = q;
+	for (uint64_t i = a1 + threadIdx.x; i < end; i += blockDim.x)
+		out[i] = v;
+}
+
+struct KtRun
+{
+	uint64_t pos;
+	uint32_t count;
+	int16_t value;
+};
+
+// pass C: classify every token and write what it expands to
+__global__ void __launch_bounds__(KT_THREADS)
+    k_kt_expand(const uint16_t* __restrict__ tokens, uint64_t token_stride, uint64_t token_cap,
+                const KdImage* __restrict__ info, const uint32_t* __restrict__ blk_state,
+                const uint64_t* __restrict__ blk_out, uint32_t nblk, int16_t* __restrict__ out_base, uint64_t out_stride,
+                uint64_t n_values)
+{
+	__shared__ KtSpan sm[33];
+	__shared__ KtRun queue[KT_BLOCK / 2];
+	__shared__ uint32_t queue_len;
+
+	const uint32_t img = blockIdx.y;
+	const uint64_t m = min(info[img].tokens, token_cap);
+	const uint64_t cta_base = (uint64_t)blockIdx.x * KT_BLOCK;
+	if (cta_base >= m)
+		return;
+	int16_t* out = out_base + out_stride * img;
+	const uint64_t base = cta_base + (uint64_t)threadIdx.x * KT_ITEMS;
+	uint32_t u[KT_ITEMS + 2];
+	const int valid = (base < m) ? kt_load(tokens + token_stride * img, m, base, u) : 0;
+	if (threadIdx.x == 0)
+		queue_len = 0;
+
+	KtSpan total;
+	const KtSpan before = kt_block_excl_scan(kt_thread_span(u, valid), sm, &total);
+	const uint32_t entry = blk_state[(uint64_t)nblk * img + blockIdx.x];
+	uint32_t state = (before.map >> (2 * entry)) & 3u;
+	uint64_t pos = blk_out[(uint64_t)nblk * img + blockIdx.x] + before.out[entry];
+
+#pragma unroll
+	for (int j = 0; j < KT_ITEMS; j++)
+	{
+		if (j < valid)
+		{
+			const uint32_t cur = u[j + 2];
+			if (state == ST_R)
+			{
+				// an RLE count: (cur - 1) more copies of the value before it (kagari.c:342-354)
+				const uint32_t count = cur - 1u;
+				const int16_t v = kt_value(u[j + 1]);
+				if (pos + count <= n_values)
+				{
+					if (count >= KT_LONG)
+					{
+						const uint32_t slot = atomicAdd(&queue_len, 1u);
+						queue[slot].pos = pos;
+						queue[slot].count = count;
+						queue[slot].value = v;
+					}
+					else
+						for (uint32_t k = 0; k < count; k++)
+							out[pos + k] = v;
+				}
+				pos += count;
+				state = ST_A;
+			}
+			else
+			{
+				if (pos < n_values)
+					out[pos] = kt_value(cur);
+				pos += 1;
+				state = kt_next(state, cur == u[j + 1], cur == u[j]);
+			}
+		}
+	}
+	__syncthreads();
+	const uint32_t nq = queue_len;
+	for (uint32_t i = 0; i < nq; i++)
+		kt_fill_cooperative(out, queue[i].pos, queue[i].count, queue[i].value);
 }

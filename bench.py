@@ -1,0 +1,472 @@
+#!/usr/bin/env python
+"""bench.py -- encode+decode throughput of the Ako hot path on B200 (and the reference's CPU path beside it).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--batch B] [--workload NAME]
+
+One JSON line on stdout (rank 0). A *step* is one pass of the hot path over one batch of synthetic input:
+B images are encoded to .ako and decoded back. Workloads (BASELINE.json configs):
+
+    c2   (default)  1632x2464 RGBA8, DD 13/7, -q 16 -g 16          (configs[1], the metric's config)
+    c1              1024x1280 RGBA8, CDF 5/3, -q 16                (configs[0])
+    c4              1920x1080 RGBA8, CDF 5/3, -q 16                (configs[3], the sharded batch shape)
+    dwt             8192x8192 RGBA8, forward+inverse DWT only, all three wavelets (configs[2]) -- extra report
+
+value  = W*H*B*N / step time, inputs and outputs resident in HBM (CUDA events on the library's stream).
+e2e    = the same work through akoEncodeExt / akoDecodeExt with pinned HOST buffers (H2D/D2H inside).
+Multi-GPU (torchrun): every rank runs the same per-rank batch on its own GPU, no collective on the data
+path ("weak"); time = max over ranks.
+"""
+import argparse
+import ctypes as C
+import json
+import multiprocessing as mp
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+WORKLOADS = {
+    # name: (w, h, wavelet, q, g, seed0, text)
+    "c2": (1632, 2464, 0, 16, 16, 2, "DD137 -q16 -g16 encode+decode of synthetic 1632x2464 RGBA8 (configs[1])"),
+    "c1": (1024, 1280, 1, 16, 0, 1, "CDF53 -q16 encode+decode of synthetic 1024x1280 RGBA8 (configs[0])"),
+    "c4": (1920, 1080, 1, 16, 0, 1000, "CDF53 -q16 encode+decode of synthetic 1920x1080 RGBA8 (configs[3] shape)"),
+}
+CHANNELS = 4
+L2_BYTES = 126 * 1024 * 1024
+
+
+def read_peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            p = json.load(f)
+        return float(p["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# ------------------------------------------------------------------------------------------------ CPU arm
+
+_CPU = {}
+
+
+def _cpu_init():
+    import oracle_lib as ol
+    ref = ol.load_ref() if os.path.exists(ol.ref_path()) else None
+    _CPU["orc"] = ol.load_oracle()
+    _CPU["ref"] = ref
+    _CPU["ol"] = ol
+
+
+def _cpu_job(args):
+    """Encode+decode `reps` times one synthetic image with the reference (or the oracle port); returns seconds."""
+    w, h, wavelet, q, g, seed, reps = args
+    ol, orc, ref = _CPU["ol"], _CPU["orc"], _CPU["ref"]
+    img = ol.synth(orc, w, h, seed)
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        if ref is not None:
+            blob, st = ol.ref_encode(ref, img, wavelet=wavelet, q=q, g=g)
+            out, st = ol.ref_decode(ref, blob)
+        else:
+            blob, st = ol.orc_encode(orc, img, wavelet=wavelet, q=q, g=g)
+            out, st = ol.orc_decode(orc, blob)
+    return time.perf_counter() - t0, len(blob)
+
+
+def cpu_measure(workload, jobs_per_core=1, reps=1, cores=None):
+    """All host cores, one worker process per core over disjoint images (the reference is single-threaded)."""
+    import oracle_lib as ol
+    w, h, wavelet, q, g, seed0, _ = WORKLOADS[workload]
+    cores = cores or len(os.sched_getaffinity(0))
+    kind = "reference" if os.path.exists(ol.ref_path()) else "port"
+    jobs = [(w, h, wavelet, q, g, seed0 + i, reps) for i in range(cores * jobs_per_core)]
+    ctx = mp.get_context("fork")
+    with ctx.Pool(cores, initializer=_cpu_init) as pool:
+        pool.map(_cpu_job, [(64, 64, wavelet, q, g, 1, 1)] * cores)  # warm the workers
+        t0 = time.perf_counter()
+        res = pool.map(_cpu_job, jobs, chunksize=1)
+        wall = time.perf_counter() - t0
+    images = len(jobs) * reps
+    per_core = np.mean([r[0] for r in res]) / reps
+    return {
+        "value": w * h * images / wall / 1e6, "unit": "MPix/s", "cores": cores, "kind": kind,
+        "sample": f"{images} images ({workload}: {w}x{h} RGBA8) encode+decode, {cores} worker processes, "
+                  f"wall {wall:.2f} s; one core does one image in {per_core * 1e3:.0f} ms "
+                  f"({w * h / per_core / 1e6:.1f} MPix/s/core)",
+        "wall_s": wall, "images": images,
+    }
+
+
+# ------------------------------------------------------------------------------------------------ clocks
+
+class ClockSampler:
+    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+             "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.gpu), "-lms", "100"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------ ours
+
+def algorithmic_bytes_lift(w, h, images):
+    """a lifting kernel reads each int16 sample once and writes each int16 coefficient once:
+    4 B per sample of the level it transforms. Summed over the launches of one pyramid."""
+    total = 0
+    cw, ch = w, h
+    while cw > 2 and ch > 2:
+        total += 4 * cw * ch * CHANNELS * images
+        cw, ch = (cw + 1) // 2, (ch + 1) // 2
+    return total
+
+
+def run_ours(args, rank, world):
+    import torch
+
+    import ako_b200
+    import oracle_lib as ol
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- ako_b200 has no CPU fallback")
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    os.environ["AKO_CUDA_DEVICE"] = str(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist_
+        dist = dist_
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    w, h, wavelet, q, g, seed0, text = WORKLOADS[args.workload]
+    B = args.batch
+    px = w * h
+    img_bytes = px * CHANNELS
+    settings = ako_b200.default_settings(wavelet=wavelet, quantization=q, gate=g)
+    ctx = ako_b200.Context(local)
+    L = ako_b200.load()
+    stream = torch.cuda.ExternalStream(ctx.stream, device=torch.device("cuda", local))
+
+    # input pool larger than L2 so that every step's input comes from HBM
+    pool_images = max(B, -(-int(1.5 * L2_BYTES) // img_bytes))
+    pool_images = -(-pool_images // B) * B
+    orc = ol.load_oracle()
+    host_pool = torch.empty((pool_images, h, w, CHANNELS), dtype=torch.uint8).pin_memory()
+    distinct = min(pool_images, 4)
+    for i in range(distinct):
+        host_pool[i].copy_(torch.from_numpy(ol.synth(orc, w, h, seed0 + i + rank * 64)))
+    for i in range(distinct, pool_images):
+        host_pool[i].copy_(host_pool[i % distinct])
+    dev_pool = host_pool.to(f"cuda:{local}")
+    bound = ctx.encode_bound(settings, CHANNELS, w, h)
+    blob_stride = -(-bound // 256) * 256
+    dev_blobs = torch.empty((B, blob_stride), dtype=torch.uint8, device=f"cuda:{local}")
+    dev_out = torch.empty((B, h, w, CHANNELS), dtype=torch.uint8, device=f"cuda:{local}")
+    torch.cuda.synchronize()
+
+    def step_device(i):
+        first = (i * B) % pool_images
+        d_in = dev_pool[first].data_ptr()
+        done, st, sizes = ctx.encode_batch_device(settings, CHANNELS, w, h, B, d_in, img_bytes, dev_blobs.data_ptr(),
+                                                  blob_stride)
+        if done != B:
+            raise RuntimeError(f"encode failed: {ako_b200.status_string(st)}")
+        done, st = ctx.decode_batch_device(B, dev_blobs.data_ptr(), blob_stride, sizes, dev_out.data_ptr(), img_bytes)
+        if done != B:
+            raise RuntimeError(f"decode failed: {ako_b200.status_string(st)}")
+        return sizes
+
+    # ---- parity gate before any timing: bit-exact vs the oracle on this rank's first image
+    sizes = step_device(0)
+    ctx.sync()
+    want_blob, _ = ol.orc_encode(orc, host_pool[0].numpy(), wavelet=wavelet, q=q, g=g)
+    got_blob = dev_blobs[0, :sizes[0]].cpu().numpy().tobytes()
+    want_px, _ = ol.orc_decode(orc, want_blob)
+    bit_exact = (got_blob == want_blob) and bool(np.array_equal(dev_out[0].cpu().numpy(), want_px))
+    if not bit_exact:
+        raise RuntimeError("bench.py: GPU output is not bit-exact against the oracle; refusing to time it")
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for i in range(args.warmup):
+        step_device(i)
+    sampler = ClockSampler(local)
+    barrier()
+    sampler.start()
+    launches0 = ctx.launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record(stream)
+    for i in range(args.steps):
+        step_device(args.warmup + i)
+    ev1.record(stream)
+    barrier()
+    clocks = sampler.stop()
+    launches = ctx.launch_count() - launches0
+    elapsed_ms = ev0.elapsed_time(ev1)
+    if dist is not None:
+        t = torch.tensor([elapsed_ms], device=f"cuda:{local}")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        elapsed_ms = float(t.item())
+    ms_per_step = elapsed_ms / args.steps
+    value = px * B * world / (ms_per_step * 1e-3) / 1e6
+
+    # ---- e2e: akoEncodeExt / akoDecodeExt with pinned host buffers, copies inside the timed region
+    cb = L.akoB200PinnedCallbacks()
+    free_fn = C.CFUNCTYPE(None, C.c_void_p)(cb.free)
+    sset = settings
+
+    def step_host(i):
+        h2d = d2h = 0
+        for k in range(B):
+            src = host_pool[(i * B + k) % pool_images]
+            out = C.c_void_p()
+            st = C.c_int(0)
+            n = L.akoEncodeExt(C.byref(cb), C.byref(sset), CHANNELS, w, h, src.data_ptr(), C.byref(out), C.byref(st))
+            if n == 0:
+                raise RuntimeError("akoEncodeExt: " + ako_b200.status_string(st.value))
+            ch_, w_, h_ = C.c_size_t(), C.c_size_t(), C.c_size_t()
+            p = L.akoDecodeExt(C.byref(cb), n, out, None, C.byref(ch_), C.byref(w_), C.byref(h_), C.byref(st))
+            if not p:
+                raise RuntimeError("akoDecodeExt: " + ako_b200.status_string(st.value))
+            free_fn(out)
+            free_fn(p)
+            h2d += img_bytes + n
+            d2h += n + img_bytes
+        return h2d, d2h
+
+    e2e_steps = max(1, min(args.steps, 20))
+    for i in range(min(args.warmup, 3)):
+        step_host(i)
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(e2e_steps):
+        h2d, d2h = step_host(i)
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    if dist is not None:
+        t = torch.tensor([e2e_s], device=f"cuda:{local}")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t.item())
+    e2e_value = px * B * world * e2e_steps / e2e_s / 1e6
+
+    # ---- roofline of the dominant kernel: per-kernel CUDA events on the launching stream (outside the timed region)
+    ctx.profile_reset()
+    ctx.profile(True)
+    prof_steps = 3
+    for i in range(prof_steps):
+        step_device(i)
+    ctx.sync()
+    prof = ctx.profile_get()
+    ctx.profile(False)
+    total_ms = sum(ms for _, ms in prof.values()) or 1.0
+    top = max(prof.items(), key=lambda kv: kv[1][1])
+    peak, peak_src = read_peaks()
+    lift_names = [k for k in prof if k.startswith("lift_") or k.startswith("unlift_")]
+    dwt_name = max(lift_names, key=lambda k: prof[k][1]) if lift_names else None
+    roofline = None
+    if dwt_name:
+        # every launch of a (un)lift kernel moves 4 B per sample of its level (read once + write once)
+        nl, ms = prof[dwt_name]
+        same_dir = [k for k in lift_names if k.split("_")[0] == dwt_name.split("_")[0]]
+        bytes_all = algorithmic_bytes_lift(w, h, B) * prof_steps
+        ms_all = sum(prof[k][1] for k in same_dir)
+        achieved = bytes_all / (ms_all * 1e-3) / 1e9
+        roofline = {"bound": "hbm", "kernel": "+".join(sorted(same_dir)), "achieved": round(achieved, 1),
+                    "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4), "traffic": None,
+                    "peak_source": peak_src, "launches": sum(prof[k][0] for k in same_dir),
+                    "share_of_step": round(ms_all / total_ms, 4),
+                    "algorithmic_bytes_per_step": bytes_all // prof_steps}
+    kernels = {k: {"launches": v[0] // prof_steps, "ms_per_step": round(v[1] / prof_steps, 4)}
+               for k, v in sorted(prof.items(), key=lambda kv: -kv[1][1])}
+
+    line = None
+    if rank == 0:
+        cpu = None
+        if world == 1 or True:
+            try:
+                cpu = cpu_measure(args.workload, jobs_per_core=1, reps=args.cpu_reps)
+                cpu = {k: (round(v, 2) if isinstance(v, float) else v) for k, v in cpu.items()
+                       if k not in ("wall_s", "images")}
+            except Exception as e:  # the GPU number stands on its own
+                cpu = {"value": None, "unit": "MPix/s", "cores": 0, "kind": "unavailable", "sample": repr(e)}
+        line = {
+            "metric": "encode+decode MPix/s (Ako hot path, bit-exact)", "value": round(value, 1), "unit": "MPix/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms_per_step, 4),
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "i16", "data": "synthetic",
+            "config": {"workload": text, "images_per_step_per_gpu": B, "channels": CHANNELS,
+                       "l2_policy": f"inputs rotate through a pool of {pool_images} images "
+                                    f"({pool_images * img_bytes >> 20} MiB > 126 MiB L2); no explicit flush",
+                       "parallelism": f"{world} independent shards, no collective on the data path",
+                       "step": "akoB200EncodeBatchDevice + akoB200DecodeBatchDevice, device resident"},
+            "bit_exact_vs_oracle": bit_exact,
+            "clocks": clocks,
+            "e2e": {"value": round(e2e_value, 1), "unit": "MPix/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "api": "akoEncodeExt + akoDecodeExt, pinned host buffers (akoB200PinnedCallbacks)",
+                    "steps": e2e_steps},
+            "gpu_launches": int(launches),
+            "roofline": roofline,
+            "top_kernel": {"name": top[0], "share_of_step": round(top[1][1] / total_ms, 4)},
+            "kernels": kernels,
+            "cpu_baseline": cpu,
+        }
+    ctx.close()
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+    return line
+
+
+def run_dwt(args):
+    """configs[2]: forward / inverse DWT only on 8192x8192 RGBA8 planes, HBM GB/s against the roofline."""
+    import torch
+
+    import ako_b200
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    ctx = ako_b200.Context(local)
+    L = ako_b200.load()
+    w = h = args.dwt_size
+    peak, peak_src = read_peaks()
+    n = ctx.stream_size(CHANNELS, w, h) // 2
+    gen = torch.Generator(device="cuda").manual_seed(1)
+    base = torch.randint(-255, 256, (CHANNELS, h, w), dtype=torch.int16, device="cuda", generator=gen)
+    planes = torch.empty_like(base)
+    stream_t = torch.empty(n + 64, dtype=torch.int16, device="cuda")
+    ts = torch.cuda.ExternalStream(ctx.stream)
+    out = {}
+    for wavelet, name in ((1, "cdf53"), (0, "dd137"), (2, "haar")):
+        s = ako_b200.default_settings(wavelet=wavelet, quantization=0, gate=0)
+        res = {}
+        for direction in ("forward", "inverse"):
+            times = []
+            for it in range(args.warmup + args.steps):
+                if direction == "forward":
+                    planes.copy_(base)  # akoB200Lift destroys its input; the copy also evicts L2 (2x268 MB)
+                    torch.cuda.synchronize()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record(ts)
+                if direction == "forward":
+                    st = L.akoB200Lift(ctx.h, C.byref(s), CHANNELS, w, h, planes.data_ptr(), stream_t.data_ptr())
+                else:
+                    st = L.akoB200Unlift(ctx.h, C.byref(s), CHANNELS, w, h, stream_t.data_ptr(), planes.data_ptr())
+                e1.record(ts)
+                ctx.sync()
+                assert st == 0
+                if it >= args.warmup:
+                    times.append(e0.elapsed_time(e1))
+            if direction == "inverse":
+                assert torch.equal(planes, base), "DWT round trip is not exact"
+            ms = float(np.median(times))
+            gbs = 4 * w * h * CHANNELS / (ms * 1e-3) / 1e9
+            res[direction] = {"ms": round(ms, 4), "GBps": round(gbs, 1), "frac_of_measured_peak": round(gbs / peak, 4),
+                              "frac_of_8TBps": round(gbs / 8000, 4)}
+        out[name] = res
+    ctx.close()
+    return {"metric": "DWT-only HBM GB/s (algorithmic 16 B/pixel per direction)", "size": f"{w}x{h} RGBA8 int16 planes",
+            "peak": peak, "peak_source": peak_src, "results": out}
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return None
+    w, h, wavelet, q, g, seed0, text = WORKLOADS[args.workload]
+    # each step: every core encodes+decodes one image; bounded so K+W steps end within minutes
+    t_steps = []
+    res = None
+    for i in range(args.warmup + args.steps):
+        res = cpu_measure(args.workload, jobs_per_core=1, reps=1)
+        if i >= args.warmup:
+            t_steps.append(res["wall_s"])
+    ms = float(np.mean(t_steps)) * 1e3
+    value = w * h * res["images"] / (ms * 1e-3) / 1e6
+    return {
+        "impl": "reference", "metric": "encode+decode MPix/s (Ako hot path, bit-exact)", "value": round(value, 2),
+        "unit": "MPix/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms, 2),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "i16", "data": "synthetic",
+        "config": {"workload": text, "images_per_step": res["images"], "channels": CHANNELS,
+                   "parallelism": f"{res['cores']} host worker processes, one image each per step (rank 0 only)"},
+        "cpu_baseline": {"value": round(value, 2), "unit": "MPix/s", "cores": res["cores"], "kind": res["kind"],
+                         "sample": res["sample"]},
+        "e2e": {"value": round(value, 2), "unit": "MPix/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="c2", choices=list(WORKLOADS) + ["dwt"])
+    ap.add_argument("--batch", type=int, default=8, help="images per step per GPU")
+    ap.add_argument("--cpu-reps", type=int, default=1)
+    ap.add_argument("--dwt-size", type=int, default=8192)
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+
+    if args.impl == "reference":
+        line = run_reference(args, rank, world)
+    elif args.workload == "dwt":
+        line = run_dwt(args) if rank == 0 else None
+    else:
+        args.warmup = max(args.warmup, 3)
+        line = run_ours(args, rank, world)
+    if rank == 0 and line is not None:
+        print(json.dumps(line), flush=True)
+
+
+if __name__ == "__main__":
+    main()
