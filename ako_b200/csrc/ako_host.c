@@ -450,19 +450,68 @@ AKO_API enum akoStatus akoB200CopyToHost(akoB200Context* ctx, void* dst, const v
 /* Pinned realloc needs the old size: keep it in a 64-byte prefix (keeps 64-byte alignment). */
 #define PIN_PREFIX 64
 
+/* cudaHostAlloc / cudaFreeHost cost milliseconds for image-sized blocks, so freed blocks are kept in a small
+ * cache (prefix word 0 = user size, word 1 = capacity) and handed out again to requests they fit. */
+#define PIN_CACHE_SLOTS 16
+#define PIN_CACHE_MAX_BYTES ((size_t)1 << 30)
+static pthread_mutex_t g_pin_lock = PTHREAD_MUTEX_INITIALIZER;
+static uint8_t* g_pin_cache[PIN_CACHE_SLOTS];
+static size_t g_pin_cached_bytes = 0;
+
 static void* pinned_malloc(size_t bytes)
 {
-	uint8_t* raw = akod_pinned_alloc(bytes + PIN_PREFIX);
+	uint8_t* raw = NULL;
+	pthread_mutex_lock(&g_pin_lock);
+	{
+		int best = -1;
+		for (int i = 0; i < PIN_CACHE_SLOTS; i++)
+			if (g_pin_cache[i] != NULL)
+			{
+				const size_t cap = ((size_t*)g_pin_cache[i])[1];
+				if (cap >= bytes && cap <= bytes * 2 + 4096 &&
+				    (best < 0 || cap < ((size_t*)g_pin_cache[best])[1]))
+					best = i;
+			}
+		if (best >= 0)
+		{
+			raw = g_pin_cache[best];
+			g_pin_cache[best] = NULL;
+			g_pin_cached_bytes -= ((size_t*)raw)[1];
+		}
+	}
+	pthread_mutex_unlock(&g_pin_lock);
+
 	if (raw == NULL)
-		return NULL;
-	*(size_t*)raw = bytes;
+	{
+		const size_t cap = (bytes + 4095) & ~(size_t)4095;
+		raw = akod_pinned_alloc(cap + PIN_PREFIX);
+		if (raw == NULL)
+			return NULL;
+		((size_t*)raw)[1] = cap;
+	}
+	((size_t*)raw)[0] = bytes;
 	return raw + PIN_PREFIX;
 }
 
 static void pinned_free(void* p)
 {
-	if (p != NULL)
-		akod_pinned_free((uint8_t*)p - PIN_PREFIX);
+	if (p == NULL)
+		return;
+	uint8_t* raw = (uint8_t*)p - PIN_PREFIX;
+	const size_t cap = ((size_t*)raw)[1];
+	pthread_mutex_lock(&g_pin_lock);
+	if (g_pin_cached_bytes + cap <= PIN_CACHE_MAX_BYTES)
+		for (int i = 0; i < PIN_CACHE_SLOTS; i++)
+			if (g_pin_cache[i] == NULL)
+			{
+				g_pin_cache[i] = raw;
+				g_pin_cached_bytes += cap;
+				raw = NULL;
+				break;
+			}
+	pthread_mutex_unlock(&g_pin_lock);
+	if (raw != NULL)
+		akod_pinned_free(raw);
 }
 
 static void* pinned_realloc(void* p, size_t bytes)

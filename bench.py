@@ -333,7 +333,9 @@ def run_ours(args, rank, world):
     line = None
     if rank == 0:
         cpu = None
-        if world == 1 or True:
+        if args.skip_cpu:
+            cpu = {"value": None, "unit": "MPix/s", "cores": 0, "kind": "skipped", "sample": "--skip-cpu"}
+        else:
             try:
                 cpu = cpu_measure(args.workload, jobs_per_core=1, reps=args.cpu_reps)
                 cpu = {k: (round(v, 2) if isinstance(v, float) else v) for k, v in cpu.items()
@@ -453,6 +455,7 @@ def main():
     ap.add_argument("--batch", type=int, default=8, help="images per step per GPU")
     ap.add_argument("--cpu-reps", type=int, default=1)
     ap.add_argument("--dwt-size", type=int, default=8192)
+    ap.add_argument("--skip-cpu", action="store_true", help="profiling runs: do not time the CPU reference")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
