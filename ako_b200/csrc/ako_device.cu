@@ -9,6 +9,7 @@
 #include "kagari_dec.cuh"
 #include "kagari_enc.cuh"
 #include "lift.cuh"
+#include "lift_strip.cuh"
 
 // ------------------------------------------------------------------------------------------------
 // context
@@ -298,6 +299,37 @@ static int launch_lift_level(akodContext* c, const LiftParams& p, uint32_t n_ima
 	return AKOD_OK;
 }
 
+// strip kernel: pick the rows-per-CTA so that the grid fills the machine a few times over while the
+// warm-up rows (2*LAT per CTA) stay a small fraction
+template <int WL>
+static int launch_lift_strip(akodContext* c, const LiftParams& p, uint32_t n_images)
+{
+	constexpr int LAT = StripGeom<WL>::LAT;
+	const uint32_t strips = (p.tw + FS_TW - 1) / FS_TW;
+	const uint64_t want = (uint64_t)c->sm_count * 6;
+	uint32_t split = 0;
+	for (uint32_t k = 32; k >= 4; k >>= 1)
+	{
+		split = 8 * k - 2 * LAT;
+		const uint64_t ctas = (uint64_t)strips * ((p.th + split - 1) / split) * p.channels * n_images;
+		if (ctas >= want)
+			break;
+	}
+	StripParams sp;
+	sp.p = p;
+	sp.split = split;
+	bool plain = true;
+	for (uint32_t ch = 0; ch < p.channels; ch++)
+		plain = plain && p.q[ch] <= 1 && p.g[ch] == 0;
+	const dim3 grid(strips, (p.th + split - 1) / split, p.channels * n_images);
+	static const char* const names[3] = {"lift_strip_dd137", "lift_strip_cdf53", "lift_strip_haar"};
+	if (plain)
+		AKOD_LAUNCH(c, names[WL], (k_lift_strip<WL, true>), grid, FS_THREADS, 0, sp);
+	else
+		AKOD_LAUNCH(c, names[WL], (k_lift_strip<WL, false>), grid, FS_THREADS, 0, sp);
+	return AKOD_OK;
+}
+
 template <int WL>
 static int launch_unlift_level(akodContext* c, const UnliftParams& p, uint32_t n_images)
 {
@@ -360,7 +392,17 @@ extern "C" int akod_lift(akodContext* c, const akodPlan* plan, int16_t* d_planes
 			p.qmagic[ch] = (p.q[ch] > 1) ? (uint32_t)((((uint64_t)1 << 32) + p.q[ch] - 1) / (uint64_t)p.q[ch]) : 0;
 		}
 		int rc;
-		if (L->wavelet == AKOD_DD137)
+		static const bool no_strip = getenv("AKO_B200_NO_STRIP") != nullptr;
+		if (!no_strip && lift_strip_eligible(p))
+		{
+			if (L->wavelet == AKOD_DD137)
+				rc = launch_lift_strip<AKOD_DD137>(c, p, n);
+			else if (L->wavelet == AKOD_CDF53)
+				rc = launch_lift_strip<AKOD_CDF53>(c, p, n);
+			else
+				rc = launch_lift_strip<AKOD_HAAR>(c, p, n);
+		}
+		else if (L->wavelet == AKOD_DD137)
 			rc = launch_lift_level<AKOD_DD137>(c, p, n);
 		else if (L->wavelet == AKOD_CDF53)
 			rc = launch_lift_level<AKOD_CDF53>(c, p, n);
