@@ -10,6 +10,7 @@
 #include "kagari_enc.cuh"
 #include "lift.cuh"
 #include "lift_strip.cuh"
+#include "unlift_strip.cuh"
 
 // ------------------------------------------------------------------------------------------------
 // context
@@ -331,6 +332,29 @@ static int launch_lift_strip(akodContext* c, const LiftParams& p, uint32_t n_ima
 }
 
 template <int WL>
+static int launch_unlift_strip(akodContext* c, const UnliftParams& p, uint32_t n_images)
+{
+	constexpr int LAT = StripGeom<WL>::LAT;
+	const uint32_t strips = (p.hw + US_TW - 1) / US_TW;
+	const uint64_t want = (uint64_t)c->sm_count * 6;
+	uint32_t split = 0;
+	for (uint32_t k = 32; k >= 4; k >>= 1)
+	{
+		split = 8 * k - 2 * LAT;
+		const uint64_t ctas = (uint64_t)strips * ((p.hh + split - 1) / split) * p.channels * n_images;
+		if (ctas >= want)
+			break;
+	}
+	UnstripParams up;
+	up.p = p;
+	up.split = split;
+	const dim3 grid(strips, (p.hh + split - 1) / split, p.channels * n_images);
+	static const char* const names[3] = {"unlift_strip_dd137", "unlift_strip_cdf53", "unlift_strip_haar"};
+	AKOD_LAUNCH(c, names[WL], k_unlift_strip<WL>, grid, US_THREADS, 0, up);
+	return AKOD_OK;
+}
+
+template <int WL>
 static int launch_unlift_level(akodContext* c, const UnliftParams& p, uint32_t n_images)
 {
 	const dim3 grid((p.hw + LIFT_TW - 1) / LIFT_TW, (p.hh + LIFT_TH - 1) / LIFT_TH, p.channels * n_images);
@@ -485,7 +509,17 @@ extern "C" int akod_unlift(akodContext* c, const akodPlan* plan, const int16_t* 
 		for (uint32_t ch = 0; ch < plan->channels; ch++)
 			p.off_c[ch] = L->off_c[ch];
 		int rc;
-		if (L->wavelet == AKOD_DD137)
+		static const bool no_strip = getenv("AKO_B200_NO_STRIP") != nullptr;
+		if (!no_strip && unlift_strip_eligible(p))
+		{
+			if (L->wavelet == AKOD_DD137)
+				rc = launch_unlift_strip<AKOD_DD137>(c, p, n);
+			else if (L->wavelet == AKOD_CDF53)
+				rc = launch_unlift_strip<AKOD_CDF53>(c, p, n);
+			else
+				rc = launch_unlift_strip<AKOD_HAAR>(c, p, n);
+		}
+		else if (L->wavelet == AKOD_DD137)
 			rc = launch_unlift_level<AKOD_DD137>(c, p, n);
 		else if (L->wavelet == AKOD_CDF53)
 			rc = launch_unlift_level<AKOD_CDF53>(c, p, n);

@@ -228,9 +228,13 @@ __global__ void __launch_bounds__(FS_THREADS, 6) k_lift_strip(const StripParams 
 				{
 					if (c0 + a == 0) // H(-1) = H(-2) = H(0)
 						H[2] = H[3] = H[4];
-					const int rem = tw - (c0 + a); // H(t) = H(t-1); t is 8 or 16 columns into an edge chunk
+					const int rem = tw - (c0 + a); // H(t) = H(t-1); t is 4, 8, 12 or 16 columns into an edge chunk
+					if (rem == 4)
+						H[8] = H[7];
 					if (rem == 8)
 						H[12] = H[11];
+					if (rem == 12)
+						H[16] = H[15];
 					if (rem == 16)
 						H[20] = H[19];
 				}
@@ -356,7 +360,7 @@ __global__ void __launch_bounds__(FS_THREADS, 6) k_lift_strip(const StripParams 
 // host-side eligibility of a level for the strip kernel
 static inline bool lift_strip_eligible(const LiftParams& p)
 {
-	return p.wrap == AKOD_WRAP_CLAMP && (p.cw % 16) == 0 && p.cw >= 64 && p.th >= 8 && (p.in_rs % 8) == 0 &&
+	return p.wrap == AKOD_WRAP_CLAMP && (p.cw % 8) == 0 && p.cw >= 64 && p.th >= 8 && (p.in_rs % 8) == 0 &&
 	       (p.in_ps % 8) == 0 && (p.in_is % 8) == 0 && ((uintptr_t)p.in % 16) == 0 && (p.ll_rs % 2) == 0 &&
 	       (p.ll_ps % 2) == 0 && (p.ll_is % 2) == 0 && ((uintptr_t)p.ll % 4) == 0 && (p.stream_is % 2) == 0 &&
 	       ((uintptr_t)p.stream % 4) == 0 && (uint64_t)p.cw * p.ch < ((uint64_t)1 << 31);

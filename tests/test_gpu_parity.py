@@ -61,7 +61,8 @@ def test_format_stage(orc, ctx, color):
 LIFT_SHAPES = [(64, 64, 4), (65, 63, 3), (33, 47, 1), (16, 17, 2), (3, 3, 4), (5, 9, 3), (100, 7, 4), (129, 70, 4),
                (200, 131, 2), (257, 66, 1), (128, 128, 1), (15, 300, 1),
                # strip-kernel geometry: several / partial 128-column strips, several row splits, odd heights
-               (528, 70, 1), (272, 601, 2), (1040, 48, 1), (64, 17, 3), (2064, 1100, 1)]
+               (528, 70, 1), (272, 601, 2), (1040, 48, 1), (64, 17, 3), (2064, 1100, 1), (264, 40, 1), (408, 616, 2),
+               (248, 33, 1), (968, 72, 1)]
 
 
 @pytest.mark.parametrize("wrap", [0, 1, 2, 3])
