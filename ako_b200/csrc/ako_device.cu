@@ -544,13 +544,13 @@ extern "C" int akod_kagari_encode(akodContext* c, uint64_t n_values, const int16
 	const uint64_t per_img = nblocks;
 
 	void* ws;
-	const size_t need = (size_t)per_img * n_images * (sizeof(long long) + sizeof(uint32_t) + sizeof(uint64_t));
+	const size_t need = (size_t)per_img * n_images * (sizeof(uint64_t) + 2 * sizeof(uint32_t)) + 64;
 	int rc = akod_workspace(c, AKOD_WS_KAGARI, need, &ws);
 	if (rc != AKOD_OK)
 		return rc;
-	long long* blk_start = (long long*)ws;
-	uint64_t* blk_off = (uint64_t*)(blk_start + per_img * n_images);
-	uint32_t* blk_bits = (uint32_t*)(blk_off + per_img * n_images);
+	uint64_t* blk_off = (uint64_t*)ws;
+	uint32_t* blk_start = (uint32_t*)(blk_off + per_img * n_images);
+	uint32_t* blk_bits = blk_start + per_img * n_images;
 
 	const dim3 grid(nblocks, n_images);
 	AKOD_LAUNCH(c, "kagari_starts", k_kg_starts, grid, KG_THREADS, 0, d_in, in_stride, n_values, blk_start, nblocks);
@@ -561,8 +561,8 @@ extern "C" int akod_kagari_encode(akodContext* c, uint64_t n_values, const int16
 	const dim3 zgrid((nblocks + 255) / 256, n_images);
 	AKOD_LAUNCH(c, "kagari_zero_edges", k_kg_zero_edges, zgrid, 256, 0, blk_off, blk_bits, nblocks, d_out, out_stride,
 	            out_cap * 8);
-	AKOD_LAUNCH(c, "kagari_pack", k_kg_pack, grid, KG_THREADS, 0, d_in, in_stride, n_values, blk_start, blk_off, nblocks,
-	            d_out, out_stride, out_cap * 8);
+	AKOD_LAUNCH(c, "kagari_pack", k_kg_pack, grid, KG_THREADS, 0, d_in, in_stride, n_values, blk_start, blk_off, blk_bits,
+	            nblocks, d_out, out_stride, out_cap * 8);
 	return AKOD_OK;
 }
 

@@ -194,3 +194,46 @@ __device__ __forceinline__ long long block_excl_max(long long v, long long* sm, 
 	__syncthreads();
 	return r;
 }
+
+// Block-wide exclusive max of one uint32 per thread (identity 0); *total gets the block max. sm: 33 uint32.
+__device__ __forceinline__ uint32_t block_excl_max_u32(uint32_t v, uint32_t* sm, uint32_t* total)
+{
+	const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+	uint32_t incl = v;
+#pragma unroll
+	for (int d = 1; d < 32; d <<= 1)
+	{
+		const uint32_t o = __shfl_up_sync(AKOD_FULL_MASK, incl, d);
+		if (lane >= d)
+			incl = max(incl, o);
+	}
+	uint32_t excl = __shfl_up_sync(AKOD_FULL_MASK, incl, 1);
+	if (lane == 0)
+		excl = 0;
+	if (lane == 31)
+		sm[wid] = incl;
+	__syncthreads();
+	if (wid == 0)
+	{
+		uint32_t w = (lane < nw) ? sm[lane] : 0;
+		uint32_t wi = w;
+#pragma unroll
+		for (int d = 1; d < 32; d <<= 1)
+		{
+			const uint32_t o = __shfl_up_sync(AKOD_FULL_MASK, wi, d);
+			if (lane >= d)
+				wi = max(wi, o);
+		}
+		uint32_t we = __shfl_up_sync(AKOD_FULL_MASK, wi, 1);
+		if (lane == 0)
+			we = 0;
+		sm[lane] = we;
+		if (lane == 31)
+			sm[32] = wi;
+	}
+	__syncthreads();
+	const uint32_t r = max(sm[wid], excl);
+	*total = sm[32];
+	__syncthreads();
+	return r;
+}

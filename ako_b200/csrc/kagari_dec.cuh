@@ -616,27 +616,27 @@ __device__ __forceinline__ int16_t kt_value(uint32_t u)
 	return (int16_t)((z >> 1) ^ (0u - (z & 1u))); // kagari.c:175-178
 }
 
-// fills out[pos, pos+count) with v; called by all threads of the CTA
-__device__ __forceinline__ void kt_fill_cooperative(int16_t* __restrict__ out, uint64_t pos, uint32_t count, int16_t v)
+// fills out[pos, pos+count) with v; called by the 32 lanes of one warp (runs are spread over the CTA's warps)
+__device__ __forceinline__ void kt_fill_warp(int16_t* __restrict__ out, uint64_t pos, uint32_t count, int16_t v, int lane)
 {
 	const uint64_t end = pos + count;
 	const uint64_t a0 = (pos + 7) & ~(uint64_t)7, a1 = end & ~(uint64_t)7; // 16-byte aligned body
 	if (a0 >= a1)
 	{
-		for (uint64_t i = pos + threadIdx.x; i < end; i += blockDim.x)
+		for (uint64_t i = pos + lane; i < end; i += 32)
 			out[i] = v;
 		return;
 	}
-	for (uint64_t i = pos + threadIdx.x; i < a0; i += blockDim.x)
-		out[i] = v;
+	if (pos + lane < a0)
+		out[pos + lane] = v; // at most 7 head elements
 	const uint32_t vv = (uint32_t)(uint16_t)v * 0x10001u;
 	const uint4 q = make_uint4(vv, vv, vv, vv);
 	uint4* body = reinterpret_cast<uint4*>(out + a0);
 	const uint64_t nq = (a1 - a0) >> 3;
-	for (uint64_t i = threadIdx.x; i < nq; i += blockDim.x)
+	for (uint64_t i = lane; i < nq; i += 32)
 		body[i] = q;
-	for (uint64_t i = a1 + threadIdx.x; i < end; i += blockDim.x)
-		out[i] = v;
+	if (a1 + lane < end)
+		out[a1 + lane] = v; // at most 7 tail elements
 }
 
 struct KtRun
@@ -713,6 +713,7 @@ __global__ void __launch_bounds__(KT_THREADS)
 	}
 	__syncthreads();
 	const uint32_t nq = queue_len;
-	for (uint32_t i = 0; i < nq; i++)
-		kt_fill_cooperative(out, queue[i].pos, queue[i].count, queue[i].value);
+	const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+	for (uint32_t i = wid; i < nq; i += KT_THREADS / 32)
+		kt_fill_warp(out, queue[i].pos, queue[i].count, queue[i].value, lane);
 }

@@ -13,6 +13,9 @@
 //   3. k_kg_pack     : codes OR-ed into a shared-memory bit buffer, written MSB-first as whole 32-bit words;
 //                      the two words a block may share with its neighbours are merged with atomicOr
 //                      (k_kg_zero_edges clears them first).
+// Quantised streams are mostly long runs of zeros: a thread whose 8 values continue a run that also goes on
+// after them emits nothing unless the run counter crosses 1, 2 or 65534 inside it, and skips all per-element work.
+// Run starts are carried as (index + 1) in 32 bits (0 = none); the host refuses streams of 2^32 values or more.
 // blockIdx.y is the image of a same-shape batch.
 #pragma once
 
@@ -74,81 +77,90 @@ __device__ __forceinline__ KgCode kg_element(int16_t a, uint32_t k, bool last)
 	return out;
 }
 
-// loads this thread's KG_ITEMS values plus the one before and the one after; returns how many are valid
-__device__ __forceinline__ int kg_load(const int16_t* __restrict__ in, uint64_t n, uint64_t base, int16_t v[KG_ITEMS],
-                                       int16_t& before, int16_t& after, bool& has_before, bool& has_after)
+// what a thread knows about its KG_ITEMS values after loading them
+struct KgChunk
 {
-	int valid = 0;
+	int16_t v[KG_ITEMS];
+	int16_t after;
+	int valid;           // how many of v[] exist
+	bool has_after;      // an element follows the chunk
+	uint32_t start_mask; // bit j: v[j] starts a run (differs from its predecessor, or is element 0)
+	uint32_t last_start; // (index + 1) of the last run start inside the chunk, 0 if none
+};
+
+__device__ __forceinline__ KgChunk kg_load(const int16_t* __restrict__ in, uint64_t n, uint64_t base)
+{
+	KgChunk c;
+	c.valid = 0;
 	if (base + KG_ITEMS <= n)
 	{
 		// 128-bit load: base is a multiple of 8 and the stream is 16-byte aligned
-		*reinterpret_cast<uint4*>(v) = __ldg(reinterpret_cast<const uint4*>(in + base));
-		valid = KG_ITEMS;
+		*reinterpret_cast<uint4*>(c.v) = __ldg(reinterpret_cast<const uint4*>(in + base));
+		c.valid = KG_ITEMS;
 	}
 	else
 	{
 #pragma unroll
 		for (int j = 0; j < KG_ITEMS; j++)
 		{
-			v[j] = 0;
+			c.v[j] = 0;
 			if (base + j < n)
 			{
-				v[j] = in[base + j];
-				valid = j + 1;
+				c.v[j] = in[base + j];
+				c.valid = j + 1;
 			}
 		}
 	}
-	has_before = base > 0 && base <= n;
-	before = has_before ? in[base - 1] : (int16_t)0;
-	has_after = base + KG_ITEMS < n;
-	after = has_after ? in[base + KG_ITEMS] : (int16_t)0;
-	return valid;
-}
-
-// pass 1: blk_start[b] = largest i in block b with (i == 0 || a[i] != a[i-1]), or -1
-__global__ void __launch_bounds__(KG_THREADS)
-    k_kg_starts(const int16_t* __restrict__ in, uint64_t in_stride, uint64_t n, long long* __restrict__ blk_start,
-                uint32_t nblocks)
-{
-	__shared__ long long sm[33];
-	in += in_stride * blockIdx.y;
-	blk_start += (uint64_t)nblocks * blockIdx.y;
-	const uint64_t base = (uint64_t)blockIdx.x * KG_BLOCK + (uint64_t)threadIdx.x * KG_ITEMS;
-	int16_t v[KG_ITEMS], before, after;
-	bool hb, ha;
-	const int valid = kg_load(in, n, base, v, before, after, hb, ha);
-	long long last = -1;
+	const bool has_before = base > 0 && base <= n;
+	const int16_t before = has_before ? __ldg(in + base - 1) : (int16_t)0;
+	c.has_after = base + KG_ITEMS < n;
+	c.after = c.has_after ? __ldg(in + base + KG_ITEMS) : (int16_t)0;
+	c.start_mask = 0;
+	c.last_start = 0;
 #pragma unroll
 	for (int j = 0; j < KG_ITEMS; j++)
 	{
-		if (j < valid)
+		const bool start = (j < c.valid) && ((j == 0) ? (!has_before || c.v[0] != before) : (c.v[j] != c.v[j - 1]));
+		if (start)
 		{
-			const bool start = (j == 0) ? (!hb || v[0] != before) : (v[j] != v[j - 1]);
-			if (start)
-				last = (long long)(base + j);
+			c.start_mask |= 1u << j;
+			c.last_start = (uint32_t)(base + j) + 1u;
 		}
 	}
-	long long total;
-	block_excl_max(last, sm, &total);
+	return c;
+}
+
+// pass 1: blk_start[b] = (largest i in block b that starts a run) + 1, or 0
+__global__ void __launch_bounds__(KG_THREADS)
+    k_kg_starts(const int16_t* __restrict__ in, uint64_t in_stride, uint64_t n, uint32_t* __restrict__ blk_start,
+                uint32_t nblocks)
+{
+	__shared__ uint32_t sm[33];
+	in += in_stride * blockIdx.y;
+	blk_start += (uint64_t)nblocks * blockIdx.y;
+	const uint64_t base = (uint64_t)blockIdx.x * KG_BLOCK + (uint64_t)threadIdx.x * KG_ITEMS;
+	const KgChunk c = kg_load(in, n, base);
+	uint32_t total;
+	block_excl_max_u32(c.last_start, sm, &total);
 	if (threadIdx.x == 0)
 		blk_start[blockIdx.x] = total;
 }
 
-// exclusive max-scan over the blocks of one image (one CTA per image); identity -1
-__global__ void __launch_bounds__(1024) k_kg_scan_max(long long* __restrict__ blk, uint32_t nblocks)
+// exclusive max-scan over the blocks of one image (one CTA per image); identity 0
+__global__ void __launch_bounds__(1024) k_kg_scan_max(uint32_t* __restrict__ blk, uint32_t nblocks)
 {
-	__shared__ long long sm[33];
+	__shared__ uint32_t sm[33];
 	blk += (uint64_t)nblocks * blockIdx.x;
-	long long carry = -1;
+	uint32_t carry = 0;
 	for (uint32_t b0 = 0; b0 < nblocks; b0 += 1024)
 	{
 		const uint32_t b = b0 + threadIdx.x;
-		const long long v = (b < nblocks) ? blk[b] : -1;
-		long long total;
-		const long long ex = block_excl_max(v, sm, &total);
+		const uint32_t v = (b < nblocks) ? blk[b] : 0;
+		uint32_t total;
+		const uint32_t ex = block_excl_max_u32(v, sm, &total);
 		if (b < nblocks)
-			blk[b] = akod_max(carry, ex);
-		carry = akod_max(carry, total);
+			blk[b] = max(carry, ex);
+		carry = max(carry, total);
 	}
 }
 
@@ -175,41 +187,49 @@ __global__ void __launch_bounds__(1024)
 		total[blockIdx.x] = carry;
 }
 
-// shared by pass 2 and 3: per-thread codes of its KG_ITEMS elements
-__device__ __forceinline__ uint32_t kg_thread_codes(const int16_t* __restrict__ in, uint64_t n, uint64_t base,
-                                                    long long carry_start, long long* sm_max, KgCode codes[KG_ITEMS])
+// shared by pass 2 and 3: the codes of a thread's KG_ITEMS elements; returns their total bit count.
+// EMIT = false only counts bits.
+template <bool EMIT>
+__device__ __forceinline__ uint32_t kg_thread_codes(const KgChunk& c, uint64_t n, uint64_t base, uint32_t carry_start,
+                                                    uint32_t* sm_max, KgCode codes[KG_ITEMS])
 {
-	int16_t v[KG_ITEMS], before, after;
-	bool hb, ha;
-	const int valid = kg_load(in, n, base, v, before, after, hb, ha);
+	// run start reaching into this thread = max(block carry, starts of earlier threads); all are (index + 1)
+	uint32_t dummy;
+	uint32_t run_start = max(carry_start, block_excl_max_u32(c.last_start, sm_max, &dummy));
 
-	// run start reaching into this thread = max(block carry, starts of earlier threads)
-	long long local_last = -1;
-	bool start[KG_ITEMS];
-#pragma unroll
-	for (int j = 0; j < KG_ITEMS; j++)
+	if (EMIT)
 	{
-		start[j] = (j < valid) && ((j == 0) ? (!hb || v[0] != before) : (v[j] != v[j - 1]));
-		if (start[j])
-			local_last = (long long)(base + j);
+#pragma unroll
+		for (int j = 0; j < KG_ITEMS; j++)
+		{
+			codes[j].code = 0;
+			codes[j].len = 0;
+		}
 	}
-	long long dummy;
-	long long run_start = akod_max(carry_start, block_excl_max(local_last, sm_max, &dummy));
+
+	// fast path: all 8 values continue one run that also continues after them
+	if (c.valid == KG_ITEMS && c.start_mask == 0 && c.has_after && c.after == c.v[KG_ITEMS - 1])
+	{
+		const uint32_t k0 = (uint32_t)base + 1u - run_start; // position of v[0] in its run (>= 1)
+		const uint32_t c0 = ((k0 - 1) % 65534u) + 1u;
+		if (c0 >= 3 && c0 + (KG_ITEMS - 1) < 65534u)
+			return 0; // the run counter stays strictly between 2 and 65534: nothing is emitted
+	}
 
 	uint32_t bits = 0;
 #pragma unroll
 	for (int j = 0; j < KG_ITEMS; j++)
 	{
-		codes[j].code = 0;
-		codes[j].len = 0;
-		if (j < valid)
+		if (j < c.valid)
 		{
-			if (start[j])
-				run_start = (long long)(base + j);
-			const bool last = (j + 1 < valid) ? (v[j + 1] != v[j])
-			                                  : ((base + j + 1 >= n) || (j + 1 == KG_ITEMS ? (after != v[j]) : true));
-			codes[j] = kg_element(v[j], (uint32_t)((long long)(base + j) - run_start), last); // n < 2^32 (host-checked)
-			bits += codes[j].len;
+			if (c.start_mask & (1u << j))
+				run_start = (uint32_t)(base + j) + 1u;
+			const bool last = (j + 1 < c.valid) ? (c.v[j + 1] != c.v[j])
+			                                    : ((base + j + 1 >= n) || (j + 1 == KG_ITEMS ? (c.after != c.v[j]) : true));
+			const KgCode e = kg_element(c.v[j], (uint32_t)(base + j) + 1u - run_start, last);
+			if (EMIT)
+				codes[j] = e;
+			bits += e.len;
 		}
 	}
 	return bits;
@@ -217,15 +237,16 @@ __device__ __forceinline__ uint32_t kg_thread_codes(const int16_t* __restrict__ 
 
 // pass 2: bits emitted by each block
 __global__ void __launch_bounds__(KG_THREADS)
-    k_kg_lengths(const int16_t* __restrict__ in, uint64_t in_stride, uint64_t n, const long long* __restrict__ blk_carry,
+    k_kg_lengths(const int16_t* __restrict__ in, uint64_t in_stride, uint64_t n, const uint32_t* __restrict__ blk_carry,
                  uint32_t* __restrict__ blk_bits, uint32_t nblocks)
 {
-	__shared__ long long sm_max[33];
+	__shared__ uint32_t sm_max[33];
 	__shared__ uint32_t sm_sum[33];
 	in += in_stride * blockIdx.y;
 	const uint64_t base = (uint64_t)blockIdx.x * KG_BLOCK + (uint64_t)threadIdx.x * KG_ITEMS;
-	KgCode codes[KG_ITEMS];
-	const uint32_t bits = kg_thread_codes(in, n, base, blk_carry[(uint64_t)nblocks * blockIdx.y + blockIdx.x], sm_max, codes);
+	const KgChunk c = kg_load(in, n, base);
+	const uint32_t bits =
+	    kg_thread_codes<false>(c, n, base, blk_carry[(uint64_t)nblocks * blockIdx.y + blockIdx.x], sm_max, nullptr);
 	uint32_t total;
 	block_excl_sum(bits, sm_sum, &total);
 	if (threadIdx.x == 0)
@@ -251,43 +272,51 @@ __global__ void __launch_bounds__(256)
 
 // pass 3: pack
 __global__ void __launch_bounds__(KG_THREADS)
-    k_kg_pack(const int16_t* __restrict__ in, uint64_t in_stride, uint64_t n, const long long* __restrict__ blk_carry,
-              const uint64_t* __restrict__ blk_off, uint32_t nblocks, uint8_t* __restrict__ out, uint64_t out_stride,
-              uint64_t cap_bits)
+    k_kg_pack(const int16_t* __restrict__ in, uint64_t in_stride, uint64_t n, const uint32_t* __restrict__ blk_carry,
+              const uint64_t* __restrict__ blk_off, const uint32_t* __restrict__ blk_bits, uint32_t nblocks,
+              uint8_t* __restrict__ out, uint64_t out_stride, uint64_t cap_bits)
 {
-	__shared__ long long sm_max[33];
+	__shared__ uint32_t sm_max[33];
 	__shared__ uint32_t sm_sum[33];
 	__shared__ uint32_t bitbuf[KG_BLOCK + 2]; // 32 bits per value at most, +1 word of misalignment, +1 spill
 
-	in += in_stride * blockIdx.y;
-	const uint64_t base = (uint64_t)blockIdx.x * KG_BLOCK + (uint64_t)threadIdx.x * KG_ITEMS;
-	KgCode codes[KG_ITEMS];
-	const uint32_t bits = kg_thread_codes(in, n, base, blk_carry[(uint64_t)nblocks * blockIdx.y + blockIdx.x], sm_max, codes);
-
-	for (int i = threadIdx.x; i < KG_BLOCK + 2; i += KG_THREADS)
-		bitbuf[i] = 0;
-	uint32_t total;
-	const uint32_t excl = block_excl_sum(bits, sm_sum, &total); // has __syncthreads inside: bitbuf is clear after it
+	// a block that emits nothing (inside a long run) has nothing to do at all
+	const uint32_t total = blk_bits[(uint64_t)nblocks * blockIdx.y + blockIdx.x];
 	if (total == 0)
 		return;
-
 	const uint64_t g0 = blk_off[(uint64_t)nblocks * blockIdx.y + blockIdx.x];
 	if (g0 + total > cap_bits) // would not fit: the caller reports the failure from the bit count
 		return;
-	uint32_t pos = (uint32_t)(g0 & 31) + excl; // bit position inside bitbuf
-#pragma unroll
-	for (int j = 0; j < KG_ITEMS; j++)
+
+	in += in_stride * blockIdx.y;
+	const uint64_t base = (uint64_t)blockIdx.x * KG_BLOCK + (uint64_t)threadIdx.x * KG_ITEMS;
+	const KgChunk c = kg_load(in, n, base);
+	KgCode codes[KG_ITEMS];
+	const uint32_t bits =
+	    kg_thread_codes<true>(c, n, base, blk_carry[(uint64_t)nblocks * blockIdx.y + blockIdx.x], sm_max, codes);
+
+	for (int i = threadIdx.x; i < KG_BLOCK + 2; i += KG_THREADS)
+		bitbuf[i] = 0;
+	uint32_t check;
+	const uint32_t excl = block_excl_sum(bits, sm_sum, &check); // has __syncthreads inside: bitbuf is clear after it
+
+	if (bits)
 	{
-		const uint32_t len = codes[j].len;
-		if (len)
+		uint32_t pos = (uint32_t)(g0 & 31) + excl; // bit position inside bitbuf
+#pragma unroll
+		for (int j = 0; j < KG_ITEMS; j++)
 		{
-			const uint32_t w = pos >> 5, sh = pos & 31;
-			// MSB-first: bit 'pos' of the stream is bit (31 - pos%32) of word pos/32
-			const uint64_t wide = (uint64_t)codes[j].code << (64 - sh - len);
-			atomicOr(&bitbuf[w], (uint32_t)(wide >> 32));
-			if (sh + len > 32)
-				atomicOr(&bitbuf[w + 1], (uint32_t)wide);
-			pos += len;
+			const uint32_t len = codes[j].len;
+			if (len)
+			{
+				const uint32_t w = pos >> 5, sh = pos & 31;
+				// MSB-first: bit 'pos' of the stream is bit (31 - pos%32) of word pos/32
+				const uint64_t wide = (uint64_t)codes[j].code << (64 - sh - len);
+				atomicOr(&bitbuf[w], (uint32_t)(wide >> 32));
+				if (sh + len > 32)
+					atomicOr(&bitbuf[w + 1], (uint32_t)wide);
+				pos += len;
+			}
 		}
 	}
 	__syncthreads();
