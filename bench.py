@@ -388,6 +388,8 @@ def run_dwt(args):
     ts = torch.cuda.ExternalStream(ctx.stream)
     out = {}
     for wavelet, name in ((1, "cdf53"), (0, "dd137"), (2, "haar")):
+        if name not in args.dwt_wavelets.split(","):
+            continue
         s = ako_b200.default_settings(wavelet=wavelet, quantization=0, gate=0)
         res = {}
         for direction in ("forward", "inverse"):
@@ -455,6 +457,7 @@ def main():
     ap.add_argument("--batch", type=int, default=8, help="images per step per GPU")
     ap.add_argument("--cpu-reps", type=int, default=1)
     ap.add_argument("--dwt-size", type=int, default=8192)
+    ap.add_argument("--dwt-wavelets", default="cdf53,dd137,haar")
     ap.add_argument("--skip-cpu", action="store_true", help="profiling runs: do not time the CPU reference")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))

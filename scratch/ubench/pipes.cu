@@ -1,0 +1,139 @@
+// Throughput microbenchmark for the integer ops the lifting kernels are made of (B200, sm_100a).
+// Each kernel runs N dependent-chain-free ops per thread on 8 independent accumulators; reports ops/clk/SM.
+#include <cstdint>
+#include <cstdio>
+#include <cuda_runtime.h>
+
+#define ITERS 4096
+#define CHAINS 8
+
+template <int OP>
+__device__ __forceinline__ uint32_t op(uint32_t a, uint32_t b)
+{
+	uint32_t d;
+	if (OP == 0) asm volatile("mad.lo.s32 %0, %1, %2, %1;" : "=r"(d) : "r"(a), "r"(b));                 // IMAD
+	if (OP == 1) asm volatile("mul.hi.s32 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b));                      // IMAD.HI
+	if (OP == 2) asm volatile("dp2a.lo.s32.s32 %0, %1, %2, %1;" : "=r"(d) : "r"(a), "r"(b));             // IDP.2A
+	if (OP == 3) asm volatile("dp4a.s32.s32 %0, %1, %2, %1;" : "=r"(d) : "r"(a), "r"(b));                // IDP.4A
+	if (OP == 4) asm volatile("prmt.b32 %0, %1, %2, 0x5410;" : "=r"(d) : "r"(a), "r"(b));                // PRMT
+	if (OP == 5) asm volatile("shr.s32 %0, %1, 3;\n\tadd.s32 %0, %0, %2;" : "=r"(d) : "r"(a), "r"(b));   // LEA.HI.SX32 ?
+	if (OP == 6) asm volatile("shr.s32 %0, %1, 16;" : "=r"(d) : "r"(a));                                 // SHF
+	if (OP == 7) asm volatile("lop3.b32 %0, %1, %2, %1, 0x96;" : "=r"(d) : "r"(a), "r"(b));              // LOP3
+	if (OP == 8) d = __vadd2(a, b);                                                                          // VIADD.16x2
+	if (OP == 9) asm volatile("add.s32 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b));                         // IADD3 / IMAD.IADD
+	if (OP == 10) asm volatile("mad.hi.s32 %0, %1, %2, %1;" : "=r"(d) : "r"(a), "r"(b));                 // IMAD.HI with addend
+	if (OP == 11) asm volatile("cvt.s32.s16 %0, %1;" : "=r"(d) : "h"((unsigned short)a));                // sign extend
+	if (OP == 12) d = __vmaxs2(a, b);                                                                        // VIMNMX.S16x2
+	if (OP == 13) asm volatile("mad.wide.s32 %0, %1, %2, %0;" : "+l"(*(unsigned long long*)&d) : "r"(a), "r"(b));
+	return d;
+}
+
+template <int OP>
+__global__ void __launch_bounds__(256) k(uint32_t* out, uint32_t seed, long long* cycles)
+{
+	uint32_t a[CHAINS];
+#pragma unroll
+	for (int i = 0; i < CHAINS; i++)
+		a[i] = seed * (threadIdx.x + 1) + i;
+	const uint32_t b = seed | 3;
+	long long t0 = clock64();
+#pragma unroll 16
+	for (int it = 0; it < ITERS; it++)
+	{
+#pragma unroll
+		for (int i = 0; i < CHAINS; i++)
+			a[i] = op<OP>(a[i], b);
+	}
+	long long t1 = clock64();
+	uint32_t s = 0;
+#pragma unroll
+	for (int i = 0; i < CHAINS; i++)
+		s ^= a[i];
+	out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+	if (threadIdx.x == 0)
+		cycles[blockIdx.x] = t1 - t0;
+}
+
+// ALU + FMA mix: alternate PRMT (alu) and IMAD (fma) on independent chains
+__global__ void __launch_bounds__(256) kmix(uint32_t* out, uint32_t seed, long long* cycles)
+{
+	uint32_t a[CHAINS];
+#pragma unroll
+	for (int i = 0; i < CHAINS; i++)
+		a[i] = seed * (threadIdx.x + 1) + i;
+	const uint32_t b = seed | 3;
+	long long t0 = clock64();
+#pragma unroll 16
+	for (int it = 0; it < ITERS; it++)
+	{
+#pragma unroll
+		for (int i = 0; i < CHAINS; i += 2)
+		{
+			a[i] = op<4>(a[i], b);
+			a[i + 1] = op<0>(a[i + 1], b);
+		}
+	}
+	long long t1 = clock64();
+	uint32_t s = 0;
+#pragma unroll
+	for (int i = 0; i < CHAINS; i++)
+		s ^= a[i];
+	out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+	if (threadIdx.x == 0)
+		cycles[blockIdx.x] = t1 - t0;
+}
+
+template <int OP>
+void run(const char* name, uint32_t* d_out, long long* d_cyc)
+{
+	const int blocks = 148 * 4, threads = 256; // 4 CTAs x 8 warps = 32 warps per SM
+	k<OP><<<blocks, threads>>>(d_out, 12345, d_cyc);
+	cudaDeviceSynchronize();
+	k<OP><<<blocks, threads>>>(d_out, 12345, d_cyc);
+	cudaDeviceSynchronize();
+	long long h[148 * 4];
+	cudaMemcpy(h, d_cyc, sizeof(h), cudaMemcpyDeviceToHost);
+	double avg = 0;
+	for (int i = 0; i < blocks; i++)
+		avg += (double)h[i];
+	avg /= blocks;
+	// per SM: 4 CTAs x 256 threads x ITERS x CHAINS ops in ~avg cycles (all CTAs resident together)
+	printf("%-28s %8.1f thread-ops/clk/SM   (%.0f cycles)\n", name, 4.0 * threads * ITERS * CHAINS / avg, avg);
+}
+
+int main()
+{
+	uint32_t* d_out;
+	long long* d_cyc;
+	cudaMalloc(&d_out, 148 * 4 * 256 * 4);
+	cudaMalloc(&d_cyc, 148 * 4 * 8);
+	run<0>("IMAD (mad.lo)", d_out, d_cyc);
+	run<1>("IMAD.HI (mul.hi.s32)", d_out, d_cyc);
+	run<10>("IMAD.HI + addend (mad.hi)", d_out, d_cyc);
+	run<13>("IMAD.WIDE", d_out, d_cyc);
+	run<2>("IDP.2A (dp2a)", d_out, d_cyc);
+	run<3>("IDP.4A (dp4a)", d_out, d_cyc);
+	run<4>("PRMT", d_out, d_cyc);
+	run<5>("shr+add (LEA.HI.SX32?)", d_out, d_cyc);
+	run<6>("SHF.R.S32", d_out, d_cyc);
+	run<7>("LOP3", d_out, d_cyc);
+	run<8>("VIADD.16x2", d_out, d_cyc);
+	run<9>("add.s32", d_out, d_cyc);
+	run<11>("cvt.s32.s16", d_out, d_cyc);
+	run<12>("VIMNMX.S16x2", d_out, d_cyc);
+	{
+		const int blocks = 148 * 4, threads = 256;
+		kmix<<<blocks, threads>>>(d_out, 12345, d_cyc);
+		cudaDeviceSynchronize();
+		kmix<<<blocks, threads>>>(d_out, 12345, d_cyc);
+		cudaDeviceSynchronize();
+		long long h[148 * 4];
+		cudaMemcpy(h, d_cyc, sizeof(h), cudaMemcpyDeviceToHost);
+		double avg = 0;
+		for (int i = 0; i < blocks; i++)
+			avg += (double)h[i];
+		avg /= blocks;
+		printf("%-28s %8.1f thread-ops/clk/SM   (%.0f cycles)\n", "PRMT+IMAD interleaved", 4.0 * threads * ITERS * CHAINS / avg, avg);
+	}
+	return 0;
+}
