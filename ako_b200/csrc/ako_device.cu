@@ -414,6 +414,11 @@ extern "C" int akod_lift(akodContext* c, const akodPlan* plan, int16_t* d_planes
 			p.q[ch] = L->q[ch] < 1 ? 1 : L->q[ch];
 			p.g[ch] = L->g[ch];
 			p.qmagic[ch] = (p.q[ch] > 1) ? (uint32_t)((((uint64_t)1 << 32) + p.q[ch] - 1) / (uint64_t)p.q[ch]) : 0;
+			int c2 = 0;
+			while ((1 << c2) < p.q[ch])
+				c2++;
+			p.qshift[ch] = 15 + c2;
+			p.qmul[ch] = (uint32_t)((((uint64_t)1 << p.qshift[ch]) / (uint64_t)p.q[ch]) + 1);
 		}
 		int rc;
 		static const bool no_strip = getenv("AKO_B200_NO_STRIP") != nullptr;

@@ -130,6 +130,8 @@ struct LiftParams
 	int16_t q[AKOD_MAX_CHANNELS];
 	int16_t g[AKOD_MAX_CHANNELS];
 	uint32_t qmagic[AKOD_MAX_CHANNELS]; // ceil(2^32 / q) for q > 1
+	uint32_t qmul[AKOD_MAX_CHANNELS];   // strip kernel: floor(2^qshift / q) + 1, see strip_quant
+	int32_t qshift[AKOD_MAX_CHANNELS];  // 15 + ceil(log2 q)
 };
 
 // lifting.c:163 -- (v < -g || v > g) ? v / q : 0, with the truncating division done as an exact
