@@ -332,10 +332,11 @@ static int launch_lift_strip(akodContext* c, const LiftParams& p, uint32_t n_ima
 }
 
 template <int WL>
-static int launch_unlift_strip(akodContext* c, const UnliftParams& p, uint32_t n_images)
+static int launch_unlift_strip(akodContext* c, const UnliftParams& p, uint32_t n_images, bool v1)
 {
 	constexpr int LAT = StripGeom<WL>::LAT;
-	const uint32_t strips = (p.hw + US_TW - 1) / US_TW;
+	const uint32_t width = v1 ? US_TW : UT_TW;
+	const uint32_t strips = (p.hw + width - 1) / width;
 	const uint64_t want = (uint64_t)c->sm_count * 6;
 	uint32_t split = 0;
 	for (uint32_t k = 32; k >= 4; k >>= 1)
@@ -350,7 +351,11 @@ static int launch_unlift_strip(akodContext* c, const UnliftParams& p, uint32_t n
 	up.split = split;
 	const dim3 grid(strips, (p.hh + split - 1) / split, p.channels * n_images);
 	static const char* const names[3] = {"unlift_strip_dd137", "unlift_strip_cdf53", "unlift_strip_haar"};
-	AKOD_LAUNCH(c, names[WL], k_unlift_strip<WL>, grid, US_THREADS, 0, up);
+	static const char* const names_v1[3] = {"unlift_strip_v1_dd137", "unlift_strip_v1_cdf53", "unlift_strip_v1_haar"};
+	if (v1)
+		AKOD_LAUNCH(c, names_v1[WL], k_unlift_strip_v1<WL>, grid, US_THREADS, 0, up);
+	else
+		AKOD_LAUNCH(c, names[WL], k_unlift_strip<WL>, grid, UT_THREADS, 0, up);
 	return AKOD_OK;
 }
 
@@ -515,14 +520,15 @@ extern "C" int akod_unlift(akodContext* c, const akodPlan* plan, const int16_t* 
 			p.off_c[ch] = L->off_c[ch];
 		int rc;
 		static const bool no_strip = getenv("AKO_B200_NO_STRIP") != nullptr;
-		if (!no_strip && unlift_strip_eligible(p))
+		const bool v2 = !no_strip && unlift_strip_eligible(p), v1 = !no_strip && !v2 && unlift_strip_v1_eligible(p);
+		if (v2 || v1)
 		{
 			if (L->wavelet == AKOD_DD137)
-				rc = launch_unlift_strip<AKOD_DD137>(c, p, n);
+				rc = launch_unlift_strip<AKOD_DD137>(c, p, n, v1);
 			else if (L->wavelet == AKOD_CDF53)
-				rc = launch_unlift_strip<AKOD_CDF53>(c, p, n);
+				rc = launch_unlift_strip<AKOD_CDF53>(c, p, n, v1);
 			else
-				rc = launch_unlift_strip<AKOD_HAAR>(c, p, n);
+				rc = launch_unlift_strip<AKOD_HAAR>(c, p, n, v1);
 		}
 		else if (L->wavelet == AKOD_DD137)
 			rc = launch_unlift_level<AKOD_DD137>(c, p, n);

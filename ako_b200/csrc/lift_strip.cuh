@@ -43,6 +43,7 @@ constexpr int FS_XW = 2 * FS_TW + 16;  // staged samples per row (8 halo samples
 constexpr int FS_XP = 280;             // X row pitch in elements: 140 words, 140 mod 32 = 12 -> conflict-free LDS.128 by row
 constexpr int FS_HP = 264;             // [L x128 | H x128] row pitch: 132 words, 132 mod 32 = 4 -> conflict-free STS.128 by row
 constexpr int FS_XBUF = FS_ROWS * FS_XP;
+constexpr int FS_STAGES = 3;           // staged input buffers: loads run two steps ahead of the arithmetic
 
 template <int WL>
 struct StripGeom
@@ -406,9 +407,9 @@ __global__ void __launch_bounds__(FS_THREADS, 6) k_lift_strip(const StripParams 
 	constexpr int LAT = StripGeom<WL>::LAT;
 	const LiftParams& p = sp.p;
 
-	__shared__ __align__(16) int16_t X[2 * FS_XBUF];
+	__shared__ __align__(16) int16_t X[FS_STAGES * FS_XBUF];
 	__shared__ __align__(16) int16_t HB[FS_ROWS * FS_HP];
-	__shared__ __align__(8) uint64_t bars[2];
+	__shared__ __align__(8) uint64_t bars[FS_STAGES];
 
 	const int tid = threadIdx.x;
 	const uint32_t img = blockIdx.z / p.channels, chn = blockIdx.z - img * p.channels;
@@ -472,8 +473,9 @@ __global__ void __launch_bounds__(FS_THREADS, 6) k_lift_strip(const StripParams 
 
 	if (tid == 0)
 	{
-		mbar_init(&bars[0], 1);
-		mbar_init(&bars[1], 1);
+#pragma unroll
+		for (int i = 0; i < FS_STAGES; i++)
+			mbar_init(&bars[i], 1);
 		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 	}
 	__syncthreads();
@@ -496,16 +498,20 @@ __global__ void __launch_bounds__(FS_THREADS, 6) k_lift_strip(const StripParams 
 
 	const int j_first = i_begin - LAT;
 	const int j_last = i_end + LAT; // exclusive
-	issue(j_first, 0);
-	__syncthreads(); // edge fills of the first buffer
+#pragma unroll
+	for (int i = 0; i < FS_STAGES - 1; i++)
+		if (j_first + i * FS_STEP < j_last)
+			issue(j_first + i * FS_STEP, i);
+	__syncthreads(); // edge fills of the first buffers
 
-	int step = 0;
-	for (int js = j_first; js < j_last; js += FS_STEP, step++)
+	int buf = 0, nbuf = FS_STAGES - 1;
+	uint32_t phase = 0;
+	for (int js = j_first; js < j_last; js += FS_STEP)
 	{
-		const int buf = step & 1;
-		if (js + FS_STEP < j_last)
-			issue(js + FS_STEP, buf ^ 1);
-		mbar_wait(&bars[buf], (uint32_t)(step >> 1) & 1u);
+		// buffer nbuf was last read by the H pass of the previous step, which every thread has left
+		if (js + (FS_STAGES - 1) * FS_STEP < j_last)
+			issue(js + (FS_STAGES - 1) * FS_STEP, nbuf);
+		mbar_wait(&bars[buf], phase);
 
 		// ---------------- H pass: thread = (row, chunk of 16 coefficient pairs)
 		{
@@ -605,6 +611,12 @@ __global__ void __launch_bounds__(FS_THREADS, 6) k_lift_strip(const StripParams 
 				vstep_e(std::true_type{});
 		}
 		__syncthreads(); // HB is rewritten by the next step; X[buf] by the load issued in the next step
+		nbuf = buf;
+		if (++buf == FS_STAGES)
+		{
+			buf = 0;
+			phase ^= 1u;
+		}
 	}
 }
 

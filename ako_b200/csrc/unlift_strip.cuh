@@ -1,317 +1,438 @@
-// unlift_strip.cuh -- the fast inverse-lifting kernel, mirror image of lift_strip.cuh. Same arithmetic as
-// k_unlift_level (lift.cuh), which stays the general kernel (other wrap modes, unaligned widths, tiny levels).
+// unlift_strip.cuh -- the fast inverse-lifting kernel, mirror image of lift_strip.cuh (same strip marching, same
+// arithmetic style: dp2a tap sums, hi-domain results, LEA.HI-fused truncation -- see the header of that file).
+// Same results as k_unlift_level (lift.cuh), which stays the general kernel.
 //
-// A CTA owns 120 coefficient columns (+4 halo each side = 128 staged) and marches down the level, 8
-// coefficient rows (16 output rows) per step:
-//   * staging: the 8 rows of LL (64-bit loads) and of C, B, D (32-bit loads, or 16-bit when the subband
-//     starts at an odd int16 offset of the stream) are prefetched into registers one step ahead;
+// A CTA owns 120 coefficient columns (+4 halo each side = 128 processed, 136 staged) and marches down the
+// level, 8 coefficient rows (16 output rows) per step:
+//   * loads: the 8 rows of LL and of the C, B, D subbands of the NEXT step are fetched by the TMA engine, one
+//     cp.async.bulk per row, completion on an mbarrier (double buffered). The subbands sit at arbitrary int16
+//     offsets of the coefficient stream, so the copy starts at the 16-byte boundary below the first wanted
+//     element and the V pass reads with the per-CTA shift (whole words by address, an odd element by a funnel
+//     shift). Requires half width % 8 == 0; other shapes use unlift_strip_v1.cuh;
 //   * V pass first (lifting.c:118-129): one thread per pair of adjacent columns of one side (left = LL/C,
-//     right = B/D); the sliding windows live in registers for the whole strip height. Inverse quantisation
-//     (lifting.c:30-40) is fused here. Even and odd rows go to shared memory as [left 128 | right 128];
-//   * H pass (lifting.c:131-133): one thread per (row, 8 coefficients): four 128-bit shared loads, 11 even
-//     + 8 odd samples from registers, two 128-bit global stores of interleaved samples.
-// Boundary rules (CLAMP): highpass inputs are clamped by the loader (H(-1)=H(-2)=H(0), H(t)=H(t-1)); the
-// computed evens are overridden where produced (E(-1)=E(0), E(t)=E(t+1)=E(t-1)); a last odd row / column
-// dropped by the plus-one rule is simply not written.
+//     right = B/D); sliding windows in registers for the whole strip height. Inverse quantisation
+//     (lifting.c:30-40) is a multiply in the hi domain, whose wrap is the int16 wrap. Even and odd rows go to
+//     shared memory as [left 128 | right 128]; the even row of a step is one (DD137) or zero rows ahead of
+//     the odd row, rows are independent in the H pass so each carries its own output row number;
+//   * H pass (lifting.c:131-133): one thread per (row, 8 coefficients): four 128-bit shared loads, two
+//     128-bit global stores of interleaved samples.
+// Boundary rules (CLAMP): rows are clamped by the loader's row index; columns outside the level hold garbage
+// after the V pass (columns are independent there) and the H pass overrides them in registers:
+// H(-1)=H(-2)=H(0), H(t)=H(t-1), E(-1)=E(0), E(t)=E(t+1)=E(t-1). A last odd row / column dropped by the
+// plus-one rule is simply not written.
 #pragma once
 
 #include "lift_strip.cuh"
+#include "unlift_strip_v1.cuh"
 
-constexpr int US_TW = 120;           // coefficient columns a CTA produces
-constexpr int US_SW = 128;           // staged columns (4 halo each side)
-constexpr int US_STEP = 8;           // coefficient rows per step
-constexpr int US_THREADS = 128;
-constexpr int US_SP = 136;           // staged row pitch (elements): 68 words, 68 mod 32 = 4
-constexpr int US_VP = 264;           // V-pass output row pitch: [left 128 | right 128] + pad, 132 words
-constexpr int US_LL_LOADS = (US_STEP * US_SW / 4) / US_THREADS;      // 2  64-bit loads per thread
-constexpr int US_HP_LOADS = (3 * US_STEP * US_SW / 2) / US_THREADS + 1; // 12 words per thread + the 65th word of a row
+constexpr int UT_TW = 120;           // coefficient columns a CTA produces
+constexpr int UT_STEP = 8;           // coefficient rows per step
+constexpr int UT_THREADS = 128;
+constexpr int UT_SP = 152;           // staged row pitch (elements): 136 columns + up to 7 of shift, 16-byte multiple
+constexpr int UT_LLW = 136;          // staged LL columns  [c0-8, c0+128)
+constexpr int UT_HPW = 144;          // staged subband elements (window starts up to 7 elements early)
+constexpr int UT_VP = 264;           // V-pass output row pitch: [left 128 | right 128] + pad, 132 words
+constexpr int UT_SBUF = 4 * UT_STEP * UT_SP; // one stage: LL, C, B, D rows
 
-struct UnstripParams
+template <int WL>
+struct UnstripGeom
 {
-	UnliftParams p;
-	uint32_t split;
+	static constexpr int LAT = StripGeom<WL>::LAT;              // the odd row a step finishes is this far behind its input row
+	static constexpr int LEV = (WL == AKOD_DD137) ? 1 : 0;      // ... and the even row this far
 };
 
-template <int WL>
-__device__ __forceinline__ int ustrip_even(int lp, int l2, int l1, int h, int p1)
-{
-	if (WL == AKOD_HAAR)
-		return lp;
-	if (WL == AKOD_CDF53)
-		return sx16(lp - (l1 + h) / 4);
-	return sx16(lp - (-l2 - p1 + 9 * (l1 + h)) / 32);
-}
+// ------------------------------------------------------------------------------------------------
+// V pass: per thread two adjacent columns (a = low half, b = high half of every packed word).
+// row() consumes lowpass word wl = L(j) and highpass word wh = H(j) (already inverse-quantised) and returns
+// the packed even row E(j - LEV) and odd row O(j - LAT).
 
 template <int WL>
-__device__ __forceinline__ int ustrip_odd(int hp, int e, int l1, int p1, int p2)
+struct UnstripV;
+
+template <>
+struct UnstripV<AKOD_HAAR>
 {
-	if (WL == AKOD_HAAR)
-		return e + hp;
-	if (WL == AKOD_CDF53)
-		return hp + (e + p1) / 2;
-	return hp - (l1 + p2 - 9 * (e + p1)) / 16;
-}
+	__device__ __forceinline__ void init() {}
+	template <bool EDGE>
+	__device__ __forceinline__ void row(uint32_t wl, uint32_t wh, int, int, uint32_t& even, uint32_t& odd)
+	{
+		even = wl;
+		odd = pair_hi((uint32_t)(hd_lo(wl) + hd_lo(wh)), (uint32_t)(hd_hi(wl) + hd_hi(wh))); // O = E + H
+	}
+};
+
+template <>
+struct UnstripV<AKOD_CDF53>
+{
+	uint32_t wh1;  // H(j-1)
+	int ea1, eb1;  // hi-domain E(j-1)
+	__device__ __forceinline__ void init()
+	{
+		wh1 = 0;
+		ea1 = eb1 = 0;
+	}
+	template <bool EDGE>
+	__device__ __forceinline__ void row(uint32_t wl, uint32_t wh, int j, int hh, uint32_t& even, uint32_t& odd)
+	{
+		constexpr uint32_t KM = dpw(-1, -1, 0, 0), KP = dpw(1, 1, 0, 0);
+		// E(j) = L(j) - (H(j-1) + H(j)) / 4
+		int ea = hi_step<2>(dp2_lo(pair_lo(wh1, wh), KM, 0), hd_lo(wl));
+		int eb = hi_step<2>(dp2_lo(pair_hi(wh1, wh), KM, 0), hd_hi(wl));
+		if (EDGE && j >= hh)
+		{
+			ea = ea1; // E(t) = E(t-1)
+			eb = eb1;
+		}
+		// O(j-1) = H(j-1) + (E(j-1) + E(j)) / 2
+		const int oa = hi_step<1>(dp2_lo(pair_hi((uint32_t)ea1, (uint32_t)ea), KP, 0), hd_lo(wh1));
+		const int ob = hi_step<1>(dp2_lo(pair_hi((uint32_t)eb1, (uint32_t)eb), KP, 0), hd_hi(wh1));
+		even = pair_hi((uint32_t)ea, (uint32_t)eb);
+		odd = pair_hi((uint32_t)oa, (uint32_t)ob);
+		ea1 = ea;
+		eb1 = eb;
+		wh1 = wh;
+	}
+};
+
+template <>
+struct UnstripV<AKOD_DD137>
+{
+	uint32_t wh1, wh2, wh3;          // H(j-1), H(j-2), H(j-3)
+	uint32_t wl1;                    // L(j-1)
+	uint32_t tha2, tha3, thb2, thb3; // th?2 = (H(j-2), H(j-1)), th?3 = (H(j-3), H(j-2)) per column
+	int ea2, eb2;                    // hi-domain E(j-2)
+	uint32_t tea3, tea4, teb3, teb4; // te?3 = (E(j-3), E(j-2)), te?4 = (E(j-4), E(j-3))
+	__device__ __forceinline__ void init()
+	{
+		wh1 = wh2 = wh3 = wl1 = tha2 = tha3 = thb2 = thb3 = tea3 = tea4 = teb3 = teb4 = 0;
+		ea2 = eb2 = 0;
+	}
+	template <bool EDGE>
+	__device__ __forceinline__ void row(uint32_t wl, uint32_t wh, int j, int hh, uint32_t& even, uint32_t& odd)
+	{
+		constexpr uint32_t KH = dpw(1, -9, -9, 1), KL = dpw(-1, 9, 9, -1);
+		const uint32_t tha1 = pair_lo(wh1, wh), thb1 = pair_hi(wh1, wh); // (H(j-1), H(j))
+		// E(j-1) = L(j-1) - (-H(j-3) + 9 H(j-2) + 9 H(j-1) - H(j)) / 32
+		int ea1 = hi_step<5>(dp2_hi(tha1, KH, dp2_lo(tha3, KH, 0)), hd_lo(wl1));
+		int eb1 = hi_step<5>(dp2_hi(thb1, KH, dp2_lo(thb3, KH, 0)), hd_hi(wl1));
+		if (EDGE)
+		{
+			if (j - 1 == 0)
+			{
+				// E(-1) = E(0): everything older than E(0) becomes E(0)
+				ea2 = ea1;
+				eb2 = eb1;
+				tea3 = tea4 = pair_hi((uint32_t)ea1, (uint32_t)ea1);
+				teb3 = teb4 = pair_hi((uint32_t)eb1, (uint32_t)eb1);
+			}
+			if (j - 1 >= hh)
+			{
+				ea1 = ea2; // E(t) = E(t+1) = E(t-1)
+				eb1 = eb2;
+			}
+		}
+		const uint32_t tea2 = pair_hi((uint32_t)ea2, (uint32_t)ea1), teb2 = pair_hi((uint32_t)eb2, (uint32_t)eb1); // (E(j-2), E(j-1))
+		// O(j-3) = H(j-3) - (E(j-4) - 9 E(j-3) - 9 E(j-2) + E(j-1)) / 16
+		const int oa = hi_step<4>(dp2_hi(tea2, KL, dp2_lo(tea4, KL, 0)), hd_lo(wh3));
+		const int ob = hi_step<4>(dp2_hi(teb2, KL, dp2_lo(teb4, KL, 0)), hd_hi(wh3));
+		even = pair_hi((uint32_t)ea1, (uint32_t)eb1);
+		odd = pair_hi((uint32_t)oa, (uint32_t)ob);
+		tea4 = tea3;
+		teb4 = teb3;
+		tea3 = tea2;
+		teb3 = teb2;
+		ea2 = ea1;
+		eb2 = eb1;
+		tha3 = tha2;
+		thb3 = thb2;
+		tha2 = tha1;
+		thb2 = thb1;
+		wh3 = wh2;
+		wh2 = wh1;
+		wh1 = wh;
+		wl1 = wl;
+	}
+};
+
+// ------------------------------------------------------------------------------------------------
+// H pass: lw[8] / hw[8] are the packed lowpass / highpass values of columns c = base - 4 + k, k = 0..15, of one
+// row; produces the 8 interleaved (even, odd) sample pairs of columns k = 4..11.
+// rem = columns left in the level counted from this chunk's first column (a multiple of 8).
 
 template <int WL>
-__global__ void __launch_bounds__(US_THREADS, 6) k_unlift_strip(const UnstripParams up)
+__device__ __forceinline__ void unstrip_hpass(const uint32_t (&lw)[8], uint32_t (&hw)[8], bool left_edge, int rem,
+                                              uint32_t (&out)[8])
 {
-	constexpr int LAT = StripGeom<WL>::LAT;
+	// lowpass of column k in the hi domain
+	auto lbase = [&](int k) { return (k & 1) ? hd_hi(lw[k >> 1]) : hd_lo(lw[k >> 1]); };
+	auto hbase = [&](int k) { return (k & 1) ? hd_hi(hw[k >> 1]) : hd_lo(hw[k >> 1]); };
+
+	if (WL == AKOD_HAAR)
+	{
+#pragma unroll
+		for (int k = 4; k < 12; k++)
+		{
+			const int e = lbase(k);
+			out[k - 4] = pair_hi((uint32_t)e, (uint32_t)(e + hbase(k)));
+		}
+		return;
+	}
+
+	// highpass clamps on the inputs: H(-1) = H(-2) = H(0) (column 0 is k = 4), H(t) = H(t-1) (column t is k = rem + 4)
+	if (left_edge)
+		hw[1] = pair_lo(hw[2], hw[2]);
+	if (rem == 8)
+		hw[6] = pair_hi(hw[5], hw[5]);
+
+	int e[16];
+	if (WL == AKOD_CDF53)
+	{
+		// E(k) = L(k) - (H(k-1) + H(k)) / 4                                       k = 4..12
+		constexpr uint32_t KM = dpw(-1, -1, 0, 0);
+#pragma unroll
+		for (int k = 4; k <= 12; k++)
+		{
+			int n;
+			if (k & 1)
+				n = dp2_lo(hw[k >> 1], KM, 0);
+			else
+				n = dp2_lo(__byte_perm(hw[(k >> 1) - 1], hw[k >> 1], 0x5432), KM, 0); // (H(k-1), H(k))
+			e[k] = hi_step<2>(n, lbase(k));
+		}
+		if (rem == 8)
+			e[12] = e[11]; // E(t) = E(t-1)
+		// O(k) = H(k) + (E(k) + E(k+1)) / 2                                       k = 4..11
+		constexpr uint32_t KP = dpw(1, 1, 0, 0);
+#pragma unroll
+		for (int k = 4; k < 12; k++)
+		{
+			const int o = hi_step<1>(dp2_lo(pair_hi((uint32_t)e[k], (uint32_t)e[k + 1]), KP, 0), hbase(k));
+			out[k - 4] = pair_hi((uint32_t)e[k], (uint32_t)o);
+		}
+	}
+	else
+	{
+		// E(k) = L(k) - (-H(k-2) + 9 H(k-1) + 9 H(k) - H(k+1)) / 32               k = 3..13
+		constexpr uint32_t KH = dpw(1, -9, -9, 1);
+		uint32_t ho[8]; // ho[m] = (H(2m-1), H(2m))
+#pragma unroll
+		for (int m = 1; m <= 7; m++)
+			ho[m] = __byte_perm(hw[m - 1], hw[m], 0x5432);
+#pragma unroll
+		for (int k = 3; k <= 13; k++)
+		{
+			int n;
+			if (k & 1) // taps (k-2, k-1) = ho[(k-1)/2], (k, k+1) = ho[(k+1)/2]
+				n = dp2_hi(ho[(k + 1) >> 1], KH, dp2_lo(ho[(k - 1) >> 1], KH, 0));
+			else       // taps (k-2, k-1) = hw[k/2 - 1], (k, k+1) = hw[k/2]
+				n = dp2_hi(hw[k >> 1], KH, dp2_lo(hw[(k >> 1) - 1], KH, 0));
+			e[k] = hi_step<5>(n, lbase(k));
+		}
+		if (left_edge)
+			e[3] = e[4]; // E(-1) = E(0)
+		if (rem == 8)
+			e[12] = e[13] = e[11]; // E(t) = E(t+1) = E(t-1)
+		// O(k) = H(k) - (E(k-1) - 9 E(k) - 9 E(k+1) + E(k+2)) / 16                k = 4..11
+		constexpr uint32_t KL = dpw(-1, 9, 9, -1);
+		uint32_t te[16]; // te[k] = (E(k), E(k+1))
+#pragma unroll
+		for (int k = 3; k <= 12; k++)
+			te[k] = pair_hi((uint32_t)e[k], (uint32_t)e[k + 1]);
+#pragma unroll
+		for (int k = 4; k < 12; k++)
+		{
+			const int o = hi_step<4>(dp2_hi(te[k + 1], KL, dp2_lo(te[k - 1], KL, 0)), hbase(k));
+			out[k - 4] = pair_hi((uint32_t)e[k], (uint32_t)o);
+		}
+	}
+}
+
+// ------------------------------------------------------------------------------------------------
+
+template <int WL>
+__global__ void __launch_bounds__(UT_THREADS, 6) k_unlift_strip(const UnstripParams up)
+{
+	constexpr int LAT = UnstripGeom<WL>::LAT, LEV = UnstripGeom<WL>::LEV;
 	const UnliftParams& p = up.p;
 
-	__shared__ __align__(16) int16_t S[4 * US_STEP * US_SP];  // staged LL, C, B, D rows
-	__shared__ __align__(16) int16_t VB[2 * US_STEP * US_VP]; // vertically reconstructed rows
+	__shared__ __align__(16) int16_t S[2 * UT_SBUF];            // staged LL, C, B, D rows, two stages
+	__shared__ __align__(16) int16_t VB[2 * UT_STEP * UT_VP];   // vertically reconstructed rows
+	__shared__ __align__(8) uint64_t bars[2];
 
 	const int tid = threadIdx.x;
 	const uint32_t img = blockIdx.z / p.channels, chn = blockIdx.z - img * p.channels;
 	const int hw = (int)p.hw, hh = (int)p.hh;
-	const int c0 = blockIdx.x * US_TW;
+	const int c0 = blockIdx.x * UT_TW;
 	const int i_begin = blockIdx.y * (int)up.split;
 	const int i_end = min(i_begin + (int)up.split, hh);
 	const uint32_t band = p.hw * p.hh;
 	const int16_t* __restrict__ in_ll = p.ll + p.ll_is * img + p.ll_ps * chn;
 	const int16_t* __restrict__ in_c = p.stream + p.stream_is * img + p.off_c[chn];
 	const int q = (int)__ldg(in_c - 1); // lift head: the decoder learns q from the stream (misc.c:262-268)
-	const int shift1 = (int)(p.off_c[chn] & 1); // 1: C/B/D start at an odd int16 offset of the stream
-	const int fshift = 16 * shift1;
 	int16_t* __restrict__ out = p.out + p.out_is * img + p.out_ps * chn;
 
-	// ---- loader
-	uint2 pre_ll[US_LL_LOADS];
-	uint32_t pre_hp[US_HP_LOADS];
-	auto prefetch = [&](int js) {
-#pragma unroll
-		for (int k = 0; k < US_LL_LOADS; k++)
+	// ---- loader geometry. Staged column index x <-> level column c0 - 8 + x. Subband rows start at element
+	// offset off_c + band*b + j*hw of the stream: hw % 8 == 0 and band % 8 == 0, so the misalignment sh (in
+	// elements) of a row against 16 bytes is the same for every row of the three subbands.
+	const int sh = (int)((p.stream_is * img + p.off_c[chn]) & 7);
+	const int x0 = (c0 == 0) ? 8 : 0;                        // first staged column that exists (left edge: columns < 0 do not)
+	const int ll_x1 = min(UT_LLW, hw - (c0 - 8));            // one past the last LL column staged (a multiple of 8)
+	const int hp_x1 = min(UT_HPW, (hw - (c0 - 8) + sh) & ~7); // same for the shifted subband window
+	const int hp_tail = min(UT_HPW, hw - (c0 - 8) + sh) - hp_x1; // 0..7 row-end elements the 16-byte copies cannot reach
+	const uint32_t ll_bytes = (uint32_t)(ll_x1 - x0) * 2, hp_bytes = (uint32_t)(hp_x1 - x0) * 2;
+
+	auto issue = [&](int js, int buf) {
+		int16_t* dstbuf = S + buf * UT_SBUF;
+		if (tid < 32)
 		{
-			const int id = tid + US_THREADS * k;
-			const int r = id >> 5, v = id & 31;
+			if (tid == 0)
+				mbar_expect_tx(&bars[buf], UT_STEP * (ll_bytes + 3 * hp_bytes));
+			__syncwarp();
+			const int b = tid >> 3, r = tid & 7; // band 0 = LL, 1..3 = C, B, D
 			const int j = min(max(js + r, 0), hh - 1);
-			const int c = c0 - 4 + 4 * v;
-			const int16_t* row = in_ll + (uint32_t)(j * (int)p.ll_rs);
-			if (c >= 0 && c + 4 <= hw)
-				pre_ll[k] = __ldg(reinterpret_cast<const uint2*>(row + c));
+			int16_t* dst = dstbuf + (b * UT_STEP + r) * UT_SP + x0;
+			if (b == 0)
+				bulk_g2s(dst, in_ll + (uint32_t)(j * (int)p.ll_rs) + (c0 - 8 + x0), ll_bytes, &bars[buf]);
 			else
-			{
-				const uint32_t e = (uint16_t)__ldg(row + (c < 0 ? 0 : hw - 1));
-				pre_ll[k] = make_uint2(e * 0x10001u, e * 0x10001u);
-			}
+				bulk_g2s(dst, in_c + (uint64_t)(b - 1) * band + (uint32_t)(j * hw) + (c0 - 8 + x0 - sh), hp_bytes, &bars[buf]);
 		}
-		// Always aligned 32-bit loads: when the subband starts at an odd int16 offset the staged row starts one
-		// column earlier (c0-5) and the V pass realigns pairs with a funnel shift. 65 words cover the 128 staged
-		// columns at either parity: slots 0..11 are words 0..63 of the 24 band rows, slot 12 is word 64 (24 threads).
-#pragma unroll
-		for (int k = 0; k < US_HP_LOADS; k++)
+		else if (hp_tail > 0)
 		{
-			int bnd, r, m;
-			if (k < US_HP_LOADS - 1)
+			// right-edge strip: the last (< 8) elements of each subband row, element by element
+			for (int i = tid - 32; i < 3 * UT_STEP * hp_tail; i += UT_THREADS - 32)
 			{
-				const int id = tid + US_THREADS * k;
-				bnd = id >> 9, r = (id >> 6) & 7, m = id & 63; // band 0..2 = C, B, D
-			}
-			else
-				bnd = tid >> 3, r = tid & 7, m = 64;
-			if (k < US_HP_LOADS - 1 || tid < 3 * US_STEP)
-			{
+				const int e = i % hp_tail, rb = i / hp_tail;
+				const int b = rb >> 3, r = rb & 7;
 				const int j = min(max(js + r, 0), hh - 1);
-				const int c = c0 - 4 - shift1 + 2 * m;
-				const int16_t* row = in_c + (uint64_t)bnd * band + (uint32_t)(j * hw);
-				if (c >= 0 && c + 2 <= hw)
-					pre_hp[k] = __ldg(reinterpret_cast<const uint32_t*>(row + c));
-				else
-				{
-					// CLAMP, element by element (edge strips only)
-					const int ca = min(max(c, 0), hw - 1), cb = min(max(c + 1, 0), hw - 1);
-					pre_hp[k] = (uint32_t)(uint16_t)__ldg(row + ca) | ((uint32_t)(uint16_t)__ldg(row + cb) << 16);
-				}
+				dstbuf[((b + 1) * UT_STEP + r) * UT_SP + hp_x1 + e] =
+				    __ldg(in_c + (uint64_t)b * band + (uint32_t)(j * hw) + (c0 - 8 - sh + hp_x1 + e));
 			}
-		}
-	};
-	auto commit = [&]() {
-#pragma unroll
-		for (int k = 0; k < US_LL_LOADS; k++)
-		{
-			const int id = tid + US_THREADS * k;
-			*reinterpret_cast<uint2*>(&S[(id >> 5) * US_SP + 4 * (id & 31)]) = pre_ll[k];
-		}
-#pragma unroll
-		for (int k = 0; k < US_HP_LOADS; k++)
-		{
-			int bnd, r, m;
-			if (k < US_HP_LOADS - 1)
-			{
-				const int id = tid + US_THREADS * k;
-				bnd = id >> 9, r = (id >> 6) & 7, m = id & 63;
-			}
-			else
-				bnd = tid >> 3, r = tid & 7, m = 64;
-			if (k < US_HP_LOADS - 1 || tid < 3 * US_STEP)
-				*reinterpret_cast<uint32_t*>(&S[((bnd + 1) * US_STEP + r) * US_SP + 2 * m]) = pre_hp[k];
 		}
 	};
 
-	// ---- V-pass state (two adjacent columns of one side per thread)
+	if (tid == 0)
+	{
+		mbar_init(&bars[0], 1);
+		mbar_init(&bars[1], 1);
+		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+	}
+	__syncthreads();
+
+	// ---- V-pass geometry: thread = (side, column pair); staged columns 4 + 2t, 5 + 2t
 	const bool right_side = tid >= 64;
-	const int vword = tid & 63; // word (column pair) inside the side's 128 staged columns
-	const int16_t* s_lo = S + (right_side ? 2 * US_STEP * US_SP : 0);             // LL or B
-	const int16_t* s_hi = S + (right_side ? 3 * US_STEP * US_SP : US_STEP * US_SP); // C or D
-	int h1[2] = {0, 0}, h2[2] = {0, 0}, h3[2] = {0, 0}, l1[2] = {0, 0};
-	int ev2[2] = {0, 0}, ev3[2] = {0, 0}, ev4[2] = {0, 0};
+	const int vt = tid & 63;
+	const int lo_band = right_side ? 2 : 0, hi_band = right_side ? 3 : 1;   // (LL, C) or (B, D)
+	const int hp_word = 2 + vt + (sh >> 1);                                 // word of the pair in a shifted subband row
+	const bool odd_shift = (sh & 1) != 0;
+	const int qhi = q << 16;
+	UnstripV<WL> vs;
+	vs.init();
 
 	const int j_first = i_begin - LAT, j_last = i_end + LAT;
-	const uint32_t n_out = (uint32_t)(i_end - i_begin);
-	prefetch(j_first);
+	issue(j_first, 0);
+	__syncthreads(); // tail fills of the first buffer
 
-	for (int js = j_first; js < j_last; js += US_STEP)
+	int buf = 0;
+	uint32_t phase = 0;
+	for (int js = j_first; js < j_last; js += UT_STEP)
 	{
-		commit();
-		__syncthreads();
-		if (js + US_STEP < j_last)
-			prefetch(js + US_STEP);
+		if (js + UT_STEP < j_last)
+			issue(js + UT_STEP, buf ^ 1);
+		mbar_wait(&bars[buf], phase);
 
 		// ---------------- V pass
 		{
-			const uint32_t* plo = reinterpret_cast<const uint32_t*>(s_lo) + vword;
-			const uint32_t* phi = reinterpret_cast<const uint32_t*>(s_hi) + vword;
-			uint32_t* vb = reinterpret_cast<uint32_t*>(VB) + (right_side ? 64 : 0) + vword;
+			const uint32_t* sb = reinterpret_cast<const uint32_t*>(S + buf * UT_SBUF);
+			const uint32_t* plo = sb + (lo_band * UT_STEP) * (UT_SP / 2) + (right_side ? hp_word : 2 + vt);
+			const uint32_t* phi = sb + (hi_band * UT_STEP) * (UT_SP / 2) + hp_word;
+			uint32_t* vb = reinterpret_cast<uint32_t*>(VB) + tid;
+			const bool interior = (js - LAT > 0) && (js + UT_STEP <= hh);
+
+			auto vstep = [&](auto edge_tag, auto odd_tag, auto quant_tag) {
+				constexpr bool EDGE = decltype(edge_tag)::value;
+				constexpr bool ODD = decltype(odd_tag)::value;
+				constexpr bool QUANT = decltype(quant_tag)::value;
 #pragma unroll
-			for (int k = 0; k < US_STEP; k++)
-			{
-				const int j = js + k;
-				// staged highpass rows may be shifted by one column (see the loader): realign with a funnel shift
-				const uint32_t wh = __funnelshift_r(phi[k * (US_SP / 2)], phi[k * (US_SP / 2) + 1], fshift);
-				const uint32_t wl = right_side ? __funnelshift_r(plo[k * (US_SP / 2)], plo[k * (US_SP / 2) + 1], fshift)
-				                               : plo[k * (US_SP / 2)];
-				int lv[2] = {lo16(wl), hi16(wl)};
-				int hv[2] = {lo16(wh), hi16(wh)};
+				for (int k = 0; k < UT_STEP; k++)
+				{
+					uint32_t wh = phi[k * (UT_SP / 2)];
+					if (ODD)
+						wh = __funnelshift_r(wh, phi[k * (UT_SP / 2) + 1], 16);
+					uint32_t wl = plo[k * (UT_SP / 2)];
+					if (ODD && right_side)
+						wl = __funnelshift_r(wl, plo[k * (UT_SP / 2) + 1], 16);
+					if (QUANT)
+					{
+						// lifting.c:30-40: all three highpass subbands; LL is never quantised.
+						// (x << 16) * q wraps exactly like the int16 store of x * q.
+						wh = pair_hi(wh * (uint32_t)qhi, (wh & 0xffff0000u) * (uint32_t)q);
+						if (right_side)
+							wl = pair_hi(wl * (uint32_t)qhi, (wl & 0xffff0000u) * (uint32_t)q);
+					}
+					uint32_t even, odd;
+					vs.template row<EDGE>(wl, wh, js + k, hh, even, odd);
+					vb[(2 * k) * (UT_VP / 2)] = even;
+					vb[(2 * k + 1) * (UT_VP / 2)] = odd;
+				}
+			};
+			auto vstep_o = [&](auto edge_tag, auto quant_tag) {
+				if (odd_shift)
+					vstep(edge_tag, std::true_type{}, quant_tag);
+				else
+					vstep(edge_tag, std::false_type{}, quant_tag);
+			};
+			auto vstep_e = [&](auto edge_tag) {
 				if (q > 1)
-				{
-					// lifting.c:30-40: all three highpasses; LL is never quantised
-					hv[0] = sx16(hv[0] * q);
-					hv[1] = sx16(hv[1] * q);
-					if (right_side)
-					{
-						lv[0] = sx16(lv[0] * q);
-						lv[1] = sx16(lv[1] * q);
-					}
-				}
-				int even[2], odd[2];
-#pragma unroll
-				for (int s = 0; s < 2; s++)
-				{
-					if (WL == AKOD_DD137)
-					{
-						int e = ustrip_even<WL>(l1[s], h3[s], h2[s], h1[s], hv[s]); // even(j-1)
-						if (j - 1 == 0)
-							ev2[s] = e; // E(-1) = E(0)
-						if (j - 1 >= hh)
-							e = ev2[s]; // E(t) = E(t+1) = E(t-1)
-						odd[s] = ustrip_odd<WL>(h3[s], ev3[s], ev4[s], ev2[s], e); // odd(j-3)
-						even[s] = ev3[s];
-						ev4[s] = ev3[s];
-						ev3[s] = ev2[s];
-						ev2[s] = e;
-						h3[s] = h2[s];
-						h2[s] = h1[s];
-						h1[s] = hv[s];
-						l1[s] = lv[s];
-					}
-					else if (WL == AKOD_CDF53)
-					{
-						int e = ustrip_even<WL>(lv[s], 0, h1[s], hv[s], 0); // even(j)
-						if (j >= hh)
-							e = ev2[s]; // E(t) = E(t-1)
-						odd[s] = ustrip_odd<WL>(h1[s], ev2[s], 0, e, 0); // odd(j-1)
-						even[s] = ev2[s];
-						ev2[s] = e;
-						h1[s] = hv[s];
-					}
-					else
-					{
-						even[s] = lv[s];
-						odd[s] = ustrip_odd<WL>(hv[s], lv[s], 0, 0, 0);
-					}
-				}
-				vb[(2 * k) * (US_VP / 2)] = pack2(even[0], even[1]);
-				vb[(2 * k + 1) * (US_VP / 2)] = pack2(odd[0], odd[1]);
-			}
+					vstep_o(edge_tag, std::true_type{});
+				else
+					vstep_o(edge_tag, std::false_type{});
+			};
+			if (interior)
+				vstep_e(std::false_type{});
+			else
+				vstep_e(std::true_type{});
 		}
 		__syncthreads();
 
 		// ---------------- H pass: item = (row, chunk of 8 coefficients); 16 rows x 15 chunks
-		const int r0 = js - LAT; // coefficient row of VB rows 0,1
 #pragma unroll
 		for (int round = 0; round < 2; round++)
 		{
 			// consecutive lanes take consecutive chunks of a row: conflict-free 128-bit shared loads and
 			// contiguous global stores
-			const int item = tid + US_THREADS * round;
-			const int r = item / (US_TW / 8), chunk = item - r * (US_TW / 8);
+			const int item = tid + UT_THREADS * round;
+			const int r = item / (UT_TW / 8), chunk = item - r * (UT_TW / 8);
 			const int a = chunk * 8;
-			const int cr = r0 + (r >> 1); // coefficient row this VB row belongs to
+			const int cr = js + (r >> 1) - ((r & 1) ? LAT : LEV); // coefficient row this VB row belongs to
 			const uint32_t oy = (uint32_t)(2 * cr + (r & 1));
-			if (r < 2 * US_STEP && c0 + a < hw && (uint32_t)(cr - i_begin) < n_out && oy < p.th)
+			if (r < 2 * UT_STEP && c0 + a < hw && (uint32_t)(cr - i_begin) < (uint32_t)(i_end - i_begin) && oy < p.th)
 			{
 				// VB columns [a, a+16) hold coefficients c = c0 + a - 4 + k
-				int L[16], Hc[16];
-				{
-					const uint4 l0 = *reinterpret_cast<const uint4*>(&VB[r * US_VP + a]);
-					const uint4 l1v = *reinterpret_cast<const uint4*>(&VB[r * US_VP + a + 8]);
-					const uint4 g0 = *reinterpret_cast<const uint4*>(&VB[r * US_VP + 128 + a]);
-					const uint4 g1 = *reinterpret_cast<const uint4*>(&VB[r * US_VP + 128 + a + 8]);
-					const uint32_t lw[8] = {l0.x, l0.y, l0.z, l0.w, l1v.x, l1v.y, l1v.z, l1v.w};
-					const uint32_t gw[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
-#pragma unroll
-					for (int k = 0; k < 8; k++)
-					{
-						L[2 * k] = lo16(lw[k]);
-						L[2 * k + 1] = hi16(lw[k]);
-						Hc[2 * k] = lo16(gw[k]);
-						Hc[2 * k + 1] = hi16(gw[k]);
-					}
-				}
-				int e[16];
-#pragma unroll
-				for (int k = 3; k <= 13; k++)
-				{
-					if (WL == AKOD_DD137)
-						e[k] = ustrip_even<WL>(L[k], Hc[k - 2], Hc[k - 1], Hc[k], Hc[k + 1]);
-					else
-						e[k] = ustrip_even<WL>(L[k], 0, Hc[k - 1], Hc[k], 0);
-				}
-				if (WL != AKOD_HAAR)
-				{
-					if (c0 + a == 0)
-						e[3] = e[4]; // E(-1) = E(0)
-					const int rem = hw - (c0 + a); // E(t) = E(t+1) = E(t-1); t is 4 or 8 columns into an edge chunk
-					if (rem == 4)
-						e[8] = e[9] = e[7];
-					if (rem == 8)
-						e[12] = e[13] = e[11];
-				}
+				const uint4 l0 = *reinterpret_cast<const uint4*>(&VB[r * UT_VP + a]);
+				const uint4 l1 = *reinterpret_cast<const uint4*>(&VB[r * UT_VP + a + 8]);
+				const uint4 g0 = *reinterpret_cast<const uint4*>(&VB[r * UT_VP + 128 + a]);
+				const uint4 g1 = *reinterpret_cast<const uint4*>(&VB[r * UT_VP + 128 + a + 8]);
+				const uint32_t lw[8] = {l0.x, l0.y, l0.z, l0.w, l1.x, l1.y, l1.z, l1.w};
+				uint32_t gw[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
 				uint32_t w[8];
-#pragma unroll
-				for (int k = 4; k < 12; k++)
-				{
-					int o;
-					if (WL == AKOD_DD137)
-						o = ustrip_odd<WL>(Hc[k], e[k], e[k - 1], e[k + 1], e[k + 2]);
-					else
-						o = ustrip_odd<WL>(Hc[k], e[k], 0, e[k + 1], 0);
-					w[k - 4] = pack2(e[k], o);
-				}
+				unstrip_hpass<WL>(lw, gw, c0 + a == 0, hw - (c0 + a), w);
 				uint4* dst = reinterpret_cast<uint4*>(out + (uint64_t)oy * p.out_rs + 2 * (c0 + a));
 				dst[0] = make_uint4(w[0], w[1], w[2], w[3]);
-				if (c0 + a + 4 < hw)
-					dst[1] = make_uint4(w[4], w[5], w[6], w[7]);
+				dst[1] = make_uint4(w[4], w[5], w[6], w[7]);
 			}
 		}
-		__syncthreads();
+		__syncthreads(); // VB is rewritten by the next step; S[buf] by the load issued in the next step
+		buf ^= 1;
+		if (buf == 0)
+			phase ^= 1u;
 	}
 }
 
 static inline bool unlift_strip_eligible(const UnliftParams& p)
 {
-	return p.wrap == AKOD_WRAP_CLAMP && (p.tw % 8) == 0 && p.tw == 2 * p.hw && p.hw >= 32 && p.hh >= 8 &&
+	return p.wrap == AKOD_WRAP_CLAMP && (p.hw % 8) == 0 && p.tw == 2 * p.hw && p.hw >= 32 && p.hh >= 8 &&
 	       (p.out_rs % 8) == 0 && (p.out_ps % 8) == 0 && (p.out_is % 8) == 0 && ((uintptr_t)p.out % 16) == 0 &&
-	       (p.ll_rs % 4) == 0 && (p.ll_ps % 4) == 0 && (p.ll_is % 4) == 0 && ((uintptr_t)p.ll % 8) == 0 &&
-	       (p.stream_is % 2) == 0 && ((uintptr_t)p.stream % 4) == 0 && (uint64_t)p.tw * p.th < ((uint64_t)1 << 31);
+	       (p.ll_rs % 8) == 0 && (p.ll_ps % 8) == 0 && (p.ll_is % 8) == 0 && ((uintptr_t)p.ll % 16) == 0 &&
+	       (p.stream_is % 8) == 0 && ((uintptr_t)p.stream % 16) == 0 && p.off_c[0] >= 16 &&
+	       (uint64_t)p.tw * p.th < ((uint64_t)1 << 31);
 }
