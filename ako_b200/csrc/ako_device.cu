@@ -9,6 +9,7 @@
 #include "kagari_dec.cuh"
 #include "kagari_enc.cuh"
 #include "lift.cuh"
+#include "lift_small.cuh"
 #include "lift_strip.cuh"
 #include "unlift_strip.cuh"
 
@@ -368,6 +369,48 @@ static int launch_unlift_level(akodContext* c, const UnliftParams& p, uint32_t n
 	return AKOD_OK;
 }
 
+// the tail of the pyramid (levels l0 .. levels-1) in one launch; see lift_small.cuh
+static int launch_small(akodContext* c, const akodPlan* plan, uint32_t l0, bool forward, int16_t* planes, uint32_t planes_rs,
+                        uint64_t planes_ps, uint64_t planes_is, int16_t* stream, uint64_t stream_is, uint32_t n_images)
+{
+	static bool attr_done = false;
+	const size_t smem = sizeof(int16_t) * 2 * (size_t)SM_CAP;
+	if (!attr_done)
+	{
+		AKOD_TRY(cudaFuncSetAttribute(k_lift_small, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+		AKOD_TRY(cudaFuncSetAttribute(k_unlift_small, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+		attr_done = true;
+	}
+	SmallParams sp;
+	memset(&sp, 0, sizeof(sp));
+	sp.planes = planes;
+	sp.planes_rs = planes_rs;
+	sp.planes_ps = planes_ps;
+	sp.planes_is = planes_is;
+	sp.stream = stream;
+	sp.stream_is = stream_is;
+	sp.cw0 = plan->level[l0].cw;
+	sp.ch0 = plan->level[l0].ch;
+	sp.levels = plan->levels - l0;
+	sp.channels = plan->channels;
+	sp.wrap = plan->wrap;
+	sp.wavelet = plan->wavelet;
+	const uint32_t c1 = plan->channels > 1 ? 1 : 0;
+	for (uint32_t s = 0; s < sp.levels; s++)
+	{
+		const akodLevel* L = &plan->level[l0 + s];
+		sp.lq[s].qy = L->q[0];
+		sp.lq[s].qc = L->q[c1];
+		sp.lq[s].gy = L->g[0];
+		sp.lq[s].gc = L->g[c1];
+	}
+	if (forward)
+		AKOD_LAUNCH(c, "lift_small", k_lift_small, plan->channels * n_images, SM_THREADS, smem, sp);
+	else
+		AKOD_LAUNCH(c, "unlift_small", k_unlift_small, plan->channels * n_images, SM_THREADS, smem, sp);
+	return AKOD_OK;
+}
+
 extern "C" int akod_lift(akodContext* c, const akodPlan* plan, int16_t* d_planes, int16_t* d_scratch, int16_t* d_stream,
                          const akodBatch* b)
 {
@@ -381,9 +424,12 @@ extern "C" int akod_lift(akodContext* c, const akodPlan* plan, int16_t* d_planes
 	uint64_t src_is = planes_is, dst_is = scratch_is;
 	uint64_t src_ps = (uint64_t)plan->w * plan->h; // level 0 planes keep the full-image plane stride
 
+	static const bool no_small = getenv("AKO_B200_NO_SMALL") != nullptr;
 	for (uint32_t l = 0; l < plan->levels; l++)
 	{
 		const akodLevel* L = &plan->level[l];
+		if (!no_small && small_eligible(L->cw, L->ch, plan->levels - l))
+			return launch_small(c, plan, l, true, src, L->cw, src_ps, src_is, d_stream, stream_is, n);
 		LiftParams p;
 		memset(&p, 0, sizeof(p));
 		p.in = src;
@@ -483,7 +529,25 @@ extern "C" int akod_unlift(akodContext* c, const akodPlan* plan, const int16_t* 
 
 	// The finest level must land in d_planes; alternate buffers backwards from there.
 	// level index l (0 = finest) writes to planes if l is even, scratch if odd.
-	for (uint32_t l = plan->levels; l-- > 0;)
+	static const bool no_small = getenv("AKO_B200_NO_SMALL") != nullptr;
+	uint32_t l_top = plan->levels; // levels l_top .. levels-1 are done by the small kernel
+	if (!no_small)
+		for (uint32_t l = 0; l < plan->levels; l++)
+			if (small_eligible(plan->level[l].cw, plan->level[l].ch, plan->levels - l))
+			{
+				l_top = l;
+				break;
+			}
+	if (l_top < plan->levels)
+	{
+		const akodLevel* L = &plan->level[l_top];
+		const bool to_planes = (l_top % 2) == 0;
+		int rc = launch_small(c, plan, l_top, false, to_planes ? d_planes : d_scratch, L->cw, (uint64_t)L->cw * L->ch,
+		                      to_planes ? planes_is : scratch_is, const_cast<int16_t*>(d_stream), stream_is, n);
+		if (rc != AKOD_OK)
+			return rc;
+	}
+	for (uint32_t l = l_top; l-- > 0;)
 	{
 		const akodLevel* L = &plan->level[l];
 		UnliftParams p;

@@ -46,6 +46,7 @@ typedef struct
 {
 	uint32_t w, h, channels, levels;
 	int32_t wrap;
+	int32_t wavelet; /* the settings' wavelet (levels carry the effective one) */
 	uint32_t lp_w, lp_h;
 	uint64_t off_lp[AKOD_MAX_CHANNELS];
 	uint64_t stream_len; /* int16 count == akoTileDataSize()*channels/2 */

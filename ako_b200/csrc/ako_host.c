@@ -293,6 +293,7 @@ static void build_plan(akodPlan* p, const struct akoSettings* s, size_t channels
 	p->h = (uint32_t)h;
 	p->channels = (uint32_t)channels;
 	p->wrap = (int32_t)s->wrap;
+	p->wavelet = (s->wavelet == AKO_WAVELET_HAAR) ? AKOD_HAAR : (s->wavelet == AKO_WAVELET_CDF53) ? AKOD_CDF53 : AKOD_DD137;
 
 	size_t cw = w, ch = h;
 	uint32_t levels = 0;
