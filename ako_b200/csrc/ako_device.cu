@@ -320,15 +320,20 @@ static int launch_lift_strip(akodContext* c, const LiftParams& p, uint32_t n_ima
 	StripParams sp;
 	sp.p = p;
 	sp.split = split;
-	bool plain = true;
+	bool plain = true, gate = false;
 	for (uint32_t ch = 0; ch < p.channels; ch++)
+	{
 		plain = plain && p.q[ch] <= 1 && p.g[ch] == 0;
+		gate = gate || p.g[ch] >= p.q[ch];
+	}
 	const dim3 grid(strips, (p.th + split - 1) / split, p.channels * n_images);
 	static const char* const names[3] = {"lift_strip_dd137", "lift_strip_cdf53", "lift_strip_haar"};
 	if (plain)
-		AKOD_LAUNCH(c, names[WL], (k_lift_strip<WL, true>), grid, FS_THREADS, 0, sp);
+		AKOD_LAUNCH(c, names[WL], (k_lift_strip<WL, FS_PLAIN>), grid, FS_THREADS, 0, sp);
+	else if (!gate)
+		AKOD_LAUNCH(c, names[WL], (k_lift_strip<WL, FS_QUANT>), grid, FS_THREADS, 0, sp);
 	else
-		AKOD_LAUNCH(c, names[WL], (k_lift_strip<WL, false>), grid, FS_THREADS, 0, sp);
+		AKOD_LAUNCH(c, names[WL], (k_lift_strip<WL, FS_GATE>), grid, FS_THREADS, 0, sp);
 	return AKOD_OK;
 }
 
@@ -829,5 +834,42 @@ extern "C" int akod_walk_blocks(akodContext* c, const uint8_t* d_blob, uint64_t 
                                 uint64_t* d_off, uint64_t* d_size)
 {
 	AKOD_LAUNCH(c, "walk_blocks", k_walk_blocks, 1, 32, 0, d_blob, input_size, n_tiles, d_off, d_size);
+	return AKOD_OK;
+}
+
+// the same walk for n blobs at d_blobs + i*stride, one thread each; off/size are [n][tiles]
+__global__ void k_walk_blocks_batch(const uint8_t* __restrict__ blobs, uint64_t stride, const uint64_t* __restrict__ input_size,
+                                    uint32_t n_tiles, uint32_t n, uint64_t* __restrict__ off, uint64_t* __restrict__ size)
+{
+	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n)
+		return;
+	const uint8_t* blob = blobs + stride * i;
+	const uint64_t in_size = input_size[i];
+	uint64_t pos = 16;
+	bool ok = true;
+	for (uint32_t t = 0; t < n_tiles; t++)
+	{
+		uint64_t s = 0;
+		if (ok && pos + 4 <= in_size)
+		{
+			s = (uint64_t)blob[pos] | ((uint64_t)blob[pos + 1] << 8) | ((uint64_t)blob[pos + 2] << 16) |
+			    ((uint64_t)blob[pos + 3] << 24);
+			if (s == 0 || pos + 4 + s > in_size)
+				s = 0;
+		}
+		if (s == 0)
+			ok = false;
+		off[(uint64_t)i * n_tiles + t] = pos + 4;
+		size[(uint64_t)i * n_tiles + t] = s;
+		pos += 4 + s;
+	}
+}
+
+extern "C" int akod_walk_blocks_batch(akodContext* c, const uint8_t* d_blobs, uint64_t stride, const uint64_t* d_input_size,
+                                      uint32_t n_tiles, uint32_t n, uint64_t* d_off, uint64_t* d_size)
+{
+	AKOD_LAUNCH(c, "walk_blocks", k_walk_blocks_batch, (n + 63) / 64, 64, 0, d_blobs, stride, d_input_size, n_tiles, n, d_off,
+	            d_size);
 	return AKOD_OK;
 }

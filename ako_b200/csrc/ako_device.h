@@ -144,6 +144,9 @@ int akod_assemble(akodContext*, const uint8_t head16[16], uint32_t n_tiles, uint
  * d_size[t] = its block_size; stops (size 0) if it would run past input_size */
 int akod_walk_blocks(akodContext*, const uint8_t* d_blob, uint64_t input_size, uint32_t n_tiles, uint64_t* d_off,
                      uint64_t* d_size);
+/* the same for n blobs at d_blobs + i*stride with d_input_size[i] bytes; d_off / d_size are [n][n_tiles] */
+int akod_walk_blocks_batch(akodContext*, const uint8_t* d_blobs, uint64_t stride, const uint64_t* d_input_size,
+                           uint32_t n_tiles, uint32_t n, uint64_t* d_off, uint64_t* d_size);
 
 #ifdef __cplusplus
 }

@@ -1494,9 +1494,37 @@ AKO_API size_t akoB200DecodeBatchDevice(akoB200Context* ctx, size_t n_images, co
 	}
 	uint64_t* off = blk;
 	uint64_t* size = blk + tiles * n_images;
-	for (size_t i = 0; i < n_images && st == AKO_OK; i++)
-		st = walk_blocks_device(ctx, (const uint8_t*)d_in + in_stride * i, in_sizes[i], &s, channels, w, h,
-		                        off + tiles * i, size + tiles * i);
+	if (s.compression == AKO_COMPRESSION_NONE)
+	{
+		for (size_t i = 0; i < n_images && st == AKO_OK; i++)
+			st = walk_blocks_device(ctx, (const uint8_t*)d_in + in_stride * i, in_sizes[i], &s, channels, w, h,
+			                        off + tiles * i, size + tiles * i);
+	}
+	else
+	{
+		/* one kernel walks the block heads of every blob, one read-back brings offsets and sizes home */
+		void* small;
+		uint64_t* sizes64 = malloc(sizeof(uint64_t) * n_images);
+		if (sizes64 == NULL)
+			st = AKO_NO_ENOUGH_MEMORY;
+		if (st == AKO_OK)
+			st = from_dev(akod_workspace(ctx->dev, AKOD_WS_SMALL, sizeof(uint64_t) * n_images * (2 * tiles + 1) + 64, &small));
+		if (st == AKO_OK)
+		{
+			uint64_t* d_sizes = small;
+			uint64_t* d_off = d_sizes + n_images;
+			for (size_t i = 0; i < n_images; i++)
+				sizes64[i] = in_sizes[i];
+			if ((st = upload_words(ctx, d_sizes, sizes64, n_images)) == AKO_OK &&
+			    (st = from_dev(akod_walk_blocks_batch(ctx->dev, d_in, in_stride, d_sizes, (uint32_t)tiles, (uint32_t)n_images,
+			                                          d_off, d_off + tiles * n_images))) == AKO_OK)
+				st = download_words(ctx, blk, d_off, 2 * tiles * n_images);
+			for (size_t k = 0; k < tiles * n_images && st == AKO_OK; k++)
+				if (size[k] == 0)
+					st = AKO_BROKEN_INPUT;
+		}
+		free(sizes64);
+	}
 	if (st == AKO_OK)
 		st = decode_core(ctx, NULL, &s, channels, w, h, n_images, d_in, in_stride, off, size, d_out, out_stride, &ok);
 

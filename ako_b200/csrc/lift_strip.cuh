@@ -400,10 +400,16 @@ struct StripV<AKOD_DD137>
 };
 
 // ------------------------------------------------------------------------------------------------
-// PLAIN: q == 1 and gate == 0 on every channel (the quantise step is the identity).
-template <int WL, bool PLAIN>
+// MODE (chosen by the host per launch, so that the kernel holds one copy of its V pass per mode):
+//   FS_PLAIN  q == 1 and gate == 0 on every channel: the quantise step is the identity
+//   FS_QUANT  some channel has q > 1, no channel needs the gate (|v| <= g < q already quantises to zero)
+//   FS_GATE   some channel has g >= q
+constexpr int FS_PLAIN = 0, FS_QUANT = 1, FS_GATE = 2;
+
+template <int WL, int MODE>
 __global__ void __launch_bounds__(FS_THREADS, 6) k_lift_strip(const StripParams sp)
 {
+	constexpr bool PLAIN = MODE == FS_PLAIN, GATE = MODE == FS_GATE;
 	constexpr int LAT = StripGeom<WL>::LAT;
 	const LiftParams& p = sp.p;
 
@@ -492,7 +498,6 @@ __global__ void __launch_bounds__(FS_THREADS, 6) k_lift_strip(const StripParams 
 	// precedes each channel's block, so the parity alternates from channel to channel): pairs are stored with
 	// one 32-bit store when aligned, two 16-bit stores otherwise. Uniform per CTA.
 	const bool odd_offset = (p.off_c[chn] & 1) != 0;
-	const bool gate = sq.g >= sq.q; // |v| <= g < q already quantises to zero
 	StripV<WL> vs;
 	vs.init();
 
@@ -553,10 +558,8 @@ __global__ void __launch_bounds__(FS_THREADS, 6) k_lift_strip(const StripParams 
 			int16_t* const row_hi = out_hi + (int64_t)i0 * (int64_t)hi_rs;
 			int16_t* const row_lo = out_lo + (int64_t)i0 * (int64_t)lo_rs;
 
-			auto vstep = [&](auto edge_tag, auto odd_tag, auto gate_tag) {
+			auto vstep = [&](auto edge_tag) {
 				constexpr bool EDGE = decltype(edge_tag)::value;
-				constexpr bool ODD = decltype(odd_tag)::value;
-				constexpr bool GATE = decltype(gate_tag)::value;
 #pragma unroll
 				for (int k = 0; k < FS_STEP; k++)
 				{
@@ -576,14 +579,15 @@ __global__ void __launch_bounds__(FS_THREADS, 6) k_lift_strip(const StripParams 
 							wlo = pair_hi((uint32_t)la, (uint32_t)lb);
 						else
 							wlo = pack2(strip_quant<GATE>(la, sq), strip_quant<GATE>(lb, sq));
-						if (ODD)
+						// odd_offset is uniform per CTA: the branches below do not diverge
+						if (odd_offset)
 						{
 							dh[0] = (int16_t)whi;
 							dh[1] = (int16_t)(whi >> 16);
 						}
 						else
 							*reinterpret_cast<uint32_t*>(dh) = whi;
-						if (ODD && right_half)
+						if (odd_offset && right_half)
 						{
 							dl[0] = (int16_t)wlo;
 							dl[1] = (int16_t)(wlo >> 16);
@@ -593,22 +597,10 @@ __global__ void __launch_bounds__(FS_THREADS, 6) k_lift_strip(const StripParams 
 					}
 				}
 			};
-			auto vstep_oe = [&](auto edge_tag, auto gate_tag) {
-				if (odd_offset)
-					vstep(edge_tag, std::true_type{}, gate_tag);
-				else
-					vstep(edge_tag, std::false_type{}, gate_tag);
-			};
-			auto vstep_e = [&](auto edge_tag) {
-				if (!PLAIN && gate)
-					vstep_oe(edge_tag, std::true_type{});
-				else
-					vstep_oe(edge_tag, std::false_type{});
-			};
 			if (interior)
-				vstep_e(std::false_type{});
+				vstep(std::false_type{});
 			else
-				vstep_e(std::true_type{});
+				vstep(std::true_type{});
 		}
 		__syncthreads(); // HB is rewritten by the next step; X[buf] by the load issued in the next step
 		nbuf = buf;

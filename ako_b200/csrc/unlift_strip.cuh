@@ -348,18 +348,18 @@ __global__ void __launch_bounds__(UT_THREADS, 6) k_unlift_strip(const UnstripPar
 			uint32_t* vb = reinterpret_cast<uint32_t*>(VB) + tid;
 			const bool interior = (js - LAT > 0) && (js + UT_STEP <= hh);
 
-			auto vstep = [&](auto edge_tag, auto odd_tag, auto quant_tag) {
+			auto vstep = [&](auto edge_tag, auto quant_tag) {
 				constexpr bool EDGE = decltype(edge_tag)::value;
-				constexpr bool ODD = decltype(odd_tag)::value;
 				constexpr bool QUANT = decltype(quant_tag)::value;
 #pragma unroll
 				for (int k = 0; k < UT_STEP; k++)
 				{
+					// odd_shift is uniform per CTA
 					uint32_t wh = phi[k * (UT_SP / 2)];
-					if (ODD)
+					if (odd_shift)
 						wh = __funnelshift_r(wh, phi[k * (UT_SP / 2) + 1], 16);
 					uint32_t wl = plo[k * (UT_SP / 2)];
-					if (ODD && right_side)
+					if (odd_shift && right_side)
 						wl = __funnelshift_r(wl, plo[k * (UT_SP / 2) + 1], 16);
 					if (QUANT)
 					{
@@ -375,17 +375,11 @@ __global__ void __launch_bounds__(UT_THREADS, 6) k_unlift_strip(const UnstripPar
 					vb[(2 * k + 1) * (UT_VP / 2)] = odd;
 				}
 			};
-			auto vstep_o = [&](auto edge_tag, auto quant_tag) {
-				if (odd_shift)
-					vstep(edge_tag, std::true_type{}, quant_tag);
-				else
-					vstep(edge_tag, std::false_type{}, quant_tag);
-			};
 			auto vstep_e = [&](auto edge_tag) {
 				if (q > 1)
-					vstep_o(edge_tag, std::true_type{});
+					vstep(edge_tag, std::true_type{});
 				else
-					vstep_o(edge_tag, std::false_type{});
+					vstep(edge_tag, std::false_type{});
 			};
 			if (interior)
 				vstep_e(std::false_type{});
