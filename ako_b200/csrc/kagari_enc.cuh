@@ -190,12 +190,24 @@ __global__ void __launch_bounds__(1024)
 // shared by pass 2 and 3: the codes of a thread's KG_ITEMS elements; returns their total bit count.
 // EMIT = false only counts bits.
 template <bool EMIT>
+__device__ __forceinline__ uint32_t kg_codes(const KgChunk& c, uint64_t n, uint64_t base, uint32_t run_start,
+                                             KgCode codes[KG_ITEMS]);
+
+template <bool EMIT>
 __device__ __forceinline__ uint32_t kg_thread_codes(const KgChunk& c, uint64_t n, uint64_t base, uint32_t carry_start,
                                                     uint32_t* sm_max, KgCode codes[KG_ITEMS])
 {
 	// run start reaching into this thread = max(block carry, starts of earlier threads); all are (index + 1)
 	uint32_t dummy;
-	uint32_t run_start = max(carry_start, block_excl_max_u32(c.last_start, sm_max, &dummy));
+	const uint32_t run_start = max(carry_start, block_excl_max_u32(c.last_start, sm_max, &dummy));
+	return kg_codes<EMIT>(c, n, base, run_start, codes);
+}
+
+// run_start = (index + 1) of the start of the run that reaches into this thread's first value
+template <bool EMIT>
+__device__ __forceinline__ uint32_t kg_codes(const KgChunk& c, uint64_t n, uint64_t base, uint32_t run_start,
+                                             KgCode codes[KG_ITEMS])
+{
 
 	if (EMIT)
 	{
@@ -330,5 +342,228 @@ __global__ void __launch_bounds__(KG_THREADS)
 			atomicOr(&words[i], be);
 		else
 			words[i] = be;
+	}
+}
+
+// ------------------------------------------------------------------------------------------------
+// Single-pass encoder. The three passes above read the stream three times and compute every code twice;
+// this kernel reads it once. Blocks take a ticket (so that every lower-numbered block of the image is
+// already running) and two chained scans with decoupled look-back run over the blocks of an image:
+//   * run starts (a max-scan): a block that contains a run start publishes it at once; a block that lies
+//     entirely inside a run publishes "pass", looks back for the nearest published start and re-publishes;
+//   * bit offsets (a 64-bit sum): every block publishes its own bit count, looks back, publishes the
+//     inclusive count. Together with the count travel the LAST 31 BITS of the bit string, so that a block
+//     can complete the 32-bit word its predecessors left unfinished: a word is written by the block that
+//     holds its last bit, with plain stores -- no atomics, no pre-zeroed output.
+// Flags live in the same 8-byte words as the payload (the 16-byte bit state repeats the flag in both
+// halves and readers retry on a mismatch), so no fences are needed.
+
+constexpr uint64_t KGF_NONE = 0, KGF_PART = 1, KGF_INCL = 2;
+constexpr uint64_t KGF_MASK = ((uint64_t)1 << 62) - 1;
+
+struct __align__(16) KgBitState
+{
+	unsigned long long a; // flag << 62 | bit count
+	unsigned long long b; // flag << 62 | last (up to 31) bits of the string, right aligned
+};
+
+__device__ __forceinline__ uint64_t kgf_ld(const unsigned long long* p)
+{
+	unsigned long long v;
+	asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+	return v;
+}
+
+__device__ __forceinline__ void kgf_st(unsigned long long* p, uint64_t v)
+{
+	asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"((unsigned long long)v) : "memory");
+}
+
+__device__ __forceinline__ void kgf_st_bits(KgBitState* p, uint64_t flag, uint64_t count, uint32_t last31)
+{
+	asm volatile("st.relaxed.gpu.global.v2.u64 [%0], {%1, %2};" ::"l"(p), "l"((unsigned long long)((flag << 62) | count)),
+	             "l"((unsigned long long)((flag << 62) | last31))
+	             : "memory");
+}
+
+// nearest published run start before block b; called by all 32 lanes of warp 0
+__device__ __forceinline__ uint32_t kgf_lookback_run(const unsigned long long* state, long long b, int lane)
+{
+	long long p0 = b - 1;
+	for (;;)
+	{
+		const long long p = p0 - lane;
+		uint64_t v = KGF_INCL << 62; // before the stream: no start
+		if (p >= 0)
+		{
+			do
+				v = kgf_ld(state + p);
+			while ((v >> 62) == KGF_NONE);
+		}
+		const uint32_t incl = __ballot_sync(AKOD_FULL_MASK, (v >> 62) == KGF_INCL);
+		if (incl)
+			return __shfl_sync(AKOD_FULL_MASK, (uint32_t)v, __ffs(incl) - 1);
+		p0 -= 32;
+	}
+}
+
+// bits before block b and the last (up to 31) of them; called by all 32 lanes of warp 0
+__device__ __forceinline__ void kgf_lookback_bits(const KgBitState* state, long long b, int lane, uint64_t& prefix,
+                                                  uint32_t& tail31)
+{
+	uint64_t sum = 0;
+	uint32_t coll = 0, ncoll = 0;
+	long long p0 = b - 1;
+	for (;;)
+	{
+		const long long p = p0 - lane;
+		uint64_t a = KGF_INCL << 62, bb = KGF_INCL << 62;
+		if (p >= 0)
+		{
+			do
+			{
+				a = kgf_ld(&state[p].a);
+				bb = kgf_ld(&state[p].b);
+			} while ((a >> 62) == KGF_NONE || (a >> 62) != (bb >> 62));
+		}
+		const uint32_t incl = __ballot_sync(AKOD_FULL_MASK, (a >> 62) == KGF_INCL);
+		const int first = incl ? __ffs(incl) - 1 : 32; // lanes 0..first are the blocks between here and the inclusive one
+		uint64_t contrib = (lane <= first) ? (a & KGF_MASK) : 0;
+#pragma unroll
+		for (int d = 16; d > 0; d >>= 1)
+			contrib += __shfl_xor_sync(AKOD_FULL_MASK, contrib, d);
+		sum += contrib;
+		const uint32_t nb = (uint32_t)min((unsigned long long)(a & KGF_MASK), 31ull);
+		const uint32_t last = (uint32_t)bb & 0x7FFFFFFFu;
+		const int upto = min(first, 31);
+		for (int l = 0; l <= upto && ncoll < 31; l++)
+		{
+			const uint32_t nb_l = __shfl_sync(AKOD_FULL_MASK, nb, l), last_l = __shfl_sync(AKOD_FULL_MASK, last, l);
+			const uint32_t take = min(nb_l, 31u - ncoll);
+			coll |= (last_l & ((1u << take) - 1u)) << ncoll; // older bits go above the ones collected so far
+			ncoll += take;
+		}
+		if (first < 32)
+			break;
+		p0 -= 32;
+	}
+	prefix = sum;
+	tail31 = coll;
+}
+
+__global__ void __launch_bounds__(KG_THREADS)
+    k_kg_fused(const int16_t* __restrict__ in, uint64_t in_stride, uint64_t n, unsigned long long* __restrict__ run_state,
+               KgBitState* __restrict__ bit_state, uint32_t* __restrict__ ticket, uint32_t nblocks, uint8_t* __restrict__ out,
+               uint64_t out_stride, uint64_t cap_bits, uint64_t* __restrict__ total_bits)
+{
+	__shared__ uint32_t sm_max[33];
+	__shared__ uint32_t sm_sum[33];
+	__shared__ uint32_t bitbuf[KG_BLOCK + 2]; // 32 bits per value at most, +2 words of slack for the peeks
+	__shared__ uint32_t s_bid, s_carry, s_tail;
+	__shared__ uint64_t s_prefix;
+
+	const uint32_t img = blockIdx.y;
+	const int tid = threadIdx.x, lane = tid & 31;
+	if (tid == 0)
+		s_bid = atomicAdd(&ticket[img], 1u);
+	for (int i = tid; i < KG_BLOCK + 2; i += KG_THREADS)
+		bitbuf[i] = 0;
+	__syncthreads();
+	const uint32_t b = s_bid;
+	in += in_stride * img;
+	run_state += (uint64_t)nblocks * img;
+	bit_state += (uint64_t)nblocks * img;
+
+	const uint64_t base = (uint64_t)b * KG_BLOCK + (uint64_t)tid * KG_ITEMS;
+	const KgChunk c = kg_load(in, n, base);
+	uint32_t blk_last;
+	const uint32_t excl_start = block_excl_max_u32(c.last_start, sm_max, &blk_last);
+
+	// ---- run-start carry
+	if (tid < 32)
+	{
+		const bool cont = __shfl_sync(AKOD_FULL_MASK, (c.start_mask & 1u) == 0, 0); // the block's first value continues a run
+		if (lane == 0)
+			kgf_st(&run_state[b], blk_last ? ((KGF_INCL << 62) | blk_last) : (KGF_PART << 62));
+		uint32_t carry = 0;
+		if (cont)
+			carry = kgf_lookback_run(run_state, (long long)b, lane);
+		if (lane == 0)
+		{
+			if (!blk_last)
+				kgf_st(&run_state[b], (KGF_INCL << 62) | carry);
+			s_carry = carry;
+		}
+	}
+	__syncthreads();
+
+	// ---- codes, packed at bit 0 of bitbuf
+	KgCode codes[KG_ITEMS];
+	const uint32_t bits = kg_codes<true>(c, n, base, max(s_carry, excl_start), codes);
+	uint32_t total;
+	const uint32_t excl = block_excl_sum(bits, sm_sum, &total);
+	if (bits)
+	{
+		uint32_t pos = excl;
+#pragma unroll
+		for (int j = 0; j < KG_ITEMS; j++)
+		{
+			const uint32_t len = codes[j].len;
+			if (len)
+			{
+				const uint32_t w = pos >> 5, sh = pos & 31;
+				// MSB-first: bit 'pos' of the string is bit (31 - pos%32) of word pos/32
+				const uint64_t wide = (uint64_t)codes[j].code << (64 - sh - len);
+				atomicOr(&bitbuf[w], (uint32_t)(wide >> 32));
+				if (sh + len > 32)
+					atomicOr(&bitbuf[w + 1], (uint32_t)wide);
+				pos += len;
+			}
+		}
+	}
+	__syncthreads();
+
+	// ---- bit offset
+	if (tid < 32)
+	{
+		// own last (up to 31) bits
+		const uint32_t m = min(total, 31u);
+		uint32_t own = 0;
+		if (m)
+		{
+			const uint32_t pos = total - m;
+			own = __funnelshift_l(bitbuf[(pos >> 5) + 1], bitbuf[pos >> 5], pos & 31) >> (32 - m);
+		}
+		if (lane == 0)
+			kgf_st_bits(&bit_state[b], KGF_PART, total, own);
+		uint64_t prefix;
+		uint32_t tail31;
+		kgf_lookback_bits(bit_state, (long long)b, lane, prefix, tail31);
+		if (lane == 0)
+		{
+			const uint32_t incl_tail = (total >= 31) ? own : (((tail31 << total) | own) & 0x7FFFFFFFu);
+			kgf_st_bits(&bit_state[b], KGF_INCL, prefix + total, incl_tail);
+			s_prefix = prefix;
+			s_tail = tail31;
+			if (b == nblocks - 1)
+				total_bits[img] = prefix + total;
+		}
+	}
+	__syncthreads();
+
+	// ---- output: the words whose last bit lies in this block (the final block also writes the unfinished one)
+	const uint64_t prefix = s_prefix;
+	if (prefix + total > cap_bits) // would not fit: the caller reports the failure from the bit count
+		return;
+	const uint32_t r = (uint32_t)(prefix & 31);
+	uint32_t nwords = (r + total) >> 5;
+	if (b == nblocks - 1 && ((r + total) & 31))
+		nwords++;
+	uint32_t* words = reinterpret_cast<uint32_t*>(out + out_stride * img) + (prefix >> 5);
+	const uint32_t tailword = s_tail;
+	for (uint32_t k = tid; k < nwords; k += KG_THREADS)
+	{
+		const uint32_t w = __funnelshift_r(bitbuf[k], k ? bitbuf[k - 1] : tailword, r);
+		words[k] = __byte_perm(w, 0, 0x0123); // bytes of the file are MSB-first
 	}
 }
