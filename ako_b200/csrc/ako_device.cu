@@ -29,6 +29,8 @@ extern "C" int akod_context_create(int device, akodContext** out)
 	c->device = device;
 	c->profiling = false;
 	c->launch_count = 0;
+	c->next_bytes = 0;
+	c->small_attr_done = false;
 	c->mailbox = nullptr;
 	for (int i = 0; i < AKOD_WS_COUNT; i++)
 	{
@@ -229,6 +231,13 @@ extern "C" size_t akod_profile_get(akodContext* c, size_t cap, const char** name
 	return c->prof.size();
 }
 
+extern "C" size_t akod_profile_get_bytes(akodContext* c, size_t cap, uint64_t* bytes)
+{
+	for (size_t i = 0; i < c->prof.size() && i < cap; i++)
+		bytes[i] = c->prof[i].bytes;
+	return c->prof.size();
+}
+
 extern "C" uint64_t akod_launch_count(akodContext* c)
 {
 	return c->launch_count;
@@ -252,6 +261,7 @@ extern "C" int akod_format_forward(akodContext* c, int discard, int color, uint3
 	const uint64_t in_is = b ? b->in_stride : 0, pl_is = b ? b->planes_stride : 0;
 	const bool fast = channels == 4 && (w % 8) == 0 && (in_stride_px % 4) == 0 && ((uintptr_t)d_in % 16) == 0 &&
 	                  ((uintptr_t)d_planes % 16) == 0 && (in_is % 16) == 0 && (pl_is % 8) == 0;
+	AKOD_BYTES(c, (uint64_t)3 * w * h * channels * n); // u8 in, int16 out
 	if (fast)
 	{
 		const dim3 grid(akod_stream_grid(c, (uint64_t)(w / 8) * h, 256, 8), n);
@@ -274,6 +284,7 @@ extern "C" int akod_format_inverse(akodContext* c, int color, uint32_t channels,
 	const uint64_t out_is = b ? b->in_stride : 0, pl_is = b ? b->planes_stride : 0;
 	const bool fast = channels == 4 && (w % 8) == 0 && (out_stride_px % 4) == 0 && ((uintptr_t)d_out % 16) == 0 &&
 	                  ((uintptr_t)d_planes % 16) == 0 && (out_is % 16) == 0 && (pl_is % 8) == 0;
+	AKOD_BYTES(c, (uint64_t)3 * w * h * channels * n); // int16 in, u8 out
 	if (fast)
 	{
 		const dim3 grid(akod_stream_grid(c, (uint64_t)(w / 8) * h, 256, 8), n);
@@ -297,26 +308,41 @@ static int launch_lift_level(akodContext* c, const LiftParams& p, uint32_t n_ima
 {
 	const dim3 grid((p.tw + LIFT_TW - 1) / LIFT_TW, (p.th + LIFT_TH - 1) / LIFT_TH, p.channels * n_images);
 	static const char* const names[3] = {"lift_dd137", "lift_cdf53", "lift_haar"};
+	AKOD_BYTES(c, (uint64_t)4 * p.cw * p.ch * p.channels * n_images);
 	AKOD_LAUNCH(c, names[WL], k_lift_level<WL>, grid, LIFT_THREADS, lift_smem_bytes<WL>(), p);
 	return AKOD_OK;
 }
 
 // strip kernel: pick the rows-per-CTA so that the grid fills the machine a few times over while the
 // warm-up rows (2*LAT per CTA) stay a small fraction
+// Rows per CTA for the strip kernels. A CTA marches 8k - 2*LAT output rows after 2*LAT warm-up rows, so larger k
+// means less redundant work but fewer CTAs. Pick the k whose grid wastes least: (last-wave occupancy) x (useful
+// fraction of the rows a CTA touches). 'slots' = CTAs resident on the whole GPU at once.
+static uint32_t strip_split(uint32_t rows, uint64_t ctas_per_row_split, uint64_t slots, int lat)
+{
+	uint32_t best = 0;
+	double best_eff = -1.0;
+	for (uint32_t k = 32; k >= 4; k >>= 1)
+	{
+		const uint32_t split = 8 * k - 2 * (uint32_t)lat;
+		const uint64_t ctas = ctas_per_row_split * ((rows + split - 1) / split);
+		const uint64_t waves = (ctas + slots - 1) / slots;
+		const double eff = ((double)ctas / (double)(waves * slots)) * ((double)split / (double)(split + 2 * lat));
+		if (eff > best_eff + 1e-9)
+		{
+			best_eff = eff;
+			best = split;
+		}
+	}
+	return best;
+}
+
 template <int WL>
 static int launch_lift_strip(akodContext* c, const LiftParams& p, uint32_t n_images)
 {
 	constexpr int LAT = StripGeom<WL>::LAT;
 	const uint32_t strips = (p.tw + FS_TW - 1) / FS_TW;
-	const uint64_t want = (uint64_t)c->sm_count * 6;
-	uint32_t split = 0;
-	for (uint32_t k = 32; k >= 4; k >>= 1)
-	{
-		split = 8 * k - 2 * LAT;
-		const uint64_t ctas = (uint64_t)strips * ((p.th + split - 1) / split) * p.channels * n_images;
-		if (ctas >= want)
-			break;
-	}
+	const uint32_t split = strip_split(p.th, (uint64_t)strips * p.channels * n_images, (uint64_t)c->sm_count * 6, LAT);
 	StripParams sp;
 	sp.p = p;
 	sp.split = split;
@@ -328,6 +354,7 @@ static int launch_lift_strip(akodContext* c, const LiftParams& p, uint32_t n_ima
 	}
 	const dim3 grid(strips, (p.th + split - 1) / split, p.channels * n_images);
 	static const char* const names[3] = {"lift_strip_dd137", "lift_strip_cdf53", "lift_strip_haar"};
+	AKOD_BYTES(c, (uint64_t)4 * p.cw * p.ch * p.channels * n_images); // every sample read once, every coefficient written once
 	if (plain)
 		AKOD_LAUNCH(c, names[WL], (k_lift_strip<WL, FS_PLAIN>), grid, FS_THREADS, 0, sp);
 	else if (!gate)
@@ -343,21 +370,14 @@ static int launch_unlift_strip(akodContext* c, const UnliftParams& p, uint32_t n
 	constexpr int LAT = StripGeom<WL>::LAT;
 	const uint32_t width = v1 ? US_TW : UT_TW;
 	const uint32_t strips = (p.hw + width - 1) / width;
-	const uint64_t want = (uint64_t)c->sm_count * 6;
-	uint32_t split = 0;
-	for (uint32_t k = 32; k >= 4; k >>= 1)
-	{
-		split = 8 * k - 2 * LAT;
-		const uint64_t ctas = (uint64_t)strips * ((p.hh + split - 1) / split) * p.channels * n_images;
-		if (ctas >= want)
-			break;
-	}
+	const uint32_t split = strip_split(p.hh, (uint64_t)strips * p.channels * n_images, (uint64_t)c->sm_count * 6, LAT);
 	UnstripParams up;
 	up.p = p;
 	up.split = split;
 	const dim3 grid(strips, (p.hh + split - 1) / split, p.channels * n_images);
 	static const char* const names[3] = {"unlift_strip_dd137", "unlift_strip_cdf53", "unlift_strip_haar"};
 	static const char* const names_v1[3] = {"unlift_strip_v1_dd137", "unlift_strip_v1_cdf53", "unlift_strip_v1_haar"};
+	AKOD_BYTES(c, (uint64_t)4 * p.tw * p.th * p.channels * n_images);
 	if (v1)
 		AKOD_LAUNCH(c, names_v1[WL], k_unlift_strip_v1<WL>, grid, US_THREADS, 0, up);
 	else
@@ -370,6 +390,7 @@ static int launch_unlift_level(akodContext* c, const UnliftParams& p, uint32_t n
 {
 	const dim3 grid((p.hw + LIFT_TW - 1) / LIFT_TW, (p.hh + LIFT_TH - 1) / LIFT_TH, p.channels * n_images);
 	static const char* const names[3] = {"unlift_dd137", "unlift_cdf53", "unlift_haar"};
+	AKOD_BYTES(c, (uint64_t)4 * p.tw * p.th * p.channels * n_images);
 	AKOD_LAUNCH(c, names[WL], k_unlift_level<WL>, grid, LIFT_THREADS, unlift_smem_bytes<WL>(), p);
 	return AKOD_OK;
 }
@@ -378,13 +399,13 @@ static int launch_unlift_level(akodContext* c, const UnliftParams& p, uint32_t n
 static int launch_small(akodContext* c, const akodPlan* plan, uint32_t l0, bool forward, int16_t* planes, uint32_t planes_rs,
                         uint64_t planes_ps, uint64_t planes_is, int16_t* stream, uint64_t stream_is, uint32_t n_images)
 {
-	static bool attr_done = false;
 	const size_t smem = sizeof(int16_t) * 2 * (size_t)SM_CAP;
-	if (!attr_done)
+	if (!c->small_attr_done)
 	{
+		AKOD_TRY(cudaSetDevice(c->device));
 		AKOD_TRY(cudaFuncSetAttribute(k_lift_small, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
 		AKOD_TRY(cudaFuncSetAttribute(k_unlift_small, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-		attr_done = true;
+		c->small_attr_done = true;
 	}
 	SmallParams sp;
 	memset(&sp, 0, sizeof(sp));
@@ -408,6 +429,12 @@ static int launch_small(akodContext* c, const akodPlan* plan, uint32_t l0, bool 
 		sp.lq[s].qc = L->q[c1];
 		sp.lq[s].gy = L->g[0];
 		sp.lq[s].gc = L->g[c1];
+	}
+	{
+		uint64_t samples = 0;
+		for (uint32_t s = 0; s < sp.levels; s++)
+			samples += (uint64_t)plan->level[l0 + s].cw * plan->level[l0 + s].ch;
+		AKOD_BYTES(c, 4 * samples * plan->channels * n_images);
 	}
 	if (forward)
 		AKOD_LAUNCH(c, "lift_small", k_lift_small, plan->channels * n_images, SM_THREADS, smem, sp);
@@ -654,14 +681,17 @@ extern "C" int akod_kagari_encode(akodContext* c, uint64_t n_values, const int16
 	uint32_t* blk_bits = blk_start + per_img * n_images;
 
 	const dim3 grid(nblocks, n_images);
+	AKOD_BYTES(c, 2 * n_values * n_images);
 	AKOD_LAUNCH(c, "kagari_starts", k_kg_starts, grid, KG_THREADS, 0, d_in, in_stride, n_values, blk_start, nblocks);
 	AKOD_LAUNCH(c, "kagari_scan_max", k_kg_scan_max, n_images, 1024, 0, blk_start, nblocks);
+	AKOD_BYTES(c, 2 * n_values * n_images);
 	AKOD_LAUNCH(c, "kagari_lengths", k_kg_lengths, grid, KG_THREADS, 0, d_in, in_stride, n_values, blk_start, blk_bits,
 	            nblocks);
 	AKOD_LAUNCH(c, "kagari_scan_sum", k_kg_scan_sum, n_images, 1024, 0, blk_bits, blk_off, nblocks, d_bits);
 	const dim3 zgrid((nblocks + 255) / 256, n_images);
 	AKOD_LAUNCH(c, "kagari_zero_edges", k_kg_zero_edges, zgrid, 256, 0, blk_off, blk_bits, nblocks, d_out, out_stride,
 	            out_cap * 8);
+	AKOD_BYTES(c, 2 * n_values * n_images); // + the blob bytes, not known on the host
 	AKOD_LAUNCH(c, "kagari_pack", k_kg_pack, grid, KG_THREADS, 0, d_in, in_stride, n_values, blk_start, blk_off, blk_bits,
 	            nblocks, d_out, out_stride, out_cap * 8);
 	return AKOD_OK;
@@ -739,6 +769,7 @@ extern "C" int akod_kagari_decode(akodContext* c, uint64_t n_values, const uint8
 	AKOD_LAUNCH(c, "kagari_dec_spans", k_kt_spans, grid2, KT_THREADS, 0, tokens, token_cap, token_cap, info, blk_span, nblk2);
 	AKOD_LAUNCH(c, "kagari_dec_resolve", k_kt_resolve, n_images, 32, 0, blk_span, nblk2, blk_state, blk_out, info, n_values,
 	            token_cap, d_result);
+	AKOD_BYTES(c, 2 * n_values * n_images + 2 * token_cap * n_images);
 	AKOD_LAUNCH(c, "kagari_dec_expand", k_kt_expand, grid2, KT_THREADS, 0, tokens, token_cap, token_cap, info, blk_state,
 	            blk_out, nblk2, d_out, out_stride, n_values);
 	// Streams that did not self-synchronise within KD_MAX_RUNS (adversarial input) are decoded by one thread

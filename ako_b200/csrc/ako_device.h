@@ -103,6 +103,8 @@ void* akod_mailbox(akodContext*);
 void akod_profile_enable(akodContext*, int enable);
 void akod_profile_reset(akodContext*);
 size_t akod_profile_get(akodContext*, size_t cap, const char** names, uint64_t* launches, double* total_ms);
+/* algorithmic bytes per kernel name, same order as akod_profile_get */
+size_t akod_profile_get_bytes(akodContext*, size_t cap, uint64_t* bytes);
 uint64_t akod_launch_count(akodContext*);
 
 /* ---- stages (all asynchronous on the context's stream) ---- */

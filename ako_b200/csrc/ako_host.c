@@ -554,6 +554,11 @@ AKO_API size_t akoB200ProfileGet(akoB200Context* ctx, size_t cap, const char** n
 	return akod_profile_get(ctx->dev, cap, names, launches, total_ms);
 }
 
+AKO_API size_t akoB200ProfileGetBytes(akoB200Context* ctx, size_t cap, uint64_t* bytes)
+{
+	return akod_profile_get_bytes(ctx->dev, cap, bytes);
+}
+
 AKO_API uint64_t akoB200LaunchCount(akoB200Context* ctx)
 {
 	return akod_launch_count(ctx->dev);

@@ -15,6 +15,7 @@ struct akodProfEntry
 	const char* name;
 	uint64_t launches;
 	double ms;
+	uint64_t bytes; // algorithmic bytes declared by the launchers (AKOD_BYTES), summed over launches
 };
 
 struct akodPending
@@ -34,6 +35,8 @@ struct akodContext
 	// accounting
 	bool profiling;
 	uint64_t launch_count;
+	uint64_t next_bytes; // algorithmic bytes of the next launch (consumed by AKOD_LAUNCH)
+	bool small_attr_done; // cudaFuncSetAttribute for the small-pyramid kernels done on this device
 	std::vector<akodProfEntry> prof;
 	std::vector<akodPending> pending;
 	std::vector<cudaEvent_t> event_pool;
@@ -61,7 +64,7 @@ static inline int akod_prof_entry(akodContext* c, const char* name)
 	for (size_t i = 0; i < c->prof.size(); i++)
 		if (c->prof[i].name == name || strcmp(c->prof[i].name, name) == 0)
 			return (int)i;
-	c->prof.push_back(akodProfEntry{name, 0, 0.0});
+	c->prof.push_back(akodProfEntry{name, 0, 0.0, 0});
 	return (int)c->prof.size() - 1;
 }
 
@@ -78,6 +81,9 @@ static inline cudaEvent_t akod_event_get(akodContext* c)
 	return e;
 }
 
+// Declares the algorithmic bytes of the launch that follows; roofline accounting only.
+#define AKOD_BYTES(ctx, n) ((ctx)->next_bytes = (uint64_t)(n))
+
 // Every kernel of the library is launched through this macro: it counts the launch (always) and,
 // when profiling is enabled, brackets it with CUDA events on the context's stream.
 #define AKOD_LAUNCH(ctx, label, kernel, grid, block, smem, ...)                              \
@@ -86,6 +92,8 @@ static inline cudaEvent_t akod_event_get(akodContext* c)
 		akodContext* akod_l_c = (ctx);                                                       \
 		const int akod_l_e = akod_prof_entry(akod_l_c, label);                               \
 		akod_l_c->prof[akod_l_e].launches++;                                                 \
+		akod_l_c->prof[akod_l_e].bytes += akod_l_c->next_bytes;                              \
+		akod_l_c->next_bytes = 0;                                                            \
 		akod_l_c->launch_count++;                                                            \
 		akodPending akod_l_p;                                                                \
 		if (akod_l_c->profiling)                                                             \

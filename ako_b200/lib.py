@@ -103,6 +103,8 @@ def load():
     L.akoB200ProfileGet.restype = c_size_t
     L.akoB200ProfileGet.argtypes = [c_void_p, c_size_t, C.POINTER(C.c_char_p), C.POINTER(C.c_uint64),
                                     C.POINTER(C.c_double)]
+    L.akoB200ProfileGetBytes.restype = c_size_t
+    L.akoB200ProfileGetBytes.argtypes = [c_void_p, c_size_t, C.POINTER(C.c_uint64)]
     L.akoB200LaunchCount.restype = C.c_uint64
     L.akoB200LaunchCount.argtypes = [c_void_p]
     L.akoB200EncodeBound.restype = c_size_t
@@ -250,6 +252,16 @@ class Context:
         ms = (C.c_double * 64)()
         n = self.L.akoB200ProfileGet(self.h, 64, names, launches, ms)
         return {names[i].decode(): (int(launches[i]), float(ms[i])) for i in range(min(n, 64))}
+
+    def profile_get_bytes(self):
+        """kernel name -> algorithmic bytes its launches moved."""
+        names = (C.c_char_p * 64)()
+        launches = (C.c_uint64 * 64)()
+        ms = (C.c_double * 64)()
+        nbytes = (C.c_uint64 * 64)()
+        n = self.L.akoB200ProfileGet(self.h, 64, names, launches, ms)
+        self.L.akoB200ProfileGetBytes(self.h, 64, nbytes)
+        return {names[i].decode(): int(nbytes[i]) for i in range(min(n, 64))}
 
     def launch_count(self):
         return int(self.L.akoB200LaunchCount(self.h))

@@ -42,6 +42,17 @@ CHANNELS = 4
 L2_BYTES = 126 * 1024 * 1024
 
 
+def _read_traffic():
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            return json.load(f)
+    except Exception:
+        return {}
+
+
+TRAFFIC = _read_traffic()
+
+
 def read_peaks():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -107,6 +118,8 @@ def cpu_measure(workload, jobs_per_core=1, reps=1, cores=None):
 # ------------------------------------------------------------------------------------------------ clocks
 
 class ClockSampler:
+    """SM clock and throttle reasons sampled DURING the timed region: NVML in a thread (5 ms period), or the
+    profiling recipe's nvidia-smi line when pynvml is missing."""
     QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
              "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
@@ -115,8 +128,45 @@ class ClockSampler:
         self.gpu = gpu_index
         self.proc = None
         self.lines = []
+        self.sm, self.reasons, self.mx = [], set(), None
+        self.nvml = None
+        self.stop_flag = False
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            visible = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(visible.split(",")[gpu_index]) if visible and visible.split(",")[gpu_index].isdigit() else gpu_index
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.nvml = pynvml
+        except Exception:
+            self.nvml = None
+
+    def _poll(self):
+        n = self.nvml
+        bits = {"hw_slowdown": n.nvmlClocksThrottleReasonHwSlowdown,
+                "hw_thermal_slowdown": n.nvmlClocksThrottleReasonHwThermalSlowdown,
+                "sw_thermal_slowdown": n.nvmlClocksThrottleReasonSwThermalSlowdown,
+                "sw_power_cap": n.nvmlClocksThrottleReasonSwPowerCap}
+        while not self.stop_flag:
+            try:
+                self.sm.append(float(n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM)))
+                r = n.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle)
+                for name, bit in bits.items():
+                    if r & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(0.002)
 
     def start(self):
+        if self.nvml is not None:
+            try:
+                self.mx = float(self.nvml.nvmlDeviceGetMaxClockInfo(self.handle, self.nvml.NVML_CLOCK_SM))
+            except Exception:
+                self.mx = None
+            self.thread = threading.Thread(target=self._poll, daemon=True)
+            self.thread.start()
+            return
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits",
                                           "-i", str(self.gpu), "-lms", "100"], stdout=subprocess.PIPE,
@@ -131,6 +181,11 @@ class ClockSampler:
             self.lines.append(line.strip())
 
     def stop(self):
+        if self.nvml is not None:
+            self.stop_flag = True
+            self.thread.join(timeout=1)
+            return {"sm_mhz": float(np.median(self.sm)) if self.sm else None, "sm_max_mhz": self.mx,
+                    "reasons": sorted(self.reasons), "samples": len(self.sm), "source": "nvml, 5 ms period, timed region only"}
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
@@ -152,7 +207,7 @@ class ClockSampler:
                 if val.lower().startswith("active"):
                     reasons.add(name)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "source": "nvidia-smi -lms 100"}
 
 
 # ------------------------------------------------------------------------------------------------ ours
@@ -261,29 +316,42 @@ def run_ours(args, rank, world):
     ms_per_step = elapsed_ms / args.steps
     value = px * B * world / (ms_per_step * 1e-3) / 1e6
 
+    # the only cross-rank data of the path: per-image blob sizes, gathered on the host side (ako_b200/shard.py);
+    # global image g = k*world + rank is local image k of this rank
+    from ako_b200 import shard
+    all_sizes = shard.gather_sizes(sizes, B * world, rank, world, dist, f"cuda:{local}")
+    blob_bytes_batch = int(all_sizes.sum())
+
     # ---- e2e: akoEncodeExt / akoDecodeExt with pinned host buffers, copies inside the timed region
     cb = L.akoB200PinnedCallbacks()
     free_fn = C.CFUNCTYPE(None, C.c_void_p)(cb.free)
     sset = settings
 
+    def host_image(idx):
+        """One image through the drop-in API: akoEncodeExt then akoDecodeExt, host buffers in, host buffers out."""
+        src = host_pool[idx % pool_images]
+        out = C.c_void_p()
+        st = C.c_int(0)
+        n = L.akoEncodeExt(C.byref(cb), C.byref(sset), CHANNELS, w, h, src.data_ptr(), C.byref(out), C.byref(st))
+        if n == 0:
+            raise RuntimeError("akoEncodeExt: " + ako_b200.status_string(st.value))
+        ch_, w_, h_ = C.c_size_t(), C.c_size_t(), C.c_size_t()
+        p = L.akoDecodeExt(C.byref(cb), n, out, None, C.byref(ch_), C.byref(w_), C.byref(h_), C.byref(st))
+        if not p:
+            raise RuntimeError("akoDecodeExt: " + ako_b200.status_string(st.value))
+        free_fn(out)
+        free_fn(p)
+        return img_bytes + n, n + img_bytes
+
+    # The C API is re-entrant (one pooled context + stream per concurrent call), so a caller with a batch drives
+    # it from a few threads: H2D of one image overlaps the kernels and the D2H of others.
+    from concurrent.futures import ThreadPoolExecutor
+    host_threads = max(1, min(args.host_threads, B))
+    pool_exec = ThreadPoolExecutor(host_threads)
+
     def step_host(i):
-        h2d = d2h = 0
-        for k in range(B):
-            src = host_pool[(i * B + k) % pool_images]
-            out = C.c_void_p()
-            st = C.c_int(0)
-            n = L.akoEncodeExt(C.byref(cb), C.byref(sset), CHANNELS, w, h, src.data_ptr(), C.byref(out), C.byref(st))
-            if n == 0:
-                raise RuntimeError("akoEncodeExt: " + ako_b200.status_string(st.value))
-            ch_, w_, h_ = C.c_size_t(), C.c_size_t(), C.c_size_t()
-            p = L.akoDecodeExt(C.byref(cb), n, out, None, C.byref(ch_), C.byref(w_), C.byref(h_), C.byref(st))
-            if not p:
-                raise RuntimeError("akoDecodeExt: " + ako_b200.status_string(st.value))
-            free_fn(out)
-            free_fn(p)
-            h2d += img_bytes + n
-            d2h += n + img_bytes
-        return h2d, d2h
+        res = list(pool_exec.map(host_image, range(i * B, i * B + B)))
+        return sum(r[0] for r in res), sum(r[1] for r in res)
 
     e2e_steps = max(1, min(args.steps, 20))
     for i in range(min(args.warmup, 3)):
@@ -294,6 +362,7 @@ def run_ours(args, rank, world):
         h2d, d2h = step_host(i)
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
+    pool_exec.shutdown()
     if dist is not None:
         t = torch.tensor([e2e_s], device=f"cuda:{local}")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -310,23 +379,33 @@ def run_ours(args, rank, world):
     prof = ctx.profile_get()
     ctx.profile(False)
     total_ms = sum(ms for _, ms in prof.values()) or 1.0
+    nbytes = ctx.profile_get_bytes()
     top = max(prof.items(), key=lambda kv: kv[1][1])
     peak, peak_src = read_peaks()
-    lift_names = [k for k in prof if k.startswith("lift_") or k.startswith("unlift_")]
-    dwt_name = max(lift_names, key=lambda k: prof[k][1]) if lift_names else None
-    roofline = None
-    if dwt_name:
-        # every launch of a (un)lift kernel moves 4 B per sample of its level (read once + write once)
-        nl, ms = prof[dwt_name]
-        same_dir = [k for k in lift_names if k.split("_")[0] == dwt_name.split("_")[0]]
-        bytes_all = algorithmic_bytes_lift(w, h, B) * prof_steps
-        ms_all = sum(prof[k][1] for k in same_dir)
-        achieved = bytes_all / (ms_all * 1e-3) / 1e9
-        roofline = {"bound": "hbm", "kernel": "+".join(sorted(same_dir)), "achieved": round(achieved, 1),
-                    "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4), "traffic": None,
-                    "peak_source": peak_src, "launches": sum(prof[k][0] for k in same_dir),
-                    "share_of_step": round(ms_all / total_ms, 4),
-                    "algorithmic_bytes_per_step": bytes_all // prof_steps}
+
+    def roof(name):
+        """achieved = algorithmic bytes per launch / average launch duration (CUDA events on the library's stream)."""
+        nl, ms = prof[name]
+        if not nbytes.get(name) or ms <= 0:
+            return None
+        achieved = nbytes[name] / (ms * 1e-3) / 1e9
+        r = {"bound": "hbm", "kernel": name, "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
+             "frac": round(achieved / peak, 4), "traffic": None, "peak_source": peak_src,
+             "launches_per_step": nl // prof_steps, "share_of_step": round(ms / total_ms, 4),
+             "algorithmic_bytes_per_launch": nbytes[name] // max(nl, 1),
+             "avg_launch_us": round(ms * 1e3 / max(nl, 1), 2)}
+        cap = TRAFFIC.get(name)
+        if cap:
+            # dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full capture of this kernel, scaled from the
+            # captured launch's algorithmic bytes to this run's average launch
+            r["traffic"] = int(cap["dram_bytes"] * r["algorithmic_bytes_per_launch"] / cap["algorithmic_bytes"])
+            r["traffic_source"] = cap["source"]
+        return r
+
+    with_bytes = [k for k in prof if nbytes.get(k)]
+    dominant = max(with_bytes, key=lambda k: prof[k][1]) if with_bytes else None
+    roofline = roof(dominant) if dominant else None
+    roofline_all = [r for r in (roof(k) for k in sorted(with_bytes, key=lambda k: -prof[k][1])[:8]) if r]
     kernels = {k: {"launches": v[0] // prof_steps, "ms_per_step": round(v[1] / prof_steps, 4)}
                for k, v in sorted(prof.items(), key=lambda kv: -kv[1][1])}
 
@@ -352,12 +431,14 @@ def run_ours(args, rank, world):
                        "parallelism": f"{world} independent shards, no collective on the data path",
                        "step": "akoB200EncodeBatchDevice + akoB200DecodeBatchDevice, device resident"},
             "bit_exact_vs_oracle": bit_exact,
+            "blob_bytes_per_step": blob_bytes_batch,
             "clocks": clocks,
             "e2e": {"value": round(e2e_value, 1), "unit": "MPix/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "api": "akoEncodeExt + akoDecodeExt, pinned host buffers (akoB200PinnedCallbacks)",
+                    "api": f"akoEncodeExt + akoDecodeExt, pinned host buffers (akoB200PinnedCallbacks), {host_threads} caller threads",
                     "steps": e2e_steps},
             "gpu_launches": int(launches),
             "roofline": roofline,
+            "roofline_other_kernels": roofline_all[1:] if roofline_all else [],
             "top_kernel": {"name": top[0], "share_of_step": round(top[1][1] / total_ms, 4)},
             "kernels": kernels,
             "cpu_baseline": cpu,
@@ -448,6 +529,7 @@ def run_reference(args, rank, world):
 
 
 def main():
+    sys.setswitchinterval(0.0005)  # let the clock-sampling thread run between the ctypes calls of the timed loop
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
@@ -456,6 +538,7 @@ def main():
     ap.add_argument("--workload", default="c2", choices=list(WORKLOADS) + ["dwt"])
     ap.add_argument("--batch", type=int, default=8, help="images per step per GPU")
     ap.add_argument("--cpu-reps", type=int, default=1)
+    ap.add_argument("--host-threads", type=int, default=4, help="caller threads of the end-to-end (host pointer) leg")
     ap.add_argument("--dwt-size", type=int, default=8192)
     ap.add_argument("--dwt-wavelets", default="cdf53,dd137,haar")
     ap.add_argument("--skip-cpu", action="store_true", help="profiling runs: do not time the CPU reference")

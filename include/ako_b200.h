@@ -50,6 +50,9 @@ void akoB200ProfileEnable(akoB200Context*, int enable);
 void akoB200ProfileReset(akoB200Context*);
 /* number of distinct kernels seen; fills up to cap entries. names[i] points at static strings. */
 size_t akoB200ProfileGet(akoB200Context*, size_t cap, const char** names, uint64_t* launches, double* total_ms);
+/* Algorithmic bytes (compulsory reads + writes) the launches of each kernel name moved, in the
+ * order of akoB200ProfileGet; accounted whether or not timing is enabled. */
+size_t akoB200ProfileGetBytes(akoB200Context*, size_t cap, uint64_t* bytes);
 uint64_t akoB200LaunchCount(akoB200Context*);
 
 /* ---- whole codec, device resident ---------------------------------------------------- */

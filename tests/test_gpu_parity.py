@@ -335,3 +335,16 @@ def test_big_lossless_roundtrip_property(wavelet):
     assert st == 0
     out, st, _ = ako_b200.decode(blob)
     assert st == 0 and np.array_equal(out, img)
+
+
+def test_c5_lossless_16384_known_answer_and_roundtrip():
+    """BASELINE configs[4]: 16384x16384 RGBA8, CDF 5/3, q=0 g=0, one tile, one 3.66 Gbit entropy stream.
+    Known answer from the unmodified reference + exact round trip."""
+    orc = ol.load_oracle()
+    w, h, wavelet, q, g, seed, size, blob_sha, _ = KATS_BIG[3]
+    img = ol.synth(orc, w, h, seed)
+    blob, st = ako_b200.encode(img, S(wavelet=wavelet, q=q, g=g))
+    assert st == 0 and len(blob) == size
+    assert sha(blob) == blob_sha
+    out, st, _ = ako_b200.decode(blob)
+    assert st == 0 and np.array_equal(out, img)
