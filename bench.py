@@ -238,6 +238,8 @@ def run_ours(args, rank, world):
     if world > 1:
         import torch.distributed as dist_
         dist = dist_
+        # keep stdout for the one JSON line: NCCL's version / debug lines go to stderr
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
     w, h, wavelet, q, g, seed0, text = WORKLOADS[args.workload]
