@@ -737,6 +737,9 @@ extern "C" int akod_kagari_decode(akodContext* c, uint64_t n_values, const uint8
 	const size_t o_span = carve(sizeof(KtSpan) * nblk2 * n_images);
 	const size_t o_state = carve(sizeof(uint32_t) * nblk2 * n_images);
 	const size_t o_out = carve(sizeof(uint64_t) * nblk2 * n_images);
+	const uint32_t big_cap = (uint32_t)(n_values / KT_BIG) + 16;
+	const size_t o_big = carve(sizeof(KtRun) * (size_t)big_cap * n_images);
+	const size_t o_bigc = carve(sizeof(uint32_t) * n_images);
 	void* ws;
 	int rc = akod_workspace(c, AKOD_WS_KAGARI, bytes, &ws);
 	if (rc != AKOD_OK)
@@ -752,7 +755,10 @@ extern "C" int akod_kagari_decode(akodContext* c, uint64_t n_values, const uint8
 	KtSpan* blk_span = (KtSpan*)(w8 + o_span);
 	uint32_t* blk_state = (uint32_t*)(w8 + o_state);
 	uint64_t* blk_out = (uint64_t*)(w8 + o_out);
+	KtRun* big_list = (KtRun*)(w8 + o_big);
+	uint32_t* big_count = (uint32_t*)(w8 + o_bigc);
 
+	AKOD_TRY(cudaMemsetAsync(big_count, 0, sizeof(uint32_t) * n_images, c->stream));
 	AKOD_LAUNCH(c, "kagari_dec_init", k_kd_init, (n_images + 63) / 64, 64, 0, info, n_images);
 	const dim3 grid1(nblk1, n_images);
 	for (int run = 0; run < KD_MAX_RUNS; run++)
@@ -769,9 +775,17 @@ extern "C" int akod_kagari_decode(akodContext* c, uint64_t n_values, const uint8
 	AKOD_LAUNCH(c, "kagari_dec_spans", k_kt_spans, grid2, KT_THREADS, 0, tokens, token_cap, token_cap, info, blk_span, nblk2);
 	AKOD_LAUNCH(c, "kagari_dec_resolve", k_kt_resolve, n_images, 32, 0, blk_span, nblk2, blk_state, blk_out, info, n_values,
 	            token_cap, d_result);
-	AKOD_BYTES(c, 2 * n_values * n_images + 2 * token_cap * n_images);
 	AKOD_LAUNCH(c, "kagari_dec_expand", k_kt_expand, grid2, KT_THREADS, 0, tokens, token_cap, token_cap, info, blk_state,
-	            blk_out, nblk2, d_out, out_stride, n_values);
+	            blk_out, nblk2, d_out, out_stride, n_values, big_list, big_count, big_cap);
+	{
+		// enough warps to saturate HBM with stores, whatever the number of big runs turns out to be
+		const uint64_t pieces_max = (uint64_t)big_cap;
+		const uint32_t want = (uint32_t)c->sm_count * 8;
+		const uint32_t gx = (uint32_t)((pieces_max + 7) / 8 < want ? (pieces_max + 7) / 8 : want);
+		const dim3 gridf(gx ? gx : 1, n_images);
+		AKOD_BYTES(c, 2 * n_values * n_images);
+		AKOD_LAUNCH(c, "kagari_dec_fill", k_kt_fill, gridf, 256, 0, big_list, big_count, big_cap, d_out, out_stride);
+	}
 	// Streams that did not self-synchronise within KD_MAX_RUNS (adversarial input) are decoded by one thread
 	// on the device; a no-op for every other image.
 	AKOD_LAUNCH(c, "kagari_dec_rescue", k_kd_sequential, n_images, 32, 0, d_in, d_off, d_size, n_values, d_out, out_stride,

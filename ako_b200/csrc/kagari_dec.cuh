@@ -646,12 +646,17 @@ struct KtRun
 	int16_t value;
 };
 
-// pass C: classify every token and write what it expands to
+constexpr uint32_t KT_BIG = 2048;   // runs at least this long leave the CTA: they go to a list that k_kt_fill spreads over the GPU
+constexpr uint32_t KT_PIECE = 4096; // ... in pieces of at most this many values (one warp each)
+
+// pass C: classify every token and write what it expands to. Quantised planes are mostly a few very long
+// runs; whichever CTA meets their tokens would have to write megabytes alone, so those runs are only
+// recorded here (big_list, at most n_values / KT_BIG pieces per image) and written by k_kt_fill.
 __global__ void __launch_bounds__(KT_THREADS)
     k_kt_expand(const uint16_t* __restrict__ tokens, uint64_t token_stride, uint64_t token_cap,
                 const KdImage* __restrict__ info, const uint32_t* __restrict__ blk_state,
                 const uint64_t* __restrict__ blk_out, uint32_t nblk, int16_t* __restrict__ out_base, uint64_t out_stride,
-                uint64_t n_values)
+                uint64_t n_values, KtRun* __restrict__ big_list, uint32_t* __restrict__ big_count, uint32_t big_cap)
 {
 	__shared__ KtSpan sm[33];
 	__shared__ KtRun queue[KT_BLOCK / 2];
@@ -688,7 +693,21 @@ __global__ void __launch_bounds__(KT_THREADS)
 				const int16_t v = kt_value(u[j + 1]);
 				if (pos + count <= n_values)
 				{
-					if (count >= KT_LONG)
+					if (count >= KT_BIG)
+					{
+						const uint32_t pieces = (count + KT_PIECE - 1) / KT_PIECE;
+						const uint32_t first = atomicAdd(&big_count[img], pieces);
+						for (uint32_t k = 0; k < pieces; k++)
+							if (first + k < big_cap) // cannot overflow for a stream that expands to n_values
+							{
+								KtRun r;
+								r.pos = pos + (uint64_t)k * KT_PIECE;
+								r.count = min(KT_PIECE, count - k * KT_PIECE);
+								r.value = v;
+								big_list[(uint64_t)big_cap * img + first + k] = r;
+							}
+					}
+					else if (count >= KT_LONG)
 					{
 						const uint32_t slot = atomicAdd(&queue_len, 1u);
 						queue[slot].pos = pos;
@@ -716,4 +735,21 @@ __global__ void __launch_bounds__(KT_THREADS)
 	const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
 	for (uint32_t i = wid; i < nq; i += KT_THREADS / 32)
 		kt_fill_warp(out, queue[i].pos, queue[i].count, queue[i].value, lane);
+}
+
+// pass D: the big runs, one warp per piece, spread over the whole GPU
+__global__ void __launch_bounds__(256)
+    k_kt_fill(const KtRun* __restrict__ big_list, const uint32_t* __restrict__ big_count, uint32_t big_cap,
+              int16_t* __restrict__ out_base, uint64_t out_stride)
+{
+	const uint32_t img = blockIdx.y;
+	const uint32_t n = min(big_count[img], big_cap);
+	const uint32_t warps = gridDim.x * (blockDim.x >> 5);
+	const int lane = threadIdx.x & 31;
+	int16_t* out = out_base + out_stride * img;
+	for (uint32_t i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); i < n; i += warps)
+	{
+		const KtRun r = big_list[(uint64_t)big_cap * img + i];
+		kt_fill_warp(out, r.pos, r.count, r.value, lane);
+	}
 }
