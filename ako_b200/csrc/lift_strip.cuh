@@ -43,7 +43,7 @@ constexpr int FS_XW = 2 * FS_TW + 16;  // staged samples per row (8 halo samples
 constexpr int FS_XP = 280;             // X row pitch in elements: 140 words, 140 mod 32 = 12 -> conflict-free LDS.128 by row
 constexpr int FS_HP = 264;             // [L x128 | H x128] row pitch: 132 words, 132 mod 32 = 4 -> conflict-free STS.128 by row
 constexpr int FS_XBUF = FS_ROWS * FS_XP;
-constexpr int FS_STAGES = 3;           // staged input buffers: loads run two steps ahead of the arithmetic
+constexpr int FS_STAGES = 2;           // staged input buffers: loads run one step ahead of the arithmetic
 
 template <int WL>
 struct StripGeom
@@ -414,7 +414,7 @@ __global__ void __launch_bounds__(FS_THREADS, 6) k_lift_strip(const StripParams 
 	const LiftParams& p = sp.p;
 
 	__shared__ __align__(16) int16_t X[FS_STAGES * FS_XBUF];
-	__shared__ __align__(16) int16_t HB[FS_ROWS * FS_HP];
+	__shared__ __align__(16) int16_t HB[2 * FS_ROWS * FS_HP]; // double buffered: one barrier per step
 	__shared__ __align__(8) uint64_t bars[FS_STAGES];
 
 	const int tid = threadIdx.x;
@@ -509,10 +509,11 @@ __global__ void __launch_bounds__(FS_THREADS, 6) k_lift_strip(const StripParams 
 			issue(j_first + i * FS_STEP, i);
 	__syncthreads(); // edge fills of the first buffers
 
-	int buf = 0, nbuf = FS_STAGES - 1;
+	int buf = 0, nbuf = FS_STAGES - 1, hb = 0;
 	uint32_t phase = 0;
 	for (int js = j_first; js < j_last; js += FS_STEP)
 	{
+		int16_t* const HBs = HB + hb * (FS_ROWS * FS_HP);
 		// buffer nbuf was last read by the H pass of the previous step, which every thread has left
 		if (js + (FS_STAGES - 1) * FS_STEP < j_last)
 			issue(js + (FS_STAGES - 1) * FS_STEP, nbuf);
@@ -538,8 +539,8 @@ __global__ void __launch_bounds__(FS_THREADS, 6) k_lift_strip(const StripParams 
 				}
 				uint32_t lw[8], hw[8];
 				strip_hpass<WL>(w, c0 + a == 0, tw - (c0 + a), lw, hw);
-				uint4* dl = reinterpret_cast<uint4*>(&HB[r * FS_HP + a]);
-				uint4* dh = reinterpret_cast<uint4*>(&HB[r * FS_HP + FS_TW + a]);
+				uint4* dl = reinterpret_cast<uint4*>(&HBs[r * FS_HP + a]);
+				uint4* dh = reinterpret_cast<uint4*>(&HBs[r * FS_HP + FS_TW + a]);
 				dl[0] = make_uint4(lw[0], lw[1], lw[2], lw[3]);
 				dl[1] = make_uint4(lw[4], lw[5], lw[6], lw[7]);
 				dh[0] = make_uint4(hw[0], hw[1], hw[2], hw[3]);
@@ -551,7 +552,7 @@ __global__ void __launch_bounds__(FS_THREADS, 6) k_lift_strip(const StripParams 
 		// ---------------- V pass: marching, state in registers
 		if (vvalid)
 		{
-			const uint32_t* col = reinterpret_cast<const uint32_t*>(HB) + tid;
+			const uint32_t* col = reinterpret_cast<const uint32_t*>(HBs) + tid;
 			const int i0 = js - LAT; // output row of this step's first input row
 			// all eight output rows inside [i_begin, i_end) and no boundary rule fires in this step
 			const bool interior = (i0 >= i_begin) && (i0 + FS_STEP <= i_end) && (js > LAT) && (js + FS_STEP <= th);
@@ -602,7 +603,10 @@ __global__ void __launch_bounds__(FS_THREADS, 6) k_lift_strip(const StripParams 
 			else
 				vstep(std::true_type{});
 		}
-		__syncthreads(); // HB is rewritten by the next step; X[buf] by the load issued in the next step
+		// No barrier here: the next step's H pass writes the other HB buffer; this one is rewritten two steps on,
+		// behind the next step's barrier. X[buf] is reloaded by the issue() at the top of the next step -- every
+		// thread has left this step's H pass (it is behind the barrier above) by then.
+		hb ^= 1;
 		nbuf = buf;
 		if (++buf == FS_STAGES)
 		{

@@ -256,7 +256,7 @@ __global__ void __launch_bounds__(UT_THREADS, 6) k_unlift_strip(const UnstripPar
 	const UnliftParams& p = up.p;
 
 	__shared__ __align__(16) int16_t S[2 * UT_SBUF];            // staged LL, C, B, D rows, two stages
-	__shared__ __align__(16) int16_t VB[2 * UT_STEP * UT_VP];   // vertically reconstructed rows
+	__shared__ __align__(16) int16_t VB[2 * 2 * UT_STEP * UT_VP]; // vertically reconstructed rows, double buffered
 	__shared__ __align__(8) uint64_t bars[2];
 
 	const int tid = threadIdx.x;
@@ -336,6 +336,7 @@ __global__ void __launch_bounds__(UT_THREADS, 6) k_unlift_strip(const UnstripPar
 	uint32_t phase = 0;
 	for (int js = j_first; js < j_last; js += UT_STEP)
 	{
+		int16_t* const VBs = VB + buf * (2 * UT_STEP * UT_VP);
 		if (js + UT_STEP < j_last)
 			issue(js + UT_STEP, buf ^ 1);
 		mbar_wait(&bars[buf], phase);
@@ -345,7 +346,7 @@ __global__ void __launch_bounds__(UT_THREADS, 6) k_unlift_strip(const UnstripPar
 			const uint32_t* sb = reinterpret_cast<const uint32_t*>(S + buf * UT_SBUF);
 			const uint32_t* plo = sb + (lo_band * UT_STEP) * (UT_SP / 2) + (right_side ? hp_word : 2 + vt);
 			const uint32_t* phi = sb + (hi_band * UT_STEP) * (UT_SP / 2) + hp_word;
-			uint32_t* vb = reinterpret_cast<uint32_t*>(VB) + tid;
+			uint32_t* vb = reinterpret_cast<uint32_t*>(VBs) + tid;
 			const bool interior = (js - LAT > 0) && (js + UT_STEP <= hh);
 
 			auto vstep = [&](auto edge_tag, auto quant_tag) {
@@ -402,10 +403,10 @@ __global__ void __launch_bounds__(UT_THREADS, 6) k_unlift_strip(const UnstripPar
 			if (r < 2 * UT_STEP && c0 + a < hw && (uint32_t)(cr - i_begin) < (uint32_t)(i_end - i_begin) && oy < p.th)
 			{
 				// VB columns [a, a+16) hold coefficients c = c0 + a - 4 + k
-				const uint4 l0 = *reinterpret_cast<const uint4*>(&VB[r * UT_VP + a]);
-				const uint4 l1 = *reinterpret_cast<const uint4*>(&VB[r * UT_VP + a + 8]);
-				const uint4 g0 = *reinterpret_cast<const uint4*>(&VB[r * UT_VP + 128 + a]);
-				const uint4 g1 = *reinterpret_cast<const uint4*>(&VB[r * UT_VP + 128 + a + 8]);
+				const uint4 l0 = *reinterpret_cast<const uint4*>(&VBs[r * UT_VP + a]);
+				const uint4 l1 = *reinterpret_cast<const uint4*>(&VBs[r * UT_VP + a + 8]);
+				const uint4 g0 = *reinterpret_cast<const uint4*>(&VBs[r * UT_VP + 128 + a]);
+				const uint4 g1 = *reinterpret_cast<const uint4*>(&VBs[r * UT_VP + 128 + a + 8]);
 				const uint32_t lw[8] = {l0.x, l0.y, l0.z, l0.w, l1.x, l1.y, l1.z, l1.w};
 				uint32_t gw[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
 				uint32_t w[8];
@@ -415,7 +416,10 @@ __global__ void __launch_bounds__(UT_THREADS, 6) k_unlift_strip(const UnstripPar
 				dst[1] = make_uint4(w[4], w[5], w[6], w[7]);
 			}
 		}
-		__syncthreads(); // VB is rewritten by the next step; S[buf] by the load issued in the next step
+		// No barrier here: the next step's V pass writes the other VB buffer. S[buf] is reloaded by the issue() of
+		// the next step, whose V pass (reading S[buf^1]) every thread enters only after leaving this step's V pass;
+		// the loads into S[buf] are issued by warp 0 after IT has left this step's V pass, and all other warps
+		// left it before the barrier above.
 		buf ^= 1;
 		if (buf == 0)
 			phase ^= 1u;
