@@ -672,13 +672,14 @@ extern "C" int akod_kagari_encode(akodContext* c, uint64_t n_values, const int16
 		            nblocks, d_out, out_stride, out_cap * 8, d_bits);
 		return AKOD_OK;
 	}
-	const size_t need = (size_t)per_img * n_images * (sizeof(uint64_t) + 2 * sizeof(uint32_t)) + 64;
+	const size_t need = (size_t)per_img * n_images * (sizeof(uint64_t) + 2 * sizeof(uint32_t) + sizeof(uint32_t) * KG_SLOT_WORDS) + 64;
 	int rc = akod_workspace(c, AKOD_WS_KAGARI, need, &ws);
 	if (rc != AKOD_OK)
 		return rc;
 	uint64_t* blk_off = (uint64_t*)ws;
 	uint32_t* blk_start = (uint32_t*)(blk_off + per_img * n_images);
 	uint32_t* blk_bits = blk_start + per_img * n_images;
+	uint32_t* slots = blk_bits + per_img * n_images; // KG_SLOT_WORDS per block
 
 	const dim3 grid(nblocks, n_images);
 	AKOD_BYTES(c, 2 * n_values * n_images);
@@ -686,14 +687,14 @@ extern "C" int akod_kagari_encode(akodContext* c, uint64_t n_values, const int16
 	AKOD_LAUNCH(c, "kagari_scan_max", k_kg_scan_max, n_images, 1024, 0, blk_start, nblocks);
 	AKOD_BYTES(c, 2 * n_values * n_images);
 	AKOD_LAUNCH(c, "kagari_lengths", k_kg_lengths, grid, KG_THREADS, 0, d_in, in_stride, n_values, blk_start, blk_bits,
-	            nblocks);
+	            nblocks, slots);
 	AKOD_LAUNCH(c, "kagari_scan_sum", k_kg_scan_sum, n_images, 1024, 0, blk_bits, blk_off, nblocks, d_bits);
 	const dim3 zgrid((nblocks + 255) / 256, n_images);
 	AKOD_LAUNCH(c, "kagari_zero_edges", k_kg_zero_edges, zgrid, 256, 0, blk_off, blk_bits, nblocks, d_out, out_stride,
 	            out_cap * 8);
 	AKOD_BYTES(c, 2 * n_values * n_images); // + the blob bytes, not known on the host
 	AKOD_LAUNCH(c, "kagari_pack", k_kg_pack, grid, KG_THREADS, 0, d_in, in_stride, n_values, blk_start, blk_off, blk_bits,
-	            nblocks, d_out, out_stride, out_cap * 8);
+	            nblocks, d_out, out_stride, out_cap * 8, slots);
 	return AKOD_OK;
 }
 

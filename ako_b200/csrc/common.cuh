@@ -245,3 +245,29 @@ __device__ __forceinline__ uint32_t block_excl_max_u32(uint32_t v, uint32_t* sm,
 	__syncthreads();
 	return r;
 }
+
+// Block-wide "last nonzero value of the threads before me" for values that are non-decreasing in thread order
+// wherever they are nonzero (run starts carried as index + 1), which makes it an exclusive max: one ballot and one
+// shuffle per warp instead of a five-step scan. *total = last nonzero value of the block. sm: 33 uint32.
+__device__ __forceinline__ uint32_t block_excl_last_start(uint32_t v, uint32_t* sm, uint32_t* total)
+{
+	const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+	const uint32_t mask = __ballot_sync(AKOD_FULL_MASK, v != 0);
+	const uint32_t lower = mask & ((1u << lane) - 1u);
+	const uint32_t from_lower = __shfl_sync(AKOD_FULL_MASK, v, lower ? 31 - __clz(lower) : 0);
+	const uint32_t warp_last = __shfl_sync(AKOD_FULL_MASK, v, mask ? 31 - __clz(mask) : 0);
+	if (lane == 0)
+		sm[wid] = mask ? warp_last : 0u;
+	__syncthreads();
+	uint32_t carry = 0, all = 0;
+	for (int w = 0; w < nw; w++)
+	{
+		const uint32_t x = sm[w];
+		all = max(all, x);
+		if (w < wid)
+			carry = max(carry, x);
+	}
+	*total = all;
+	__syncthreads();
+	return lower ? from_lower : carry;
+}

@@ -57,7 +57,9 @@ __device__ __forceinline__ KgCode kg_value(int16_t x)
 // the whole bit string of one element; k = position in run, last = (next differs or end of stream)
 __device__ __forceinline__ KgCode kg_element(int16_t a, uint32_t k, bool last)
 {
-	uint32_t c = (k == 0) ? 0u : ((k - 1) % 65534u) + 1u;
+	uint32_t c = k; // run counter: 0 for the first element of a run, then 1..65534 cyclically
+	if (k > 65534u)
+		c = ((k - 1) % 65534u) + 1u;
 	KgCode out;
 	out.code = 0;
 	out.len = 0;
@@ -88,39 +90,75 @@ struct KgChunk
 	uint32_t last_start; // (index + 1) of the last run start inside the chunk, 0 if none
 };
 
+// Must be called by whole warps (neighbouring values travel by shuffle): thread t of a warp holds the 8 values
+// that follow those of thread t-1.
 __device__ __forceinline__ KgChunk kg_load(const int16_t* __restrict__ in, uint64_t n, uint64_t base)
 {
 	KgChunk c;
-	c.valid = 0;
-	if (base + KG_ITEMS <= n)
+	const int lane = threadIdx.x & 31;
+	uint32_t w[4] = {0, 0, 0, 0};
+	const bool full = base + KG_ITEMS <= n;
+	if (full)
 	{
 		// 128-bit load: base is a multiple of 8 and the stream is 16-byte aligned
-		*reinterpret_cast<uint4*>(c.v) = __ldg(reinterpret_cast<const uint4*>(in + base));
-		c.valid = KG_ITEMS;
+		const uint4 q = __ldg(reinterpret_cast<const uint4*>(in + base));
+		w[0] = q.x;
+		w[1] = q.y;
+		w[2] = q.z;
+		w[3] = q.w;
 	}
-	else
+	// the value before / after the chunk comes from the neighbouring lane when that lane holds a full chunk
+	uint32_t before = __shfl_up_sync(AKOD_FULL_MASK, w[3], 1) >> 16;
+	uint32_t after = __shfl_down_sync(AKOD_FULL_MASK, w[0], 1) & 0xFFFFu;
+	const bool next_full = base + 2 * KG_ITEMS <= n;
+	const bool has_before = base > 0 && base <= n;
+	c.has_after = base + KG_ITEMS < n;
+	if (lane == 0 || !full)
+		before = has_before ? (uint32_t)(uint16_t)__ldg(in + base - 1) : 0u;
+	if (lane == 31 || !next_full)
+		after = c.has_after ? (uint32_t)(uint16_t)__ldg(in + base + KG_ITEMS) : 0u;
+	c.after = (int16_t)after;
+
+	if (full)
 	{
+		*reinterpret_cast<uint4*>(c.v) = make_uint4(w[0], w[1], w[2], w[3]);
+		c.valid = KG_ITEMS;
+		// element j differs from its predecessor <=> half j of (w ^ w shifted by one element) is nonzero
+		uint32_t mask = 0;
+		uint32_t prev_word = before << 16;
 #pragma unroll
-		for (int j = 0; j < KG_ITEMS; j++)
+		for (int i = 0; i < 4; i++)
 		{
-			c.v[j] = 0;
-			if (base + j < n)
-			{
-				c.v[j] = in[base + j];
-				c.valid = j + 1;
-			}
+			const uint32_t d = w[i] ^ __funnelshift_l(prev_word, w[i], 16);
+			mask |= ((d & 0xFFFFu) ? 1u : 0u) << (2 * i);
+			mask |= ((d >> 16) ? 1u : 0u) << (2 * i + 1);
+			prev_word = w[i];
+		}
+		if (!has_before)
+			mask |= 1u; // element 0 of the stream starts a run
+		c.start_mask = mask;
+		c.last_start = mask ? (uint32_t)base + (31 - __clz(mask)) + 1u : 0u;
+		return c;
+	}
+
+	c.valid = 0;
+#pragma unroll
+	for (int j = 0; j < KG_ITEMS; j++)
+	{
+		c.v[j] = 0;
+		if (base + j < n)
+		{
+			c.v[j] = in[base + j];
+			c.valid = j + 1;
 		}
 	}
-	const bool has_before = base > 0 && base <= n;
-	const int16_t before = has_before ? __ldg(in + base - 1) : (int16_t)0;
-	c.has_after = base + KG_ITEMS < n;
-	c.after = c.has_after ? __ldg(in + base + KG_ITEMS) : (int16_t)0;
 	c.start_mask = 0;
 	c.last_start = 0;
 #pragma unroll
 	for (int j = 0; j < KG_ITEMS; j++)
 	{
-		const bool start = (j < c.valid) && ((j == 0) ? (!has_before || c.v[0] != before) : (c.v[j] != c.v[j - 1]));
+		const bool start =
+		    (j < c.valid) && ((j == 0) ? (!has_before || c.v[0] != (int16_t)before) : (c.v[j] != c.v[j - 1]));
 		if (start)
 		{
 			c.start_mask |= 1u << j;
@@ -141,7 +179,7 @@ __global__ void __launch_bounds__(KG_THREADS)
 	const uint64_t base = (uint64_t)blockIdx.x * KG_BLOCK + (uint64_t)threadIdx.x * KG_ITEMS;
 	const KgChunk c = kg_load(in, n, base);
 	uint32_t total;
-	block_excl_max_u32(c.last_start, sm, &total);
+	block_excl_last_start(c.last_start, sm, &total);
 	if (threadIdx.x == 0)
 		blk_start[blockIdx.x] = total;
 }
@@ -157,7 +195,7 @@ __global__ void __launch_bounds__(1024) k_kg_scan_max(uint32_t* __restrict__ blk
 		const uint32_t b = b0 + threadIdx.x;
 		const uint32_t v = (b < nblocks) ? blk[b] : 0;
 		uint32_t total;
-		const uint32_t ex = block_excl_max_u32(v, sm, &total);
+		const uint32_t ex = block_excl_last_start(v, sm, &total);
 		if (b < nblocks)
 			blk[b] = max(carry, ex);
 		carry = max(carry, total);
@@ -199,7 +237,7 @@ __device__ __forceinline__ uint32_t kg_thread_codes(const KgChunk& c, uint64_t n
 {
 	// run start reaching into this thread = max(block carry, starts of earlier threads); all are (index + 1)
 	uint32_t dummy;
-	const uint32_t run_start = max(carry_start, block_excl_max_u32(c.last_start, sm_max, &dummy));
+	const uint32_t run_start = max(carry_start, block_excl_last_start(c.last_start, sm_max, &dummy));
 	return kg_codes<EMIT>(c, n, base, run_start, codes);
 }
 
@@ -223,7 +261,9 @@ __device__ __forceinline__ uint32_t kg_codes(const KgChunk& c, uint64_t n, uint6
 	if (c.valid == KG_ITEMS && c.start_mask == 0 && c.has_after && c.after == c.v[KG_ITEMS - 1])
 	{
 		const uint32_t k0 = (uint32_t)base + 1u - run_start; // position of v[0] in its run (>= 1)
-		const uint32_t c0 = ((k0 - 1) % 65534u) + 1u;
+		uint32_t c0 = k0;
+		if (k0 > 65534u)
+			c0 = ((k0 - 1) % 65534u) + 1u;
 		if (c0 >= 3 && c0 + (KG_ITEMS - 1) < 65534u)
 			return 0; // the run counter stays strictly between 2 and 65534: nothing is emitted
 	}
@@ -247,22 +287,62 @@ __device__ __forceinline__ uint32_t kg_codes(const KgChunk& c, uint64_t n, uint6
 	return bits;
 }
 
-// pass 2: bits emitted by each block
+// Every block owns a slot of KG_SLOT_WORDS words in a scratch buffer: pass 2 leaves the block's bit string there
+// (packed from bit 0) when it fits, and pass 3 only has to shift it into place. Blocks whose string is longer
+// (more than 8 bits per value on average) are re-encoded by pass 3 as before.
+constexpr uint32_t KG_SLOT_WORDS = KG_BLOCK / 4;
+constexpr uint32_t KG_SLOT_BITS = KG_SLOT_WORDS * 32;
+
+// ORs the codes of one thread into a shared-memory bit buffer; 'pos' is the bit position of the first code
+__device__ __forceinline__ void kg_put_codes(uint32_t* bitbuf, uint32_t pos, const KgCode codes[KG_ITEMS])
+{
+#pragma unroll
+	for (int j = 0; j < KG_ITEMS; j++)
+	{
+		const uint32_t len = codes[j].len;
+		if (len)
+		{
+			const uint32_t w = pos >> 5, sh = pos & 31;
+			// MSB-first: bit 'pos' of the stream is bit (31 - pos%32) of word pos/32
+			const uint64_t wide = (uint64_t)codes[j].code << (64 - sh - len);
+			atomicOr(&bitbuf[w], (uint32_t)(wide >> 32));
+			if (sh + len > 32)
+				atomicOr(&bitbuf[w + 1], (uint32_t)wide);
+			pos += len;
+		}
+	}
+}
+
+// pass 2: bits emitted by each block (+ the bit string itself into the block's slot when it fits)
 __global__ void __launch_bounds__(KG_THREADS)
     k_kg_lengths(const int16_t* __restrict__ in, uint64_t in_stride, uint64_t n, const uint32_t* __restrict__ blk_carry,
-                 uint32_t* __restrict__ blk_bits, uint32_t nblocks)
+                 uint32_t* __restrict__ blk_bits, uint32_t nblocks, uint32_t* __restrict__ slots)
 {
 	__shared__ uint32_t sm_max[33];
 	__shared__ uint32_t sm_sum[33];
+	__shared__ uint32_t bitbuf[KG_SLOT_WORDS + 2];
 	in += in_stride * blockIdx.y;
 	const uint64_t base = (uint64_t)blockIdx.x * KG_BLOCK + (uint64_t)threadIdx.x * KG_ITEMS;
 	const KgChunk c = kg_load(in, n, base);
+	KgCode codes[KG_ITEMS];
 	const uint32_t bits =
-	    kg_thread_codes<false>(c, n, base, blk_carry[(uint64_t)nblocks * blockIdx.y + blockIdx.x], sm_max, nullptr);
+	    kg_thread_codes<true>(c, n, base, blk_carry[(uint64_t)nblocks * blockIdx.y + blockIdx.x], sm_max, codes);
 	uint32_t total;
-	block_excl_sum(bits, sm_sum, &total);
+	const uint32_t excl = block_excl_sum(bits, sm_sum, &total);
 	if (threadIdx.x == 0)
 		blk_bits[(uint64_t)nblocks * blockIdx.y + blockIdx.x] = total;
+	if (total == 0 || total > KG_SLOT_BITS)
+		return;
+	const uint32_t nwords = (total + 31) >> 5;
+	for (uint32_t i = threadIdx.x; i < nwords + 1; i += KG_THREADS)
+		bitbuf[i] = 0;
+	__syncthreads();
+	if (bits)
+		kg_put_codes(bitbuf, excl, codes);
+	__syncthreads();
+	uint32_t* slot = slots + ((uint64_t)nblocks * blockIdx.y + blockIdx.x) * KG_SLOT_WORDS;
+	for (uint32_t i = threadIdx.x; i < nwords; i += KG_THREADS)
+		slot[i] = bitbuf[i];
 }
 
 // clears the (up to two) 32-bit words each block shares with its neighbours, and the final word
@@ -286,7 +366,7 @@ __global__ void __launch_bounds__(256)
 __global__ void __launch_bounds__(KG_THREADS)
     k_kg_pack(const int16_t* __restrict__ in, uint64_t in_stride, uint64_t n, const uint32_t* __restrict__ blk_carry,
               const uint64_t* __restrict__ blk_off, const uint32_t* __restrict__ blk_bits, uint32_t nblocks,
-              uint8_t* __restrict__ out, uint64_t out_stride, uint64_t cap_bits)
+              uint8_t* __restrict__ out, uint64_t out_stride, uint64_t cap_bits, const uint32_t* __restrict__ slots)
 {
 	__shared__ uint32_t sm_max[33];
 	__shared__ uint32_t sm_sum[33];
@@ -299,6 +379,25 @@ __global__ void __launch_bounds__(KG_THREADS)
 	const uint64_t g0 = blk_off[(uint64_t)nblocks * blockIdx.y + blockIdx.x];
 	if (g0 + total > cap_bits) // would not fit: the caller reports the failure from the bit count
 		return;
+
+	if (total <= KG_SLOT_BITS)
+	{
+		// pass 2 left the bit string in the block's slot: shift it to its bit offset and store
+		const uint32_t* slot = slots + ((uint64_t)nblocks * blockIdx.y + blockIdx.x) * KG_SLOT_WORDS;
+		const uint32_t r = (uint32_t)(g0 & 31), nin = (total + 31) >> 5;
+		const uint32_t nout = (r + total + 31) >> 5;
+		uint32_t* dstw = reinterpret_cast<uint32_t*>(out + out_stride * blockIdx.y) + (g0 >> 5);
+		for (uint32_t k = threadIdx.x; k < nout; k += KG_THREADS)
+		{
+			const uint32_t lo = (k < nin) ? __ldg(slot + k) : 0u, hi = (k > 0) ? __ldg(slot + k - 1) : 0u;
+			const uint32_t be = __byte_perm(__funnelshift_r(lo, hi, r), 0, 0x0123); // bytes of the file are MSB-first
+			if (k == 0 || k == nout - 1)
+				atomicOr(&dstw[k], be);
+			else
+				dstw[k] = be;
+		}
+		return;
+	}
 
 	in += in_stride * blockIdx.y;
 	const uint64_t base = (uint64_t)blockIdx.x * KG_BLOCK + (uint64_t)threadIdx.x * KG_ITEMS;
@@ -477,7 +576,7 @@ __global__ void __launch_bounds__(KG_THREADS)
 	const uint64_t base = (uint64_t)b * KG_BLOCK + (uint64_t)tid * KG_ITEMS;
 	const KgChunk c = kg_load(in, n, base);
 	uint32_t blk_last;
-	const uint32_t excl_start = block_excl_max_u32(c.last_start, sm_max, &blk_last);
+	const uint32_t excl_start = block_excl_last_start(c.last_start, sm_max, &blk_last);
 
 	// ---- run-start carry
 	if (tid < 32)
