@@ -672,7 +672,7 @@ extern "C" int akod_kagari_encode(akodContext* c, uint64_t n_values, const int16
 		            nblocks, d_out, out_stride, out_cap * 8, d_bits);
 		return AKOD_OK;
 	}
-	const size_t need = (size_t)per_img * n_images * (sizeof(uint64_t) + 2 * sizeof(uint32_t) + sizeof(uint32_t) * KG_SLOT_WORDS) + 64;
+	const size_t need = (size_t)per_img * n_images * (sizeof(uint64_t) + 3 * sizeof(uint32_t) + sizeof(uint32_t) * KG_SLOT_WORDS + 1) + 64;
 	int rc = akod_workspace(c, AKOD_WS_KAGARI, need, &ws);
 	if (rc != AKOD_OK)
 		return rc;
@@ -680,14 +680,16 @@ extern "C" int akod_kagari_encode(akodContext* c, uint64_t n_values, const int16
 	uint32_t* blk_start = (uint32_t*)(blk_off + per_img * n_images);
 	uint32_t* blk_bits = blk_start + per_img * n_images;
 	uint32_t* slots = blk_bits + per_img * n_images; // KG_SLOT_WORDS per block
+	uint32_t* blk_own = slots + per_img * n_images * KG_SLOT_WORDS;
+	uint8_t* blk_first = (uint8_t*)(blk_own + per_img * n_images);
 
 	const dim3 grid(nblocks, n_images);
 	AKOD_BYTES(c, 2 * n_values * n_images);
-	AKOD_LAUNCH(c, "kagari_starts", k_kg_starts, grid, KG_THREADS, 0, d_in, in_stride, n_values, blk_start, nblocks);
-	AKOD_LAUNCH(c, "kagari_scan_max", k_kg_scan_max, n_images, 1024, 0, blk_start, nblocks);
+	AKOD_LAUNCH(c, "kagari_starts", k_kg_starts, grid, KG_THREADS, 0, d_in, in_stride, n_values, blk_own, blk_first, nblocks);
+	AKOD_LAUNCH(c, "kagari_scan_max", k_kg_scan_max, n_images, 1024, 0, blk_own, blk_start, nblocks);
 	AKOD_BYTES(c, 2 * n_values * n_images);
 	AKOD_LAUNCH(c, "kagari_lengths", k_kg_lengths, grid, KG_THREADS, 0, d_in, in_stride, n_values, blk_start, blk_bits,
-	            nblocks, slots);
+	            nblocks, slots, blk_own, blk_first);
 	AKOD_LAUNCH(c, "kagari_scan_sum", k_kg_scan_sum, n_images, 1024, 0, blk_bits, blk_off, nblocks, d_bits);
 	const dim3 zgrid((nblocks + 255) / 256, n_images);
 	AKOD_LAUNCH(c, "kagari_zero_edges", k_kg_zero_edges, zgrid, 256, 0, blk_off, blk_bits, nblocks, d_out, out_stride,

@@ -168,27 +168,34 @@ __device__ __forceinline__ KgChunk kg_load(const int16_t* __restrict__ in, uint6
 	return c;
 }
 
-// pass 1: blk_start[b] = (largest i in block b that starts a run) + 1, or 0
+// pass 1: blk_own[b] = (largest i in block b that starts a run) + 1, or 0; blk_first[b] = 1 when the block's first
+// value starts a run
 __global__ void __launch_bounds__(KG_THREADS)
-    k_kg_starts(const int16_t* __restrict__ in, uint64_t in_stride, uint64_t n, uint32_t* __restrict__ blk_start,
-                uint32_t nblocks)
+    k_kg_starts(const int16_t* __restrict__ in, uint64_t in_stride, uint64_t n, uint32_t* __restrict__ blk_own,
+                uint8_t* __restrict__ blk_first, uint32_t nblocks)
 {
 	__shared__ uint32_t sm[33];
 	in += in_stride * blockIdx.y;
-	blk_start += (uint64_t)nblocks * blockIdx.y;
+	blk_own += (uint64_t)nblocks * blockIdx.y;
+	blk_first += (uint64_t)nblocks * blockIdx.y;
 	const uint64_t base = (uint64_t)blockIdx.x * KG_BLOCK + (uint64_t)threadIdx.x * KG_ITEMS;
 	const KgChunk c = kg_load(in, n, base);
 	uint32_t total;
 	block_excl_last_start(c.last_start, sm, &total);
 	if (threadIdx.x == 0)
-		blk_start[blockIdx.x] = total;
+	{
+		blk_own[blockIdx.x] = total;
+		blk_first[blockIdx.x] = (uint8_t)(c.start_mask & 1u);
+	}
 }
 
 // exclusive max-scan over the blocks of one image (one CTA per image); identity 0
-__global__ void __launch_bounds__(1024) k_kg_scan_max(uint32_t* __restrict__ blk, uint32_t nblocks)
+__global__ void __launch_bounds__(1024)
+    k_kg_scan_max(const uint32_t* __restrict__ blk, uint32_t* __restrict__ blk_carry, uint32_t nblocks)
 {
 	__shared__ uint32_t sm[33];
 	blk += (uint64_t)nblocks * blockIdx.x;
+	blk_carry += (uint64_t)nblocks * blockIdx.x;
 	uint32_t carry = 0;
 	for (uint32_t b0 = 0; b0 < nblocks; b0 += 1024)
 	{
@@ -197,7 +204,7 @@ __global__ void __launch_bounds__(1024) k_kg_scan_max(uint32_t* __restrict__ blk
 		uint32_t total;
 		const uint32_t ex = block_excl_last_start(v, sm, &total);
 		if (b < nblocks)
-			blk[b] = max(carry, ex);
+			blk_carry[b] = max(carry, ex);
 		carry = max(carry, total);
 	}
 }
@@ -316,11 +323,32 @@ __device__ __forceinline__ void kg_put_codes(uint32_t* bitbuf, uint32_t pos, con
 // pass 2: bits emitted by each block (+ the bit string itself into the block's slot when it fits)
 __global__ void __launch_bounds__(KG_THREADS)
     k_kg_lengths(const int16_t* __restrict__ in, uint64_t in_stride, uint64_t n, const uint32_t* __restrict__ blk_carry,
-                 uint32_t* __restrict__ blk_bits, uint32_t nblocks, uint32_t* __restrict__ slots)
+                 uint32_t* __restrict__ blk_bits, uint32_t nblocks, uint32_t* __restrict__ slots,
+                 const uint32_t* __restrict__ blk_own, const uint8_t* __restrict__ blk_first)
 {
 	__shared__ uint32_t sm_max[33];
 	__shared__ uint32_t sm_sum[33];
 	__shared__ uint32_t bitbuf[KG_SLOT_WORDS + 2];
+	{
+		// A block that lies entirely inside one run which also goes on behind it emits nothing, unless the run
+		// counter passes 1, 2 or 65534 inside it (the same rule as the per-thread fast path of kg_codes). Pass 1
+		// left everything needed to see that without touching the stream: quantised planes are mostly such blocks.
+		const uint64_t bi = (uint64_t)nblocks * blockIdx.y + blockIdx.x;
+		const uint64_t first = (uint64_t)blockIdx.x * KG_BLOCK;
+		if (blk_own[bi] == 0 && blockIdx.x + 1 < nblocks && blk_first[bi + 1] == 0 && first + KG_BLOCK <= n)
+		{
+			const uint32_t k0 = (uint32_t)first + 1u - blk_carry[bi]; // position of the block's first value in its run
+			uint32_t c0 = k0;
+			if (k0 > 65534u)
+				c0 = ((k0 - 1) % 65534u) + 1u;
+			if (c0 >= 3 && c0 + (KG_BLOCK - 1) < 65534u)
+			{
+				if (threadIdx.x == 0)
+					blk_bits[bi] = 0;
+				return;
+			}
+		}
+	}
 	in += in_stride * blockIdx.y;
 	const uint64_t base = (uint64_t)blockIdx.x * KG_BLOCK + (uint64_t)threadIdx.x * KG_ITEMS;
 	const KgChunk c = kg_load(in, n, base);
