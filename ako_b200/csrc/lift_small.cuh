@@ -51,9 +51,38 @@ __device__ __forceinline__ int sm_level_wavelet(int wavelet, int tw, int th) // 
 	return AKOD_DD137;
 }
 
-// tap through the wrap mode's index map (period t, element stride 'stride'); zero outside for WRAP_ZERO
+// Walks a rows x cols index space with all SM_THREADS threads, element by element (row-major), without a division
+// per element: the small levels have fewer columns than a warp has lanes, so a (warp = row, lane = column)
+// mapping would leave most lanes idle.
+struct SmWalk
+{
+	int row, col, dq, dr, cols;
+	__device__ __forceinline__ SmWalk(int cols_) : cols(cols_)
+	{
+		row = (int)threadIdx.x / cols;
+		col = (int)threadIdx.x - row * cols;
+		dq = SM_THREADS / cols;
+		dr = SM_THREADS - dq * cols;
+	}
+	__device__ __forceinline__ void next()
+	{
+		col += dr;
+		row += dq;
+		if (col >= cols)
+		{
+			col -= cols;
+			row++;
+		}
+	}
+};
+
+// tap through the wrap mode's index map (period t, element stride 'stride'); zero outside for WRAP_ZERO.
+// CLAMP (the default wrap mode, known at compile time in the level functions) is a branch-free index clamp.
+template <bool CLAMP>
 __device__ __forceinline__ int sm_tap(const int16_t* a, int stride, int wrap, int v, int t)
 {
+	if (CLAMP)
+		return (int)a[min(max(v, 0), t - 1) * stride];
 	const int m = wrap_map(v, t, wrap);
 	return (m < 0) ? 0 : (int)a[m * stride];
 }
@@ -81,29 +110,28 @@ __device__ __forceinline__ void sm_offsets(const SmallParams& p, uint32_t chn, u
 // ------------------------------------------------------------------------------------------------
 // forward
 
-template <int WL>
+template <int WL, bool CLAMP>
 __device__ __forceinline__ void sm_forward_level(int16_t* A, int16_t* Bf, int cw, int ch, int tw, int th, int wrap,
                                                  int q, int g, uint32_t magic, int16_t* out_c, int16_t* ll_next)
 {
-	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = SM_THREADS / 32;
 	const int bw = 2 * tw; // row pitch of the H-pass output [L | H]
 
 	// ---- H pass, highpass: Bf[y][tw + c]
-	for (int y = warp; y < ch; y += nwarps)
+	for (SmWalk it(tw); it.row < ch; it.next())
 	{
+		const int y = it.row, c = it.col;
 		const int16_t* row = A + y * cw;
-		for (int c = lane; c < tw; c += 32)
 		{
 			const int e = row[2 * c], o = row[min(2 * c + 1, cw - 1)]; // odd width: duplicate last column
 			int h;
 			if (WL == AKOD_DD137)
 			{
-				const int l1 = sm_tap(row, 2, wrap, c - 1, tw), p1 = sm_tap(row, 2, wrap, c + 1, tw);
-				const int p2 = (wrap == AKOD_WRAP_MIRROR && c >= tw - 2) ? l1 : sm_tap(row, 2, wrap, c + 2, tw);
+				const int l1 = sm_tap<CLAMP>(row, 2, wrap, c - 1, tw), p1 = sm_tap<CLAMP>(row, 2, wrap, c + 1, tw);
+				const int p2 = (!CLAMP && wrap == AKOD_WRAP_MIRROR && c >= tw - 2) ? l1 : sm_tap<CLAMP>(row, 2, wrap, c + 2, tw);
 				h = hp_forward<WL>(o, e, l1, p1, p2);
 			}
 			else if (WL == AKOD_CDF53)
-				h = hp_forward<WL>(o, e, 0, sm_tap(row, 2, wrap, c + 1, tw), 0);
+				h = hp_forward<WL>(o, e, 0, sm_tap<CLAMP>(row, 2, wrap, c + 1, tw), 0);
 			else
 				h = hp_forward<WL>(o, e, 0, 0, 0);
 			Bf[y * bw + tw + c] = (int16_t)h;
@@ -111,22 +139,22 @@ __device__ __forceinline__ void sm_forward_level(int16_t* A, int16_t* Bf, int cw
 	}
 	__syncthreads();
 	// ---- H pass, lowpass: Bf[y][c]
-	for (int y = warp; y < ch; y += nwarps)
+	for (SmWalk it(tw); it.row < ch; it.next())
 	{
+		const int y = it.row, c = it.col;
 		const int16_t* row = A + y * cw;
 		const int16_t* hrow = Bf + y * bw + tw;
-		for (int c = lane; c < tw; c += 32)
 		{
 			const int e = row[2 * c];
 			int l;
 			if (WL == AKOD_DD137)
 			{
-				const int l1 = sm_tap(hrow, 1, wrap, c - 1, tw), p1 = sm_tap(hrow, 1, wrap, c + 1, tw);
-				const int l2 = (wrap == AKOD_WRAP_MIRROR && c <= 1) ? p1 : sm_tap(hrow, 1, wrap, c - 2, tw);
+				const int l1 = sm_tap<CLAMP>(hrow, 1, wrap, c - 1, tw), p1 = sm_tap<CLAMP>(hrow, 1, wrap, c + 1, tw);
+				const int l2 = (!CLAMP && wrap == AKOD_WRAP_MIRROR && c <= 1) ? p1 : sm_tap<CLAMP>(hrow, 1, wrap, c - 2, tw);
 				l = lp_forward<WL>(e, l2, l1, hrow[c], p1);
 			}
 			else if (WL == AKOD_CDF53)
-				l = lp_forward<WL>(e, 0, sm_tap(hrow, 1, wrap, c - 1, tw), hrow[c], 0);
+				l = lp_forward<WL>(e, 0, sm_tap<CLAMP>(hrow, 1, wrap, c - 1, tw), hrow[c], 0);
 			else
 				l = e;
 			Bf[y * bw + c] = (int16_t)l;
@@ -135,21 +163,21 @@ __device__ __forceinline__ void sm_forward_level(int16_t* A, int16_t* Bf, int cw
 	__syncthreads();
 	// ---- V pass, highpass of every column of [L | H]: HV[r][col] overwrites A (dead now)
 	int16_t* HV = A;
-	for (int r = warp; r < th; r += nwarps)
+	for (SmWalk it(bw); it.row < th; it.next())
 	{
-		for (int col = lane; col < bw; col += 32)
+		const int r = it.row, col = it.col;
 		{
 			const int16_t* colp = Bf + col;
 			const int e = colp[(2 * r) * bw], o = colp[min(2 * r + 1, ch - 1) * bw]; // odd height: duplicate last row
 			int h;
 			if (WL == AKOD_DD137)
 			{
-				const int l1 = sm_tap(colp, 2 * bw, wrap, r - 1, th), p1 = sm_tap(colp, 2 * bw, wrap, r + 1, th);
-				const int p2 = (wrap == AKOD_WRAP_MIRROR && r >= th - 2) ? l1 : sm_tap(colp, 2 * bw, wrap, r + 2, th);
+				const int l1 = sm_tap<CLAMP>(colp, 2 * bw, wrap, r - 1, th), p1 = sm_tap<CLAMP>(colp, 2 * bw, wrap, r + 1, th);
+				const int p2 = (!CLAMP && wrap == AKOD_WRAP_MIRROR && r >= th - 2) ? l1 : sm_tap<CLAMP>(colp, 2 * bw, wrap, r + 2, th);
 				h = hp_forward<WL>(o, e, l1, p1, p2);
 			}
 			else if (WL == AKOD_CDF53)
-				h = hp_forward<WL>(o, e, 0, sm_tap(colp, 2 * bw, wrap, r + 1, th), 0);
+				h = hp_forward<WL>(o, e, 0, sm_tap<CLAMP>(colp, 2 * bw, wrap, r + 1, th), 0);
 			else
 				h = hp_forward<WL>(o, e, 0, 0, 0);
 			HV[r * bw + col] = (int16_t)h;
@@ -159,9 +187,9 @@ __device__ __forceinline__ void sm_forward_level(int16_t* A, int16_t* Bf, int cw
 	// ---- V pass, lowpass + gate/quantise + stores. LL goes to ll_next (shared), C/B/D to the stream.
 	int16_t* out_b = out_c + tw * th;
 	int16_t* out_d = out_b + tw * th;
-	for (int r = warp; r < th; r += nwarps)
+	for (SmWalk it(bw); it.row < th; it.next())
 	{
-		for (int col = lane; col < bw; col += 32)
+		const int r = it.row, col = it.col;
 		{
 			const int16_t* hcol = HV + col;
 			const int e = Bf[(2 * r) * bw + col];
@@ -169,12 +197,12 @@ __device__ __forceinline__ void sm_forward_level(int16_t* A, int16_t* Bf, int cw
 			int l;
 			if (WL == AKOD_DD137)
 			{
-				const int l1 = sm_tap(hcol, bw, wrap, r - 1, th), p1 = sm_tap(hcol, bw, wrap, r + 1, th);
-				const int l2 = (wrap == AKOD_WRAP_MIRROR && r <= 1) ? p1 : sm_tap(hcol, bw, wrap, r - 2, th);
+				const int l1 = sm_tap<CLAMP>(hcol, bw, wrap, r - 1, th), p1 = sm_tap<CLAMP>(hcol, bw, wrap, r + 1, th);
+				const int l2 = (!CLAMP && wrap == AKOD_WRAP_MIRROR && r <= 1) ? p1 : sm_tap<CLAMP>(hcol, bw, wrap, r - 2, th);
 				l = lp_forward<WL>(e, l2, l1, hv, p1);
 			}
 			else if (WL == AKOD_CDF53)
-				l = lp_forward<WL>(e, 0, sm_tap(hcol, bw, wrap, r - 1, th), hv, 0);
+				l = lp_forward<WL>(e, 0, sm_tap<CLAMP>(hcol, bw, wrap, r - 1, th), hv, 0);
 			else
 				l = e;
 			if (col < tw)
@@ -204,11 +232,8 @@ __global__ void __launch_bounds__(SM_THREADS, 1) k_lift_small(const SmallParams 
 		sm_offsets(p, chn, off_c, lw, lh);
 	const int16_t* in = p.planes + p.planes_is * img + p.planes_ps * chn;
 	int16_t* stream = p.stream + p.stream_is * img;
-	for (uint32_t i = threadIdx.x; i < p.cw0 * p.ch0; i += SM_THREADS)
-	{
-		const uint32_t y = i / p.cw0, x = i - y * p.cw0;
-		A[i] = __ldg(in + (uint64_t)y * p.planes_rs + x);
-	}
+	for (SmWalk it((int)p.cw0); it.row < (int)p.ch0; it.next())
+		A[it.row * (int)p.cw0 + it.col] = __ldg(in + (uint64_t)it.row * p.planes_rs + it.col);
 	__syncthreads();
 
 	int16_t* cur = A; // dense lw[s] x lh[s]
@@ -224,12 +249,17 @@ __global__ void __launch_bounds__(SM_THREADS, 1) k_lift_small(const SmallParams 
 		if (threadIdx.x == 0)
 			out_c[-1] = (int16_t)q; // akoLiftHead
 		int16_t* ll_next = cur + th * 2 * tw; // behind the V-highpass scratch that overwrites 'cur'
-		if (wl == AKOD_DD137)
-			sm_forward_level<AKOD_DD137>(cur, Bf, cw, ch, tw, th, p.wrap, q, g, magic, out_c, ll_next);
+		const bool clamp = p.wrap == AKOD_WRAP_CLAMP;
+		if (wl == AKOD_DD137 && clamp)
+			sm_forward_level<AKOD_DD137, true>(cur, Bf, cw, ch, tw, th, p.wrap, q, g, magic, out_c, ll_next);
+		else if (wl == AKOD_DD137)
+			sm_forward_level<AKOD_DD137, false>(cur, Bf, cw, ch, tw, th, p.wrap, q, g, magic, out_c, ll_next);
+		else if (wl == AKOD_CDF53 && clamp)
+			sm_forward_level<AKOD_CDF53, true>(cur, Bf, cw, ch, tw, th, p.wrap, q, g, magic, out_c, ll_next);
 		else if (wl == AKOD_CDF53)
-			sm_forward_level<AKOD_CDF53>(cur, Bf, cw, ch, tw, th, p.wrap, q, g, magic, out_c, ll_next);
+			sm_forward_level<AKOD_CDF53, false>(cur, Bf, cw, ch, tw, th, p.wrap, q, g, magic, out_c, ll_next);
 		else
-			sm_forward_level<AKOD_HAAR>(cur, Bf, cw, ch, tw, th, p.wrap, q, g, magic, out_c, ll_next);
+			sm_forward_level<AKOD_HAAR, true>(cur, Bf, cw, ch, tw, th, p.wrap, q, g, magic, out_c, ll_next);
 		cur = ll_next;
 	}
 	// lowpass section (lifting.c:280-291)
@@ -241,13 +271,12 @@ __global__ void __launch_bounds__(SM_THREADS, 1) k_lift_small(const SmallParams 
 // ------------------------------------------------------------------------------------------------
 // inverse
 
-template <int WL>
+template <int WL, bool CLAMP>
 __device__ __forceinline__ void sm_inverse_level(int16_t* R, int16_t* T, int hw, int hh, int tw, int th, int wrap, int q,
                                                  const int16_t* __restrict__ in_c)
 {
 	// R = [LL hw*hh | C | B | D] (the three subbands staged here, inverse-quantised); result (tw x th, dense)
 	// is written back to R[0..). T = 2hh rows x [left hw | right hw].
-	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = SM_THREADS / 32;
 	const int band = hw * hh, bw = 2 * hw;
 	int16_t* LL = R;
 	int16_t* HC = R + band; // C, then B, then D
@@ -260,9 +289,9 @@ __device__ __forceinline__ void sm_inverse_level(int16_t* R, int16_t* T, int hw,
 	}
 	__syncthreads();
 	// ---- V pass, even rows: T[2r][col]
-	for (int r = warp; r < hh; r += nwarps)
+	for (SmWalk it(bw); it.row < hh; it.next())
 	{
-		for (int col = lane; col < bw; col += 32)
+		const int r = it.row, col = it.col;
 		{
 			const bool left = col < hw;
 			const int c = left ? col : col - hw;
@@ -272,12 +301,12 @@ __device__ __forceinline__ void sm_inverse_level(int16_t* R, int16_t* T, int hw,
 			int e;
 			if (WL == AKOD_DD137)
 			{
-				const int l1 = sm_tap(hcol, hw, wrap, r - 1, hh), p1 = sm_tap(hcol, hw, wrap, r + 1, hh);
-				const int l2 = (wrap == AKOD_WRAP_MIRROR && r <= 1) ? p1 : sm_tap(hcol, hw, wrap, r - 2, hh);
+				const int l1 = sm_tap<CLAMP>(hcol, hw, wrap, r - 1, hh), p1 = sm_tap<CLAMP>(hcol, hw, wrap, r + 1, hh);
+				const int l2 = (!CLAMP && wrap == AKOD_WRAP_MIRROR && r <= 1) ? p1 : sm_tap<CLAMP>(hcol, hw, wrap, r - 2, hh);
 				e = even_inverse<WL>(lp, l2, l1, h0, p1);
 			}
 			else if (WL == AKOD_CDF53)
-				e = even_inverse<WL>(lp, 0, sm_tap(hcol, hw, wrap, r - 1, hh), h0, 0);
+				e = even_inverse<WL>(lp, 0, sm_tap<CLAMP>(hcol, hw, wrap, r - 1, hh), h0, 0);
 			else
 				e = lp;
 			T[(2 * r) * bw + col] = (int16_t)e;
@@ -285,9 +314,9 @@ __device__ __forceinline__ void sm_inverse_level(int16_t* R, int16_t* T, int hw,
 	}
 	__syncthreads();
 	// ---- V pass, odd rows: T[2r+1][col]
-	for (int r = warp; r < hh; r += nwarps)
+	for (SmWalk it(bw); it.row < hh; it.next())
 	{
-		for (int col = lane; col < bw; col += 32)
+		const int r = it.row, col = it.col;
 		{
 			const bool left = col < hw;
 			const int c = left ? col : col - hw;
@@ -297,12 +326,12 @@ __device__ __forceinline__ void sm_inverse_level(int16_t* R, int16_t* T, int hw,
 			int o;
 			if (WL == AKOD_DD137)
 			{
-				const int l1 = sm_tap(ecol, 2 * bw, wrap, r - 1, hh), p1 = sm_tap(ecol, 2 * bw, wrap, r + 1, hh);
-				const int p2 = (wrap == AKOD_WRAP_MIRROR && r >= hh - 2) ? l1 : sm_tap(ecol, 2 * bw, wrap, r + 2, hh);
+				const int l1 = sm_tap<CLAMP>(ecol, 2 * bw, wrap, r - 1, hh), p1 = sm_tap<CLAMP>(ecol, 2 * bw, wrap, r + 1, hh);
+				const int p2 = (!CLAMP && wrap == AKOD_WRAP_MIRROR && r >= hh - 2) ? l1 : sm_tap<CLAMP>(ecol, 2 * bw, wrap, r + 2, hh);
 				o = odd_inverse<WL>(h0, e0, l1, p1, p2);
 			}
 			else if (WL == AKOD_CDF53)
-				o = odd_inverse<WL>(h0, e0, 0, sm_tap(ecol, 2 * bw, wrap, r + 1, hh), 0);
+				o = odd_inverse<WL>(h0, e0, 0, sm_tap<CLAMP>(ecol, 2 * bw, wrap, r + 1, hh), 0);
 			else
 				o = odd_inverse<WL>(h0, e0, 0, 0, 0);
 			T[(2 * r + 1) * bw + col] = (int16_t)o;
@@ -311,21 +340,21 @@ __device__ __forceinline__ void sm_inverse_level(int16_t* R, int16_t* T, int hw,
 	__syncthreads();
 	// ---- H pass, even samples of the th real rows: R[y][2c]  (LL and the staged subbands are dead now)
 	const int hwt = (tw + 1) / 2; // == hw
-	for (int y = warp; y < th; y += nwarps)
+	for (SmWalk it(hwt); it.row < th; it.next())
 	{
+		const int y = it.row, c = it.col;
 		const int16_t* lrow = T + y * bw;
 		const int16_t* hrow = lrow + hw;
-		for (int c = lane; c < hwt; c += 32)
 		{
 			int e;
 			if (WL == AKOD_DD137)
 			{
-				const int l1 = sm_tap(hrow, 1, wrap, c - 1, hw), p1 = sm_tap(hrow, 1, wrap, c + 1, hw);
-				const int l2 = (wrap == AKOD_WRAP_MIRROR && c <= 1) ? p1 : sm_tap(hrow, 1, wrap, c - 2, hw);
+				const int l1 = sm_tap<CLAMP>(hrow, 1, wrap, c - 1, hw), p1 = sm_tap<CLAMP>(hrow, 1, wrap, c + 1, hw);
+				const int l2 = (!CLAMP && wrap == AKOD_WRAP_MIRROR && c <= 1) ? p1 : sm_tap<CLAMP>(hrow, 1, wrap, c - 2, hw);
 				e = even_inverse<WL>(lrow[c], l2, l1, hrow[c], p1);
 			}
 			else if (WL == AKOD_CDF53)
-				e = even_inverse<WL>(lrow[c], 0, sm_tap(hrow, 1, wrap, c - 1, hw), hrow[c], 0);
+				e = even_inverse<WL>(lrow[c], 0, sm_tap<CLAMP>(hrow, 1, wrap, c - 1, hw), hrow[c], 0);
 			else
 				e = lrow[c];
 			R[y * tw + 2 * c] = (int16_t)e;
@@ -333,24 +362,23 @@ __device__ __forceinline__ void sm_inverse_level(int16_t* R, int16_t* T, int hw,
 	}
 	__syncthreads();
 	// ---- H pass, odd samples (a last odd column dropped by the plus-one rule is not written)
-	for (int y = warp; y < th; y += nwarps)
+	for (SmWalk it(hwt); it.row < th; it.next())
 	{
+		const int y = it.row, c = it.col;
 		const int16_t* hrow = T + y * bw + hw;
 		int16_t* orow = R + y * tw;
-		for (int c = lane; c < hwt; c += 32)
+		if (2 * c + 1 < tw)
 		{
-			if (2 * c + 1 >= tw)
-				continue;
 			// even samples of this row sit at orow[2m]; the last one may stand in for a dropped column
 			int o;
 			if (WL == AKOD_DD137)
 			{
-				const int l1 = sm_tap(orow, 2, wrap, c - 1, hw), p1 = sm_tap(orow, 2, wrap, c + 1, hw);
-				const int p2 = (wrap == AKOD_WRAP_MIRROR && c >= hw - 2) ? l1 : sm_tap(orow, 2, wrap, c + 2, hw);
+				const int l1 = sm_tap<CLAMP>(orow, 2, wrap, c - 1, hw), p1 = sm_tap<CLAMP>(orow, 2, wrap, c + 1, hw);
+				const int p2 = (!CLAMP && wrap == AKOD_WRAP_MIRROR && c >= hw - 2) ? l1 : sm_tap<CLAMP>(orow, 2, wrap, c + 2, hw);
 				o = odd_inverse<WL>(hrow[c], orow[2 * c], l1, p1, p2);
 			}
 			else if (WL == AKOD_CDF53)
-				o = odd_inverse<WL>(hrow[c], orow[2 * c], 0, sm_tap(orow, 2, wrap, c + 1, hw), 0);
+				o = odd_inverse<WL>(hrow[c], orow[2 * c], 0, sm_tap<CLAMP>(orow, 2, wrap, c + 1, hw), 0);
 			else
 				o = odd_inverse<WL>(hrow[c], orow[2 * c], 0, 0, 0);
 			orow[2 * c + 1] = (int16_t)o;
@@ -382,20 +410,22 @@ __global__ void __launch_bounds__(SM_THREADS, 1) k_unlift_small(const SmallParam
 		const int wl = sm_level_wavelet(p.wavelet, hw, hh);
 		const int16_t* in_c = stream + off_c[s];
 		const int q = (int)__ldg(in_c - 1); // the decoder learns q from the lift head (misc.c:262-268)
-		if (wl == AKOD_DD137)
-			sm_inverse_level<AKOD_DD137>(R, T, hw, hh, tw, th, p.wrap, q, in_c);
+		const bool clamp = p.wrap == AKOD_WRAP_CLAMP;
+		if (wl == AKOD_DD137 && clamp)
+			sm_inverse_level<AKOD_DD137, true>(R, T, hw, hh, tw, th, p.wrap, q, in_c);
+		else if (wl == AKOD_DD137)
+			sm_inverse_level<AKOD_DD137, false>(R, T, hw, hh, tw, th, p.wrap, q, in_c);
+		else if (wl == AKOD_CDF53 && clamp)
+			sm_inverse_level<AKOD_CDF53, true>(R, T, hw, hh, tw, th, p.wrap, q, in_c);
 		else if (wl == AKOD_CDF53)
-			sm_inverse_level<AKOD_CDF53>(R, T, hw, hh, tw, th, p.wrap, q, in_c);
+			sm_inverse_level<AKOD_CDF53, false>(R, T, hw, hh, tw, th, p.wrap, q, in_c);
 		else
-			sm_inverse_level<AKOD_HAAR>(R, T, hw, hh, tw, th, p.wrap, q, in_c);
+			sm_inverse_level<AKOD_HAAR, true>(R, T, hw, hh, tw, th, p.wrap, q, in_c);
 	}
 
 	int16_t* out = p.planes + p.planes_is * img + p.planes_ps * chn;
-	for (uint32_t i = threadIdx.x; i < p.cw0 * p.ch0; i += SM_THREADS)
-	{
-		const uint32_t y = i / p.cw0, x = i - y * p.cw0;
-		out[(uint64_t)y * p.planes_rs + x] = R[i];
-	}
+	for (SmWalk it((int)p.cw0); it.row < (int)p.ch0; it.next())
+		out[(uint64_t)it.row * p.planes_rs + it.col] = R[it.row * (int)p.cw0 + it.col];
 }
 
 // host side: can the small kernels take the pyramid from a cw x ch plane downwards?
