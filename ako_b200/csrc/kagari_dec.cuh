@@ -3,11 +3,11 @@
 //
 // Two sequential dependencies are broken up:
 //
-// (1) Codeword boundaries. next(p) = p + 2*clz(bits at p) + 1. The stream is cut into 256-bit subsequences,
+// (1) Codeword boundaries. next(p) = p + 2*clz(bits at p) + 1. The stream is cut into 128-bit subsequences,
 //     one thread each. Every thread first decodes from its subsequence start as if it were a boundary, then
 //     threads repeatedly restart from their predecessor's real end until nothing changes: Elias gamma codes
 //     self-synchronise after a few codewords, so this takes 2-3 rounds; it is correct for any input because
-//     it only stops at the fixed point. The same is done between CTAs (64 Kibit each) by re-running the
+//     it only stops at the fixed point. The same is done between CTAs (32 Kibit each) by re-running the
 //     kernel with the previous run's CTA ends; a run that changes nothing proves the chain consistent.
 //
 // (2) Which codeword is a value and which an RLE count (kagari.c:337-355). Written over the raw codeword
@@ -117,9 +117,9 @@ __global__ void k_kd_sequential(const uint8_t* __restrict__ in_base, const uint6
 // ------------------------------------------------------------------------------------------------
 // phase 1: codeword boundaries
 
-constexpr int KD_SUB_BITS = 256;                           // bits per thread
+constexpr int KD_SUB_BITS = 128;                           // bits per thread
 constexpr int KD_THREADS = 256;
-constexpr int KD_CTA_BITS = KD_SUB_BITS * KD_THREADS;      // 65536 bits = 8 KiB of stream per CTA
+constexpr int KD_CTA_BITS = KD_SUB_BITS * KD_THREADS;      // 32768 bits = 4 KiB of stream per CTA
 constexpr int KD_CTA_WORDS = KD_CTA_BITS / 32;
 constexpr uint32_t KD_STOP = 0xFFFFFFFFu;                  // "the chain ended before this point"
 constexpr uint64_t KD_STOP64 = ~(uint64_t)0;
@@ -159,7 +159,7 @@ struct KdSubState
 	uint32_t count; // codewords that start in it
 };
 
-// stages 8 KiB (+ 2 words look-ahead) of the stream as big-endian words; bytes past 'size' read as zero
+// stages one CTA's worth (+ 2 words look-ahead) of the stream as big-endian words; bytes past 'size' read as zero
 __device__ __forceinline__ void kd_stage_bits(uint32_t* sm, const uint8_t* __restrict__ in, uint64_t size,
                                               uint64_t first_byte)
 {
