@@ -776,7 +776,7 @@ extern "C" int akod_kagari_decode(akodContext* c, uint64_t n_values, const uint8
 	            token_cap, token_cap);
 	const dim3 grid2(nblk2, n_images);
 	AKOD_LAUNCH(c, "kagari_dec_spans", k_kt_spans, grid2, KT_THREADS, 0, tokens, token_cap, token_cap, info, blk_span, nblk2);
-	AKOD_LAUNCH(c, "kagari_dec_resolve", k_kt_resolve, n_images, 32, 0, blk_span, nblk2, blk_state, blk_out, info, n_values,
+	AKOD_LAUNCH(c, "kagari_dec_resolve", k_kt_resolve, n_images, KR_THREADS, 0, blk_span, nblk2, blk_state, blk_out, info, n_values,
 	            token_cap, d_result);
 	AKOD_LAUNCH(c, "kagari_dec_expand", k_kt_expand, grid2, KT_THREADS, 0, tokens, token_cap, token_cap, info, blk_state,
 	            blk_out, nblk2, d_out, out_stride, n_values, big_list, big_count, big_cap);
@@ -847,7 +847,46 @@ __global__ void __launch_bounds__(256)
 		dst += 4;
 	}
 	const uint8_t* src = blocks + blocks_stride * img + block_off[t];
-	for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < size; i += (uint64_t)gridDim.x * blockDim.x)
+	// The block region is 16-byte aligned, its place in the blob is not: every thread produces one 16-byte aligned
+	// chunk of the destination from two aligned 16-byte loads, shifted by the byte misalignment.
+	const uint32_t mis = (uint32_t)((uintptr_t)dst & 15);             // dst = dst_al + mis
+	const uint64_t lead = mis ? min((uint64_t)(16 - mis), size) : 0;  // bytes before the first aligned chunk
+	const uint64_t nchunks = (size - lead) / 16;
+	const uint64_t stride = (uint64_t)gridDim.x * blockDim.x, tid0 = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (tid0 < lead)
+		dst[tid0] = src[tid0];
+	const uint32_t sh = (uint32_t)(lead & 15);                        // chunk k reads src bytes [lead + 16k, +16): offset sh in aligned words
+	const uint4* src4 = reinterpret_cast<const uint4*>(src);
+	uint4* dst4 = reinterpret_cast<uint4*>(dst + lead);
+	for (uint64_t k = tid0; k < nchunks; k += stride)
+	{
+		const uint64_t s0 = (lead + 16 * k) >> 4;
+		const uint4 a = __ldg(src4 + s0);
+		uint4 o = a;
+		if (sh)
+		{
+			const uint4 b = __ldg(src4 + s0 + 1); // stays inside the 16-byte padded block region
+			const uint32_t w[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+			const uint32_t wo = sh >> 2, bs = 8 * (sh & 3);
+			uint32_t r[4];
+#pragma unroll
+			for (int i = 0; i < 4; i++)
+			{
+				// bytes [sh + 4i, sh + 4i + 4) of the 32-byte window (little endian)
+				uint32_t lo = 0, hi = 0;
+#pragma unroll
+				for (int j = 0; j < 8; j++)
+				{
+					lo = (j == (int)wo + i) ? w[j] : lo;
+					hi = (j == (int)wo + i + 1) ? w[j] : hi;
+				}
+				r[i] = __funnelshift_r(lo, hi, bs);
+			}
+			o = make_uint4(r[0], r[1], r[2], r[3]);
+		}
+		dst4[k] = o;
+	}
+	for (uint64_t i = lead + 16 * nchunks + tid0; i < size; i += stride)
 		dst[i] = src[i];
 }
 

@@ -555,54 +555,101 @@ __global__ void __launch_bounds__(KT_THREADS)
 		blk_span[(uint64_t)nblk * img + blockIdx.x] = total;
 }
 
-// pass B: one warp per image resolves every CTA's entry state and output base; validates the block
-__global__ void __launch_bounds__(32)
+// pass B: one CTA per image resolves every expand-CTA's entry state and output base, and validates the block.
+// Three levels: every thread composes the spans of its own chunk of CTAs; warp 0 chains the 1024 thread
+// composites (32 per lane, then the 32 lanes in order) with 64-bit output counts; every thread then walks its
+// chunk again from its resolved (state, base). A 458 MB lossless block has ~150 000 spans.
+constexpr int KR_THREADS = 1024;
+
+__global__ void __launch_bounds__(KR_THREADS)
     k_kt_resolve(const KtSpan* __restrict__ blk_span, uint32_t nblk, uint32_t* __restrict__ blk_state,
                  uint64_t* __restrict__ blk_out, KdImage* __restrict__ info, uint64_t n_values, uint64_t token_cap,
                  uint64_t* __restrict__ result)
 {
-	const uint32_t img = blockIdx.x, lane = threadIdx.x;
+	__shared__ uint32_t s_map[KR_THREADS];
+	__shared__ uint32_t s_out[KR_THREADS][4];
+	__shared__ uint32_t s_state[KR_THREADS];
+	__shared__ uint64_t s_base[KR_THREADS];
+	__shared__ uint64_t s_grand;
+
+	const uint32_t img = blockIdx.x, t = threadIdx.x;
 	blk_span += (uint64_t)nblk * img;
 	blk_state += (uint64_t)nblk * img;
 	blk_out += (uint64_t)nblk * img;
 	const uint64_t m = min(info[img].tokens, token_cap);
 	const uint32_t used = (uint32_t)((m + KT_BLOCK - 1) / KT_BLOCK);
-	const uint32_t chunk = (used + 31) / 32;
-	const uint32_t b0 = min(lane * chunk, used), b1 = min(b0 + chunk, used);
+	const uint32_t chunk = (used + KR_THREADS - 1) / KR_THREADS;
+	const uint32_t b0 = min(t * chunk, used), b1 = min(b0 + chunk, used);
 
-	// spans carry 32-bit output counts; the running base is 64-bit, so lanes first reduce (state map only
-	// matters across lanes) and the 64-bit sums are rebuilt in the second walk
+	// a thread's chunk expands to fewer than 2^32 values for any stream that can be valid (n_values < 2^32)
 	KtSpan mine = kt_identity();
 	for (uint32_t b = b0; b < b1; b++)
 		mine = kt_compose(mine, blk_span[b]);
-	// entry state of each lane: sequential over 32 lanes (maps only)
-	uint32_t state = ST_V;
-	uint64_t base = 0;
-	for (int l = 0; l < 32; l++)
+	s_map[t] = mine.map;
+#pragma unroll
+	for (int k = 0; k < 4; k++)
+		s_out[t][k] = mine.out[k];
+	__syncthreads();
+
+	if (t < 32)
 	{
-		const uint32_t map_l = __shfl_sync(AKOD_FULL_MASK, mine.map, l);
-		const uint32_t o0 = __shfl_sync(AKOD_FULL_MASK, mine.out[0], l), o1 = __shfl_sync(AKOD_FULL_MASK, mine.out[1], l);
-		const uint32_t o2 = __shfl_sync(AKOD_FULL_MASK, mine.out[2], l), o3 = __shfl_sync(AKOD_FULL_MASK, mine.out[3], l);
-		if ((int)lane > l)
+		// lane composite over its 32 thread composites, 64-bit counts
+		uint32_t lmap = (ST_V) | (ST_A << 2) | (ST_S << 4) | (ST_R << 6);
+		uint64_t lout[4] = {0, 0, 0, 0};
+		for (int i = 0; i < 32; i++)
 		{
-			const uint32_t o = state == 0 ? o0 : state == 1 ? o1 : state == 2 ? o2 : o3;
-			base += o;
-			state = (map_l >> (2 * state)) & 3u;
+			const uint32_t c = t * 32 + i, cmap = s_map[c];
+			uint32_t nmap = 0;
+#pragma unroll
+			for (int st = 0; st < 4; st++)
+			{
+				const uint32_t mid = (lmap >> (2 * st)) & 3u;
+				nmap |= ((cmap >> (2 * mid)) & 3u) << (2 * st);
+				lout[st] += s_out[c][mid];
+			}
+			lmap = nmap;
 		}
+		// entry (state, base) of each lane: the 32 lanes in order
+		uint32_t state = ST_V;
+		uint64_t base = 0;
+		for (int l = 0; l < 32; l++)
+		{
+			const uint32_t map_l = __shfl_sync(AKOD_FULL_MASK, lmap, l);
+			const uint64_t o0 = __shfl_sync(AKOD_FULL_MASK, lout[0], l), o1 = __shfl_sync(AKOD_FULL_MASK, lout[1], l);
+			const uint64_t o2 = __shfl_sync(AKOD_FULL_MASK, lout[2], l), o3 = __shfl_sync(AKOD_FULL_MASK, lout[3], l);
+			if ((int)t > l)
+			{
+				base += state == 0 ? o0 : state == 1 ? o1 : state == 2 ? o2 : o3;
+				state = (map_l >> (2 * state)) & 3u;
+			}
+		}
+		// entry (state, base) of each of the lane's 32 threads
+		for (int i = 0; i < 32; i++)
+		{
+			const uint32_t c = t * 32 + i;
+			s_state[c] = state;
+			s_base[c] = base;
+			base += s_out[c][state];
+			state = (s_map[c] >> (2 * state)) & 3u;
+		}
+		if (t == 31)
+			s_grand = base;
 	}
-	// note: a lane's chunk can expand to more than 2^32 values only for n_values >= 2^32, which the host refuses
+	__syncthreads();
+
+	uint32_t state = s_state[t];
+	uint64_t base = s_base[t];
 	for (uint32_t b = b0; b < b1; b++)
 	{
 		blk_state[b] = state;
 		blk_out[b] = base;
-		const KtSpan s = blk_span[b];
-		base += s.out[state];
-		state = (s.map >> (2 * state)) & 3u;
+		const KtSpan sp = blk_span[b];
+		base += sp.out[state];
+		state = (sp.map >> (2 * state)) & 3u;
 	}
-	// lane 31 (or the last lane with work) holds the grand total
-	const uint64_t grand = __shfl_sync(AKOD_FULL_MASK, base, 31);
-	if (lane == 0)
+	if (t == 0)
 	{
+		const uint64_t grand = s_grand;
 		info[img].outputs = grand;
 		const bool ok = grand == n_values && info[img].tokens <= token_cap && !kd_needs_rescue(info, img) &&
 		                info[img].stop_pos != KD_STOP64;
