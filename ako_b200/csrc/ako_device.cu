@@ -700,6 +700,92 @@ extern "C" int akod_kagari_encode(akodContext* c, uint64_t n_values, const int16
 	return AKOD_OK;
 }
 
+// passes 1 and 2 of the encoder only: d_bits[i] = exact bit length of image i's Kagari stream (ratio search probes)
+extern "C" int akod_kagari_bits(akodContext* c, uint64_t n_values, const int16_t* d_in, uint64_t in_stride, uint64_t* d_bits,
+                                uint32_t n_images)
+{
+	if (n_values == 0 || n_values >= ((uint64_t)1 << 32))
+		return AKOD_ERROR;
+	const uint32_t nblocks = (uint32_t)((n_values + KG_BLOCK - 1) / KG_BLOCK);
+	const uint64_t per_img = nblocks;
+	void* ws;
+	const size_t need = (size_t)per_img * n_images * (sizeof(uint64_t) + 3 * sizeof(uint32_t) + sizeof(uint32_t) * KG_SLOT_WORDS + 1) + 64;
+	int rc = akod_workspace(c, AKOD_WS_KAGARI, need, &ws);
+	if (rc != AKOD_OK)
+		return rc;
+	uint64_t* blk_off = (uint64_t*)ws;
+	uint32_t* blk_start = (uint32_t*)(blk_off + per_img * n_images);
+	uint32_t* blk_bits = blk_start + per_img * n_images;
+	uint32_t* slots = blk_bits + per_img * n_images;
+	uint32_t* blk_own = slots + per_img * n_images * KG_SLOT_WORDS;
+	uint8_t* blk_first = (uint8_t*)(blk_own + per_img * n_images);
+	const dim3 grid(nblocks, n_images);
+	AKOD_BYTES(c, 2 * n_values * n_images);
+	AKOD_LAUNCH(c, "kagari_starts", k_kg_starts, grid, KG_THREADS, 0, d_in, in_stride, n_values, blk_own, blk_first, nblocks);
+	AKOD_LAUNCH(c, "kagari_scan_max", k_kg_scan_max, n_images, 1024, 0, blk_own, blk_start, nblocks);
+	AKOD_BYTES(c, 2 * n_values * n_images);
+	AKOD_LAUNCH(c, "kagari_lengths", k_kg_lengths, grid, KG_THREADS, 0, d_in, in_stride, n_values, blk_start, blk_bits,
+	            nblocks, slots, blk_own, blk_first);
+	AKOD_LAUNCH(c, "kagari_scan_sum", k_kg_scan_sum, n_images, 1024, 0, blk_bits, blk_off, nblocks, d_bits);
+	return AKOD_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// ratio search support: quantise + gate an UNQUANTISED coefficient stream again with another schedule
+
+struct RequantParams
+{
+	const int16_t* in;
+	int16_t* out;
+	uint64_t off_c; // channel 0's C subband; channel ch sits ch * (1 + 3*band) further
+	uint32_t band;  // tw * th
+	uint32_t channels;
+	int16_t q[AKOD_MAX_CHANNELS], g[AKOD_MAX_CHANNELS];
+	uint32_t qmagic[AKOD_MAX_CHANNELS];
+};
+
+__global__ void __launch_bounds__(256) k_requant(const RequantParams p)
+{
+	const uint32_t ch = blockIdx.y;
+	const uint64_t base = p.off_c + (uint64_t)ch * (1 + 3ull * p.band);
+	const int q = p.q[ch], g = p.g[ch];
+	const uint32_t magic = p.qmagic[ch];
+	if (blockIdx.x == 0 && threadIdx.x == 0)
+		p.out[base - 1] = (int16_t)q; // akoLiftHead
+	const uint64_t n = 3ull * p.band;
+	for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x)
+		p.out[base + i] = gate_quantize(p.in[base + i], q, g, magic);
+}
+
+// d_in: stream produced with q = 1, g = 0 on every level; d_out: what akod_lift would have produced with 'plan'
+extern "C" int akod_requantize(akodContext* c, const akodPlan* plan, const int16_t* d_in, int16_t* d_out)
+{
+	const uint64_t lp = (uint64_t)plan->lp_w * plan->lp_h * plan->channels;
+	AKOD_TRY(cudaMemcpyAsync(d_out, d_in, sizeof(int16_t) * lp, cudaMemcpyDeviceToDevice, c->stream));
+	for (uint32_t l = 0; l < plan->levels; l++)
+	{
+		const akodLevel* L = &plan->level[l];
+		RequantParams p;
+		memset(&p, 0, sizeof(p));
+		p.in = d_in;
+		p.out = d_out;
+		p.off_c = L->off_c[0];
+		p.band = L->tw * L->th;
+		p.channels = plan->channels;
+		for (uint32_t ch = 0; ch < plan->channels; ch++)
+		{
+			p.q[ch] = L->q[ch] < 1 ? 1 : L->q[ch];
+			p.g[ch] = L->g[ch];
+			p.qmagic[ch] = (p.q[ch] > 1) ? (uint32_t)((((uint64_t)1 << 32) + p.q[ch] - 1) / (uint64_t)p.q[ch]) : 0;
+		}
+		const uint64_t n = 3ull * p.band;
+		const dim3 grid(akod_stream_grid(c, n, 256, 8), plan->channels);
+		AKOD_BYTES(c, 4 * n * plan->channels);
+		AKOD_LAUNCH(c, "requantize", k_requant, grid, 256, 0, p);
+	}
+	return AKOD_OK;
+}
+
 extern "C" int akod_kagari_decode(akodContext* c, uint64_t n_values, const uint8_t* d_in, const uint64_t* d_off,
                                   const uint64_t* d_size, uint64_t max_in_size, int16_t* d_out, uint64_t out_stride,
                                   uint64_t* d_result, uint32_t n_images)

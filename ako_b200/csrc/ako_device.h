@@ -93,6 +93,7 @@ enum
 	AKOD_WS_BLOCKS, /* per-tile compressed blocks before assembly */
 	AKOD_WS_OUTPUT, /* assembled blob / decoded image */
 	AKOD_WS_SMALL,  /* sizes, flags */
+	AKOD_WS_SEARCH, /* unquantised coefficient stream kept across the probes of a ratio search */
 	AKOD_WS_COUNT
 };
 int akod_workspace(akodContext*, int slot, size_t bytes, void** out);
@@ -128,6 +129,12 @@ int akod_unlift(akodContext*, const akodPlan*, const int16_t* d_stream, int16_t*
  * image whose stream would not fit in out_cap bytes (out_cap a multiple of 4); the caller sees that in d_bits. */
 int akod_kagari_encode(akodContext*, uint64_t n_values, const int16_t* d_in, uint64_t in_stride, uint8_t* d_out,
                        uint64_t out_stride, uint64_t out_cap, uint64_t* d_bits, uint32_t n_images);
+
+/* Size probe: d_bits[i] = exact bit length of image i's Kagari stream, nothing is packed. */
+int akod_kagari_bits(akodContext*, uint64_t n_values, const int16_t* d_in, uint64_t in_stride, uint64_t* d_bits,
+                     uint32_t n_images);
+/* d_in: a stream lifted with q = 1, gate = 0 on every level. d_out: the stream akod_lift produces with 'plan'. */
+int akod_requantize(akodContext*, const akodPlan*, const int16_t* d_in, int16_t* d_out);
 
 /* Kagari decode of n_images blocks. Block i: d_size[i] bytes at d_in + d_off[i] (DEVICE arrays).
  * d_result[i] (uint64, device): bytes consumed, or 0 when the block is malformed. */

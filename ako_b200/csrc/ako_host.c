@@ -792,21 +792,48 @@ AKO_API size_t akoB200EncodeBound(const struct akoSettings* s_in, size_t channel
 
 /* Same-shape batch core. n images at d_in + i*in_stride -> n blobs at d_out + i*out_stride.
  * 'cb' only for events (may be NULL). */
-static size_t encode_core(akoB200Context* ctx, const struct akoCallbacks* cb, const struct akoSettings* s_in,
-                          size_t channels, size_t w, size_t h, size_t n, const uint8_t* d_in, size_t in_stride,
-                          uint8_t* d_out, size_t out_stride, size_t out_capacity, size_t* out_sizes,
-                          enum akoStatus* out_status)
+/* Ratio search support (akoB200EncodeRatio): the UNQUANTISED coefficient stream of every tile of ONE image is kept
+ * on the device, so that a probe with another quantisation only re-quantises it and measures the Kagari length. */
+enum
+{
+	SC_FILL = 1, /* format + lift with q = 1, gate = 0 into the cache, nothing else */
+	SC_USE = 2   /* take the tile's stream from the cache (re-quantised with the call's settings) */
+};
+struct search_cache
+{
+	int mode;
+	int size_only;  /* SC_USE or no cache: stop after the Kagari length scan, report sizes, write no blob */
+	int16_t* d_raw; /* device, every tile's stream back to back (8-element aligned) */
+};
+
+static void resolve_color(struct akoSettings* s) /* encode.c:59-64 */
+{
+	if (s->color == AKO_COLOR_YCOCG && (s->quantization > 0 || s->gate > 0))
+		s->color = AKO_COLOR_YCOCG_Q;
+	else if (s->color == AKO_COLOR_YCOCG_Q && (s->quantization <= 0 && s->gate <= 0))
+		s->color = AKO_COLOR_YCOCG;
+}
+
+static size_t encode_core_ex(akoB200Context* ctx, const struct akoCallbacks* cb, const struct akoSettings* s_in,
+                             size_t channels, size_t w, size_t h, size_t n, const uint8_t* d_in, size_t in_stride,
+                             uint8_t* d_out, size_t out_stride, size_t out_capacity, size_t* out_sizes,
+                             enum akoStatus* out_status, const struct search_cache* sc)
 {
 	enum akoStatus st = AKO_OK;
 	struct akoSettings s = (s_in != NULL) ? *s_in : akoDefaultSettings();
 	size_t done = 0;
 	uint64_t* host_off = NULL;
+	const int fill = (sc != NULL && sc->mode == SC_FILL);
+	const int use = (sc != NULL && sc->mode == SC_USE);
+	const int size_only = (sc != NULL && sc->size_only);
 
-	/* encode.c:59-64 */
-	if (s.color == AKO_COLOR_YCOCG && (s.quantization > 0 || s.gate > 0))
-		s.color = AKO_COLOR_YCOCG_Q;
-	else if (s.color == AKO_COLOR_YCOCG_Q && (s.quantization <= 0 && s.gate <= 0))
-		s.color = AKO_COLOR_YCOCG;
+	if (!fill) /* a cache fill names the colour it wants */
+		resolve_color(&s);
+	if (sc != NULL && (n != 1 || s.wavelet == AKO_WAVELET_NONE || s.compression == AKO_COMPRESSION_NONE))
+	{
+		st = AKO_ERROR;
+		goto done;
+	}
 
 	if (d_in == NULL)
 	{
@@ -829,7 +856,7 @@ static size_t encode_core(akoB200Context* ctx, const struct akoCallbacks* cb, co
 		st = AKO_ERROR;
 		goto done;
 	}
-	if (out_capacity < akoB200EncodeBound(&s, channels, w, h))
+	if (!fill && !size_only && out_capacity < akoB200EncodeBound(&s, channels, w, h))
 	{
 		st = AKO_NO_ENOUGH_MEMORY;
 		goto done;
@@ -899,29 +926,43 @@ static size_t encode_core(akoB200Context* ctx, const struct akoCallbacks* cb, co
 	batch.stream_stride = stream_cap;
 
 	size_t tx = 0, ty = 0;
+	size_t cache_cursor = 0; /* elements */
 	for (size_t t = 0; t < tiles && st == AKO_OK; t++)
 	{
 		const size_t tw = tile_dimension(tx, w, td), th = tile_dimension(ty, h, td);
 		const uint8_t* tile_in = d_in + (w * ty + tx) * channels;
+		int16_t* cached = (sc != NULL && sc->d_raw != NULL) ? sc->d_raw + cache_cursor : NULL;
+		cache_cursor += align_up(host_data[t] / 2, 8);
 
-		fire(cb, ctx, t, tiles, AKO_EVENT_FORMAT_START);
-		st = from_dev(akod_format_forward(ctx->dev, s.discard_non_visible, (int)s.color, (uint32_t)channels, (uint32_t)tw,
-		                                  (uint32_t)th, w, tile_in, planes, &batch));
-		fire(cb, ctx, t, tiles, AKO_EVENT_FORMAT_END);
+		if (!use)
+		{
+			fire(cb, ctx, t, tiles, AKO_EVENT_FORMAT_START);
+			st = from_dev(akod_format_forward(ctx->dev, s.discard_non_visible, (int)s.color, (uint32_t)channels,
+			                                  (uint32_t)tw, (uint32_t)th, w, tile_in, planes, &batch));
+			fire(cb, ctx, t, tiles, AKO_EVENT_FORMAT_END);
+		}
 
 		const int16_t* data = planes;
 		uint64_t data_stride = planes_stride;
 		if (st == AKO_OK && s.wavelet != AKO_WAVELET_NONE)
 		{
 			fire(cb, ctx, t, tiles, AKO_EVENT_WAVELET_START);
-			st = from_dev(akod_lift(ctx->dev, get_plan(ctx, &s, channels, tw, th), planes, scratch, stream, &batch));
+			if (use)
+				st = from_dev(akod_requantize(ctx->dev, get_plan(ctx, &s, channels, tw, th), cached, stream));
+			else
+				st = from_dev(akod_lift(ctx->dev, get_plan(ctx, &s, channels, tw, th), planes, scratch,
+				                        fill ? cached : stream, &batch));
 			fire(cb, ctx, t, tiles, AKO_EVENT_WAVELET_END);
 			data = stream;
 			data_stride = stream_cap;
 		}
+		if (fill)
+			goto next_tile;
 
 		fire(cb, ctx, t, tiles, AKO_EVENT_COMPRESSION_START);
-		if (st == AKO_OK && s.compression != AKO_COMPRESSION_NONE)
+		if (st == AKO_OK && size_only)
+			st = from_dev(akod_kagari_bits(ctx->dev, host_data[t] / 2, data, data_stride, d_bits + t * n, (uint32_t)n));
+		else if (st == AKO_OK && s.compression != AKO_COMPRESSION_NONE)
 		{
 			/* capacity = what the reference hands to akoKagariEncode (compression.c:40-45), rounded down to words */
 			st = from_dev(akod_kagari_encode(ctx->dev, host_data[t] / 2, data, data_stride, (uint8_t*)blocks + host_off[t],
@@ -938,6 +979,7 @@ static size_t encode_core(akoB200Context* ctx, const struct akoCallbacks* cb, co
 		}
 		fire(cb, ctx, t, tiles, AKO_EVENT_COMPRESSION_END);
 
+	next_tile:
 		tx += td;
 		if (tx >= w)
 		{
@@ -947,9 +989,16 @@ static size_t encode_core(akoB200Context* ctx, const struct akoCallbacks* cb, co
 	}
 	if (st != AKO_OK)
 		goto done;
+	if (fill)
+	{
+		done = n;
+		goto done;
+	}
 
 	/* container assembly on the device, then one small read-back of sizes */
-	if ((st = from_dev(akod_assemble(ctx->dev, head, (uint32_t)tiles, (uint32_t)n, blocks, blocks_per_image, d_block_off,
+	if (size_only)
+		st = from_dev(akod_fill_words(ctx->dev, d_total, 1, n)); /* the host adds the sizes up below */
+	else if ((st = from_dev(akod_assemble(ctx->dev, head, (uint32_t)tiles, (uint32_t)n, blocks, blocks_per_image, d_block_off,
 	                                 d_block_cap, d_bits, s.compression != AKO_COMPRESSION_NONE, d_out, out_stride,
 	                                 d_total))) != AKO_OK)
 		goto done;
@@ -977,6 +1026,14 @@ static size_t encode_core(akoB200Context* ctx, const struct akoCallbacks* cb, co
 				}
 			if (st == AKO_OK && all[tiles * n + i] == 0)
 				st = AKO_ERROR;
+			if (st == AKO_OK && size_only)
+			{
+				/* head + per tile [u32 block_size][Kagari bytes] (encode.c:170-182) */
+				uint64_t total = 16;
+				for (size_t t = 0; t < tiles; t++)
+					total += 4 + (all[t * n + i] + 7) / 8;
+				all[tiles * n + i] = total;
+			}
 			if (st == AKO_OK)
 			{
 				if (out_sizes != NULL)
@@ -992,6 +1049,15 @@ done:
 	if (out_status != NULL)
 		*out_status = st;
 	return done;
+}
+
+static size_t encode_core(akoB200Context* ctx, const struct akoCallbacks* cb, const struct akoSettings* s_in,
+                          size_t channels, size_t w, size_t h, size_t n, const uint8_t* d_in, size_t in_stride,
+                          uint8_t* d_out, size_t out_stride, size_t out_capacity, size_t* out_sizes,
+                          enum akoStatus* out_status)
+{
+	return encode_core_ex(ctx, cb, s_in, channels, w, h, n, d_in, in_stride, d_out, out_stride, out_capacity, out_sizes,
+	                      out_status, NULL);
 }
 
 AKO_API size_t akoB200EncodeBatchDevice(akoB200Context* ctx, const struct akoSettings* s, size_t channels, size_t w,
@@ -1086,6 +1152,239 @@ AKO_API size_t akoEncodeExt(const struct akoCallbacks* c, const struct akoSettin
 done:
 	if (ctx != NULL)
 		pool_release(ctx);
+	if (out_status != NULL)
+		*out_status = st;
+	return size;
+}
+
+/* ---- multi-pass ratio search (tools/akoenc.cpp:111-213, EncodePass) ---- */
+
+struct ratio_search
+{
+	akoB200Context* ctx;
+	struct akoSettings s; /* the caller's settings; quantization is replaced per pass */
+	size_t channels, w, h;
+	const uint8_t* d_in;
+	struct search_cache cache;
+	int cache_color; /* resolved colour the cache holds, -1: empty */
+	size_t passes;
+	enum akoStatus st; /* status of the last pass */
+};
+
+/* One pass of the search: the size akoEncodeExt would return for quantisation q (0 when it would fail). Only the
+ * first pass per colour model runs the colour transform and the wavelet; the rest re-quantise the cached stream. */
+static size_t ratio_probe(struct ratio_search* r, int q)
+{
+	struct akoSettings s = r->s;
+	s.quantization = q;
+	struct akoSettings resolved = s;
+	resolve_color(&resolved);
+	r->passes++;
+
+	if (r->cache_color != (int)resolved.color)
+	{
+		struct akoSettings raw = resolved;
+		raw.quantization = 0;
+		raw.gate = 0;
+		struct search_cache fill = r->cache;
+		fill.mode = SC_FILL;
+		fill.size_only = 0;
+		if (encode_core_ex(r->ctx, NULL, &raw, r->channels, r->w, r->h, 1, r->d_in, 0, NULL, 0, 0, NULL, &r->st, &fill) != 1)
+			return 0;
+		r->cache_color = (int)resolved.color;
+	}
+
+	size_t size = 0;
+	struct search_cache use = r->cache;
+	use.mode = SC_USE;
+	use.size_only = 1;
+	if (encode_core_ex(r->ctx, NULL, &s, r->channels, r->w, r->h, 1, r->d_in, 0, NULL, 0, 0, &size, &r->st, &use) != 1)
+		return 0;
+	return size;
+}
+
+static size_t absdiff(size_t a, size_t b)
+{
+	return (a > b) ? a - b : b - a;
+}
+
+AKO_API size_t akoB200EncodeRatio(const struct akoCallbacks* c, const struct akoSettings* s_in, int ratio,
+                                  size_t channels, size_t w, size_t h, const void* in, void** out,
+                                  int* out_quantization, size_t* out_passes, enum akoStatus* out_status)
+{
+	enum akoStatus st = AKO_OK;
+	const struct akoCallbacks cb = (c != NULL) ? *c : akoDefaultCallbacks();
+	struct akoSettings s = (s_in != NULL) ? *s_in : akoDefaultSettings();
+	struct ratio_search r;
+	uint8_t* blob = NULL;
+	size_t size = 0;
+	memset(&r, 0, sizeof(r));
+
+	/* akoenc.cpp:115-128: one plain pass */
+	if (ratio <= 1 || s.wavelet == AKO_WAVELET_NONE || s.compression == AKO_COMPRESSION_NONE)
+	{
+		if (ratio == 1 && s.wavelet != AKO_WAVELET_NONE && s.compression != AKO_COMPRESSION_NONE)
+		{
+			s.quantization = 0;
+			s.gate = 0;
+		}
+		if (out_quantization != NULL)
+			*out_quantization = s.quantization;
+		if (out_passes != NULL)
+			*out_passes = 1;
+		return akoEncodeExt(c, &s, channels, w, h, in, out, out_status);
+	}
+
+	if (cb.malloc == NULL || cb.realloc == NULL || cb.free == NULL)
+	{
+		st = AKO_INVALID_CALLBACKS;
+		goto done;
+	}
+	if (in == NULL)
+	{
+		st = AKO_INVALID_INPUT;
+		goto done;
+	}
+	{
+		struct akoSettings v = s;
+		uint8_t head[16];
+		resolve_color(&v);
+		if ((st = head_write(channels, w, h, &v, head)) != AKO_OK)
+			goto done;
+		if (channels == 0)
+		{
+			st = AKO_INVALID_CHANNELS_NO;
+			goto done;
+		}
+	}
+	if ((r.ctx = pool_acquire(&st)) == NULL)
+		goto done;
+
+	{
+		const size_t image_bytes = w * h * channels;
+		const size_t td = s.tiles_dimension;
+		const size_t tiles = tiles_count(w, h, td);
+		size_t cache_elems = 0;
+		{
+			size_t tx = 0, ty = 0;
+			for (size_t t = 0; t < tiles; t++)
+			{
+				cache_elems += align_up(tile_data_size(tile_dimension(tx, w, td), tile_dimension(ty, h, td)) * channels / 2, 8);
+				tx += td;
+				if (tx >= w)
+				{
+					tx = 0;
+					ty += td;
+				}
+			}
+		}
+		void *d_in, *d_raw;
+		if ((st = from_dev(akod_workspace(r.ctx->dev, AKOD_WS_INPUT, image_bytes + 64, &d_in))) != AKO_OK ||
+		    (st = from_dev(akod_workspace(r.ctx->dev, AKOD_WS_SEARCH, cache_elems * 2 + 64, &d_raw))) != AKO_OK ||
+		    (st = from_dev(akod_h2d(r.ctx->dev, d_in, in, image_bytes))) != AKO_OK)
+			goto done;
+		r.s = s;
+		r.channels = channels;
+		r.w = w;
+		r.h = h;
+		r.d_in = d_in;
+		r.cache.d_raw = d_raw;
+		r.cache_color = -1;
+
+		/* akoenc.cpp:130-192, sizes come from the Kagari length scan */
+		const size_t target_size = (w * h * channels) / (size_t)ratio;
+		const size_t error_margin = (target_size * 4) / 100;
+		size_t ceil_size = ratio_probe(&r, 0);
+		int q = 1, floor_q = 0, ceil_q = 0, last_q = 0;
+		size_t floor_size = ceil_size;
+		do
+		{
+			q *= 4;
+			ceil_size = floor_size;
+			ceil_q = floor_q;
+			floor_size = ratio_probe(&r, q);
+			floor_q = q;
+			last_q = q;
+		} while (floor_size > target_size && q <= (1 << 28)); /* the tool's q overflows here; every q this large
+		                                                           quantises alike (quantization.c:86-96) */
+		size_t last_size = floor_size;
+		while (absdiff(floor_size, ceil_size) > error_margin && abs(floor_q - ceil_q) > 1)
+		{
+			q = (ceil_q + floor_q) / 2;
+			last_size = ratio_probe(&r, q);
+			last_q = q;
+			if (last_size > target_size)
+			{
+				ceil_size = last_size;
+				ceil_q = q;
+			}
+			else
+			{
+				floor_size = last_size;
+				floor_q = q;
+			}
+		}
+
+		/* akoenc.cpp:194-210: the tool keeps the LAST pass's blob whenever its size equals the chosen bound's */
+		const int pick_floor = absdiff(floor_size, target_size) < absdiff(ceil_size, target_size);
+		const size_t chosen_size = pick_floor ? floor_size : ceil_size;
+		int final_q = pick_floor ? floor_q : ceil_q;
+		if (last_size == chosen_size)
+			final_q = last_q;
+		else
+			r.passes++; /* the tool encodes once more */
+		if (chosen_size == 0)
+		{
+			st = (r.st != AKO_OK) ? r.st : AKO_ERROR;
+			goto done;
+		}
+
+		/* the blob itself: re-quantise the cached stream once more, pack, assemble */
+		struct akoSettings fs = s;
+		fs.quantization = final_q;
+		struct akoSettings resolved = fs;
+		resolve_color(&resolved);
+		const size_t bound = akoB200EncodeBound(&fs, channels, w, h);
+		void* d_out;
+		if ((st = from_dev(akod_workspace(r.ctx->dev, AKOD_WS_OUTPUT, bound + 64, &d_out))) != AKO_OK)
+			goto done;
+		struct search_cache use = r.cache;
+		use.mode = SC_USE;
+		use.size_only = 0;
+		const struct search_cache* how = (r.cache_color == (int)resolved.color) ? &use : NULL;
+		if (encode_core_ex(r.ctx, &cb, &fs, channels, w, h, 1, d_in, 0, d_out, 0, bound, &size, &st, how) != 1)
+		{
+			size = 0;
+			goto done;
+		}
+		if ((blob = cb.malloc(size)) == NULL)
+		{
+			st = AKO_NO_ENOUGH_MEMORY;
+			size = 0;
+			goto done;
+		}
+		if ((st = from_dev(akod_d2h(r.ctx->dev, blob, d_out, size))) != AKO_OK ||
+		    (st = from_dev(akod_sync(r.ctx->dev))) != AKO_OK)
+		{
+			cb.free(blob);
+			blob = NULL;
+			size = 0;
+			goto done;
+		}
+		if (out_quantization != NULL)
+			*out_quantization = final_q;
+	}
+
+	if (out != NULL)
+		*out = blob;
+	else
+		cb.free(blob);
+
+done:
+	if (out_passes != NULL)
+		*out_passes = r.passes;
+	if (r.ctx != NULL)
+		pool_release(r.ctx);
 	if (out_status != NULL)
 		*out_status = st;
 	return size;

@@ -119,6 +119,9 @@ def load():
     L.akoB200DecodeBatchDevice.restype = c_size_t
     L.akoB200DecodeBatchDevice.argtypes = [c_void_p, c_size_t, c_void_p, c_size_t, C.POINTER(c_size_t), c_void_p,
                                            c_size_t, stp]
+    L.akoB200EncodeRatio.restype = c_size_t
+    L.akoB200EncodeRatio.argtypes = [C.POINTER(AkoCallbacks), sp, c_int, c_size_t, c_size_t, c_size_t, c_void_p,
+                                     C.POINTER(c_void_p), stp, C.POINTER(c_size_t), stp]
     L.akoB200StreamSize.restype = c_size_t
     L.akoB200StreamSize.argtypes = [c_size_t, c_size_t, c_size_t]
     L.akoB200FormatForward.argtypes = [c_void_p, sp, c_size_t, c_size_t, c_size_t, c_size_t, c_void_p, c_void_p]
@@ -163,6 +166,23 @@ def encode(image, settings=None, callbacks=None):
     free = C.CFUNCTYPE(None, c_void_p)(callbacks.free) if callbacks is not None else L.akoDefaultFree
     free(out)
     return blob, st.value
+
+
+def encode_ratio(image, ratio, settings=None):
+    """akoB200EncodeRatio == the encoder tool's EncodePass (tools/akoenc.cpp:111-213) on a host array.
+    Returns (blob bytes | None, status, quantization of the blob, passes the tool would have made)."""
+    L = load()
+    image = np.ascontiguousarray(image, dtype=np.uint8)
+    h, w, ch = image.shape
+    out = c_void_p()
+    st, q, passes = c_int(0), c_int(0), c_size_t(0)
+    n = L.akoB200EncodeRatio(None, C.byref(settings) if settings is not None else None, ratio, ch, w, h,
+                             image.ctypes.data, C.byref(out), C.byref(q), C.byref(passes), C.byref(st))
+    if n == 0:
+        return None, st.value, q.value, passes.value
+    blob = C.string_at(out.value, n)
+    L.akoDefaultFree(out)
+    return blob, st.value, q.value, passes.value
 
 
 def decode(blob, callbacks=None):

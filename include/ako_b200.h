@@ -87,6 +87,19 @@ size_t akoB200DecodeBatchDevice(akoB200Context*, size_t n_images, const void* d_
                                 const size_t* in_sizes, void* d_out, size_t out_stride,
                                 enum akoStatus* out_status);
 
+/* ---- ratio search ------------------------------------------------------------------------ */
+
+/* What the encoder tool's EncodePass does (tools/akoenc.cpp:111-213): search the quantisation that brings the
+ * .ako size within 4 % of image_bytes / ratio and return THAT blob -- same passes, same decisions, same bytes as
+ * the tool calling akoEncodeExt up to a dozen times. Here the image is uploaded once, the colour transform and the
+ * wavelet run once per colour model, and every pass only re-quantises the device-resident coefficient stream and
+ * measures its Kagari length; only the winning pass is packed. ratio 0: plain akoEncodeExt; ratio 1: lossless.
+ * Host pointers, ownership and statuses as akoEncodeExt. *out_quantization: the quantization of the returned blob;
+ * *out_passes: the number of akoEncodeExt calls the tool would have made. */
+size_t akoB200EncodeRatio(const struct akoCallbacks*, const struct akoSettings*, int ratio, size_t channels,
+                          size_t image_w, size_t image_h, const void* in, void** out, int* out_quantization,
+                          size_t* out_passes, enum akoStatus* out_status);
+
 /* ---- single stages, device resident (parity tests, DWT-only sweeps) -------------------- */
 
 /* Bytes of the coefficient stream of one tile/image: akoTileDataSize()*channels, misc.c:117-149 */

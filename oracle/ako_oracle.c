@@ -1023,3 +1023,104 @@ int orc_decode(size_t in_size, const uint8_t* in, uint8_t* out, orc_settings* ou
 		*out_s = s;
 	return st;
 }
+
+/* ------------------------------------------------------------------------------------------------
+ * Multi-pass ratio search: restates EncodePass of tools/akoenc.cpp:111-213 on top of orc_encode.
+ * 'out' receives the blob the tool would have written; *out_q the quantisation of THAT blob (the
+ * tool keeps the last pass's blob whenever its size equals the chosen bound's size, :194-210),
+ * *out_passes the number of akoEncodeExt calls made. A failed pass counts as size 0, like the tool.
+ * The q *= 4 loop (:151-166) overflows int in the tool when no q reaches the target; here it stops
+ * once q exceeds 2^28 (every q above 32765*512 quantises identically, quantization.c:86-96). */
+size_t orc_encode_pass(int ratio, const orc_settings* s_in, size_t channels, size_t w, size_t h, const uint8_t* in,
+                       uint8_t* out, int* out_q, size_t* out_passes, int* status)
+{
+	orc_settings s = *s_in;
+	size_t passes = 0;
+	size_t size = 0;
+	int used_q = s.quantization;
+
+	if (ratio == 0 || s.wavelet == W_NONE || s.compression == 2 /* AKO_COMPRESSION_NONE */)
+	{
+		size = orc_encode(&s, channels, w, h, in, out, status);
+		passes = 1;
+		goto done;
+	}
+	if (ratio == 1)
+	{
+		s.quantization = 0;
+		s.gate = 0;
+		used_q = 0;
+		size = orc_encode(&s, channels, w, h, in, out, status);
+		passes = 1;
+		goto done;
+	}
+
+	{
+		const size_t target_size = (w * h * channels) / (size_t)ratio;
+		const size_t error_margin = (target_size * 4) / 100;
+		int last_q;
+
+		s.quantization = 0;
+		size_t ceil_size = orc_encode(&s, channels, w, h, in, out, status);
+		last_q = 0;
+		passes++;
+
+		s.quantization = 1;
+		size_t floor_size = ceil_size;
+		int floor_q = 0, ceil_q = 0;
+		do
+		{
+			s.quantization *= 4;
+			ceil_size = floor_size;
+			ceil_q = floor_q;
+			floor_size = orc_encode(&s, channels, w, h, in, out, status);
+			floor_q = s.quantization;
+			last_q = s.quantization;
+			passes++;
+		} while (floor_size > target_size && s.quantization <= (1 << 28));
+
+		size_t last_size = floor_size;
+		while ((floor_size > ceil_size ? floor_size - ceil_size : ceil_size - floor_size) > error_margin &&
+		       abs(floor_q - ceil_q) > 1)
+		{
+			s.quantization = (ceil_q + floor_q) / 2;
+			last_size = orc_encode(&s, channels, w, h, in, out, status);
+			last_q = s.quantization;
+			passes++;
+			if (last_size > target_size)
+			{
+				ceil_size = last_size;
+				ceil_q = s.quantization;
+			}
+			else
+			{
+				floor_size = last_size;
+				floor_q = s.quantization;
+			}
+		}
+
+		const size_t df = floor_size > target_size ? floor_size - target_size : target_size - floor_size;
+		const size_t dc = ceil_size > target_size ? ceil_size - target_size : target_size - ceil_size;
+		const size_t chosen_size = (df < dc) ? floor_size : ceil_size;
+		const int chosen_q = (df < dc) ? floor_q : ceil_q;
+		if (last_size == chosen_size)
+		{
+			size = last_size;
+			used_q = last_q;
+		}
+		else
+		{
+			s.quantization = chosen_q;
+			size = orc_encode(&s, channels, w, h, in, out, status);
+			used_q = chosen_q;
+			passes++;
+		}
+	}
+
+done:
+	if (out_q)
+		*out_q = used_q;
+	if (out_passes)
+		*out_passes = passes;
+	return size;
+}

@@ -87,6 +87,10 @@ size_t orc_encode(const orc_settings* s, size_t channels, size_t w, size_t h, co
 /* out must hold w*h*channels bytes (query dims with orc_head_read first); returns status */
 int orc_decode(size_t in_size, const uint8_t* in, uint8_t* out, orc_settings* out_s);
 
+/* multi-pass ratio search of the encoder tool (tools/akoenc.cpp:111-213, EncodePass) */
+size_t orc_encode_pass(int ratio, const orc_settings* s, size_t channels, size_t w, size_t h, const uint8_t* in,
+                       uint8_t* out, int* out_q, size_t* out_passes, int* status);
+
 #ifdef __cplusplus
 }
 #endif

@@ -81,6 +81,9 @@ def load_oracle():
     L.orc_encode.restype = c_size_t
     L.orc_encode.argtypes = [C.POINTER(OrcSettings), c_size_t, c_size_t, c_size_t, u8p, u8p, C.POINTER(c_int)]
     L.orc_decode.argtypes = [c_size_t, u8p, u8p, C.POINTER(OrcSettings)]
+    L.orc_encode_pass.restype = c_size_t
+    L.orc_encode_pass.argtypes = [c_int, C.POINTER(OrcSettings), c_size_t, c_size_t, c_size_t, u8p, u8p,
+                                  C.POINTER(c_int), C.POINTER(c_size_t), C.POINTER(c_int)]
     return L
 
 
@@ -159,6 +162,68 @@ def orc_encode(orc, img, **kw):
     st = c_int(0)
     n = orc.orc_encode(C.byref(s), ch, w, h, _p(np.ascontiguousarray(img), u8p), _p(out, u8p), C.byref(st))
     return (out[:n].tobytes() if n else None), st.value
+
+
+def orc_encode_pass(orc, img, ratio, **kw):
+    """EncodePass of the encoder tool: (blob | None, status, q of the blob, passes)."""
+    h, w, ch = img.shape
+    s = make_settings(OrcSettings, **kw)
+    out = np.zeros(orc.orc_encode_bound(ch, w, h), dtype=np.uint8)
+    st, q, passes = c_int(0), c_int(0), c_size_t(0)
+    n = orc.orc_encode_pass(ratio, C.byref(s), ch, w, h, _p(np.ascontiguousarray(img), u8p), _p(out, u8p),
+                            C.byref(q), C.byref(passes), C.byref(st))
+    return (out[:n].tobytes() if n else None), st.value, q.value, passes.value
+
+
+def ref_encode_pass(ref, img, ratio, **kw):
+    """EncodePass (tools/akoenc.cpp:111-213) transcribed over the UNMODIFIED reference's akoEncodeExt: pins
+    orc_encode_pass. Returns (blob | None, q of the blob, passes)."""
+    passes = [0]
+
+    def enc(q, g=None):
+        k = dict(kw)
+        k["q"] = q
+        if g is not None:
+            k["g"] = g
+        passes[0] += 1
+        blob, _ = ref_encode(ref, img, **k)
+        return blob
+
+    size = lambda b: len(b) if b else 0
+    if ratio == 0 or kw.get("wavelet", 0) == 3 or kw.get("compression", 0) == 2:
+        return enc(kw.get("q", 16)), kw.get("q", 16), 1
+    if ratio == 1:
+        return enc(0, 0), 0, 1
+    h, w, ch = img.shape
+    target = (w * h * ch) // ratio
+    margin = (target * 4) // 100
+    last = enc(0)
+    last_q = 0
+    ceil_size = size(last)
+    q, floor_size, floor_q, ceil_q = 1, ceil_size, 0, 0
+    while True:
+        q *= 4
+        ceil_size, ceil_q = floor_size, floor_q
+        last, last_q = enc(q), q
+        floor_size, floor_q = size(last), q
+        if not (floor_size > target and q <= (1 << 28)):
+            break
+    last_size = floor_size
+    while abs(floor_size - ceil_size) > margin and abs(floor_q - ceil_q) > 1:
+        q = (ceil_q + floor_q) // 2
+        last, last_q = enc(q), q
+        last_size = size(last)
+        if last_size > target:
+            ceil_size, ceil_q = last_size, q
+        else:
+            floor_size, floor_q = last_size, q
+    if abs(floor_size - target) < abs(ceil_size - target):
+        chosen_size, chosen_q = floor_size, floor_q
+    else:
+        chosen_size, chosen_q = ceil_size, ceil_q
+    if last_size == chosen_size:
+        return last, last_q, passes[0]
+    return enc(chosen_q), chosen_q, passes[0]
 
 
 def orc_decode(orc, blob):

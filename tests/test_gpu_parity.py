@@ -348,3 +348,34 @@ def test_c5_lossless_16384_known_answer_and_roundtrip():
     assert sha(blob) == blob_sha
     out, st, _ = ako_b200.decode(blob)
     assert st == 0 and np.array_equal(out, img)
+
+
+RATIO_CASES = [  # (w, h, seed, ratio, settings) -- the CPU twin of this list pins the oracle to the reference
+    (320, 200, 11, 10, dict(wavelet=0, g=0)),
+    (320, 200, 11, 30, dict(wavelet=1, g=8)),
+    (257, 131, 12, 6, dict(wavelet=2, g=0)),
+    (300, 260, 13, 20, dict(wavelet=0, g=0, tiles=128)),
+    (200, 160, 14, 4000, dict(wavelet=1, g=0)),
+    (200, 160, 14, 1, dict(wavelet=0, q=40, g=5)),
+    (200, 160, 14, 0, dict(wavelet=0, q=12, g=0)),
+    (128, 128, 15, 12, dict(wavelet=0, color=1, g=0)),
+    (1632, 2464, 2, 25, dict(wavelet=0, g=16)),  # configs[1] shape
+]
+
+
+@pytest.mark.parametrize("case", RATIO_CASES, ids=lambda c: f"{c[0]}x{c[1]}-r{c[3]}")
+def test_ratio_search(orc, case):
+    """akoB200EncodeRatio against the oracle's EncodePass (tools/akoenc.cpp:111-213): same blob, same quantisation,
+    same pass count -- while running the wavelet once per colour model instead of once per pass."""
+    w, h, seed, ratio, kw = case
+    img = ol.synth(orc, w, h, seed)
+    want, want_st, want_q, want_passes = ol.orc_encode_pass(orc, img, ratio, **kw)
+    alias = {"tiles": "tiles_dimension"}
+    s = S(**{alias.get(k, k): v for k, v in kw.items()})
+    got, st, q, passes = ako_b200.encode_ratio(img, ratio, s)
+    assert got == want
+    assert (q, passes) == (want_q, want_passes)
+    if got is not None:
+        px, st, _ = ako_b200.decode(got)
+        want_px, _ = ol.orc_decode(orc, want)
+        assert st == 0 and np.array_equal(px, want_px)

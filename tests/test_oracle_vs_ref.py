@@ -294,3 +294,27 @@ def test_status_codes(orc, ref):
         rd, rst = ol.ref_decode(ref, bad)
         od, ost = ol.orc_decode(orc, bad)
         assert rd is None and od is None and rst == ost, (rst, ost)
+
+
+RATIO_CASES = [  # (w, h, seed, ratio, settings)
+    (320, 200, 11, 10, dict(wavelet=0, g=0)),
+    (320, 200, 11, 30, dict(wavelet=1, g=8)),
+    (257, 131, 12, 6, dict(wavelet=2, g=0)),
+    (300, 260, 13, 20, dict(wavelet=0, g=0, tiles=128)),
+    (200, 160, 14, 4000, dict(wavelet=1, g=0)),   # unreachable target: the q *= 4 loop runs to its end
+    (200, 160, 14, 1, dict(wavelet=0, q=40, g=5)),  # ratio 1 = lossless
+    (200, 160, 14, 0, dict(wavelet=0, q=12, g=0)),  # ratio 0 = one plain pass
+    (128, 128, 15, 12, dict(wavelet=0, color=1, g=0)),
+]
+
+
+@pytest.mark.parametrize("case", RATIO_CASES, ids=lambda c: f"{c[0]}x{c[1]}-r{c[3]}")
+def test_ratio_search_vs_reference(orc, ref, case):
+    """orc_encode_pass (EncodePass, tools/akoenc.cpp:111-213) against the same loop driven over the unmodified
+    reference's akoEncodeExt: same blob, same quantisation, same number of passes."""
+    w, h, seed, ratio, kw = case
+    img = ol.synth(orc, w, h, seed)
+    want, want_q, want_passes = ol.ref_encode_pass(ref, img, ratio, **kw)
+    got, st, q, passes = ol.orc_encode_pass(orc, img, ratio, **kw)
+    assert got == want
+    assert (q, passes) == (want_q, want_passes)
