@@ -453,8 +453,8 @@ AKO_API enum akoStatus akoB200CopyToHost(akoB200Context* ctx, void* dst, const v
 
 /* cudaHostAlloc / cudaFreeHost cost milliseconds for image-sized blocks, so freed blocks are kept in a small
  * cache (prefix word 0 = user size, word 1 = capacity) and handed out again to requests they fit. */
-#define PIN_CACHE_SLOTS 16
-#define PIN_CACHE_MAX_BYTES ((size_t)1 << 30)
+#define PIN_CACHE_SLOTS 64
+#define PIN_CACHE_MAX_BYTES ((size_t)2 << 30)
 static pthread_mutex_t g_pin_lock = PTHREAD_MUTEX_INITIALIZER;
 static uint8_t* g_pin_cache[PIN_CACHE_SLOTS];
 static size_t g_pin_cached_bytes = 0;
@@ -484,7 +484,9 @@ static void* pinned_malloc(size_t bytes)
 
 	if (raw == NULL)
 	{
-		const size_t cap = (bytes + 4095) & ~(size_t)4095;
+		/* blobs of one image shape differ by a few percent: round up so that they share cached blocks */
+		const size_t grain = (bytes < ((size_t)1 << 16)) ? 4096 : (size_t)1 << 16;
+		const size_t cap = (bytes + grain - 1) & ~(grain - 1);
 		raw = akod_pinned_alloc(cap + PIN_PREFIX);
 		if (raw == NULL)
 			return NULL;
@@ -501,15 +503,34 @@ static void pinned_free(void* p)
 	uint8_t* raw = (uint8_t*)p - PIN_PREFIX;
 	const size_t cap = ((size_t*)raw)[1];
 	pthread_mutex_lock(&g_pin_lock);
-	if (g_pin_cached_bytes + cap <= PIN_CACHE_MAX_BYTES)
+	{
+		/* a free slot, else the place of the smallest cached block when that one is smaller (page-locking cost
+		 * grows with size: the big blocks are the ones worth keeping) */
+		int slot = -1, smallest = -1;
 		for (int i = 0; i < PIN_CACHE_SLOTS; i++)
+		{
 			if (g_pin_cache[i] == NULL)
 			{
-				g_pin_cache[i] = raw;
-				g_pin_cached_bytes += cap;
-				raw = NULL;
+				slot = i;
 				break;
 			}
+			if (smallest < 0 || ((size_t*)g_pin_cache[i])[1] < ((size_t*)g_pin_cache[smallest])[1])
+				smallest = i;
+		}
+		if (slot < 0 && smallest >= 0 && ((size_t*)g_pin_cache[smallest])[1] < cap)
+			slot = smallest;
+		if (slot >= 0)
+		{
+			uint8_t* evicted = g_pin_cache[slot];
+			const size_t evicted_cap = (evicted != NULL) ? ((size_t*)evicted)[1] : 0;
+			if (g_pin_cached_bytes - evicted_cap + cap <= PIN_CACHE_MAX_BYTES)
+			{
+				g_pin_cache[slot] = raw;
+				g_pin_cached_bytes += cap - evicted_cap;
+				raw = evicted;
+			}
+		}
+	}
 	pthread_mutex_unlock(&g_pin_lock);
 	if (raw != NULL)
 		akod_pinned_free(raw);
