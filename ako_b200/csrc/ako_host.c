@@ -1859,3 +1859,353 @@ done:
 		*out_status = st;
 	return ok;
 }
+
+/* ------------------------------------------------------------------------------------------------ */
+/* batches of host images / host blobs (additive; SURVEY 8b "batch entry point", 8f4 "pipelined host I/O")      */
+
+/* The batch is cut into chunks of a few images. A chunk is one pass of the batched kernels (encode_core /
+ * decode_core with n = chunk) on its own pooled context and stream, bracketed by the host<->device copies of its
+ * images. A few worker threads (the caller is one of them) take chunks as they come, so the copies of one chunk
+ * overlap the kernels of another and the read-backs of a third: PCIe stays busy in both directions. */
+#define HOST_BATCH_CHUNK 8    /* most images per chunk ($AKO_B200_BATCH_CHUNK lowers it) */
+#define HOST_BATCH_WORKERS 8  /* most worker threads ($AKO_B200_BATCH_WORKERS picks 1..8, default 2) */
+
+static size_t env_size(const char* name, size_t fallback, size_t lo, size_t hi)
+{
+	const char* v = getenv(name);
+	if (v == NULL || v[0] == '\0')
+		return fallback;
+	const long x = strtol(v, NULL, 10);
+	return (x < (long)lo) ? lo : (x > (long)hi) ? hi : (size_t)x;
+}
+
+struct host_batch
+{
+	int decode;
+	struct akoCallbacks cb;
+	struct akoSettings s; /* encode: the caller's; decode: what blob 0's head says */
+	size_t channels, w, h, n, chunk, workers;
+	const void* const* in;
+	const size_t* in_sizes;
+	void** out;
+	size_t* out_sizes;
+
+	pthread_mutex_t lock;
+	size_t next_chunk;
+	size_t first_failed; /* index of the first image that failed, n when none did */
+	enum akoStatus st;   /* status of that image */
+};
+
+static void host_batch_fail(struct host_batch* b, size_t image, enum akoStatus st)
+{
+	pthread_mutex_lock(&b->lock);
+	if (image < b->first_failed)
+	{
+		b->first_failed = image;
+		b->st = st;
+	}
+	pthread_mutex_unlock(&b->lock);
+}
+
+static void host_batch_encode_chunk(struct host_batch* b, size_t first, size_t count)
+{
+	enum akoStatus st = AKO_OK;
+	akoB200Context* ctx = pool_acquire(&st);
+	if (ctx == NULL)
+	{
+		host_batch_fail(b, first, st);
+		return;
+	}
+	const size_t image_bytes = b->w * b->h * b->channels;
+	const size_t in_stride = align_up(image_bytes, 256);
+	const size_t out_stride = align_up(akoB200EncodeBound(&b->s, b->channels, b->w, b->h), 256);
+	void *d_in, *d_out;
+	size_t sizes[HOST_BATCH_CHUNK];
+	size_t done = 0;
+	if ((st = from_dev(akod_workspace(ctx->dev, AKOD_WS_INPUT, in_stride * count + 64, &d_in))) == AKO_OK)
+		st = from_dev(akod_workspace(ctx->dev, AKOD_WS_OUTPUT, out_stride * count + 64, &d_out));
+	for (size_t i = 0; i < count && st == AKO_OK; i++)
+	{
+		if (b->in[first + i] == NULL)
+			st = AKO_INVALID_INPUT;
+		else
+			st = from_dev(akod_h2d(ctx->dev, (uint8_t*)d_in + in_stride * i, b->in[first + i], image_bytes));
+	}
+	if (st == AKO_OK)
+		done = encode_core(ctx, NULL, &b->s, b->channels, b->w, b->h, count, d_in, in_stride, d_out, out_stride, out_stride,
+		                   sizes, &st);
+	for (size_t i = 0; i < done; i++)
+	{
+		void* blob = b->cb.malloc(sizes[i]);
+		if (blob == NULL)
+		{
+			st = AKO_NO_ENOUGH_MEMORY;
+			done = i;
+			break;
+		}
+		b->out[first + i] = blob;
+		b->out_sizes[first + i] = sizes[i];
+		const enum akoStatus cst = from_dev(akod_d2h(ctx->dev, blob, (uint8_t*)d_out + out_stride * i, sizes[i]));
+		if (cst != AKO_OK)
+		{
+			st = cst;
+			done = i;
+			break;
+		}
+	}
+	{
+		const enum akoStatus sst = from_dev(akod_sync(ctx->dev));
+		if (sst != AKO_OK && st == AKO_OK)
+		{
+			st = sst;
+			done = 0;
+		}
+	}
+	if (done != count)
+		host_batch_fail(b, first + done, (st != AKO_OK) ? st : AKO_ERROR);
+	pool_release(ctx);
+}
+
+static void host_batch_decode_chunk(struct host_batch* b, size_t first, size_t count)
+{
+	enum akoStatus st = AKO_OK;
+	const size_t tiles = tiles_count(b->w, b->h, b->s.tiles_dimension);
+	const size_t image_bytes = b->w * b->h * b->channels;
+	uint64_t* blk = malloc(sizeof(uint64_t) * tiles * 2 * count);
+	akoB200Context* ctx = NULL;
+	size_t done = 0, usable = count, largest = 0;
+	if (blk == NULL)
+	{
+		host_batch_fail(b, first, AKO_NO_ENOUGH_MEMORY);
+		return;
+	}
+
+	/* every blob must describe the batch's shape and settings; walk its block heads on the host */
+	for (size_t i = 0; i < count; i++)
+	{
+		struct akoSettings s;
+		size_t channels = 0, w = 0, h = 0;
+		const uint8_t* blob = b->in[first + i];
+		const size_t size = b->in_sizes[first + i];
+		enum akoStatus bst = AKO_OK;
+		memset(&s, 0, sizeof(s));
+		if (blob == NULL)
+			bst = AKO_INVALID_INPUT;
+		else if (size < 16)
+			bst = AKO_BROKEN_INPUT;
+		else if ((bst = head_read(blob, &channels, &w, &h, &s)) == AKO_OK)
+		{
+			if (channels != b->channels || w != b->w || h != b->h || memcmp(&s, &b->s, sizeof(s)) != 0)
+				bst = AKO_INVALID_INPUT; /* not the shape of blob 0: decode it on its own with akoDecodeExt */
+			else
+				bst = walk_blocks_host(blob, size, &s, channels, w, h, blk + tiles * i, blk + tiles * (count + i));
+		}
+		if (bst != AKO_OK)
+		{
+			host_batch_fail(b, first + i, bst);
+			usable = i;
+			break;
+		}
+		largest = (size > largest) ? size : largest;
+	}
+	if (usable == 0 || (ctx = pool_acquire(&st)) == NULL)
+	{
+		if (usable != 0)
+			host_batch_fail(b, first, st);
+		free(blk);
+		return;
+	}
+	if (usable != count) /* sizes of the usable prefix must be contiguous: [usable][tiles] */
+		memmove(blk + tiles * usable, blk + tiles * count, sizeof(uint64_t) * tiles * usable);
+
+	const size_t in_stride = align_up(largest, 256);
+	const size_t out_stride = align_up(image_bytes, 256);
+	void *d_in, *d_out;
+	if ((st = from_dev(akod_workspace(ctx->dev, AKOD_WS_INPUT, in_stride * usable + 64, &d_in))) == AKO_OK)
+		st = from_dev(akod_workspace(ctx->dev, AKOD_WS_OUTPUT, out_stride * usable + 64, &d_out));
+	for (size_t i = 0; i < usable && st == AKO_OK; i++)
+		st = from_dev(akod_h2d(ctx->dev, (uint8_t*)d_in + in_stride * i, b->in[first + i], b->in_sizes[first + i]));
+	if (st == AKO_OK)
+	{
+		st = decode_core(ctx, NULL, &b->s, b->channels, b->w, b->h, usable, d_in, in_stride, blk, blk + tiles * usable, d_out,
+		                 out_stride, &done);
+		if (st == AKO_BROKEN_INPUT && done < usable)
+			host_batch_fail(b, first + done, st); /* images before it are fine */
+		else if (st != AKO_OK)
+			done = 0;
+	}
+	for (size_t i = 0; i < done; i++)
+	{
+		uint8_t* image = b->cb.malloc(image_bytes);
+		enum akoStatus cst = AKO_NO_ENOUGH_MEMORY;
+		if (image != NULL)
+			cst = from_dev(akod_d2h(ctx->dev, image, (uint8_t*)d_out + out_stride * i, image_bytes));
+		if (cst != AKO_OK)
+		{
+			if (image != NULL)
+				b->cb.free(image);
+			st = cst;
+			done = i;
+			break;
+		}
+		b->out[first + i] = image;
+	}
+	{
+		const enum akoStatus sst = from_dev(akod_sync(ctx->dev));
+		if (sst != AKO_OK)
+		{
+			st = sst;
+			done = 0;
+		}
+	}
+	if (done != usable && st != AKO_BROKEN_INPUT)
+		host_batch_fail(b, first + done, (st != AKO_OK) ? st : AKO_ERROR);
+	pool_release(ctx);
+	free(blk);
+}
+
+static void* host_batch_worker(void* raw)
+{
+	struct host_batch* b = raw;
+	for (;;)
+	{
+		pthread_mutex_lock(&b->lock);
+		const size_t c = b->next_chunk++;
+		pthread_mutex_unlock(&b->lock);
+		const size_t first = c * b->chunk;
+		if (first >= b->n)
+			break;
+		const size_t count = (b->n - first < b->chunk) ? b->n - first : b->chunk;
+		if (b->decode)
+			host_batch_decode_chunk(b, first, count);
+		else
+			host_batch_encode_chunk(b, first, count);
+	}
+	return NULL;
+}
+
+/* returns the number of leading images that succeeded; results of later images that did succeed stay valid
+ * (out[i] != NULL), failed ones are NULL */
+static size_t host_batch_run(struct host_batch* b, enum akoStatus* out_status)
+{
+	pthread_t helpers[HOST_BATCH_WORKERS];
+	size_t started = 0;
+	const size_t chunks = (b->n + b->chunk - 1) / b->chunk;
+	pthread_mutex_init(&b->lock, NULL);
+	b->next_chunk = 0;
+	b->first_failed = b->n;
+	b->st = AKO_OK;
+	for (size_t k = 1; k < b->workers && k < chunks; k++)
+		if (pthread_create(&helpers[started], NULL, host_batch_worker, b) == 0)
+			started++;
+	host_batch_worker(b);
+	for (size_t k = 0; k < started; k++)
+		pthread_join(helpers[k], NULL);
+	pthread_mutex_destroy(&b->lock);
+	if (out_status != NULL)
+		*out_status = b->st;
+	return b->first_failed;
+}
+
+static void host_batch_geometry(struct host_batch* b)
+{
+	/* two chunks per worker when the batch allows it (one in its copy phase while the other computes), at most
+	 * HOST_BATCH_CHUNK images each */
+	b->workers = env_size("AKO_B200_BATCH_WORKERS", 2, 1, HOST_BATCH_WORKERS);
+	const size_t most = env_size("AKO_B200_BATCH_CHUNK", HOST_BATCH_CHUNK, 1, HOST_BATCH_CHUNK);
+	size_t chunk = (b->n + 2 * b->workers - 1) / (2 * b->workers);
+	chunk = (chunk > most) ? most : chunk;
+	b->chunk = (chunk < 1) ? 1 : chunk;
+}
+
+AKO_API size_t akoB200EncodeBatch(const struct akoCallbacks* c, const struct akoSettings* s, size_t channels, size_t w,
+                                  size_t h, size_t n_images, const void* const* in, void** out, size_t* out_sizes,
+                                  enum akoStatus* out_status)
+{
+	struct host_batch b;
+	enum akoStatus st = AKO_OK;
+	memset(&b, 0, sizeof(b));
+	b.cb = (c != NULL) ? *c : akoDefaultCallbacks();
+	b.s = (s != NULL) ? *s : akoDefaultSettings();
+
+	if (b.cb.malloc == NULL || b.cb.realloc == NULL || b.cb.free == NULL)
+		st = AKO_INVALID_CALLBACKS;
+	else if (n_images != 0 && (in == NULL || out == NULL || out_sizes == NULL))
+		st = AKO_INVALID_INPUT;
+	else
+	{
+		struct akoSettings v = b.s;
+		uint8_t head[16];
+		resolve_color(&v);
+		st = head_write(channels, w, h, &v, head);
+		if (st == AKO_OK && channels == 0)
+			st = AKO_INVALID_CHANNELS_NO;
+	}
+	if (st != AKO_OK || n_images == 0)
+	{
+		if (out_status != NULL)
+			*out_status = st;
+		return 0;
+	}
+	for (size_t i = 0; i < n_images; i++)
+	{
+		out[i] = NULL;
+		out_sizes[i] = 0;
+	}
+	b.channels = channels;
+	b.w = w;
+	b.h = h;
+	b.n = n_images;
+	host_batch_geometry(&b);
+	b.in = in;
+	b.out = out;
+	b.out_sizes = out_sizes;
+	return host_batch_run(&b, out_status);
+}
+
+AKO_API size_t akoB200DecodeBatch(const struct akoCallbacks* c, size_t n_images, const void* const* in,
+                                  const size_t* in_sizes, uint8_t** out, struct akoSettings* out_s, size_t* out_channels,
+                                  size_t* out_w, size_t* out_h, enum akoStatus* out_status)
+{
+	struct host_batch b;
+	enum akoStatus st = AKO_OK;
+	memset(&b, 0, sizeof(b));
+	b.decode = 1;
+	b.cb = (c != NULL) ? *c : akoDefaultCallbacks();
+
+	if (b.cb.malloc == NULL || b.cb.realloc == NULL || b.cb.free == NULL)
+		st = AKO_INVALID_CALLBACKS;
+	else if (n_images != 0 && (in == NULL || in_sizes == NULL || out == NULL || in[0] == NULL))
+		st = AKO_INVALID_INPUT;
+	else if (n_images != 0 && in_sizes[0] < 16)
+		st = AKO_BROKEN_INPUT;
+	else if (n_images != 0)
+	{
+		memset(&b.s, 0, sizeof(b.s));
+		st = head_read(in[0], &b.channels, &b.w, &b.h, &b.s);
+		if (st == AKO_OK && b.s.wavelet == AKO_WAVELET_NONE && b.s.compression != AKO_COMPRESSION_NONE)
+			st = AKO_ERROR; /* see encode_core */
+	}
+	if (st != AKO_OK || n_images == 0)
+	{
+		if (out_status != NULL)
+			*out_status = st;
+		return 0;
+	}
+	for (size_t i = 0; i < n_images; i++)
+		out[i] = NULL;
+	b.n = n_images;
+	host_batch_geometry(&b);
+	b.in = in;
+	b.in_sizes = in_sizes;
+	b.out = (void**)out;
+	if (out_s != NULL)
+		*out_s = b.s;
+	if (out_channels != NULL)
+		*out_channels = b.channels;
+	if (out_w != NULL)
+		*out_w = b.w;
+	if (out_h != NULL)
+		*out_h = b.h;
+	return host_batch_run(&b, out_status);
+}

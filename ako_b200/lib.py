@@ -119,6 +119,13 @@ def load():
     L.akoB200DecodeBatchDevice.restype = c_size_t
     L.akoB200DecodeBatchDevice.argtypes = [c_void_p, c_size_t, c_void_p, c_size_t, C.POINTER(c_size_t), c_void_p,
                                            c_size_t, stp]
+    vpp = C.POINTER(c_void_p)
+    L.akoB200EncodeBatch.restype = c_size_t
+    L.akoB200EncodeBatch.argtypes = [C.POINTER(AkoCallbacks), sp, c_size_t, c_size_t, c_size_t, c_size_t, vpp, vpp,
+                                     C.POINTER(c_size_t), stp]
+    L.akoB200DecodeBatch.restype = c_size_t
+    L.akoB200DecodeBatch.argtypes = [C.POINTER(AkoCallbacks), c_size_t, vpp, C.POINTER(c_size_t), vpp, sp,
+                                     C.POINTER(c_size_t), C.POINTER(c_size_t), C.POINTER(c_size_t), stp]
     L.akoB200EncodeRatio.restype = c_size_t
     L.akoB200EncodeRatio.argtypes = [C.POINTER(AkoCallbacks), sp, c_int, c_size_t, c_size_t, c_size_t, c_void_p,
                                      C.POINTER(c_void_p), stp, C.POINTER(c_size_t), stp]
@@ -183,6 +190,52 @@ def encode_ratio(image, ratio, settings=None):
     blob = C.string_at(out.value, n)
     L.akoDefaultFree(out)
     return blob, st.value, q.value, passes.value
+
+
+def encode_batch(images, settings=None):
+    """akoB200EncodeBatch on a list of same-shape (h, w, channels) uint8 arrays.
+    Returns (list of blob bytes | None, status, leading images that succeeded)."""
+    L = load()
+    images = [np.ascontiguousarray(im, dtype=np.uint8) for im in images]
+    n = len(images)
+    h, w, ch = images[0].shape if n else (0, 0, 0)
+    ins = (c_void_p * max(n, 1))(*[im.ctypes.data for im in images])
+    outs = (c_void_p * max(n, 1))()
+    sizes = (c_size_t * max(n, 1))()
+    st = c_int(0)
+    done = L.akoB200EncodeBatch(None, C.byref(settings) if settings is not None else None, ch, w, h, n, ins, outs, sizes,
+                                C.byref(st))
+    blobs = []
+    for i in range(n):
+        if outs[i]:
+            blobs.append(C.string_at(outs[i], sizes[i]))
+            L.akoDefaultFree(outs[i])
+        else:
+            blobs.append(None)
+    return blobs, st.value, done
+
+
+def decode_batch(blobs):
+    """akoB200DecodeBatch on a list of blobs of one shape. Returns (list of images | None, status, leading successes)."""
+    L = load()
+    n = len(blobs)
+    bufs = [np.frombuffer(b, dtype=np.uint8) for b in blobs]
+    ins = (c_void_p * max(n, 1))(*[b.ctypes.data for b in bufs])
+    sizes = (c_size_t * max(n, 1))(*[len(b) for b in blobs])
+    outs = (c_void_p * max(n, 1))()
+    s = AkoSettings()
+    ch, w, h = c_size_t(), c_size_t(), c_size_t()
+    st = c_int(0)
+    done = L.akoB200DecodeBatch(None, n, ins, sizes, outs, C.byref(s), C.byref(ch), C.byref(w), C.byref(h), C.byref(st))
+    images = []
+    for i in range(n):
+        if outs[i]:
+            nb = ch.value * w.value * h.value
+            images.append(np.frombuffer(C.string_at(outs[i], nb), dtype=np.uint8).reshape(h.value, w.value, ch.value).copy())
+            L.akoDefaultFree(outs[i])
+        else:
+            images.append(None)
+    return images, st.value, done
 
 
 def decode(blob, callbacks=None):

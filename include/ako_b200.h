@@ -87,6 +87,26 @@ size_t akoB200DecodeBatchDevice(akoB200Context*, size_t n_images, const void* d_
                                 const size_t* in_sizes, void* d_out, size_t out_stride,
                                 enum akoStatus* out_status);
 
+/* ---- batches of HOST images / HOST blobs ---------------------------------------------------- */
+
+/* n_images same-shape images at host pointers in[i] -> out[i] = blob i (allocated with callbacks->malloc, the
+ * caller frees each), out_sizes[i] its size; per image exactly what akoEncodeExt returns. Inside, the batch runs in
+ * chunks of a few images through the batched kernels on several streams, so that the upload of one chunk overlaps
+ * the kernels of another and the read-back of a third. Pinned input buffers (akoB200PinnedAlloc) and
+ * akoB200PinnedCallbacks() make every copy a DMA. Returns the number of leading images that succeeded
+ * (== n_images when all did; *out_status then AKO_OK, else the status of the first failure). Images after a
+ * failure that did succeed keep their blobs; failed ones have out[i] == NULL. Events are not fired. */
+size_t akoB200EncodeBatch(const struct akoCallbacks*, const struct akoSettings*, size_t channels, size_t image_w,
+                          size_t image_h, size_t n_images, const void* const* in, void** out, size_t* out_sizes,
+                          enum akoStatus* out_status);
+
+/* n_images blobs (host pointers in[i], in_sizes[i] bytes) that all describe the channels / dimensions / settings of
+ * blob 0 -> out[i] = w*h*channels interleaved u8 (callbacks->malloc); per image what akoDecodeExt returns. A blob
+ * of another shape fails with AKO_INVALID_INPUT. Same return convention as akoB200EncodeBatch. */
+size_t akoB200DecodeBatch(const struct akoCallbacks*, size_t n_images, const void* const* in, const size_t* in_sizes,
+                          uint8_t** out, struct akoSettings* out_s, size_t* out_channels, size_t* out_w, size_t* out_h,
+                          enum akoStatus* out_status);
+
 /* ---- ratio search ------------------------------------------------------------------------ */
 
 /* What the encoder tool's EncodePass does (tools/akoenc.cpp:111-213): search the quantisation that brings the

@@ -379,3 +379,49 @@ def test_ratio_search(orc, case):
         px, st, _ = ako_b200.decode(got)
         want_px, _ = ol.orc_decode(orc, want)
         assert st == 0 and np.array_equal(px, want_px)
+
+
+@pytest.mark.parametrize("n", [1, 2, 5, 19])
+def test_host_batch_api(orc, n):
+    """akoB200EncodeBatch / akoB200DecodeBatch (host pointers, chunks pipelined over several streams): per image the
+    bytes akoEncodeExt / akoDecodeExt return, i.e. the oracle's."""
+    w, h = 200, 152
+    imgs = [ol.synth(orc, w, h, 40 + i) for i in range(n)]
+    for kw in (dict(wavelet=0, q=16, g=16), dict(wavelet=1, q=0, g=0, tiles=64)):
+        alias = {"tiles": "tiles_dimension"}
+        s = S(**{alias.get(k, k): v for k, v in kw.items()})
+        blobs, st, done = ako_b200.encode_batch(imgs, s)
+        assert (st, done) == (0, n)
+        want = [ol.orc_encode(orc, im, **kw)[0] for im in imgs]
+        assert blobs == want
+        px, st, done = ako_b200.decode_batch(blobs)
+        assert (st, done) == (0, n)
+        for i in range(n):
+            assert np.array_equal(px[i], ol.orc_decode(orc, want[i])[0])
+
+
+def test_host_batch_api_failures(orc):
+    imgs = [ol.synth(orc, 96, 80, 60 + i) for i in range(12)]
+    blobs, st, done = ako_b200.encode_batch(imgs, S(wavelet=1, q=8))
+    assert (st, done) == (0, 12)
+    bad = list(blobs)
+    bad[9] = bad[9][:len(bad[9]) // 2]                      # truncated: AKO_BROKEN_INPUT
+    px, st, done = ako_b200.decode_batch(bad)
+    assert done == 9 and st == 15 and px[9] is None
+    assert all(np.array_equal(px[i], ol.orc_decode(orc, blobs[i])[0]) for i in range(9))
+    other, _ = ol.orc_encode(orc, ol.synth(orc, 64, 64, 1), wavelet=1, q=8)
+    bad = list(blobs)
+    bad[3] = other                                          # another shape: refused, the rest of the batch is unaffected
+    px, st, done = ako_b200.decode_batch(bad)
+    assert done == 3 and st == 9 and px[3] is None and px[11] is not None
+    # encode: invalid settings are refused before any work, like akoEncodeExt
+    blobs, st, done = ako_b200.encode_batch(imgs, S(tiles_dimension=100))
+    assert done == 0 and st == 4 and all(b is None for b in blobs)
+    # an incompressible image fails alone (AKO_ERROR), its neighbours encode
+    noise = [noise_image(96, 80, 4, 5) if i == 4 else imgs[i] for i in range(12)]
+    blobs, st, done = ako_b200.encode_batch(noise, S(wavelet=2, q=0, g=0))
+    ref_blob, ref_st = ol.orc_encode(orc, noise[4], wavelet=2, q=0, g=0)
+    if ref_blob is None:
+        assert done == 4 and st == ref_st and blobs[4] is None and blobs[0] is not None
+    else:
+        assert done == 12
