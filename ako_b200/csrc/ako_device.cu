@@ -694,7 +694,7 @@ extern "C" int akod_kagari_encode(akodContext* c, uint64_t n_values, const int16
 	const dim3 zgrid((nblocks + 255) / 256, n_images);
 	AKOD_LAUNCH(c, "kagari_zero_edges", k_kg_zero_edges, zgrid, 256, 0, blk_off, blk_bits, nblocks, d_out, out_stride,
 	            out_cap * 8);
-	AKOD_BYTES(c, 2 * n_values * n_images); // + the blob bytes, not known on the host
+	// algorithmic bytes of pass 3 = the blob bytes, known only to the caller once the sizes are read back
 	AKOD_LAUNCH(c, "kagari_pack", k_kg_pack, grid, KG_THREADS, 0, d_in, in_stride, n_values, blk_start, blk_off, blk_bits,
 	            nblocks, d_out, out_stride, out_cap * 8, slots);
 	return AKOD_OK;
@@ -864,6 +864,7 @@ extern "C" int akod_kagari_decode(akodContext* c, uint64_t n_values, const uint8
 	AKOD_LAUNCH(c, "kagari_dec_spans", k_kt_spans, grid2, KT_THREADS, 0, tokens, token_cap, token_cap, info, blk_span, nblk2);
 	AKOD_LAUNCH(c, "kagari_dec_resolve", k_kt_resolve, n_images, KR_THREADS, 0, blk_span, nblk2, blk_state, blk_out, info, n_values,
 	            token_cap, d_result);
+	AKOD_BYTES(c, 2 * n_values * n_images); // the decoded values, written by this kernel and k_kt_fill together
 	AKOD_LAUNCH(c, "kagari_dec_expand", k_kt_expand, grid2, KT_THREADS, 0, tokens, token_cap, token_cap, info, blk_state,
 	            blk_out, nblk2, d_out, out_stride, n_values, big_list, big_count, big_cap);
 	{
@@ -872,7 +873,6 @@ extern "C" int akod_kagari_decode(akodContext* c, uint64_t n_values, const uint8
 		const uint32_t want = (uint32_t)c->sm_count * 8;
 		const uint32_t gx = (uint32_t)((pieces_max + 7) / 8 < want ? (pieces_max + 7) / 8 : want);
 		const dim3 gridf(gx ? gx : 1, n_images);
-		AKOD_BYTES(c, 2 * n_values * n_images);
 		AKOD_LAUNCH(c, "kagari_dec_fill", k_kt_fill, gridf, 256, 0, big_list, big_count, big_cap, d_out, out_stride);
 	}
 	// Streams that did not self-synchronise within KD_MAX_RUNS (adversarial input) are decoded by one thread

@@ -173,6 +173,25 @@ __device__ __forceinline__ uint32_t block_excl_sum(uint32_t v, uint32_t* sm, uin
 	return r;
 }
 
+// Single-use variants for kernels that scan once per shared array: ONE barrier each. Every warp folds the NW warp
+// totals itself (one load per lane + two REDUX) instead of waiting for warp 0 to scan them, and there is no trailing barrier:
+// the caller must not write sm again before a barrier of its own.
+template <int NW>
+__device__ __forceinline__ uint32_t block_excl_sum_once(uint32_t v, uint32_t* sm, uint32_t* total)
+{
+	const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+	const uint32_t incl = warp_incl_sum(v);
+	if (lane == 31)
+		sm[wid] = incl;
+	__syncthreads();
+	// every warp folds the NW warp totals itself: one shared load per lane and two warp reductions (REDUX)
+	const uint32_t x = (lane < NW) ? sm[lane] : 0u;
+	const uint32_t all = __reduce_add_sync(AKOD_FULL_MASK, x);
+	const uint32_t before = __reduce_add_sync(AKOD_FULL_MASK, (lane < wid) ? x : 0u);
+	*total = all;
+	return before + incl - v;
+}
+
 // Block-wide exclusive max of one int64 per thread (identity = -1); *total gets the block max.
 // sm must hold 33 long long.
 __device__ __forceinline__ long long block_excl_max(long long v, long long* sm, long long* total)
@@ -269,5 +288,23 @@ __device__ __forceinline__ uint32_t block_excl_last_start(uint32_t v, uint32_t* 
 	}
 	*total = all;
 	__syncthreads();
+	return lower ? from_lower : carry;
+}
+
+template <int NW>
+__device__ __forceinline__ uint32_t block_excl_last_start_once(uint32_t v, uint32_t* sm, uint32_t* total)
+{
+	const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+	const uint32_t mask = __ballot_sync(AKOD_FULL_MASK, v != 0);
+	const uint32_t lower = mask & ((1u << lane) - 1u);
+	const uint32_t from_lower = __shfl_sync(AKOD_FULL_MASK, v, lower ? 31 - __clz(lower) : 0);
+	const uint32_t warp_last = __shfl_sync(AKOD_FULL_MASK, v, mask ? 31 - __clz(mask) : 0);
+	if (lane == 0)
+		sm[wid] = mask ? warp_last : 0u;
+	__syncthreads();
+	const uint32_t x = (lane < NW) ? sm[lane] : 0u;
+	const uint32_t all = __reduce_max_sync(AKOD_FULL_MASK, x);
+	const uint32_t carry = __reduce_max_sync(AKOD_FULL_MASK, (lane < wid) ? x : 0u);
+	*total = all;
 	return lower ? from_lower : carry;
 }

@@ -181,7 +181,7 @@ __global__ void __launch_bounds__(KG_THREADS)
 	const uint64_t base = (uint64_t)blockIdx.x * KG_BLOCK + (uint64_t)threadIdx.x * KG_ITEMS;
 	const KgChunk c = kg_load(in, n, base);
 	uint32_t total;
-	block_excl_last_start(c.last_start, sm, &total);
+	block_excl_last_start_once<KG_THREADS / 32>(c.last_start, sm, &total);
 	if (threadIdx.x == 0)
 	{
 		blk_own[blockIdx.x] = total;
@@ -244,7 +244,7 @@ __device__ __forceinline__ uint32_t kg_thread_codes(const KgChunk& c, uint64_t n
 {
 	// run start reaching into this thread = max(block carry, starts of earlier threads); all are (index + 1)
 	uint32_t dummy;
-	const uint32_t run_start = max(carry_start, block_excl_last_start(c.last_start, sm_max, &dummy));
+	const uint32_t run_start = max(carry_start, block_excl_last_start_once<KG_THREADS / 32>(c.last_start, sm_max, &dummy));
 	return kg_codes<EMIT>(c, n, base, run_start, codes);
 }
 
@@ -356,7 +356,7 @@ __global__ void __launch_bounds__(KG_THREADS)
 	const uint32_t bits =
 	    kg_thread_codes<true>(c, n, base, blk_carry[(uint64_t)nblocks * blockIdx.y + blockIdx.x], sm_max, codes);
 	uint32_t total;
-	const uint32_t excl = block_excl_sum(bits, sm_sum, &total);
+	const uint32_t excl = block_excl_sum_once<KG_THREADS / 32>(bits, sm_sum, &total);
 	if (threadIdx.x == 0)
 		blk_bits[(uint64_t)nblocks * blockIdx.y + blockIdx.x] = total;
 	if (total == 0 || total > KG_SLOT_BITS)

@@ -393,14 +393,15 @@ __global__ void __launch_bounds__(UT_THREADS, 6) k_unlift_strip(const UnstripPar
 #pragma unroll
 		for (int round = 0; round < 2; round++)
 		{
-			// consecutive lanes take consecutive chunks of a row: conflict-free 128-bit shared loads and
-			// contiguous global stores
+			// A half warp takes one row (its 16th lane idles): every quarter warp then reads 128 contiguous bytes
+			// of one VB row, so the 128-bit shared loads are conflict-free whatever the row pitch, and the global
+			// stores of a half warp are contiguous.
 			const int item = tid + UT_THREADS * round;
-			const int r = item / (UT_TW / 8), chunk = item - r * (UT_TW / 8);
+			const int r = item >> 4, chunk = item & 15;
 			const int a = chunk * 8;
 			const int cr = js + (r >> 1) - ((r & 1) ? LAT : LEV); // coefficient row this VB row belongs to
 			const uint32_t oy = (uint32_t)(2 * cr + (r & 1));
-			if (r < 2 * UT_STEP && c0 + a < hw && (uint32_t)(cr - i_begin) < (uint32_t)(i_end - i_begin) && oy < p.th)
+			if (chunk < UT_TW / 8 && c0 + a < hw && (uint32_t)(cr - i_begin) < (uint32_t)(i_end - i_begin) && oy < p.th)
 			{
 				// VB columns [a, a+16) hold coefficients c = c0 + a - 4 + k
 				const uint4 l0 = *reinterpret_cast<const uint4*>(&VBs[r * UT_VP + a]);

@@ -437,13 +437,22 @@ def run_ours(args, rank, world):
     ctx.profile_reset()
     ctx.profile(True)
     prof_steps = 3
+    prof_blob_bytes = 0
     for i in range(prof_steps):
-        step_device(i)
+        prof_blob_bytes += int(sum(step_device(i)))
     ctx.sync()
     prof = ctx.profile_get()
     ctx.profile(False)
     total_ms = sum(ms for _, ms in prof.values()) or 1.0
     nbytes = ctx.profile_get_bytes()
+    # two accounting corrections the library cannot make on its own: pass 3 of the encoder moves the blob bytes
+    # (known here from the sizes), and the decoder's output is written by expand and fill together (one entry)
+    if "kagari_pack" in prof:
+        nbytes["kagari_pack"] = prof_blob_bytes
+    if "kagari_dec_expand" in prof and "kagari_dec_fill" in prof:
+        e, f = prof.pop("kagari_dec_expand"), prof.pop("kagari_dec_fill")
+        prof["kagari_dec_expand+fill"] = (e[0] + f[0], e[1] + f[1])
+        nbytes["kagari_dec_expand+fill"] = nbytes.pop("kagari_dec_expand", 0) + nbytes.pop("kagari_dec_fill", 0)
     top = max(prof.items(), key=lambda kv: kv[1][1])
     peak, peak_src = read_peaks()
 
@@ -516,7 +525,10 @@ def run_ours(args, rank, world):
 
 
 def run_dwt(args):
-    """configs[2]: forward / inverse DWT only on 8192x8192 RGBA8 planes, HBM GB/s against the roofline."""
+    """configs[2]: forward / inverse DWT only on 8192x8192 RGBA8 planes, HBM GB/s against the roofline.
+    "pyramid" = the whole akoLift / akoUnlift (every level; 16 B/pixel algorithmic). "level0" = the dominant kernel
+    alone, the level-0 strip launch: time(pyramid of size) - time(pyramid of size/2), the half-size pyramid being
+    exactly the launches that follow level 0."""
     import torch
 
     import ako_b200
@@ -524,26 +536,25 @@ def run_dwt(args):
     torch.cuda.set_device(local)
     ctx = ako_b200.Context(local)
     L = ako_b200.load()
-    w = h = args.dwt_size
     peak, peak_src = read_peaks()
-    n = ctx.stream_size(CHANNELS, w, h) // 2
-    gen = torch.Generator(device="cuda").manual_seed(1)
-    base = torch.randint(-255, 256, (CHANNELS, h, w), dtype=torch.int16, device="cuda", generator=gen)
-    planes = torch.empty_like(base)
-    stream_t = torch.empty(n + 64, dtype=torch.int16, device="cuda")
     ts = torch.cuda.ExternalStream(ctx.stream)
-    out = {}
-    for wavelet, name in ((1, "cdf53"), (0, "dd137"), (2, "haar")):
-        if name not in args.dwt_wavelets.split(","):
-            continue
-        s = ako_b200.default_settings(wavelet=wavelet, quantization=0, gate=0)
+    flush = torch.empty(2 * L2_BYTES, dtype=torch.uint8, device="cuda")
+    gen = torch.Generator(device="cuda").manual_seed(1)
+
+    def pyramid_ms(size, s):
+        w = h = size
+        n = ctx.stream_size(CHANNELS, w, h) // 2
+        base = torch.randint(-255, 256, (CHANNELS, h, w), dtype=torch.int16, device="cuda", generator=gen)
+        planes = torch.empty_like(base)
+        stream_t = torch.empty(n + 64, dtype=torch.int16, device="cuda")
         res = {}
         for direction in ("forward", "inverse"):
             times = []
             for it in range(args.warmup + args.steps):
                 if direction == "forward":
-                    planes.copy_(base)  # akoB200Lift destroys its input; the copy also evicts L2 (2x268 MB)
-                    torch.cuda.synchronize()
+                    planes.copy_(base)  # akoB200Lift destroys its input
+                flush.zero_()           # evict L2 (252 MiB written) so that every pass reads from HBM
+                torch.cuda.synchronize()
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 e0.record(ts)
                 if direction == "forward":
@@ -557,14 +568,32 @@ def run_dwt(args):
                     times.append(e0.elapsed_time(e1))
             if direction == "inverse":
                 assert torch.equal(planes, base), "DWT round trip is not exact"
-            ms = float(np.median(times))
-            gbs = 4 * w * h * CHANNELS / (ms * 1e-3) / 1e9
+            res[direction] = float(np.median(times))
+        return res
+
+    size = args.dwt_size
+    out = {}
+    for wavelet, name in ((1, "cdf53"), (0, "dd137"), (2, "haar")):
+        if name not in args.dwt_wavelets.split(","):
+            continue
+        s = ako_b200.default_settings(wavelet=wavelet, quantization=0, gate=0)
+        full, half = pyramid_ms(size, s), pyramid_ms(size // 2, s)
+        res = {}
+        for direction in ("forward", "inverse"):
+            ms = full[direction]
+            gbs = 4 * size * size * CHANNELS / (ms * 1e-3) / 1e9
+            l0 = max(ms - half[direction], 1e-6)
+            l0_gbs = 4 * size * size * CHANNELS / (l0 * 1e-3) / 1e9
             res[direction] = {"ms": round(ms, 4), "GBps": round(gbs, 1), "frac_of_measured_peak": round(gbs / peak, 4),
-                              "frac_of_8TBps": round(gbs / 8000, 4)}
+                              "frac_of_8TBps": round(gbs / 8000, 4),
+                              "level0": {"ms": round(l0, 4), "GBps": round(l0_gbs, 1),
+                                         "frac_of_measured_peak": round(l0_gbs / peak, 4),
+                                         "frac_of_8TBps": round(l0_gbs / 8000, 4)}}
         out[name] = res
     ctx.close()
-    return {"metric": "DWT-only HBM GB/s (algorithmic 16 B/pixel per direction)", "size": f"{w}x{h} RGBA8 int16 planes",
-            "peak": peak, "peak_source": peak_src, "results": out}
+    return {"metric": "DWT-only HBM GB/s (algorithmic 16 B/pixel per direction)", "size": f"{size}x{size} RGBA8 int16 planes",
+            "peak": peak, "peak_source": peak_src, "l2_policy": "252 MiB written between passes (L2 flush)",
+            "results": out}
 
 
 def run_reference(args, rank, world):
