@@ -129,6 +129,8 @@ class ClockSampler:
         self.proc = None
         self.lines = []
         self.sm, self.reasons, self.mx = [], set(), None
+        self.stamps = []
+        self.errors = []
         self.nvml = None
         self.stop_flag = False
         try:
@@ -150,12 +152,13 @@ class ClockSampler:
         while not self.stop_flag:
             try:
                 self.sm.append(float(n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM)))
+                self.stamps.append(time.perf_counter())
                 r = n.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle)
                 for name, bit in bits.items():
                     if r & bit:
                         self.reasons.add(name)
-            except Exception:
-                pass
+            except Exception as e:  # noqa: BLE001 -- reported, not fatal
+                self.errors.append(repr(e))
             time.sleep(0.002)
 
     def start(self):
@@ -185,7 +188,8 @@ class ClockSampler:
             self.stop_flag = True
             self.thread.join(timeout=1)
             return {"sm_mhz": float(np.median(self.sm)) if self.sm else None, "sm_max_mhz": self.mx,
-                    "reasons": sorted(self.reasons), "samples": len(self.sm), "source": "nvml, 5 ms period, timed region only"}
+                    "reasons": sorted(self.reasons), "samples": len(self.sm), "source": "nvml, 2 ms period, timed region only",
+                    **({"nvml_errors": len(self.errors), "first_error": self.errors[0]} if self.errors else {})}
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
@@ -433,6 +437,28 @@ def run_ours(args, rank, world):
     e2e_s, h2d, d2h = e2e_legs[best_leg]
     e2e_value = px * B * world * e2e_steps / e2e_s / 1e6
 
+    # ---- one image alone (configs[1] as BASELINE.json words it): device-resident encode + decode latency, batch of 1
+    single = None
+    if rank == 0:
+        t_single = []
+        for i in range(8):
+            d_in = dev_pool[i % pool_images].data_ptr()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            torch.cuda.synchronize()
+            e0.record(stream)
+            done, st, sz = ctx.encode_batch_device(settings, CHANNELS, w, h, 1, d_in, img_bytes, dev_blobs.data_ptr(),
+                                                   blob_stride)
+            done2, st2 = ctx.decode_batch_device(1, dev_blobs.data_ptr(), blob_stride, sz, dev_out.data_ptr(), img_bytes)
+            e1.record(stream)
+            ctx.sync()
+            if done != 1 or done2 != 1:
+                raise RuntimeError("single-image leg failed")
+            if i >= 3:
+                t_single.append(e0.elapsed_time(e1))
+        ms1 = float(np.median(t_single))
+        single = {"encode_plus_decode_ms": round(ms1, 4), "MPix_s": round(px / (ms1 * 1e-3) / 1e6, 1),
+                  "note": "one image per call, device resident; launch- and latency-bound, the batch figure is the throughput"}
+
     # ---- roofline of the dominant kernel: per-kernel CUDA events on the launching stream (outside the timed region)
     ctx.profile_reset()
     ctx.profile(True)
@@ -511,6 +537,7 @@ def run_ours(args, rank, world):
                     "other_api": {k: {"value": round(px * B * world * e2e_steps / v[0] / 1e6, 1), "api": e2e_api[k]}
                                   for k, v in e2e_legs.items() if k != best_leg}},
             "gpu_launches": int(launches),
+            "single_image": single,
             "roofline": roofline,
             "roofline_other_kernels": roofline_all[1:] if roofline_all else [],
             "top_kernel": {"name": top[0], "share_of_step": round(top[1][1] / total_ms, 4)},
