@@ -16,6 +16,16 @@
 // ------------------------------------------------------------------------------------------------
 // context
 
+// CUDA's current device is per host thread, a context's stream and buffers live on ONE device: every entry point
+// that launches, copies or synchronises first makes the context's device current on the calling thread (contexts are
+// pooled by the host API and handed to whichever thread calls next).
+static inline void akod_use(const akodContext* c)
+{
+	int cur = -1;
+	if (cudaGetDevice(&cur) != cudaSuccess || cur != c->device)
+		cudaSetDevice(c->device);
+}
+
 extern "C" int akod_context_create(int device, akodContext** out)
 {
 	*out = nullptr;
@@ -100,6 +110,7 @@ extern "C" void* akod_stream(akodContext* c)
 
 extern "C" int akod_sync(akodContext* c)
 {
+	akod_use(c);
 	AKOD_TRY(cudaStreamSynchronize(c->stream));
 	return AKOD_OK;
 }
@@ -128,7 +139,7 @@ extern "C" void akod_free(akodContext* c, void* p)
 extern "C" void* akod_pinned_alloc(size_t bytes)
 {
 	void* p = nullptr;
-	if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocDefault) != cudaSuccess)
+	if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocPortable) != cudaSuccess) // usable from every device
 	{
 		cudaGetLastError();
 		return nullptr;
@@ -144,24 +155,28 @@ extern "C" void akod_pinned_free(void* p)
 
 extern "C" int akod_h2d(akodContext* c, void* d, const void* s, size_t n)
 {
+	akod_use(c);
 	AKOD_TRY(cudaMemcpyAsync(d, s, n, cudaMemcpyHostToDevice, c->stream));
 	return AKOD_OK;
 }
 
 extern "C" int akod_d2h(akodContext* c, void* d, const void* s, size_t n)
 {
+	akod_use(c);
 	AKOD_TRY(cudaMemcpyAsync(d, s, n, cudaMemcpyDeviceToHost, c->stream));
 	return AKOD_OK;
 }
 
 extern "C" int akod_d2d(akodContext* c, void* d, const void* s, size_t n)
 {
+	akod_use(c);
 	AKOD_TRY(cudaMemcpyAsync(d, s, n, cudaMemcpyDeviceToDevice, c->stream));
 	return AKOD_OK;
 }
 
 extern "C" int akod_memset(akodContext* c, void* d, int v, size_t n)
 {
+	akod_use(c);
 	AKOD_TRY(cudaMemsetAsync(d, v, n, c->stream));
 	return AKOD_OK;
 }
@@ -175,12 +190,14 @@ __global__ void k_fill_words(uint64_t* dst, uint64_t value, size_t count)
 
 extern "C" int akod_fill_words(akodContext* c, uint64_t* d, uint64_t value, size_t count)
 {
+	akod_use(c);
 	AKOD_LAUNCH(c, "fill_words", k_fill_words, (unsigned)((count + 255) / 256), 256, 0, d, value, count);
 	return AKOD_OK;
 }
 
 extern "C" int akod_workspace(akodContext* c, int slot, size_t bytes, void** out)
 {
+	akod_use(c);
 	*out = nullptr;
 	if (slot < 0 || slot >= AKOD_WS_COUNT)
 		return AKOD_ERROR;
@@ -214,6 +231,7 @@ extern "C" void akod_profile_enable(akodContext* c, int enable)
 
 extern "C" void akod_profile_reset(akodContext* c)
 {
+	akod_use(c);
 	akod_collect_pending(c);
 	c->prof.clear();
 	c->launch_count = 0;
@@ -221,6 +239,7 @@ extern "C" void akod_profile_reset(akodContext* c)
 
 extern "C" size_t akod_profile_get(akodContext* c, size_t cap, const char** names, uint64_t* launches, double* ms)
 {
+	akod_use(c);
 	akod_collect_pending(c);
 	for (size_t i = 0; i < c->prof.size() && i < cap; i++)
 	{
@@ -257,6 +276,7 @@ static inline unsigned akod_stream_grid(akodContext* c, uint64_t items, unsigned
 extern "C" int akod_format_forward(akodContext* c, int discard, int color, uint32_t channels, uint32_t w, uint32_t h,
                                    uint64_t in_stride_px, const uint8_t* d_in, int16_t* d_planes, const akodBatch* b)
 {
+	akod_use(c);
 	const uint32_t n = b ? b->n : 1;
 	const uint64_t in_is = b ? b->in_stride : 0, pl_is = b ? b->planes_stride : 0;
 	const bool fast = channels == 4 && (w % 8) == 0 && (in_stride_px % 4) == 0 && ((uintptr_t)d_in % 16) == 0 &&
@@ -280,6 +300,7 @@ extern "C" int akod_format_forward(akodContext* c, int discard, int color, uint3
 extern "C" int akod_format_inverse(akodContext* c, int color, uint32_t channels, uint32_t w, uint32_t h,
                                    uint64_t out_stride_px, const int16_t* d_planes, uint8_t* d_out, const akodBatch* b)
 {
+	akod_use(c);
 	const uint32_t n = b ? b->n : 1;
 	const uint64_t out_is = b ? b->in_stride : 0, pl_is = b ? b->planes_stride : 0;
 	const bool fast = channels == 4 && (w % 8) == 0 && (out_stride_px % 4) == 0 && ((uintptr_t)d_out % 16) == 0 &&
@@ -446,6 +467,7 @@ static int launch_small(akodContext* c, const akodPlan* plan, uint32_t l0, bool 
 extern "C" int akod_lift(akodContext* c, const akodPlan* plan, int16_t* d_planes, int16_t* d_scratch, int16_t* d_stream,
                          const akodBatch* b)
 {
+	akod_use(c);
 	const uint32_t n = b ? b->n : 1;
 	const uint64_t planes_is = b ? b->planes_stride : 0, scratch_is = b ? b->scratch_stride : 0;
 	const uint64_t stream_is = b ? b->stream_stride : 0;
@@ -547,6 +569,7 @@ extern "C" int akod_lift(akodContext* c, const akodPlan* plan, int16_t* d_planes
 extern "C" int akod_unlift(akodContext* c, const akodPlan* plan, const int16_t* d_stream, int16_t* d_planes,
                            int16_t* d_scratch, const akodBatch* b)
 {
+	akod_use(c);
 	const uint32_t n = b ? b->n : 1;
 	const uint64_t planes_is = b ? b->planes_stride : 0, scratch_is = b ? b->scratch_stride : 0;
 	const uint64_t stream_is = b ? b->stream_stride : 0;
@@ -645,6 +668,7 @@ extern "C" int akod_kagari_encode(akodContext* c, uint64_t n_values, const int16
                                   uint8_t* d_out, uint64_t out_stride, uint64_t out_cap, uint64_t* d_bits,
                                   uint32_t n_images)
 {
+	akod_use(c);
 	if (n_values == 0 || n_values >= ((uint64_t)1 << 32))
 		return AKOD_ERROR;
 	const uint32_t nblocks = (uint32_t)((n_values + KG_BLOCK - 1) / KG_BLOCK);
@@ -704,6 +728,7 @@ extern "C" int akod_kagari_encode(akodContext* c, uint64_t n_values, const int16
 extern "C" int akod_kagari_bits(akodContext* c, uint64_t n_values, const int16_t* d_in, uint64_t in_stride, uint64_t* d_bits,
                                 uint32_t n_images)
 {
+	akod_use(c);
 	if (n_values == 0 || n_values >= ((uint64_t)1 << 32))
 		return AKOD_ERROR;
 	const uint32_t nblocks = (uint32_t)((n_values + KG_BLOCK - 1) / KG_BLOCK);
@@ -760,6 +785,7 @@ __global__ void __launch_bounds__(256) k_requant(const RequantParams p)
 // d_in: stream produced with q = 1, g = 0 on every level; d_out: what akod_lift would have produced with 'plan'
 extern "C" int akod_requantize(akodContext* c, const akodPlan* plan, const int16_t* d_in, int16_t* d_out)
 {
+	akod_use(c);
 	const uint64_t lp = (uint64_t)plan->lp_w * plan->lp_h * plan->channels;
 	AKOD_TRY(cudaMemcpyAsync(d_out, d_in, sizeof(int16_t) * lp, cudaMemcpyDeviceToDevice, c->stream));
 	for (uint32_t l = 0; l < plan->levels; l++)
@@ -790,6 +816,7 @@ extern "C" int akod_kagari_decode(akodContext* c, uint64_t n_values, const uint8
                                   const uint64_t* d_size, uint64_t max_in_size, int16_t* d_out, uint64_t out_stride,
                                   uint64_t* d_result, uint32_t n_images)
 {
+	akod_use(c);
 	if (n_values == 0 || n_images == 0 || n_values >= ((uint64_t)1 << 32))
 		return AKOD_ERROR;
 	static const bool force_sequential = getenv("AKO_B200_SEQ_DECODE") != nullptr;
@@ -981,6 +1008,7 @@ extern "C" int akod_assemble(akodContext* c, const uint8_t head16[16], uint32_t 
                              const uint64_t* d_block_cap, const uint64_t* d_bits, int with_heads, uint8_t* d_out,
                              uint64_t out_stride, uint64_t* d_total)
 {
+	akod_use(c);
 	void* ws;
 	int rc = akod_workspace(c, AKOD_WS_KAGARI2, sizeof(uint64_t) * (size_t)n_tiles * n_images, &ws);
 	if (rc != AKOD_OK)
@@ -1027,6 +1055,7 @@ __global__ void k_walk_blocks(const uint8_t* __restrict__ blob, uint64_t input_s
 extern "C" int akod_walk_blocks(akodContext* c, const uint8_t* d_blob, uint64_t input_size, uint32_t n_tiles,
                                 uint64_t* d_off, uint64_t* d_size)
 {
+	akod_use(c);
 	AKOD_LAUNCH(c, "walk_blocks", k_walk_blocks, 1, 32, 0, d_blob, input_size, n_tiles, d_off, d_size);
 	return AKOD_OK;
 }
@@ -1063,6 +1092,7 @@ __global__ void k_walk_blocks_batch(const uint8_t* __restrict__ blobs, uint64_t 
 extern "C" int akod_walk_blocks_batch(akodContext* c, const uint8_t* d_blobs, uint64_t stride, const uint64_t* d_input_size,
                                       uint32_t n_tiles, uint32_t n, uint64_t* d_off, uint64_t* d_size)
 {
+	akod_use(c);
 	AKOD_LAUNCH(c, "walk_blocks", k_walk_blocks_batch, (n + 63) / 64, 64, 0, d_blobs, stride, d_input_size, n_tiles, n, d_off,
 	            d_size);
 	return AKOD_OK;

@@ -667,6 +667,12 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
 
+    # stdout carries exactly ONE line, the JSON: whatever libraries print there while the run lasts (NCCL's version
+    # banner, for one) is sent to stderr by pointing fd 1 at fd 2 until the line is written
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
+
     if args.impl == "reference":
         line = run_reference(args, rank, world)
     elif args.workload == "dwt":
@@ -674,8 +680,10 @@ def main():
     else:
         args.warmup = max(args.warmup, 3)
         line = run_ours(args, rank, world)
+    sys.stdout.flush()
     if rank == 0 and line is not None:
-        print(json.dumps(line), flush=True)
+        os.write(json_fd, (json.dumps(line) + "\n").encode())
+    os.close(json_fd)
 
 
 if __name__ == "__main__":

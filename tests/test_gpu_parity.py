@@ -425,3 +425,39 @@ def test_host_batch_api_failures(orc):
         assert done == 4 and st == ref_st and blobs[4] is None and blobs[0] is not None
     else:
         assert done == 12
+
+
+def test_pooled_contexts_follow_the_device_not_the_thread(orc):
+    """CUDA's current device is per thread; pooled contexts are not. With $AKO_CUDA_DEVICE naming a device other than
+    0, calls from fresh threads (whose current device is 0) and the library's own worker threads must still run on the
+    context's device. Needs two GPUs (skipped on the one-GPU box)."""
+    import threading
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    old = os.environ.get("AKO_CUDA_DEVICE")
+    os.environ["AKO_CUDA_DEVICE"] = "1"
+    try:
+        imgs = [ol.synth(orc, 160, 120, 70 + i) for i in range(20)]
+        want = [ol.orc_encode(orc, im, wavelet=0, q=16, g=0)[0] for im in imgs]
+        s = S(wavelet=0, quantization=16, gate=0)
+        assert ako_b200.encode(imgs[0], s)[0] == want[0]          # creates a pooled context on device 1, main thread
+        results = {}
+
+        def fresh_thread(i):
+            results[i] = ako_b200.encode(imgs[i], s)[0]           # pooled context, thread whose current device is 0
+        for i in range(1, 4):
+            t = threading.Thread(target=fresh_thread, args=(i,))
+            t.start()
+            t.join()
+        assert all(results[i] == want[i] for i in range(1, 4))
+        blobs, st, done = ako_b200.encode_batch(imgs, s)          # the library's own worker threads
+        assert (st, done) == (0, 20) and blobs == want
+        px, st, done = ako_b200.decode_batch(blobs)
+        assert (st, done) == (0, 20)
+        assert all(np.array_equal(px[i], ol.orc_decode(orc, want[i])[0]) for i in range(20))
+    finally:
+        if old is None:
+            os.environ.pop("AKO_CUDA_DEVICE", None)
+        else:
+            os.environ["AKO_CUDA_DEVICE"] = old
