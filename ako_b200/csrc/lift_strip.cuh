@@ -168,6 +168,14 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p)
 	return (uint32_t)__cvta_generic_to_shared(p);
 }
 
+// one LDS.128, never split by the compiler
+__device__ __forceinline__ uint4 lds128(const void* p)
+{
+	uint4 v;
+	asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(smem_u32(p)));
+	return v;
+}
+
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count)
 {
 	asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
@@ -444,6 +452,9 @@ __global__ void __launch_bounds__(FS_THREADS, 6) k_lift_strip(const StripParams 
 	const uint32_t row_bytes = (uint32_t)(xb - xa) * 2;
 	const bool edge_strip = (xa != 0) || (xb != FS_XW);
 
+	// One warp issues the step's row copies. (Spreading them over the four warps, as the inverse kernel does with
+	// its 32 copies per step, gained 1 % on 8192^2 planes and lost 2 % on the 816-column C2 planes, where 2 of 7
+	// strips take the edge-fill branch below and every warp would then diverge on it.)
 	auto issue = [&](int js, int buf) {
 		int16_t* dstbuf = X + buf * FS_XBUF;
 		if (tid < 32)

@@ -281,14 +281,17 @@ __global__ void __launch_bounds__(UT_THREADS, 6) k_unlift_strip(const UnstripPar
 	const int hp_tail = min(UT_HPW, hw - (c0 - 8) + sh) - hp_x1; // 0..7 row-end elements the 16-byte copies cannot reach
 	const uint32_t ll_bytes = (uint32_t)(ll_x1 - x0) * 2, hp_bytes = (uint32_t)(hp_x1 - x0) * 2;
 
+	// Warp b issues the 8 row copies of band b (0 = LL, 1..3 = C, B, D) and arrives on the barrier with that band's
+	// bytes: with one issuing warp that warp reached the step's __syncthreads late, every step, and the others waited.
 	auto issue = [&](int js, int buf) {
 		int16_t* dstbuf = S + buf * UT_SBUF;
-		if (tid < 32)
+		const int lane = tid & 31, b = tid >> 5;
+		if (lane < UT_STEP)
 		{
-			if (tid == 0)
-				mbar_expect_tx(&bars[buf], UT_STEP * (ll_bytes + 3 * hp_bytes));
-			__syncwarp();
-			const int b = tid >> 3, r = tid & 7; // band 0 = LL, 1..3 = C, B, D
+			if (lane == 0)
+				mbar_expect_tx(&bars[buf], UT_STEP * (b == 0 ? ll_bytes : hp_bytes));
+			__syncwarp((1u << UT_STEP) - 1u);
+			const int r = lane;
 			const int j = min(max(js + r, 0), hh - 1);
 			int16_t* dst = dstbuf + (b * UT_STEP + r) * UT_SP + x0;
 			if (b == 0)
@@ -299,21 +302,22 @@ __global__ void __launch_bounds__(UT_THREADS, 6) k_unlift_strip(const UnstripPar
 		else if (hp_tail > 0)
 		{
 			// right-edge strip: the last (< 8) elements of each subband row, element by element
-			for (int i = tid - 32; i < 3 * UT_STEP * hp_tail; i += UT_THREADS - 32)
+			for (int i = b * (32 - UT_STEP) + lane - UT_STEP; i < 3 * UT_STEP * hp_tail; i += (UT_THREADS / 32) * (32 - UT_STEP))
 			{
 				const int e = i % hp_tail, rb = i / hp_tail;
-				const int b = rb >> 3, r = rb & 7;
+				const int bb = rb >> 3, r = rb & 7;
 				const int j = min(max(js + r, 0), hh - 1);
-				dstbuf[((b + 1) * UT_STEP + r) * UT_SP + hp_x1 + e] =
-				    __ldg(in_c + (uint64_t)b * band + (uint32_t)(j * hw) + (c0 - 8 - sh + hp_x1 + e));
+				dstbuf[((bb + 1) * UT_STEP + r) * UT_SP + hp_x1 + e] =
+				    __ldg(in_c + (uint64_t)bb * band + (uint32_t)(j * hw) + (c0 - 8 - sh + hp_x1 + e));
 			}
 		}
 	};
+	static_assert(UT_THREADS / 32 == 4, "one issuing warp per band");
 
 	if (tid == 0)
 	{
-		mbar_init(&bars[0], 1);
-		mbar_init(&bars[1], 1);
+		mbar_init(&bars[0], UT_THREADS / 32); // one arrival (with its expect_tx) per warp
+		mbar_init(&bars[1], UT_THREADS / 32);
 		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 	}
 	__syncthreads();
@@ -404,10 +408,12 @@ __global__ void __launch_bounds__(UT_THREADS, 6) k_unlift_strip(const UnstripPar
 			if (chunk < UT_TW / 8 && c0 + a < hw && (uint32_t)(cr - i_begin) < (uint32_t)(i_end - i_begin) && oy < p.th)
 			{
 				// VB columns [a, a+16) hold coefficients c = c0 + a - 4 + k
-				const uint4 l0 = *reinterpret_cast<const uint4*>(&VBs[r * UT_VP + a]);
-				const uint4 l1 = *reinterpret_cast<const uint4*>(&VBs[r * UT_VP + a + 8]);
-				const uint4 g0 = *reinterpret_cast<const uint4*>(&VBs[r * UT_VP + 128 + a]);
-				const uint4 g1 = *reinterpret_cast<const uint4*>(&VBs[r * UT_VP + 128 + a + 8]);
+				// explicit 128-bit loads: left to itself the compiler splits the first one into two 64-bit loads
+				// (only part of it feeds the left-edge override), which doubles its shared-memory wavefronts
+				const uint4 l0 = lds128(&VBs[r * UT_VP + a]);
+				const uint4 l1 = lds128(&VBs[r * UT_VP + a + 8]);
+				const uint4 g0 = lds128(&VBs[r * UT_VP + 128 + a]);
+				const uint4 g1 = lds128(&VBs[r * UT_VP + 128 + a + 8]);
 				const uint32_t lw[8] = {l0.x, l0.y, l0.z, l0.w, l1.x, l1.y, l1.z, l1.w};
 				uint32_t gw[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
 				uint32_t w[8];
