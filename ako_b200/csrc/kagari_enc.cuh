@@ -169,23 +169,96 @@ __device__ __forceinline__ KgChunk kg_load(const int16_t* __restrict__ in, uint6
 }
 
 // pass 1: blk_own[b] = (largest i in block b that starts a run) + 1, or 0; blk_first[b] = 1 when the block's first
-// value starts a run
+// value starts a run. A CTA takes KG_STARTS_PER_CTA consecutive blocks. Full blocks take a lean path (one 128-bit
+// load per block, all issued before any arithmetic; four XORs against the stream shifted by one element; a warp
+// REDUX; one barrier for all blocks); the last, partial block of a stream goes through kg_load.
+constexpr int KG_STARTS_PER_CTA = 2;
+
+// last run start of this thread's 8 values at 'base' as (index + 1), 0 if none; *first_differs: value 0 starts a run
+__device__ __forceinline__ uint32_t kg_lean_last_start(const int16_t* __restrict__ in, uint64_t base, uint4 q, bool* first_differs)
+{
+	const int lane = threadIdx.x & 31;
+	// word whose HIGH half is the element before this thread's first one
+	uint32_t prev = __shfl_up_sync(AKOD_FULL_MASK, q.w, 1);
+	if (lane == 0)
+		prev = (base > 0) ? ((uint32_t)(uint16_t)__ldg(in + base - 1) << 16) : (~q.x << 16); // element 0 starts a run
+	// half j of d is nonzero <=> that element differs from its predecessor
+	const uint32_t d0 = q.x ^ __funnelshift_l(prev, q.x, 16);
+	const uint32_t d1 = q.y ^ __funnelshift_l(q.x, q.y, 16);
+	const uint32_t d2 = q.z ^ __funnelshift_l(q.y, q.z, 16);
+	const uint32_t d3 = q.w ^ __funnelshift_l(q.z, q.w, 16);
+	uint32_t last = 0;
+	if (d3)
+		last = (d3 >> 16) ? 8 : 7;
+	else if (d2)
+		last = (d2 >> 16) ? 6 : 5;
+	else if (d1)
+		last = (d1 >> 16) ? 4 : 3;
+	else if (d0)
+		last = (d0 >> 16) ? 2 : 1;
+	*first_differs = (d0 & 0xFFFFu) != 0;
+	return last ? (uint32_t)base + last : 0u;
+}
+
 __global__ void __launch_bounds__(KG_THREADS)
     k_kg_starts(const int16_t* __restrict__ in, uint64_t in_stride, uint64_t n, uint32_t* __restrict__ blk_own,
                 uint8_t* __restrict__ blk_first, uint32_t nblocks)
 {
-	__shared__ uint32_t sm[33];
+	__shared__ uint32_t sm[KG_STARTS_PER_CTA][33];
 	in += in_stride * blockIdx.y;
 	blk_own += (uint64_t)nblocks * blockIdx.y;
 	blk_first += (uint64_t)nblocks * blockIdx.y;
-	const uint64_t base = (uint64_t)blockIdx.x * KG_BLOCK + (uint64_t)threadIdx.x * KG_ITEMS;
-	const KgChunk c = kg_load(in, n, base);
-	uint32_t total;
-	block_excl_last_start_once<KG_THREADS / 32>(c.last_start, sm, &total);
-	if (threadIdx.x == 0)
+	const uint32_t b0 = blockIdx.x * KG_STARTS_PER_CTA;
+	const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+
+	if ((uint64_t)(b0 + KG_STARTS_PER_CTA) * KG_BLOCK <= n)
 	{
-		blk_own[blockIdx.x] = total;
-		blk_first[blockIdx.x] = (uint8_t)(c.start_mask & 1u);
+		uint4 q[KG_STARTS_PER_CTA];
+#pragma unroll
+		for (int k = 0; k < KG_STARTS_PER_CTA; k++)
+			q[k] = __ldg(reinterpret_cast<const uint4*>(in + (uint64_t)(b0 + k) * KG_BLOCK + (uint64_t)threadIdx.x * KG_ITEMS));
+		bool first[KG_STARTS_PER_CTA];
+#pragma unroll
+		for (int k = 0; k < KG_STARTS_PER_CTA; k++)
+		{
+			const uint64_t base = (uint64_t)(b0 + k) * KG_BLOCK + (uint64_t)threadIdx.x * KG_ITEMS;
+			const uint32_t mine = kg_lean_last_start(in, base, q[k], &first[k]);
+			const uint32_t warp_max = __reduce_max_sync(AKOD_FULL_MASK, mine);
+			if (lane == 0)
+				sm[k][wid] = warp_max;
+		}
+		__syncthreads();
+		if (threadIdx.x == 0)
+		{
+#pragma unroll
+			for (int k = 0; k < KG_STARTS_PER_CTA; k++)
+			{
+				uint32_t total = 0;
+#pragma unroll
+				for (int w = 0; w < KG_THREADS / 32; w++)
+					total = max(total, sm[k][w]);
+				blk_own[b0 + k] = total;
+				blk_first[b0 + k] = (uint8_t)first[k];
+			}
+		}
+		return;
+	}
+
+	// the end of the stream: block by block through the general loader
+	for (int k = 0; k < KG_STARTS_PER_CTA; k++)
+	{
+		const uint32_t b = b0 + k;
+		if (b >= nblocks)
+			break;
+		const uint64_t base = (uint64_t)b * KG_BLOCK + (uint64_t)threadIdx.x * KG_ITEMS;
+		const KgChunk c = kg_load(in, n, base);
+		uint32_t total;
+		block_excl_last_start_once<KG_THREADS / 32>(c.last_start, sm[k], &total);
+		if (threadIdx.x == 0)
+		{
+			blk_own[b] = total;
+			blk_first[b] = (uint8_t)(c.start_mask & 1u);
+		}
 	}
 }
 
@@ -329,15 +402,21 @@ __global__ void __launch_bounds__(KG_THREADS)
 	__shared__ uint32_t sm_max[33];
 	__shared__ uint32_t sm_sum[33];
 	__shared__ uint32_t bitbuf[KG_SLOT_WORDS + 2];
+	const uint64_t bi = (uint64_t)nblocks * blockIdx.y + blockIdx.x;
+	// the three per-block words of pass 1 are fetched together (independent loads, one round trip), not one after
+	// the other behind short-circuit tests: a CTA lives for a few microseconds and this is its critical path
+	const bool has_next = blockIdx.x + 1 < nblocks;
+	const uint32_t own = __ldg(blk_own + bi);
+	const uint32_t carry_start = __ldg(blk_carry + bi);
+	const uint32_t next_first = __ldg(blk_first + (has_next ? bi + 1 : bi));
 	{
 		// A block that lies entirely inside one run which also goes on behind it emits nothing, unless the run
 		// counter passes 1, 2 or 65534 inside it (the same rule as the per-thread fast path of kg_codes). Pass 1
 		// left everything needed to see that without touching the stream: quantised planes are mostly such blocks.
-		const uint64_t bi = (uint64_t)nblocks * blockIdx.y + blockIdx.x;
 		const uint64_t first = (uint64_t)blockIdx.x * KG_BLOCK;
-		if (blk_own[bi] == 0 && blockIdx.x + 1 < nblocks && blk_first[bi + 1] == 0 && first + KG_BLOCK <= n)
+		if (own == 0 && has_next && next_first == 0 && first + KG_BLOCK <= n)
 		{
-			const uint32_t k0 = (uint32_t)first + 1u - blk_carry[bi]; // position of the block's first value in its run
+			const uint32_t k0 = (uint32_t)first + 1u - carry_start; // position of the block's first value in its run
 			uint32_t c0 = k0;
 			if (k0 > 65534u)
 				c0 = ((k0 - 1) % 65534u) + 1u;
@@ -353,12 +432,11 @@ __global__ void __launch_bounds__(KG_THREADS)
 	const uint64_t base = (uint64_t)blockIdx.x * KG_BLOCK + (uint64_t)threadIdx.x * KG_ITEMS;
 	const KgChunk c = kg_load(in, n, base);
 	KgCode codes[KG_ITEMS];
-	const uint32_t bits =
-	    kg_thread_codes<true>(c, n, base, blk_carry[(uint64_t)nblocks * blockIdx.y + blockIdx.x], sm_max, codes);
+	const uint32_t bits = kg_thread_codes<true>(c, n, base, carry_start, sm_max, codes);
 	uint32_t total;
 	const uint32_t excl = block_excl_sum_once<KG_THREADS / 32>(bits, sm_sum, &total);
 	if (threadIdx.x == 0)
-		blk_bits[(uint64_t)nblocks * blockIdx.y + blockIdx.x] = total;
+		blk_bits[bi] = total;
 	if (total == 0 || total > KG_SLOT_BITS)
 		return;
 	const uint32_t nwords = (total + 31) >> 5;
@@ -368,7 +446,7 @@ __global__ void __launch_bounds__(KG_THREADS)
 	if (bits)
 		kg_put_codes(bitbuf, excl, codes);
 	__syncthreads();
-	uint32_t* slot = slots + ((uint64_t)nblocks * blockIdx.y + blockIdx.x) * KG_SLOT_WORDS;
+	uint32_t* slot = slots + bi * KG_SLOT_WORDS;
 	for (uint32_t i = threadIdx.x; i < nwords; i += KG_THREADS)
 		slot[i] = bitbuf[i];
 }
@@ -401,10 +479,10 @@ __global__ void __launch_bounds__(KG_THREADS)
 	__shared__ uint32_t bitbuf[KG_BLOCK + 2]; // 32 bits per value at most, +1 word of misalignment, +1 spill
 
 	// a block that emits nothing (inside a long run) has nothing to do at all
-	const uint32_t total = blk_bits[(uint64_t)nblocks * blockIdx.y + blockIdx.x];
+	const uint32_t total = __ldg(blk_bits + (uint64_t)nblocks * blockIdx.y + blockIdx.x);
+	const uint64_t g0 = __ldg(blk_off + (uint64_t)nblocks * blockIdx.y + blockIdx.x); // both loads in one round trip
 	if (total == 0)
 		return;
-	const uint64_t g0 = blk_off[(uint64_t)nblocks * blockIdx.y + blockIdx.x];
 	if (g0 + total > cap_bits) // would not fit: the caller reports the failure from the bit count
 		return;
 
