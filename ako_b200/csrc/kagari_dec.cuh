@@ -232,7 +232,8 @@ __global__ void __launch_bounds__(KD_THREADS)
 	__shared__ uint32_t sm_sum[33];
 
 	const uint32_t img = blockIdx.y, b = blockIdx.x, t = threadIdx.x;
-	const uint64_t size = in_size[img];
+	const uint64_t size = __ldg(in_size + img);
+	const uint64_t off = __ldg(in_off + img); // fetched with the size: one round trip instead of two
 	const uint64_t total_bits = size * 8;
 	const uint64_t cta_bit0 = (uint64_t)b * KD_CTA_BITS;
 	ends_prev += (uint64_t)nblk * img;
@@ -261,7 +262,11 @@ __global__ void __launch_bounds__(KD_THREADS)
 		sub[(uint64_t)b * KD_THREADS + t] = KdSubState{KD_STOP, 0};
 		return;
 	}
-	kd_stage_bits(sm, in_base + in_off[img], size, cta_bit0 >> 3);
+	// where the previous CTA's chain ended in the previous run: asked for before the staging barrier
+	uint64_t e_prev = 0;
+	if (t == 0 && run != 0 && b != 0)
+		e_prev = ends_prev[b - 1];
+	kd_stage_bits(sm, in_base + off, size, cta_bit0 >> 3);
 	__syncthreads();
 
 	const uint64_t bits_left = total_bits - cta_bit0; // codewords may not cross this (relative) position
@@ -271,10 +276,7 @@ __global__ void __launch_bounds__(KD_THREADS)
 		if (run == 0 || b == 0)
 			start = 0;
 		else
-		{
-			const uint64_t e = ends_prev[b - 1];
-			start = (e == KD_STOP64) ? KD_STOP : (uint32_t)(e - cta_bit0);
-		}
+			start = (e_prev == KD_STOP64) ? KD_STOP : (uint32_t)(e_prev - cta_bit0);
 	}
 	else
 		start = t * KD_SUB_BITS;
@@ -353,18 +355,20 @@ __global__ void __launch_bounds__(KD_THREADS)
 	__shared__ uint32_t sm[KD_CTA_WORDS + 2];
 	__shared__ uint32_t sm_sum[33];
 	const uint32_t img = blockIdx.y, b = blockIdx.x, t = threadIdx.x;
-	const uint64_t size = in_size[img];
+	const uint64_t size = __ldg(in_size + img);
+	const uint64_t off = __ldg(in_off + img);
+	const uint64_t tok0 = __ldg(blk_base + (uint64_t)nblk * img + b); // independent loads: one round trip
 	const uint64_t total_bits = size * 8;
 	const uint64_t cta_bit0 = (uint64_t)b * KD_CTA_BITS;
 	if (cta_bit0 > total_bits)
 		return;
-	kd_stage_bits(sm, in_base + in_off[img], size, cta_bit0 >> 3);
 	const KdSubState s = sub[((uint64_t)nblk * img + b) * KD_THREADS + t];
+	kd_stage_bits(sm, in_base + off, size, cta_bit0 >> 3);
 	uint32_t total;
 	const uint32_t excl = block_excl_sum(s.count, sm_sum, &total); // syncs: sm is staged after it
 	uint32_t count;
 	kd_walk<true>(sm, s.start, (t + 1) * KD_SUB_BITS, total_bits - cta_bit0, count, nullptr,
-	              tokens + token_stride * img, blk_base[(uint64_t)nblk * img + b] + excl, token_cap);
+	              tokens + token_stride * img, tok0 + excl, token_cap);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -710,7 +714,11 @@ __global__ void __launch_bounds__(KT_THREADS)
 	__shared__ uint32_t queue_len;
 
 	const uint32_t img = blockIdx.y;
-	const uint64_t m = min(info[img].tokens, token_cap);
+	// the three per-CTA words are fetched together: behind the scan's barriers they would be a second round trip
+	const uint64_t m_all = __ldg(&info[img].tokens);
+	const uint32_t entry = __ldg(blk_state + (uint64_t)nblk * img + blockIdx.x);
+	const uint64_t out0 = __ldg(blk_out + (uint64_t)nblk * img + blockIdx.x);
+	const uint64_t m = min(m_all, token_cap);
 	const uint64_t cta_base = (uint64_t)blockIdx.x * KT_BLOCK;
 	if (cta_base >= m)
 		return;
@@ -723,9 +731,8 @@ __global__ void __launch_bounds__(KT_THREADS)
 
 	KtSpan total;
 	const KtSpan before = kt_block_excl_scan(kt_thread_span(u, valid), sm, &total);
-	const uint32_t entry = blk_state[(uint64_t)nblk * img + blockIdx.x];
 	uint32_t state = (before.map >> (2 * entry)) & 3u;
-	uint64_t pos = blk_out[(uint64_t)nblk * img + blockIdx.x] + before.out[entry];
+	uint64_t pos = out0 + before.out[entry];
 
 #pragma unroll
 	for (int j = 0; j < KT_ITEMS; j++)
