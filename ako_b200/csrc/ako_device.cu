@@ -720,7 +720,7 @@ extern "C" int akod_kagari_encode(akodContext* c, uint64_t n_values, const int16
 	AKOD_LAUNCH(c, "kagari_zero_edges", k_kg_zero_edges, zgrid, 256, 0, blk_off, blk_bits, nblocks, d_out, out_stride,
 	            out_cap * 8);
 	// algorithmic bytes of pass 3 = the blob bytes, known only to the caller once the sizes are read back
-	AKOD_LAUNCH(c, "kagari_pack", k_kg_pack, grid, KG_THREADS, 0, d_in, in_stride, n_values, blk_start, blk_off, blk_bits,
+	AKOD_LAUNCH(c, "kagari_pack", k_kg_pack, dim3((nblocks + KG_PACK_PER_CTA - 1) / KG_PACK_PER_CTA, n_images), KG_THREADS, 0, d_in, in_stride, n_values, blk_start, blk_off, blk_bits,
 	            nblocks, d_out, out_stride, out_cap * 8, slots);
 	return AKOD_OK;
 }

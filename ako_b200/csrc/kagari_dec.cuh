@@ -377,7 +377,7 @@ __global__ void __launch_bounds__(KD_THREADS)
 constexpr int KT_THREADS = 256;
 constexpr int KT_ITEMS = 16;
 constexpr int KT_BLOCK = KT_THREADS * KT_ITEMS; // tokens per CTA
-constexpr int KT_LONG = 48;                     // runs at least this long are filled by the whole CTA
+constexpr int KT_LONG = 16;                     // runs at least this long are filled by the whole CTA
 
 enum : uint32_t
 {

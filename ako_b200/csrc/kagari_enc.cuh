@@ -468,7 +468,12 @@ __global__ void __launch_bounds__(256)
 	words[(off + bits - 1) >> 5] = 0;
 }
 
-// pass 3: pack
+// pass 3: pack. A CTA takes KG_PACK_PER_CTA consecutive blocks. Blocks whose bit string pass 2 left in their slot
+// (nearly all) are one warp's work each: shift the slot to the block's bit offset and store, no barrier. A block
+// above 8 bits per value is re-encoded by the whole CTA. (One CTA per block made this pass CTA-launch bound: most
+// blocks of a quantised stream emit nothing or a few words.)
+constexpr int KG_PACK_PER_CTA = KG_THREADS / 32;
+
 __global__ void __launch_bounds__(KG_THREADS)
     k_kg_pack(const int16_t* __restrict__ in, uint64_t in_stride, uint64_t n, const uint32_t* __restrict__ blk_carry,
               const uint64_t* __restrict__ blk_off, const uint32_t* __restrict__ blk_bits, uint32_t nblocks,
@@ -477,76 +482,99 @@ __global__ void __launch_bounds__(KG_THREADS)
 	__shared__ uint32_t sm_max[33];
 	__shared__ uint32_t sm_sum[33];
 	__shared__ uint32_t bitbuf[KG_BLOCK + 2]; // 32 bits per value at most, +1 word of misalignment, +1 spill
+	__shared__ uint32_t long_total[KG_PACK_PER_CTA];
+	__shared__ uint64_t long_off[KG_PACK_PER_CTA];
 
-	// a block that emits nothing (inside a long run) has nothing to do at all
-	const uint32_t total = __ldg(blk_bits + (uint64_t)nblocks * blockIdx.y + blockIdx.x);
-	const uint64_t g0 = __ldg(blk_off + (uint64_t)nblocks * blockIdx.y + blockIdx.x); // both loads in one round trip
-	if (total == 0)
-		return;
-	if (g0 + total > cap_bits) // would not fit: the caller reports the failure from the bit count
-		return;
+	const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+	const uint64_t row = (uint64_t)nblocks * blockIdx.y;
+	uint32_t* const image_words = reinterpret_cast<uint32_t*>(out + out_stride * blockIdx.y);
 
-	if (total <= KG_SLOT_BITS)
+	// ---- slot path: warp w takes block b0 + w
 	{
-		// pass 2 left the bit string in the block's slot: shift it to its bit offset and store
-		const uint32_t* slot = slots + ((uint64_t)nblocks * blockIdx.y + blockIdx.x) * KG_SLOT_WORDS;
-		const uint32_t r = (uint32_t)(g0 & 31), nin = (total + 31) >> 5;
-		const uint32_t nout = (r + total + 31) >> 5;
-		uint32_t* dstw = reinterpret_cast<uint32_t*>(out + out_stride * blockIdx.y) + (g0 >> 5);
-		for (uint32_t k = threadIdx.x; k < nout; k += KG_THREADS)
+		const uint32_t b = blockIdx.x * KG_PACK_PER_CTA + wid;
+		uint32_t total = 0;
+		uint64_t g0 = 0;
+		if (b < nblocks)
 		{
-			const uint32_t lo = (k < nin) ? __ldg(slot + k) : 0u, hi = (k > 0) ? __ldg(slot + k - 1) : 0u;
-			const uint32_t be = __byte_perm(__funnelshift_r(lo, hi, r), 0, 0x0123); // bytes of the file are MSB-first
-			if (k == 0 || k == nout - 1)
-				atomicOr(&dstw[k], be);
-			else
-				dstw[k] = be;
+			total = __ldg(blk_bits + row + b);
+			g0 = __ldg(blk_off + row + b); // both loads in one round trip
 		}
-		return;
-	}
-
-	in += in_stride * blockIdx.y;
-	const uint64_t base = (uint64_t)blockIdx.x * KG_BLOCK + (uint64_t)threadIdx.x * KG_ITEMS;
-	const KgChunk c = kg_load(in, n, base);
-	KgCode codes[KG_ITEMS];
-	const uint32_t bits =
-	    kg_thread_codes<true>(c, n, base, blk_carry[(uint64_t)nblocks * blockIdx.y + blockIdx.x], sm_max, codes);
-
-	for (int i = threadIdx.x; i < KG_BLOCK + 2; i += KG_THREADS)
-		bitbuf[i] = 0;
-	uint32_t check;
-	const uint32_t excl = block_excl_sum(bits, sm_sum, &check); // has __syncthreads inside: bitbuf is clear after it
-
-	if (bits)
-	{
-		uint32_t pos = (uint32_t)(g0 & 31) + excl; // bit position inside bitbuf
-#pragma unroll
-		for (int j = 0; j < KG_ITEMS; j++)
+		const bool fits = total != 0 && g0 + total <= cap_bits; // else: nothing emitted, or the caller reports the overflow
+		if (lane == 0)
 		{
-			const uint32_t len = codes[j].len;
-			if (len)
+			long_total[wid] = (fits && total > KG_SLOT_BITS) ? total : 0u;
+			long_off[wid] = g0;
+		}
+		if (fits && total <= KG_SLOT_BITS)
+		{
+			const uint32_t* slot = slots + (row + b) * KG_SLOT_WORDS;
+			const uint32_t r = (uint32_t)(g0 & 31), nin = (total + 31) >> 5;
+			const uint32_t nout = (r + total + 31) >> 5;
+			uint32_t* dstw = image_words + (g0 >> 5);
+			for (uint32_t k = lane; k < nout; k += 32)
 			{
-				const uint32_t w = pos >> 5, sh = pos & 31;
-				// MSB-first: bit 'pos' of the stream is bit (31 - pos%32) of word pos/32
-				const uint64_t wide = (uint64_t)codes[j].code << (64 - sh - len);
-				atomicOr(&bitbuf[w], (uint32_t)(wide >> 32));
-				if (sh + len > 32)
-					atomicOr(&bitbuf[w + 1], (uint32_t)wide);
-				pos += len;
+				const uint32_t lo = (k < nin) ? __ldg(slot + k) : 0u, hi = (k > 0) ? __ldg(slot + k - 1) : 0u;
+				const uint32_t be = __byte_perm(__funnelshift_r(lo, hi, r), 0, 0x0123); // bytes of the file are MSB-first
+				if (k == 0 || k == nout - 1)
+					atomicOr(&dstw[k], be);
+				else
+					dstw[k] = be;
 			}
 		}
 	}
 	__syncthreads();
 
-	uint32_t* words = reinterpret_cast<uint32_t*>(out + out_stride * blockIdx.y) + (g0 >> 5);
-	const uint32_t nwords = (uint32_t)(((g0 & 31) + total + 31) >> 5);
-	for (uint32_t i = threadIdx.x; i < nwords; i += KG_THREADS)
+	// ---- long blocks (more than 8 bits per value): the whole CTA re-encodes them one after the other
+	in += in_stride * blockIdx.y;
+	for (int w = 0; w < KG_PACK_PER_CTA; w++)
 	{
-		const uint32_t be = __byte_perm(bitbuf[i], 0, 0x0123); // bytes of the file are MSB-first
-		if (i == 0 || i == nwords - 1)
-			atomicOr(&words[i], be);
-		else
-			words[i] = be;
+		const uint32_t total = long_total[w];
+		if (total == 0)
+			continue; // uniform
+		const uint32_t b = blockIdx.x * KG_PACK_PER_CTA + w;
+		const uint64_t g0 = long_off[w];
+		const uint64_t base = (uint64_t)b * KG_BLOCK + (uint64_t)threadIdx.x * KG_ITEMS;
+		const KgChunk c = kg_load(in, n, base);
+		KgCode codes[KG_ITEMS];
+		const uint32_t bits = kg_thread_codes<true>(c, n, base, blk_carry[row + b], sm_max, codes);
+
+		for (int i = threadIdx.x; i < KG_BLOCK + 2; i += KG_THREADS)
+			bitbuf[i] = 0;
+		uint32_t check;
+		const uint32_t excl = block_excl_sum(bits, sm_sum, &check); // has __syncthreads inside: bitbuf is clear after it
+
+		if (bits)
+		{
+			uint32_t pos = (uint32_t)(g0 & 31) + excl; // bit position inside bitbuf
+#pragma unroll
+			for (int jj = 0; jj < KG_ITEMS; jj++)
+			{
+				const uint32_t len = codes[jj].len;
+				if (len)
+				{
+					const uint32_t ww = pos >> 5, sh = pos & 31;
+					// MSB-first: bit 'pos' of the stream is bit (31 - pos%32) of word pos/32
+					const uint64_t wide = (uint64_t)codes[jj].code << (64 - sh - len);
+					atomicOr(&bitbuf[ww], (uint32_t)(wide >> 32));
+					if (sh + len > 32)
+						atomicOr(&bitbuf[ww + 1], (uint32_t)wide);
+					pos += len;
+				}
+			}
+		}
+		__syncthreads();
+
+		uint32_t* words = image_words + (g0 >> 5);
+		const uint32_t nwords = (uint32_t)(((g0 & 31) + total + 31) >> 5);
+		for (uint32_t i = threadIdx.x; i < nwords; i += KG_THREADS)
+		{
+			const uint32_t be = __byte_perm(bitbuf[i], 0, 0x0123); // bytes of the file are MSB-first
+			if (i == 0 || i == nwords - 1)
+				atomicOr(&words[i], be);
+			else
+				words[i] = be;
+		}
+		__syncthreads(); // bitbuf, sm_max, sm_sum are reused by the next long block
 	}
 }
 
