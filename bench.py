@@ -422,19 +422,26 @@ def run_ours(args, rank, world):
         return sum(r[0] for r in res) // n_steps, sum(r[1] for r in res) // n_steps
 
     e2e_steps = max(1, min(args.steps, 20))
-    e2e_legs = {}
+    # Each leg is timed E2E_REPS times over the same e2e_steps steps and its best repetition is kept; every
+    # repetition's value is reported. (The boxes are VMs on shared hosts: PCIe-bound legs were seen to run at half
+    # rate for a whole repetition while the device-timed number did not move.)
+    E2E_REPS = 3
+    e2e_legs, e2e_all = {}, {}
     for leg, fn in (("batch", run_batch), ("calls", run_calls)):
         fn(min(args.warmup, 3))
-        barrier()
-        t0 = time.perf_counter()
-        h2d, d2h = fn(e2e_steps)
-        torch.cuda.synchronize()
-        leg_s = time.perf_counter() - t0
-        if dist is not None:
-            t = torch.tensor([leg_s], device=f"cuda:{local}")
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            leg_s = float(t.item())
-        e2e_legs[leg] = (leg_s, h2d, d2h)
+        for rep in range(E2E_REPS):
+            barrier()
+            t0 = time.perf_counter()
+            h2d, d2h = fn(e2e_steps)
+            torch.cuda.synchronize()
+            leg_s = time.perf_counter() - t0
+            if dist is not None:
+                t = torch.tensor([leg_s], device=f"cuda:{local}")
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                leg_s = float(t.item())
+            e2e_all.setdefault(leg, []).append(round(px * B * world * e2e_steps / leg_s / 1e6, 1))
+            if leg not in e2e_legs or leg_s < e2e_legs[leg][0]:
+                e2e_legs[leg] = (leg_s, h2d, d2h)
     pool_exec.shutdown()
     e2e_api = {"batch": "akoB200EncodeBatch + akoB200DecodeBatch (host pointer arrays, pinned buffers via "
                         "akoB200PinnedCallbacks; encode of step i+1 overlaps decode of step i)",
@@ -539,8 +546,10 @@ def run_ours(args, rank, world):
             "blob_bytes_per_step": blob_bytes_batch,
             "clocks": clocks,
             "e2e": {"value": round(e2e_value, 1), "unit": "MPix/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "api": e2e_api[best_leg], "steps": e2e_steps,
-                    "other_api": {k: {"value": round(px * B * world * e2e_steps / v[0] / 1e6, 1), "api": e2e_api[k]}
+                    "api": e2e_api[best_leg], "steps": e2e_steps, "repetitions": e2e_all[best_leg],
+                    "repetition_rule": f"best of {E2E_REPS} repetitions of the same {e2e_steps} steps",
+                    "other_api": {k: {"value": round(px * B * world * e2e_steps / v[0] / 1e6, 1), "api": e2e_api[k],
+                                      "repetitions": e2e_all[k]}
                                   for k, v in e2e_legs.items() if k != best_leg}},
             "gpu_launches": int(launches),
             "warmup_steps_run": warm_steps,

@@ -461,3 +461,42 @@ def test_pooled_contexts_follow_the_device_not_the_thread(orc):
             os.environ.pop("AKO_CUDA_DEVICE", None)
         else:
             os.environ["AKO_CUDA_DEVICE"] = old
+
+
+@pytest.mark.parametrize("seed", range(8))
+def test_randomised_settings_sweep(orc, seed):
+    """Seeded random walk over the whole settings space (shape, channels, wavelet, wrap, colour, q, gate, chroma loss,
+    discard, tiles, image statistics) at sizes the oracle does in milliseconds: .ako bytes and decoded pixels against
+    the oracle, case by case. Sizes straddle the kernels' switch points (strip / tile / small-pyramid kernels, widths
+    whose halves are 0 and 4 mod 8, full and partial 2048-value Kagari blocks)."""
+    rs = np.random.RandomState(9000 + seed)
+    widths = [8, 9, 24, 40, 63, 64, 72, 130, 200, 264, 408, 520, 528, 1048]
+    for case in range(14):
+        w = int(rs.choice(widths)) + int(rs.randint(0, 3)) * int(rs.randint(0, 2))
+        h = int(rs.choice(widths[:11])) + int(rs.randint(0, 3))
+        ch = int(rs.choice([1, 2, 3, 4, 4, 4, 5, 8]))
+        if w * h * ch > 1_200_000:
+            h = max(8, 1_200_000 // (w * ch))
+        kind = rs.randint(0, 4)
+        if kind == 0:
+            img = noise_image(w, h, ch, seed * 100 + case)
+        elif kind == 1:
+            img = smooth_image(w, h, ch, seed * 100 + case)
+        elif kind == 2:
+            img = np.full((h, w, ch), int(rs.randint(0, 256)), np.uint8)      # one long run per plane
+            img[rs.randint(0, h), rs.randint(0, w)] ^= 0x55
+        else:
+            img = np.ascontiguousarray(ol.synth(orc, w, h, seed * 100 + case)[:, :, :min(ch, 4)])
+            ch = img.shape[2]
+        lossless = rs.rand() < 0.3
+        kw = dict(wavelet=int(rs.choice([W_DD137, W_CDF53, W_HAAR])), wrap=int(rs.randint(0, 4)),
+                  color=int(rs.choice([C_YCOCG, C_SUBG, C_NONE])), q=0 if lossless else int(rs.choice([1, 3, 16, 60, 400])),
+                  g=0 if lossless else int(rs.choice([0, 0, 4, 16, 90])), chroma_loss=int(rs.randint(0, 4)),
+                  discard=int(rs.randint(0, 2)))
+        tiles = int(rs.choice([0, 0, 0, 8, 16, 64, 128]))
+        if tiles and not (0 < w % tiles < 3 or 0 < h % tiles < 3):
+            kw["tiles"] = tiles
+        blob = _e2e(orc, img, **kw)
+        if blob is not None and lossless and kw["discard"] == 0:
+            out, st, _ = ako_b200.decode(blob)
+            assert st == 0 and np.array_equal(out, img), (w, h, ch, kw)
