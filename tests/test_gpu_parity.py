@@ -500,3 +500,36 @@ def test_randomised_settings_sweep(orc, seed):
         if blob is not None and lossless and kw["discard"] == 0:
             out, st, _ = ako_b200.decode(blob)
             assert st == 0 and np.array_equal(out, img), (w, h, ch, kw)
+
+
+def _corrupt(rs, blob, mode):
+    b = bytearray(blob)
+    if mode == 0:      # flip a few body bits
+        for _ in range(rs.randint(1, 4)):
+            b[rs.randint(16, len(b))] ^= 1 << rs.randint(0, 8)
+    elif mode == 1:    # truncate
+        b = b[:rs.randint(16, len(b))]
+    elif mode == 2:    # corrupt the first block's size field
+        b[16 + rs.randint(0, 4)] ^= 1 << rs.randint(0, 8)
+    else:              # overwrite a span
+        a = rs.randint(20, len(b) - 4)
+        n = rs.randint(1, 16)
+        b[a:a + n] = bytes(rs.randint(0, 256, size=n).astype(np.uint8))
+    return bytes(b)
+
+
+def test_corrupted_blobs_decode_like_the_oracle(orc):
+    """Malformed input (decode.c:145-156, compression.c:58-73, kagari.c:301-366): on the SAME corrupted bytes the
+    CUDA decoder returns the oracle's status, and the oracle's pixels whenever that status is OK. (The oracle's own
+    agreement with the reference on corrupted input is pinned on the CPU: test_corrupted_blobs_oracle_vs_reference.)"""
+    rs = np.random.RandomState(123)
+    for (w, h, kw) in [(96, 80, dict(wavelet=0, q=16, g=0)), (200, 131, dict(wavelet=1, q=0, g=0)),
+                       (64, 64, dict(wavelet=2, q=8, g=4, tiles=32)), (333, 40, dict(wavelet=0, q=3, g=0, wrap=2))]:
+        blob, _ = ol.orc_encode(orc, ol.synth(orc, w, h, w), **kw)
+        for trial in range(48):
+            bad = _corrupt(rs, blob, trial % 4)
+            got, gst, _ = ako_b200.decode(bad)
+            want, wst = ol.orc_decode(orc, bad)
+            assert gst == wst, (w, h, trial, gst, wst)
+            if want is not None:
+                assert np.array_equal(got, want), (w, h, trial)

@@ -318,3 +318,45 @@ def test_ratio_search_vs_reference(orc, ref, case):
     got, st, q, passes = ol.orc_encode_pass(orc, img, ratio, **kw)
     assert got == want
     assert (q, passes) == (want_q, want_passes)
+
+
+def test_corrupted_blobs_oracle_vs_reference(orc, ref):
+    """Corrupted blobs: the oracle returns the reference's status and pixels, with ONE documented exception -- a block
+    size field that points past the end of the input. The reference does not look at input_size there (decode.c:71 is
+    a tautology) and reads beyond the caller's buffer; when its accumulator's read-ahead happens to stop
+    exactly at the forged size it even answers OK (kagari.c:119-143, compression.c:69-70). The oracle, like the CUDA
+    library, answers AKO_BROKEN_INPUT for every block that overruns the input."""
+    import struct
+    rs = np.random.RandomState(321)
+
+    def overruns(b, kw):
+        if kw.get("tiles"):
+            return True  # a forged size in a multi-tile blob shifts every later block head: not analysed here
+        return len(b) >= 20 and 20 + struct.unpack("<I", b[16:20])[0] > len(b)
+
+    for (w, h, kw) in [(96, 80, dict(wavelet=0, q=16, g=0)), (200, 131, dict(wavelet=1, q=0, g=0)),
+                       (64, 64, dict(wavelet=2, q=8, g=4, tiles=32))]:
+        blob, _ = ol.orc_encode(orc, ol.synth(orc, w, h, w), **kw)
+        for trial in range(60):
+            b = bytearray(blob)
+            mode = trial % 3
+            if mode == 0:
+                for _ in range(rs.randint(1, 4)):
+                    b[rs.randint(20, len(b))] ^= 1 << rs.randint(0, 8)
+            elif mode == 1:
+                b[16 + rs.randint(0, 4)] ^= 1 << rs.randint(0, 8)
+            else:
+                a = rs.randint(20, len(b) - 4)
+                n = rs.randint(1, 16)
+                b[a:a + n] = bytes(rs.randint(0, 256, size=n).astype(np.uint8))
+            b = bytes(b)
+            if overruns(b, kw):
+                got, st = ol.orc_decode(orc, b)
+                if not kw.get("tiles"):
+                    assert st == 15 and got is None
+                continue
+            want, wst = ol.ref_decode(ref, b)
+            got, st = ol.orc_decode(orc, b)
+            assert st == wst, (w, h, trial, st, wst)
+            if want is not None:
+                assert np.array_equal(got, want), (w, h, trial)
