@@ -453,8 +453,8 @@ AKO_API enum akoStatus akoB200CopyToHost(akoB200Context* ctx, void* dst, const v
 
 /* cudaHostAlloc / cudaFreeHost cost milliseconds for image-sized blocks, so freed blocks are kept in a small
  * cache (prefix word 0 = user size, word 1 = capacity) and handed out again to requests they fit. */
-#define PIN_CACHE_SLOTS 256
-#define PIN_CACHE_MAX_BYTES ((size_t)4 << 30)
+#define PIN_CACHE_SLOTS 512
+#define PIN_CACHE_MAX_BYTES ((size_t)6 << 30)
 static pthread_mutex_t g_pin_lock = PTHREAD_MUTEX_INITIALIZER;
 static uint8_t* g_pin_cache[PIN_CACHE_SLOTS];
 static size_t g_pin_cached_bytes = 0;

@@ -673,7 +673,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c2", choices=list(WORKLOADS) + ["dwt"])
-    ap.add_argument("--batch", type=int, default=32, help="images per step per GPU")
+    ap.add_argument("--batch", type=int, default=64, help="images per step per GPU")
     ap.add_argument("--cpu-reps", type=int, default=1)
     ap.add_argument("--host-threads", type=int, default=8, help="caller threads of the end-to-end (host pointer) leg")
     ap.add_argument("--dwt-size", type=int, default=8192)
