@@ -231,7 +231,8 @@ def run_ours(args, rank, world):
     import torch
 
     import ako_b200
-    import oracle_lib as ol
+    import oracle_lib as ol  # the checker: parity gate before timing, and the CPU baseline leg; nothing timed runs in it
+    from ako_b200.synth import synth_rgba8
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device -- ako_b200 has no CPU fallback")
@@ -262,7 +263,7 @@ def run_ours(args, rank, world):
     host_pool = torch.empty((pool_images, h, w, CHANNELS), dtype=torch.uint8).pin_memory()
     distinct = min(pool_images, 4)
     for i in range(distinct):
-        host_pool[i].copy_(torch.from_numpy(ol.synth(orc, w, h, seed0 + i + rank * 64)))
+        host_pool[i].copy_(torch.from_numpy(synth_rgba8(w, h, seed0 + i + rank * 64)))
     for i in range(distinct, pool_images):
         host_pool[i].copy_(host_pool[i % distinct])
     dev_pool = host_pool.to(f"cuda:{local}")

@@ -25,6 +25,14 @@ def test_synth_generator_matches_survey_hash(orc):
     assert sha(img.tobytes()) == "7e0d163cd4d552f8d11de3434628916df0009b37ae114b724b99892cca2c071f"
 
 
+def test_numpy_synth_generator_matches_oracle(orc):
+    """ako_b200/synth.py (what bench.py generates its inputs with) == the oracle's generator == SURVEY Appendix C."""
+    from ako_b200.synth import synth_rgba8
+    assert sha(synth_rgba8(1024, 1280, 1).tobytes()) == "7e0d163cd4d552f8d11de3434628916df0009b37ae114b724b99892cca2c071f"
+    for (w, h, seed) in [(64, 48, 1), (333, 257, 7), (130, 700, 1003), (1, 1, 0), (129, 3, 4000000000)]:
+        assert np.array_equal(synth_rgba8(w, h, seed), ol.synth(orc, w, h, seed)), (w, h, seed)
+
+
 @pytest.mark.parametrize("kat", KATS[:2] + KATS[3:4], ids=lambda k: f"{k[0]}x{k[1]}-w{k[2]}-q{k[3]}-g{k[4]}")
 def test_known_answers_oracle(orc, kat):
     w, h, wavelet, q, g, seed, size, blob_sha, dec_sha = kat
