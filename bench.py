@@ -416,7 +416,9 @@ def run_ours(args, rank, world):
         free_fn(p)
         return img_bytes + n, n + img_bytes
 
-    host_threads = max(1, min(args.host_threads, B))
+    # caller threads of the per-image leg: every rank shares the box's cores (a waiting caller spins in the driver)
+    cores_per_rank = max(1, len(os.sched_getaffinity(0)) // max(world, 1))
+    host_threads = max(2, min(args.host_threads, B, cores_per_rank))
     pool_exec = ThreadPoolExecutor(host_threads)
 
     def run_calls(n_steps):
