@@ -543,7 +543,7 @@ __device__ __forceinline__ KtSpan kt_block_excl_scan(KtSpan v, KtSpan* sm, KtSpa
 }
 
 // pass A: the span of every CTA's tokens
-__global__ void __launch_bounds__(KT_THREADS)
+__global__ void __launch_bounds__(KT_THREADS, 8)
     k_kt_spans(const uint16_t* __restrict__ tokens, uint64_t token_stride, uint64_t token_cap,
                const KdImage* __restrict__ info, KtSpan* __restrict__ blk_span, uint32_t nblk)
 {
@@ -710,7 +710,7 @@ __global__ void __launch_bounds__(KT_THREADS)
                 uint64_t n_values, KtRun* __restrict__ big_list, uint32_t* __restrict__ big_count, uint32_t big_cap)
 {
 	__shared__ KtSpan sm[33];
-	__shared__ KtRun queue[KT_BLOCK / 2];
+	__shared__ KtRun queue[KT_BLOCK / 3 + 1]; // an RLE count follows at least two value tokens
 	__shared__ uint32_t queue_len;
 
 	const uint32_t img = blockIdx.y;

@@ -394,7 +394,7 @@ __device__ __forceinline__ void kg_put_codes(uint32_t* bitbuf, uint32_t pos, con
 }
 
 // pass 2: bits emitted by each block (+ the bit string itself into the block's slot when it fits)
-__global__ void __launch_bounds__(KG_THREADS)
+__global__ void __launch_bounds__(KG_THREADS, 8)
     k_kg_lengths(const int16_t* __restrict__ in, uint64_t in_stride, uint64_t n, const uint32_t* __restrict__ blk_carry,
                  uint32_t* __restrict__ blk_bits, uint32_t nblocks, uint32_t* __restrict__ slots,
                  const uint32_t* __restrict__ blk_own, const uint8_t* __restrict__ blk_first)
