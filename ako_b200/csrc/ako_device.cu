@@ -55,7 +55,7 @@ extern "C" int akod_context_create(int device, akodContext** out)
 	}
 	c->sm_count = prop.multiProcessorCount;
 	if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess ||
-	    cudaHostAlloc(&c->mailbox, 1 << 16, cudaHostAllocDefault) != cudaSuccess)
+	    cudaHostAlloc(&c->mailbox, 1 << 16, cudaHostAllocMapped | cudaHostAllocPortable) != cudaSuccess)
 	{
 		delete c;
 		return AKOD_ERROR;
@@ -192,6 +192,26 @@ extern "C" int akod_fill_words(akodContext* c, uint64_t* d, uint64_t value, size
 {
 	akod_use(c);
 	AKOD_LAUNCH(c, "fill_words", k_fill_words, (unsigned)((count + 255) / 256), 256, 0, d, value, count);
+	return AKOD_OK;
+}
+
+// Small word arrays between the device and the context's pinned mailbox WITHOUT the copy engines: page-locked host
+// memory is directly addressable by kernels (unified addressing), so a tiny kernel moves the words. A DMA request of
+// a few bytes queues behind whatever 16 MB image copies other contexts have in flight on the same engine; a kernel
+// does not. Device writes to host memory are visible to the host once the stream has been synchronised.
+__global__ void k_copy_words(uint64_t* __restrict__ dst, const uint64_t* __restrict__ src, size_t count)
+{
+	for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (size_t)gridDim.x * blockDim.x)
+		dst[i] = src[i];
+}
+
+extern "C" int akod_copy_words(akodContext* c, uint64_t* dst, const uint64_t* src, size_t count)
+{
+	akod_use(c);
+	if (count == 0)
+		return AKOD_OK;
+	const unsigned blocks = (unsigned)((count + 255) / 256 < 64 ? (count + 255) / 256 : 64);
+	AKOD_LAUNCH(c, "copy_words", k_copy_words, blocks, 256, 0, dst, src, count);
 	return AKOD_OK;
 }
 

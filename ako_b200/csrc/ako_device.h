@@ -80,6 +80,8 @@ int akod_d2h(akodContext*, void* dst, const void* d_src, size_t bytes);
 int akod_d2d(akodContext*, void* d_dst, const void* d_src, size_t bytes);
 int akod_memset(akodContext*, void* d_dst, int value, size_t bytes);
 int akod_fill_words(akodContext*, uint64_t* d_dst, uint64_t value, size_t count);
+/* dst / src: device memory or the context's pinned mailbox (directly addressable by kernels); no copy engine */
+int akod_copy_words(akodContext*, uint64_t* dst, const uint64_t* src, size_t count);
 
 /* grow-only device workspace slots owned by the context */
 enum

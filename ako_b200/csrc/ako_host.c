@@ -638,7 +638,7 @@ static enum akoStatus upload_words(akoB200Context* ctx, uint64_t* d_dst, const u
 		if (st == AKO_OK)
 		{
 			memcpy(mail, src + o, sizeof(uint64_t) * m);
-			st = from_dev(akod_h2d(ctx->dev, d_dst + o, mail, sizeof(uint64_t) * m));
+			st = from_dev(akod_copy_words(ctx->dev, d_dst + o, mail, m)); /* a kernel reads the pinned mailbox */
 		}
 	}
 	return st;
@@ -651,7 +651,7 @@ static enum akoStatus download_words(akoB200Context* ctx, uint64_t* dst, const u
 	for (size_t o = 0; o < words && st == AKO_OK; o += MAILBOX_WORDS)
 	{
 		const size_t m = (words - o < MAILBOX_WORDS) ? words - o : MAILBOX_WORDS;
-		st = from_dev(akod_d2h(ctx->dev, mail, d_src + o, sizeof(uint64_t) * m));
+		st = from_dev(akod_copy_words(ctx->dev, mail, d_src + o, m)); /* a kernel writes the pinned mailbox */
 		if (st == AKO_OK)
 			st = from_dev(akod_sync(ctx->dev));
 		if (st == AKO_OK)
