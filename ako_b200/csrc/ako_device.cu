@@ -153,9 +153,51 @@ extern "C" void akod_pinned_free(void* p)
 		cudaFreeHost(p);
 }
 
+// Copies of up to AKOD_KERNEL_COPY_MAX bytes between device memory and PAGE-LOCKED host memory are done by a kernel
+// (page-locked memory is addressable by kernels), everything else by the copy engines. A .ako blob is tens of
+// kilobytes: as a DMA request it queues behind the 16 MB image copies that other contexts have in flight on the
+// same engine, as a kernel it does not. Visible to the host after the stream is synchronised, like the DMA.
+constexpr size_t AKOD_KERNEL_COPY_MAX = (size_t)2 << 20;
+
+__global__ void __launch_bounds__(256) k_copy_bytes(uint8_t* __restrict__ dst, const uint8_t* __restrict__ src, size_t n)
+{
+	const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x, stride = (size_t)gridDim.x * blockDim.x;
+	if ((((uintptr_t)dst | (uintptr_t)src) & 15) == 0)
+	{
+		const size_t n16 = n >> 4;
+		for (size_t i = t; i < n16; i += stride)
+			reinterpret_cast<uint4*>(dst)[i] = reinterpret_cast<const uint4*>(src)[i];
+		for (size_t i = (n16 << 4) + t; i < n; i += stride)
+			dst[i] = src[i];
+	}
+	else
+		for (size_t i = t; i < n; i += stride)
+			dst[i] = src[i];
+}
+
+static bool akod_host_pinned(const void* p)
+{
+	cudaPointerAttributes a;
+	if (cudaPointerGetAttributes(&a, p) != cudaSuccess)
+	{
+		cudaGetLastError();
+		return false;
+	}
+	return a.type == cudaMemoryTypeHost;
+}
+
+static int akod_small_copy(akodContext* c, void* d, const void* s, size_t n)
+{
+	const unsigned blocks = (unsigned)((n / 16 + 255) / 256 < 128 ? (n / 16 + 255) / 256 + 1 : 128);
+	AKOD_LAUNCH(c, "copy_bytes", k_copy_bytes, blocks, 256, 0, (uint8_t*)d, (const uint8_t*)s, n);
+	return AKOD_OK;
+}
+
 extern "C" int akod_h2d(akodContext* c, void* d, const void* s, size_t n)
 {
 	akod_use(c);
+	if (n != 0 && n <= AKOD_KERNEL_COPY_MAX && akod_host_pinned(s))
+		return akod_small_copy(c, d, s, n);
 	AKOD_TRY(cudaMemcpyAsync(d, s, n, cudaMemcpyHostToDevice, c->stream));
 	return AKOD_OK;
 }
@@ -163,6 +205,8 @@ extern "C" int akod_h2d(akodContext* c, void* d, const void* s, size_t n)
 extern "C" int akod_d2h(akodContext* c, void* d, const void* s, size_t n)
 {
 	akod_use(c);
+	if (n != 0 && n <= AKOD_KERNEL_COPY_MAX && akod_host_pinned(d))
+		return akod_small_copy(c, d, s, n);
 	AKOD_TRY(cudaMemcpyAsync(d, s, n, cudaMemcpyDeviceToHost, c->stream));
 	return AKOD_OK;
 }
