@@ -198,7 +198,7 @@ extern "C" int akod_h2d(akodContext* c, void* d, const void* s, size_t n)
 	akod_use(c);
 	if (n != 0 && n <= AKOD_KERNEL_COPY_MAX && akod_host_pinned(s))
 		return akod_small_copy(c, d, s, n);
-	AKOD_TRY(cudaMemcpyAsync(d, s, n, cudaMemcpyHostToDevice, c->stream));
+	AKOD_TRY(cudaMemcpyAsync(d, s, n, cudaMemcpyDefault, c->stream)); // unified addressing: the driver looks the pointers up
 	return AKOD_OK;
 }
 
@@ -207,7 +207,7 @@ extern "C" int akod_d2h(akodContext* c, void* d, const void* s, size_t n)
 	akod_use(c);
 	if (n != 0 && n <= AKOD_KERNEL_COPY_MAX && akod_host_pinned(d))
 		return akod_small_copy(c, d, s, n);
-	AKOD_TRY(cudaMemcpyAsync(d, s, n, cudaMemcpyDeviceToHost, c->stream));
+	AKOD_TRY(cudaMemcpyAsync(d, s, n, cudaMemcpyDefault, c->stream));
 	return AKOD_OK;
 }
 

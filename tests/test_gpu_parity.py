@@ -533,3 +533,22 @@ def test_corrupted_blobs_decode_like_the_oracle(orc):
             assert gst == wst, (w, h, trial, gst, wst)
             if want is not None:
                 assert np.array_equal(got, want), (w, h, trial)
+
+
+def test_encode_accepts_a_device_pointer(orc):
+    """akoEncodeExt copies its input with cudaMemcpyDefault: under unified addressing `in` may just as well be device
+    memory (the blob still comes back through callbacks->malloc). akoDecodeExt parses the container on the host, so its
+    input stays host memory; akoB200DecodeDevice is the entry point for device-resident blobs."""
+    import torch
+    w, h = 200, 152
+    img = ol.synth(orc, w, h, 3)
+    dev = torch.from_numpy(img).cuda()
+    L = ako_b200.load()
+    s = S(wavelet=0, quantization=16, gate=0)
+    out, st = C.c_void_p(), C.c_int(0)
+    n = L.akoEncodeExt(None, C.byref(s), 4, w, h, dev.data_ptr(), C.byref(out), C.byref(st))
+    assert n and st.value == 0
+    blob = C.string_at(out.value, n)
+    L.akoDefaultFree(out)
+    want, _ = ol.orc_encode(orc, img, wavelet=0, q=16, g=0)
+    assert blob == want
