@@ -670,24 +670,26 @@ __device__ __forceinline__ int16_t kt_value(uint32_t u)
 // fills out[pos, pos+count) with v; called by the 32 lanes of one warp (runs are spread over the CTA's warps)
 __device__ __forceinline__ void kt_fill_warp(int16_t* __restrict__ out, uint64_t pos, uint32_t count, int16_t v, int lane)
 {
-	const uint64_t end = pos + count;
-	const uint64_t a0 = (pos + 7) & ~(uint64_t)7, a1 = end & ~(uint64_t)7; // 16-byte aligned body
-	if (a0 >= a1)
+	// one 64-bit address, everything else in 32 bits relative to it (count <= 65534 from the queue, <= KT_PIECE from
+	// the big list); 'out' is 16-byte aligned, so the misalignment of the run is that of pos
+	int16_t* const o = out + pos;
+	const uint32_t head = (8u - ((uint32_t)pos & 7u)) & 7u; // elements before the first 16-byte boundary
+	if (count < head + 8u)
 	{
-		for (uint64_t i = pos + lane; i < end; i += 32)
-			out[i] = v;
+		for (uint32_t i = (uint32_t)lane; i < count; i += 32)
+			o[i] = v;
 		return;
 	}
-	if (pos + lane < a0)
-		out[pos + lane] = v; // at most 7 head elements
+	if ((uint32_t)lane < head)
+		o[lane] = v; // at most 7 head elements
 	const uint32_t vv = (uint32_t)(uint16_t)v * 0x10001u;
 	const uint4 q = make_uint4(vv, vv, vv, vv);
-	uint4* body = reinterpret_cast<uint4*>(out + a0);
-	const uint64_t nq = (a1 - a0) >> 3;
-	for (uint64_t i = lane; i < nq; i += 32)
+	uint4* const body = reinterpret_cast<uint4*>(o + head);
+	const uint32_t nq = (count - head) >> 3, tail0 = head + (nq << 3);
+	for (uint32_t i = (uint32_t)lane; i < nq; i += 32)
 		body[i] = q;
-	if (a1 + lane < end)
-		out[a1 + lane] = v; // at most 7 tail elements
+	if (tail0 + (uint32_t)lane < count)
+		o[tail0 + lane] = v; // at most 7 tail elements
 }
 
 struct KtRun
