@@ -954,7 +954,7 @@ extern "C" int akod_kagari_decode(akodContext* c, uint64_t n_values, const uint8
 	AKOD_LAUNCH(c, "kagari_dec_extract", k_kd_extract, grid1, KD_THREADS, 0, d_in, d_off, d_size, nblk1, sub, blk_base, tokens,
 	            token_cap, token_cap);
 	const dim3 grid2(nblk2, n_images);
-	AKOD_LAUNCH(c, "kagari_dec_spans", k_kt_spans, grid2, KT_THREADS, 0, tokens, token_cap, token_cap, info, blk_span, nblk2);
+	AKOD_LAUNCH(c, "kagari_dec_spans", k_kt_spans, grid2, KT_SPAN_THREADS, 0, tokens, token_cap, token_cap, info, blk_span, nblk2);
 	AKOD_LAUNCH(c, "kagari_dec_resolve", k_kt_resolve, n_images, KR_THREADS, 0, blk_span, nblk2, blk_state, blk_out, info, n_values,
 	            token_cap, d_result);
 	AKOD_BYTES(c, 2 * n_values * n_images); // the decoded values, written by this kernel and k_kt_fill together

@@ -375,8 +375,11 @@ __global__ void __launch_bounds__(KD_THREADS)
 // phase 2: classification + expansion
 
 constexpr int KT_THREADS = 256;
-constexpr int KT_ITEMS = 16;
-constexpr int KT_BLOCK = KT_THREADS * KT_ITEMS; // tokens per CTA
+constexpr int KT_ITEMS = 8;                     // tokens per thread in the expand pass: its loop body is large, 16 unrolled copies
+                                                // were 80 KB of code and a fifth of its stall samples were instruction fetch
+constexpr int KT_BLOCK = KT_THREADS * KT_ITEMS; // tokens per CTA (2048), the unit pass A and B describe
+constexpr int KT_SPAN_ITEMS = 16;               // the span pass has a small body: more tokens per thread, fewer scan steps
+constexpr int KT_SPAN_THREADS = KT_BLOCK / KT_SPAN_ITEMS;
 constexpr int KT_LONG = 16;                     // runs at least this long are filled by the whole CTA
 
 enum : uint32_t
@@ -439,26 +442,28 @@ __device__ __forceinline__ KtSpan kt_shfl_up(const KtSpan& v, int d)
 	return r;
 }
 
-// loads this thread's KT_ITEMS tokens plus the two before them
-__device__ __forceinline__ int kt_load(const uint16_t* __restrict__ tok, uint64_t m, uint64_t base, uint32_t u[KT_ITEMS + 2])
+// loads this thread's ITEMS tokens plus the two before them
+template <int ITEMS>
+__device__ __forceinline__ int kt_load(const uint16_t* __restrict__ tok, uint64_t m, uint64_t base, uint32_t u[ITEMS + 2])
 {
 	int valid = 0;
 	u[0] = (base >= 2 && base - 2 < m) ? tok[base - 2] : 0x10000u; // sentinels never compare equal
 	u[1] = (base >= 1 && base - 1 < m) ? tok[base - 1] : 0x20000u;
-	if (base + KT_ITEMS <= m)
+	if (base + ITEMS <= m)
 	{
-		uint16_t tmp[KT_ITEMS];
-		*reinterpret_cast<uint4*>(tmp) = __ldg(reinterpret_cast<const uint4*>(tok + base));
-		*reinterpret_cast<uint4*>(tmp + 8) = __ldg(reinterpret_cast<const uint4*>(tok + base + 8));
+		uint16_t tmp[ITEMS];
 #pragma unroll
-		for (int j = 0; j < KT_ITEMS; j++)
+		for (int k = 0; k < ITEMS; k += 8)
+			*reinterpret_cast<uint4*>(tmp + k) = __ldg(reinterpret_cast<const uint4*>(tok + base + k));
+#pragma unroll
+		for (int j = 0; j < ITEMS; j++)
 			u[j + 2] = tmp[j];
-		valid = KT_ITEMS;
+		valid = ITEMS;
 	}
 	else
 	{
 #pragma unroll
-		for (int j = 0; j < KT_ITEMS; j++)
+		for (int j = 0; j < ITEMS; j++)
 		{
 			u[j + 2] = 0x30000u;
 			if (base + j < m)
@@ -471,13 +476,14 @@ __device__ __forceinline__ int kt_load(const uint16_t* __restrict__ tok, uint64_
 	return valid;
 }
 
-__device__ __forceinline__ KtSpan kt_thread_span(const uint32_t u[KT_ITEMS + 2], int valid)
+template <int ITEMS>
+__device__ __forceinline__ KtSpan kt_thread_span(const uint32_t u[ITEMS + 2], int valid)
 {
 	// simulate the four entry states side by side
 	uint32_t st[4] = {ST_V, ST_A, ST_S, ST_R};
 	uint32_t out[4] = {0, 0, 0, 0};
 #pragma unroll
-	for (int j = 0; j < KT_ITEMS; j++)
+	for (int j = 0; j < ITEMS; j++)
 	{
 		if (j < valid)
 		{
@@ -543,18 +549,18 @@ __device__ __forceinline__ KtSpan kt_block_excl_scan(KtSpan v, KtSpan* sm, KtSpa
 }
 
 // pass A: the span of every CTA's tokens
-__global__ void __launch_bounds__(KT_THREADS, 8)
+__global__ void __launch_bounds__(KT_SPAN_THREADS)
     k_kt_spans(const uint16_t* __restrict__ tokens, uint64_t token_stride, uint64_t token_cap,
                const KdImage* __restrict__ info, KtSpan* __restrict__ blk_span, uint32_t nblk)
 {
 	__shared__ KtSpan sm[33];
 	const uint32_t img = blockIdx.y;
 	const uint64_t m = min(info[img].tokens, token_cap);
-	const uint64_t base = (uint64_t)blockIdx.x * KT_BLOCK + (uint64_t)threadIdx.x * KT_ITEMS;
-	uint32_t u[KT_ITEMS + 2];
-	const int valid = (base < m) ? kt_load(tokens + token_stride * img, m, base, u) : 0;
+	const uint64_t base = (uint64_t)blockIdx.x * KT_BLOCK + (uint64_t)threadIdx.x * KT_SPAN_ITEMS;
+	uint32_t u[KT_SPAN_ITEMS + 2];
+	const int valid = (base < m) ? kt_load<KT_SPAN_ITEMS>(tokens + token_stride * img, m, base, u) : 0;
 	KtSpan total;
-	kt_block_excl_scan(kt_thread_span(u, valid), sm, &total);
+	kt_block_excl_scan(kt_thread_span<KT_SPAN_ITEMS>(u, valid), sm, &total);
 	if (threadIdx.x == 0)
 		blk_span[(uint64_t)nblk * img + blockIdx.x] = total;
 }
@@ -727,12 +733,12 @@ __global__ void __launch_bounds__(KT_THREADS)
 	int16_t* out = out_base + out_stride * img;
 	const uint64_t base = cta_base + (uint64_t)threadIdx.x * KT_ITEMS;
 	uint32_t u[KT_ITEMS + 2];
-	const int valid = (base < m) ? kt_load(tokens + token_stride * img, m, base, u) : 0;
+	const int valid = (base < m) ? kt_load<KT_ITEMS>(tokens + token_stride * img, m, base, u) : 0;
 	if (threadIdx.x == 0)
 		queue_len = 0;
 
 	KtSpan total;
-	const KtSpan before = kt_block_excl_scan(kt_thread_span(u, valid), sm, &total);
+	const KtSpan before = kt_block_excl_scan(kt_thread_span<KT_ITEMS>(u, valid), sm, &total);
 	uint32_t state = (before.map >> (2 * entry)) & 3u;
 	uint64_t pos = out0 + before.out[entry];
 
