@@ -28,7 +28,7 @@ for line in text.splitlines():
         funcs[cur] = []
         continue
     if cur is not None:
-        m = re.match(r"\s+/\*([0-9a-f]{4})\*/\s+(.*?);\s*/\*", line)
+        m = re.match(r"\s+/\*([0-9a-f]{4,})\*/\s+(.*?);\s*/\*", line)
         if m:
             funcs[cur].append(f"/*{m.group(1)}*/ {m.group(2).strip()} ;")
 index = ["# SASS of the hot kernels (sm_100a), from `cuobjdump -sass ako_b200/csrc/build/ako_device.o`", "",
