@@ -42,3 +42,42 @@ def synth_rgba8(w, h, seed):
         alpha_on = (((X >> 7) + (Y >> 7) + seed) % np.uint32(5)) == 0
         out[..., 3] = np.where(alpha_on, np.clip(_tri(np.broadcast_to(X, (h, w)), 128) * 4, 0, 255), 255)
     return out
+
+
+def synth_rgba8_torch(w, h, seeds, device="cuda", y0=0):
+    """The same generator as synth_rgba8 on a torch device, for the large batches of bench.py (configs[3]: 4096
+    images, configs[4]: 16384x16384): (len(seeds), h, w, 4) uint8, rows y0 .. y0+h of the image (large images are
+    made band by band). uint32 arithmetic is carried in int64 and masked; tests/test_abi_cpu.py checks it against
+    synth_rgba8."""
+    import torch
+
+    M = 0xFFFFFFFF
+
+    def mix(v):
+        v = v ^ (v >> 16)
+        v = (v * 0x7FEB352D) & M
+        v = v ^ (v >> 15)
+        v = (v * 0x846CA68B) & M  # the int64 product wraps; its low 32 bits are exact
+        return v ^ (v >> 16)
+
+    def tri(t, period):
+        p = t % period
+        return torch.where(p < period // 2, p, period - p)
+
+    i64 = dict(dtype=torch.int64, device=device)
+    S = torch.as_tensor(list(seeds), **i64).view(-1, 1, 1)
+    X = torch.arange(w, **i64).view(1, 1, w)
+    Y = torch.arange(y0, y0 + h, **i64).view(1, h, 1)
+    n = mix(((X * 0x9E3779B1) & M) ^ mix((Y + ((S * 0x85EBCA6B) & M)) & M))
+    n0, n1, n2 = (n & 7) - 4, ((n >> 8) & 7) - 4, ((n >> 16) & 7) - 4
+    blk = mix(((((X >> 6) * 73856093) & M) ^ (((Y >> 6) * 19349663) & M)) ^ S) & 63
+    r = tri((X + 3 * S) & M, 509) * 255 // 254
+    g = tri((Y + 5 * S) & M, 383) * 255 // 191
+    b = tri((X + Y) & M, 251) * 255 // 125
+    out = torch.empty((S.shape[0], h, w, 4), dtype=torch.uint8, device=device)
+    out[..., 0] = (r // 2 + blk + 32 + n0).clamp_(0, 255)
+    out[..., 1] = (g // 2 + blk + 32 + n1).clamp_(0, 255)
+    out[..., 2] = (b // 2 + (63 - blk) + 32 + n2).clamp_(0, 255)
+    alpha_on = ((((X >> 7) + (Y >> 7) + S) & M) % 5) == 0
+    out[..., 3] = torch.where(alpha_on, (tri(X, 128) * 4).clamp(0, 255).expand(S.shape[0], h, w), 255)
+    return out

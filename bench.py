@@ -15,6 +15,11 @@ value  = W*H*B*N / step time, inputs and outputs resident in HBM (CUDA events on
 e2e    = the same work through akoEncodeExt / akoDecodeExt with pinned HOST buffers (H2D/D2H inside).
 Multi-GPU (torchrun): every rank runs the same per-rank batch on its own GPU, no collective on the data
 path ("weak"); time = max over ranks.
+
+The default run also carries every other BASELINE.json config in "secondary" (device resident, CUDA events, each
+behind its own bit-exactness gate): c1 (configs[0]), dwt (configs[2], rank 0), c4 (configs[3]: the FIXED batch of 4096
+images sharded i mod N over the ranks, strong scaling), c5 (configs[4], rank 0), plus the headline config's encode and
+decode timed separately and the shapes off the aligned fast path. --no-secondary skips them.
 """
 import argparse
 import ctypes as C
@@ -40,6 +45,11 @@ WORKLOADS = {
 }
 CHANNELS = 4
 L2_BYTES = 126 * 1024 * 1024
+
+
+def bench_config(workload, B):
+    """The same `config` object in both arms (ours and --impl reference): the workload and its batch."""
+    return {"workload": WORKLOADS[workload][6], "images_per_step_per_gpu": B, "channels": CHANNELS}
 
 
 def _read_traffic():
@@ -93,28 +103,35 @@ def _cpu_job(args):
     return t0, time.perf_counter(), len(imgs) * reps
 
 
-def cpu_measure(workload, jobs_per_core=1, reps=1, cores=None):
+def cpu_measure(workload, images=64, reps=1, cores=None):
     """All host cores, one worker process per core over disjoint images (the reference is single-threaded). Only
     akoEncodeExt + akoDecodeExt are timed (image generation is not): wall = last end - first start over the workers."""
     import oracle_lib as ol
     w, h, wavelet, q, g, seed0, _ = WORKLOADS[workload]
     cores = cores or len(os.sched_getaffinity(0))
     kind = "reference" if os.path.exists(ol.ref_path()) else "port"
-    jobs = [(w, h, wavelet, q, g, [seed0 + c * jobs_per_core + k for k in range(jobs_per_core)], reps)
-            for c in range(cores)]
+    if kind == "reference":
+        # the checker's shared object is mapped in THIS process too (the workers are forks): one small round trip
+        ref = ol.load_ref()
+        small = ol.synth(ol.load_oracle(), 64, 64, 1)
+        blob, _ = ol.ref_encode(ref, small, wavelet=wavelet, q=q, g=g)
+        ol.ref_decode(ref, blob)
+    workers = min(cores, images)
+    seeds = [[seed0 + k for k in range(c, images, workers)] for c in range(workers)]
+    jobs = [(w, h, wavelet, q, g, sd, reps) for sd in seeds]
     ctx = mp.get_context("fork")
-    with ctx.Pool(cores, initializer=_cpu_init) as pool:
-        pool.map(_cpu_job, [(64, 64, wavelet, q, g, [1], 1)] * cores)  # warm the workers
+    with ctx.Pool(workers, initializer=_cpu_init) as pool:
+        pool.map(_cpu_job, [(64, 64, wavelet, q, g, [1], 1)] * workers)  # warm the workers
         res = pool.map(_cpu_job, jobs, chunksize=1)
     wall = max(r[1] for r in res) - min(r[0] for r in res)
-    images = sum(r[2] for r in res)
+    done = sum(r[2] for r in res)
     per_core = float(np.mean([(r[1] - r[0]) / r[2] for r in res]))
     return {
-        "value": w * h * images / wall / 1e6, "unit": "MPix/s", "cores": cores, "kind": kind,
-        "sample": f"{images} images ({workload}: {w}x{h} RGBA8) encode+decode, {cores} worker processes, "
+        "value": w * h * done / wall / 1e6, "unit": "MPix/s", "cores": workers, "kind": kind,
+        "sample": f"{done} images ({workload}: {w}x{h} RGBA8) encode+decode, {workers} worker processes, "
                   f"wall {wall:.2f} s; one core does one image in {per_core * 1e3:.0f} ms "
                   f"({w * h / per_core / 1e6:.1f} MPix/s/core)",
-        "wall_s": wall, "images": images,
+        "wall_s": wall, "images": done,
     }
 
 
@@ -260,43 +277,23 @@ def run_ours(args, rank, world):
     stream = torch.cuda.ExternalStream(ctx.stream, device=torch.device("cuda", local))
 
     # input pool larger than L2 so that every step's input comes from HBM
-    pool_images = max(B, -(-int(1.5 * L2_BYTES) // img_bytes))
-    pool_images = -(-pool_images // B) * B
+    pool_images = _pool_images(img_bytes, B)
     orc = ol.load_oracle()
     host_pool = torch.empty((pool_images, h, w, CHANNELS), dtype=torch.uint8).pin_memory()
-    distinct = min(pool_images, 4)
+    distinct = min(pool_images, 8)
     for i in range(distinct):
         host_pool[i].copy_(torch.from_numpy(synth_rgba8(w, h, seed0 + i + rank * 64)))
     for i in range(distinct, pool_images):
         host_pool[i].copy_(host_pool[i % distinct])
     dev_pool = host_pool.to(f"cuda:{local}")
-    bound = ctx.encode_bound(settings, CHANNELS, w, h)
-    blob_stride = -(-bound // 256) * 256
-    dev_blobs = torch.empty((B, blob_stride), dtype=torch.uint8, device=f"cuda:{local}")
-    dev_out = torch.empty((B, h, w, CHANNELS), dtype=torch.uint8, device=f"cuda:{local}")
+    dc = DeviceCodec(torch, ako_b200, ctx, local, w, h, CHANNELS, settings, B, dev_pool)
+    dev_blobs, dev_out, blob_stride = dc.blobs, dc.out, dc.blob_stride
     torch.cuda.synchronize()
-
-    def step_device(i):
-        first = (i * B) % pool_images
-        d_in = dev_pool[first].data_ptr()
-        done, st, sizes = ctx.encode_batch_device(settings, CHANNELS, w, h, B, d_in, img_bytes, dev_blobs.data_ptr(),
-                                                  blob_stride)
-        if done != B:
-            raise RuntimeError(f"encode failed: {ako_b200.status_string(st)}")
-        done, st = ctx.decode_batch_device(B, dev_blobs.data_ptr(), blob_stride, sizes, dev_out.data_ptr(), img_bytes)
-        if done != B:
-            raise RuntimeError(f"decode failed: {ako_b200.status_string(st)}")
-        return sizes
+    step_device = dc.step
 
     # ---- parity gate before any timing: bit-exact vs the oracle on this rank's first image
-    sizes = step_device(0)
-    ctx.sync()
-    want_blob, _ = ol.orc_encode(orc, host_pool[0].numpy(), wavelet=wavelet, q=q, g=g)
-    got_blob = dev_blobs[0, :sizes[0]].cpu().numpy().tobytes()
-    want_px, _ = ol.orc_decode(orc, want_blob)
-    bit_exact = (got_blob == want_blob) and bool(np.array_equal(dev_out[0].cpu().numpy(), want_px))
-    if not bit_exact:
-        raise RuntimeError("bench.py: GPU output is not bit-exact against the oracle; refusing to time it")
+    bit_exact = dc.gate(ol, orc, dict(wavelet=wavelet, q=q, g=g))
+    sizes = dc.sizes
 
     def barrier():
         torch.cuda.synchronize()
@@ -331,6 +328,11 @@ def run_ours(args, rank, world):
         elapsed_ms = float(t.item())
     ms_per_step = elapsed_ms / args.steps
     value = px * B * world / (ms_per_step * 1e-3) / 1e6
+    sizes = dc.sizes
+    # encode and decode timed separately (BASELINE.json's metric names both), same pool, same batch
+    enc_ms, dec_ms = dc.split_timing(stream, args.steps)
+    enc_ms = _max_over_ranks(torch, dist, local, enc_ms)
+    dec_ms = _max_over_ranks(torch, dist, local, dec_ms)
 
     # the only cross-rank data of the path: per-image blob sizes, gathered on the host side (ako_b200/shard.py);
     # global image g = k*world + rank is local image k of this rank
@@ -448,6 +450,36 @@ def run_ours(args, rank, world):
             e2e_all.setdefault(leg, []).append(round(px * B * world * e2e_steps / leg_s / 1e6, 1))
             if leg not in e2e_legs or leg_s < e2e_legs[leg][0]:
                 e2e_legs[leg] = (leg_s, h2d, d2h)
+    # the plain drop-in case: NULL callbacks (malloc'd results) and PAGEABLE input buffers, what akoenc / akodec do
+    page_pool = [host_pool[i].numpy().copy() for i in range(min(pool_images, 2 * host_threads))]
+    null_cb = None
+
+    def host_image_pageable(idx):
+        src = page_pool[idx % len(page_pool)]
+        out = C.c_void_p()
+        st = C.c_int(0)
+        n = L.akoEncodeExt(null_cb, C.byref(sset), CHANNELS, w, h, src.ctypes.data, C.byref(out), C.byref(st))
+        if n == 0:
+            raise RuntimeError("akoEncodeExt: " + ako_b200.status_string(st.value))
+        ch_, w_, h_ = C.c_size_t(), C.c_size_t(), C.c_size_t()
+        p = L.akoDecodeExt(null_cb, n, out, None, C.byref(ch_), C.byref(w_), C.byref(h_), C.byref(st))
+        if not p:
+            raise RuntimeError("akoDecodeExt: " + ako_b200.status_string(st.value))
+        L.akoDefaultFree(out)
+        L.akoDefaultFree(p)
+
+    pageable = None
+    try:
+        n_page = max(B, 2 * host_threads)
+        list(pool_exec.map(host_image_pageable, range(host_threads)))
+        barrier()
+        t0 = time.perf_counter()
+        list(pool_exec.map(host_image_pageable, range(n_page)))
+        leg_s = _max_over_ranks(torch, dist, local, time.perf_counter() - t0)
+        pageable = {"value": round(px * n_page * world / leg_s / 1e6, 1), "unit": "MPix/s",
+                    "api": f"akoEncodeExt + akoDecodeExt per image, NULL callbacks, pageable buffers, {host_threads} caller threads"}
+    except Exception as e:  # noqa: BLE001
+        pageable = {"error": repr(e)}
     pool_exec.shutdown()
     e2e_api = {"batch": "akoB200EncodeBatch + akoB200DecodeBatch (host pointer arrays, pinned buffers via "
                         "akoB200PinnedCallbacks; encode of step i+1 overlaps decode of step i)",
@@ -527,6 +559,44 @@ def run_ours(args, rank, world):
     kernels = {k: {"launches": v[0] // prof_steps, "ms_per_step": round(v[1] / prof_steps, 4)}
                for k, v in sorted(prof.items(), key=lambda kv: -kv[1][1])}
 
+    env = {"torch": torch, "ako": ako_b200, "ctx": ctx, "local": local, "stream": stream, "dist": dist, "rank": rank,
+           "world": world, "ol": ol, "orc": orc}
+    try:
+        ceiling = copy_ceiling(env, img_bytes / px + blob_bytes_batch / (px * B * world))
+    except Exception as e:  # noqa: BLE001
+        ceiling = {"error": repr(e)}
+    secondary = {"encode_MPix_s": round(px * B * world / enc_ms / 1e3, 1), "encode_ms_per_step": round(enc_ms, 4),
+                 "decode_MPix_s": round(px * B * world / dec_ms / 1e3, 1), "decode_ms_per_step": round(dec_ms, 4)}
+    if not args.no_secondary:
+        # free the headline's buffers first: configs[3] holds its whole shard (34 GB at one GPU) on the device
+        del dc, dev_pool, dev_blobs, dev_out, step_device
+        torch.cuda.empty_cache()
+
+        def attempt(name, fn, everyone):
+            """Collective-bearing secondaries run on every rank; the others on rank 0 while the rest wait."""
+            out = None
+            if everyone or rank == 0:
+                try:
+                    t0 = time.perf_counter()
+                    out = fn()
+                    out["bench_wall_s"] = round(time.perf_counter() - t0, 1)
+                except Exception as e:  # noqa: BLE001 -- a secondary must not take the headline line down
+                    if everyone and dist is not None:
+                        raise
+                    out = {"error": repr(e)}
+            torch.cuda.empty_cache()
+            if dist is not None:
+                torch.cuda.synchronize()
+                dist.barrier()
+            secondary[name] = out
+
+        dwt_args = argparse.Namespace(warmup=2, steps=5, dwt_size=args.dwt_size, dwt_wavelets=args.dwt_wavelets)
+        attempt("dwt", lambda: run_dwt(dwt_args), False)
+        attempt("c1", lambda: secondary_codec(env, "c1", max(5, args.steps // 2), B), True)
+        attempt("c4", lambda: secondary_c4(env, args.c4_images, B), True)
+        attempt("c5", lambda: secondary_c5(env, args.c5_size), False)
+        attempt("shapes", lambda: secondary_shapes(env, 5), False)
+
     line = None
     if rank == 0:
         cpu = None
@@ -534,7 +604,7 @@ def run_ours(args, rank, world):
             cpu = {"value": None, "unit": "MPix/s", "cores": 0, "kind": "skipped", "sample": "--skip-cpu"}
         else:
             try:
-                cpu = cpu_measure(args.workload, jobs_per_core=4, reps=args.cpu_reps)
+                cpu = cpu_measure(args.workload, images=B, reps=args.cpu_reps)
                 cpu = {k: (round(v, 2) if isinstance(v, float) else v) for k, v in cpu.items()
                        if k not in ("wall_s", "images")}
             except Exception as e:  # the GPU number stands on its own
@@ -543,17 +613,18 @@ def run_ours(args, rank, world):
             "metric": "encode+decode MPix/s (Ako hot path, bit-exact)", "value": round(value, 1), "unit": "MPix/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms_per_step, 4),
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "i16", "data": "synthetic",
-            "config": {"workload": text, "images_per_step_per_gpu": B, "channels": CHANNELS,
-                       "l2_policy": f"inputs rotate through a pool of {pool_images} images "
-                                    f"({pool_images * img_bytes >> 20} MiB > 126 MiB L2); no explicit flush",
-                       "parallelism": f"{world} independent shards, no collective on the data path",
-                       "step": "akoB200EncodeBatchDevice + akoB200DecodeBatchDevice, device resident"},
+            "config": bench_config(args.workload, B),
+            "details": {"l2_policy": f"inputs rotate through a pool of {pool_images} images "
+                                     f"({pool_images * img_bytes >> 20} MiB > 126 MiB L2); no explicit flush",
+                        "parallelism": f"{world} independent shards, no collective on the data path",
+                        "step": "akoB200EncodeBatchDevice + akoB200DecodeBatchDevice, device resident"},
             "bit_exact_vs_oracle": bit_exact,
             "blob_bytes_per_step": blob_bytes_batch,
             "clocks": clocks,
             "e2e": {"value": round(e2e_value, 1), "unit": "MPix/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "api": e2e_api[best_leg], "steps": e2e_steps, "repetitions": e2e_all[best_leg],
                     "repetition_rule": f"best of {E2E_REPS} repetitions of the same {e2e_steps} steps",
+                    "copy_ceiling": ceiling, "pageable_drop_in": pageable,
                     "other_api": {k: {"value": round(px * B * world * e2e_steps / v[0] / 1e6, 1), "api": e2e_api[k],
                                       "repetitions": e2e_all[k]}
                                   for k, v in e2e_legs.items() if k != best_leg}},
@@ -565,12 +636,302 @@ def run_ours(args, rank, world):
             "top_kernel": {"name": top[0], "share_of_step": round(top[1][1] / total_ms, 4)},
             "kernels": kernels,
             "cpu_baseline": cpu,
+            "secondary": secondary,
         }
     ctx.close()
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
     return line
+
+
+
+# ------------------------------------------------------------------------------------------------ secondaries
+
+def _events_ms(torch, stream, fn, steps):
+    """Device time of `steps` calls of fn(i): CUDA events on the library's stream, synchronised on both sides."""
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record(stream)
+    for i in range(steps):
+        fn(i)
+    e1.record(stream)
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / steps
+
+
+def _max_over_ranks(torch, dist, local, v):
+    if dist is None:
+        return v
+    t = torch.tensor([v], device=f"cuda:{local}", dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+class DeviceCodec:
+    """One workload on one context, device resident: a pool of input images larger than L2, blobs and decoded images
+    in device buffers. encode(i) / decode() are one batch each through akoB200EncodeBatchDevice / DecodeBatchDevice."""
+
+    def __init__(self, torch, ako, ctx, local, w, h, channels, settings, B, pool):
+        self.torch, self.ako, self.ctx = torch, ako, ctx
+        self.w, self.h, self.ch, self.s, self.B = w, h, channels, settings, B
+        self.pool = pool  # (P, h, w, channels) uint8 on the device
+        self.P = pool.shape[0]
+        self.img_bytes = w * h * channels
+        self.bound = ctx.encode_bound(settings, channels, w, h)
+        self.blob_stride = -(-self.bound // 256) * 256
+        dev = f"cuda:{local}"
+        self.blobs = torch.empty((B, self.blob_stride), dtype=torch.uint8, device=dev)
+        self.out = torch.empty((B, h, w, channels), dtype=torch.uint8, device=dev)
+        self.sizes = None
+
+    def encode(self, i):
+        first = (i * self.B) % self.P
+        done, st, sizes = self.ctx.encode_batch_device(self.s, self.ch, self.w, self.h, self.B,
+                                                       self.pool[first].data_ptr(), self.img_bytes,
+                                                       self.blobs.data_ptr(), self.blob_stride)
+        if done != self.B:
+            raise RuntimeError(f"encode failed: {self.ako.status_string(st)}")
+        self.sizes = sizes
+        return sizes
+
+    def decode(self, _i=0):
+        done, st = self.ctx.decode_batch_device(self.B, self.blobs.data_ptr(), self.blob_stride, self.sizes,
+                                                self.out.data_ptr(), self.img_bytes)
+        if done != self.B:
+            raise RuntimeError(f"decode failed: {self.ako.status_string(st)}")
+
+    def step(self, i):
+        self.encode(i)
+        self.decode()
+        return self.sizes
+
+    def gate(self, ol, orc, kw):
+        """Bit-exactness of batch image 0 (blob and decoded pixels) against the oracle; raises when it differs."""
+        import numpy as np
+        sizes = self.step(0)
+        self.ctx.sync()
+        img = self.pool[0].cpu().numpy()
+        want_blob, _ = ol.orc_encode(orc, img, **kw)
+        got = self.blobs[0, :sizes[0]].cpu().numpy().tobytes()
+        want_px, _ = ol.orc_decode(orc, want_blob)
+        if got != want_blob or not np.array_equal(self.out[0].cpu().numpy(), want_px):
+            raise RuntimeError("bench.py: GPU output is not bit-exact against the oracle; refusing to time it")
+        return True
+
+    def split_timing(self, stream, steps, warm=2):
+        """encode and decode timed SEPARATELY (ms per batch each)."""
+        for i in range(warm):
+            self.encode(i)
+        enc_ms = _events_ms(self.torch, stream, self.encode, steps)
+        for i in range(warm):
+            self.decode()
+        dec_ms = _events_ms(self.torch, stream, self.decode, steps)
+        return enc_ms, dec_ms
+
+
+def _pool_images(img_bytes, B):
+    n = max(B, -(-int(1.5 * L2_BYTES) // img_bytes))
+    return -(-n // B) * B
+
+
+def secondary_codec(env, name, steps, B):
+    """configs[0] / the configs[3] shape: encode+decode, then encode alone, then decode alone, device resident."""
+    torch, ako, ctx, local, stream, dist, rank, world = (env[k] for k in ("torch", "ako", "ctx", "local", "stream", "dist", "rank", "world"))
+    from ako_b200.synth import synth_rgba8_torch
+    w, h, wavelet, q, g, seed0, text = WORKLOADS[name]
+    P = _pool_images(w * h * CHANNELS, B)
+    distinct = min(P, 8)
+    base = synth_rgba8_torch(w, h, [seed0 + i + rank * 64 for i in range(distinct)], device=f"cuda:{local}")
+    pool = base.repeat((P + distinct - 1) // distinct, 1, 1, 1)[:P].contiguous()
+    s = ako.default_settings(wavelet=wavelet, quantization=q, gate=g)
+    dc = DeviceCodec(torch, ako, ctx, local, w, h, CHANNELS, s, B, pool)
+    exact = dc.gate(env["ol"], env["orc"], dict(wavelet=wavelet, q=q, g=g))
+    for i in range(3):
+        dc.step(i)
+    ms = _max_over_ranks(torch, dist, local, _events_ms(torch, stream, dc.step, steps))
+    enc_ms, dec_ms = dc.split_timing(stream, steps)
+    enc_ms, dec_ms = _max_over_ranks(torch, dist, local, enc_ms), _max_over_ranks(torch, dist, local, dec_ms)
+    px = w * h * B * world
+    return {"workload": text, "images_per_step_per_gpu": B, "scaling": "weak", "bit_exact_vs_oracle": exact,
+            "ms_per_step": round(ms, 4), "MPix_s": round(px / ms / 1e3, 1),
+            "encode_ms": round(enc_ms, 4), "encode_MPix_s": round(px / enc_ms / 1e3, 1),
+            "decode_ms": round(dec_ms, 4), "decode_MPix_s": round(px / dec_ms / 1e3, 1),
+            "blob_bytes_per_image": int(sum(dc.sizes) // B)}
+
+
+def secondary_c4(env, n_total, B):
+    """configs[3]: the FIXED batch of n_total synthetic 1920x1080 RGBA8 images (seed 1000 + i), image i on rank
+    i mod N, no collective on the data path; device time of the whole batch, max over ranks (strong scaling)."""
+    torch, ako, ctx, local, stream, dist, rank, world = (env[k] for k in ("torch", "ako", "ctx", "local", "stream", "dist", "rank", "world"))
+    from ako_b200 import shard
+    from ako_b200.synth import synth_rgba8_torch
+    w, h, wavelet, q, g, seed0, text = WORKLOADS["c4"]
+    mine = shard.shard_indices(n_total, rank, world)
+    n_mine = len(mine) // B * B  # whole chunks (n_total and B are powers of two)
+    mine = mine[:n_mine]
+    dev = f"cuda:{local}"
+    pool = torch.empty((n_mine, h, w, CHANNELS), dtype=torch.uint8, device=dev)
+    for k in range(0, n_mine, 16):
+        pool[k:k + 16] = synth_rgba8_torch(w, h, [seed0 + i for i in mine[k:k + 16]], device=dev)
+    s = ako.default_settings(wavelet=wavelet, quantization=q, gate=g)
+    dc = DeviceCodec(torch, ako, ctx, local, w, h, CHANNELS, s, B, pool)
+    exact = dc.gate(env["ol"], env["orc"], dict(wavelet=wavelet, q=q, g=g))
+    chunks = n_mine // B
+    for i in range(min(3, chunks)):
+        dc.step(i)
+    blob_total = [0]
+
+    def whole(_):
+        blob_total[0] = 0
+        for c in range(chunks):
+            blob_total[0] += sum(dc.step(c))
+
+    if dist is not None:
+        torch.cuda.synchronize()
+        dist.barrier()
+    ms = _max_over_ranks(torch, dist, local, _events_ms(torch, stream, whole, 1))
+    enc_ms = _max_over_ranks(torch, dist, local, _events_ms(torch, stream, lambda _: [dc.encode(c) for c in range(chunks)], 1))
+    all_sizes = blob_total[0]
+    if dist is not None:
+        t = torch.tensor([all_sizes], device=dev, dtype=torch.int64)
+        dist.all_reduce(t)
+        all_sizes = int(t.item())
+    px = w * h * n_mine * world
+    return {"workload": f"batch of {n_mine * world} synthetic 1920x1080 RGBA8 images (seed 1000+i), CDF53 -q16, encode+decode, "
+                        f"image i on rank i mod {world} (configs[3])", "scaling": "strong", "images": n_mine * world,
+            "images_per_rank": n_mine, "chunk": B, "bit_exact_vs_oracle": exact, "batch_ms": round(ms, 3),
+            "MPix_s": round(px / ms / 1e3, 1), "encode_only_ms": round(enc_ms, 3),
+            "encode_MPix_s": round(px / enc_ms / 1e3, 1),
+            "decode_MPix_s": round(px / max(ms - enc_ms, 1e-6) / 1e3, 1), "blob_bytes_total": all_sizes}
+
+
+C5_KAT = (458045756, "19a2c7eb8be60101348acec4a2f68105ca48607d72c9caeab6bda5286ba9d930")  # SURVEY.md Appendix B
+
+
+def secondary_c5(env, size=16384):
+    """configs[4]: lossless (-q 0 -g 0) CDF 5/3 on one synthetic size x size RGBA8 image (seed 5): encode ms, decode
+    ms, bit-exact round trip, and the survey's known answer (blob size + SHA-256) at the full size."""
+    import hashlib
+    torch, ako, ctx, local, stream = (env[k] for k in ("torch", "ako", "ctx", "local", "stream"))
+    from ako_b200.synth import synth_rgba8_torch
+    dev = f"cuda:{local}"
+    w = h = size
+    img = torch.empty((h, w, CHANNELS), dtype=torch.uint8, device=dev)
+    for y0 in range(0, h, 1024):
+        img[y0:y0 + 1024] = synth_rgba8_torch(w, min(1024, h - y0), [5], device=dev, y0=y0)[0]
+    s = ako.default_settings(wavelet=1, quantization=0, gate=0)
+    bound = ctx.encode_bound(s, CHANNELS, w, h)
+    blob = torch.empty(bound, dtype=torch.uint8, device=dev)
+    out = torch.empty_like(img)
+    state = {}
+
+    def enc(_):
+        n, st = ctx.encode_device(s, CHANNELS, w, h, img.data_ptr(), blob.data_ptr(), bound)
+        if st != 0 or n == 0:
+            raise RuntimeError("c5 encode: " + ako.status_string(st))
+        state["n"] = n
+
+    def dec(_):
+        st, _dims, _s = ctx.decode_device(state["n"], blob.data_ptr(), out.data_ptr(), w * h * CHANNELS)
+        if st != 0:
+            raise RuntimeError("c5 decode: " + ako.status_string(st))
+
+    enc(0)
+    dec(0)
+    ctx.sync()
+    exact = bool(torch.equal(out, img))
+    if not exact:
+        raise RuntimeError("c5: lossless round trip is not exact")
+    kat = None
+    if size == 16384:
+        digest = hashlib.sha256(blob[:state["n"]].cpu().numpy().tobytes()).hexdigest()
+        kat = (state["n"], digest) == C5_KAT
+        if not kat:
+            raise RuntimeError("c5: blob differs from the reference's known answer")
+    enc_ms = _events_ms(torch, stream, enc, 3)
+    dec_ms = _events_ms(torch, stream, dec, 3)
+    ctx.profile_reset()
+    ctx.profile(True)
+    enc(0)
+    dec(0)
+    ctx.sync()
+    prof = ctx.profile_get()
+    ctx.profile(False)
+    px = w * h
+    return {"workload": f"CDF53 lossless (-q 0 -g 0) encode / decode of synthetic {w}x{h} RGBA8, one tile (configs[4])",
+            "round_trip_exact": exact, "blob_matches_reference_known_answer": kat, "blob_bytes": state["n"],
+            "encode_ms": round(enc_ms, 3), "encode_MPix_s": round(px / enc_ms / 1e3, 1),
+            "decode_ms": round(dec_ms, 3), "decode_MPix_s": round(px / dec_ms / 1e3, 1),
+            "kernels_ms": {k: round(v[1], 3) for k, v in sorted(prof.items(), key=lambda kv: -kv[1][1])[:10]}}
+
+
+SHAPES = {
+    # name: (w, h, channels, wavelet, q, g, tiles, images per step)
+    "aligned_rgba_1024x1024": (1024, 1024, 4, 0, 16, 0, 0, 64),
+    "rgb_1000x1000": (1000, 1000, 3, 0, 16, 0, 0, 64),
+    "rgba_1921x1081": (1921, 1081, 4, 0, 16, 0, 0, 32),
+    "rgba_8192x8192_tiles256": (8192, 8192, 4, 0, 16, 0, 256, 1),
+}
+
+
+def secondary_shapes(env, steps):
+    """Shapes off the aligned RGBA fast path (odd sizes, 3 channels, tiles): ns per pixel of encode+decode next to an
+    aligned RGBA image of similar size, each behind its own oracle gate."""
+    torch, ako, ctx, local, stream = (env[k] for k in ("torch", "ako", "ctx", "local", "stream"))
+    from ako_b200.synth import synth_rgba8_torch
+    dev = f"cuda:{local}"
+    res = {}
+    for name, (w, h, ch, wavelet, q, g, tiles, B) in SHAPES.items():
+        P = B if tiles else _pool_images(w * h * ch, B)
+        distinct = min(P, 4)
+        base = synth_rgba8_torch(w, h, [40 + i for i in range(distinct)], device=dev)[..., :ch].contiguous()
+        pool = base.repeat((P + distinct - 1) // distinct, 1, 1, 1)[:P].contiguous()
+        s = ako.default_settings(wavelet=wavelet, quantization=q, gate=g, tiles_dimension=tiles)
+        dc = DeviceCodec(torch, ako, ctx, local, w, h, ch, s, B, pool)
+        exact = dc.gate(env["ol"], env["orc"], dict(wavelet=wavelet, q=q, g=g, tiles=tiles))
+        for i in range(2):
+            dc.step(i)
+        ms = _events_ms(torch, stream, dc.step, steps)
+        res[name] = {"images_per_step": B, "channels": ch, "tiles_dimension": tiles, "bit_exact_vs_oracle": exact,
+                     "ms_per_step": round(ms, 4), "MPix_s": round(w * h * B / ms / 1e3, 1),
+                     "ns_per_pixel": round(ms * 1e6 / (w * h * B), 5)}
+        del dc, pool, base
+        torch.cuda.empty_cache()
+    ref_ns = res["aligned_rgba_1024x1024"]["ns_per_pixel"]
+    for name, r in res.items():
+        r["per_pixel_time_vs_aligned_rgba"] = round(r["ns_per_pixel"] / ref_ns, 3)
+    return res
+
+
+def copy_ceiling(env, img_bytes_per_px):
+    """The box's pinned copy rate with both directions busy on every rank's GPU at once: what bounds the e2e leg."""
+    torch, local, dist, world = env["torch"], env["local"], env["dist"], env["world"]
+    import time as _t
+    n = 64 << 20
+    h_in = torch.empty(n, dtype=torch.uint8).pin_memory()
+    h_out = torch.empty(n, dtype=torch.uint8).pin_memory()
+    d_a = torch.empty(n, dtype=torch.uint8, device=f"cuda:{local}")
+    d_b = torch.empty(n, dtype=torch.uint8, device=f"cuda:{local}")
+    s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+    best = 0.0
+    for rep in range(3):
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+        t0 = _t.perf_counter()
+        for _ in range(8):
+            with torch.cuda.stream(s1):
+                d_a.copy_(h_in, non_blocking=True)
+            with torch.cuda.stream(s2):
+                h_out.copy_(d_b, non_blocking=True)
+        torch.cuda.synchronize()
+        dt = _max_over_ranks(torch, dist, local, _t.perf_counter() - t0)
+        best = max(best, n * 8 / dt / 1e9)
+    return {"pinned_GBps_each_way_per_gpu_all_ranks_busy": round(best, 2),
+            "MPix_s_all_gpus": round(best * 1e9 * world / img_bytes_per_px / 1e6, 1),
+            "how": "64 MiB cudaMemcpyAsync H2D and D2H on two streams at once, 8 each, every rank at the same time; "
+                   "max time over ranks, best of 3"}
 
 
 def run_dwt(args):
@@ -653,7 +1014,7 @@ def run_reference(args, rank, world):
     t_steps = []
     res = None
     for i in range(args.warmup + args.steps):
-        res = cpu_measure(args.workload, jobs_per_core=2, reps=1)
+        res = cpu_measure(args.workload, images=args.batch, reps=1)
         if i >= args.warmup:
             t_steps.append(res["wall_s"])
     ms = float(np.mean(t_steps)) * 1e3
@@ -662,8 +1023,10 @@ def run_reference(args, rank, world):
         "impl": "reference", "metric": "encode+decode MPix/s (Ako hot path, bit-exact)", "value": round(value, 2),
         "unit": "MPix/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms, 2),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "i16", "data": "synthetic",
-        "config": {"workload": text, "images_per_step": res["images"], "channels": CHANNELS,
-                   "parallelism": f"{res['cores']} host worker processes, two images each per step (rank 0 only)"},
+        "config": bench_config(args.workload, args.batch),
+        "details": {"parallelism": f"{res['cores']} host worker processes over the step's {res['images']} images "
+                                   "(rank 0 only; the reference is single-threaded per image)",
+                    "library": "oracle/_ref/libako_ref.so = the unmodified reference, gcc -O3 -flto"},
         "cpu_baseline": {"value": round(value, 2), "unit": "MPix/s", "cores": res["cores"], "kind": res["kind"],
                          "sample": res["sample"]},
         "e2e": {"value": round(value, 2), "unit": "MPix/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -685,6 +1048,9 @@ def main():
     ap.add_argument("--dwt-size", type=int, default=8192)
     ap.add_argument("--dwt-wavelets", default="cdf53,dd137,haar")
     ap.add_argument("--skip-cpu", action="store_true", help="profiling runs: do not time the CPU reference")
+    ap.add_argument("--no-secondary", action="store_true", help="headline config only (profiling runs)")
+    ap.add_argument("--c4-images", type=int, default=4096, help="size of the fixed configs[3] batch")
+    ap.add_argument("--c5-size", type=int, default=16384, help="side of the configs[4] image")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

@@ -25,6 +25,24 @@ __device__ __forceinline__ uint32_t op(uint32_t a, uint32_t b)
 	if (OP == 11) asm volatile("cvt.s32.s16 %0, %1;" : "=r"(d) : "h"((unsigned short)a));                // sign extend
 	if (OP == 12) d = __vmaxs2(a, b);                                                                        // VIMNMX.S16x2
 	if (OP == 13) asm volatile("mad.wide.s32 %0, %1, %2, %0;" : "+l"(*(unsigned long long*)&d) : "r"(a), "r"(b));
+	if (OP == 14) d = __viaddmax_s16x2(a, b, 0x80008000u);                                                  // VIADDMNMX.S16x2 (DPX)
+	if (OP == 15) d = __vimax3_s16x2(a, b, 0x80008000u);                                                    // VIMNMX3 16x2 (DPX)
+	if (OP == 16) asm volatile("fma.rn.f16x2 %0, %1, %2, %1;" : "=r"(d) : "r"(a), "r"(b));               // HFMA2
+	if (OP == 17) asm volatile("fma.rn.f32 %0, %1, %2, %1;" : "=r"(d) : "r"(a), "r"(b));                 // FFMA
+	if (OP == 18) d = __shfl_xor_sync(0xffffffffu, a, 1) + b;                                               // SHFL (+add)
+	if (OP == 19) d = __match_any_sync(0xffffffffu, a & 7) + a;                                             // MATCH.ANY
+	if (OP == 20) d = __reduce_or_sync(0xffffffffu, a) + b;                                                 // REDUX.OR
+	if (OP == 21) d = __ballot_sync(0xffffffffu, a & 1) + a;                                                // VOTE
+	if (OP == 22) d = __funnelshift_l(a, b, a);                                                             // SHF.L.W
+	if (OP == 23) d = __clz(a) + b;                                                                         // FLO
+	if (OP == 24) d = __popc(a) + b;                                                                        // POPC
+	if (OP == 25) asm volatile("bfe.s32 %0, %1, 8, 8;" : "=r"(d) : "r"(a));                                // BFE / SGXT
+	if (OP == 26) asm volatile("cvt.rn.f32.s32 %0, %1;" : "=r"(d) : "r"(a));                              // I2F
+	if (OP == 27) asm volatile("cvt.rzi.s32.f32 %0, %1;" : "=r"(d) : "r"(a));                             // F2I
+	if (OP == 28) d = __vsub2(a, b);                                                                        // VSUB 16x2 (emulated?)
+	if (OP == 29) d = __reduce_max_sync(0xffffffffu, a) + b;                                                // REDUX.MAX
+	if (OP == 30) asm volatile("shf.r.clamp.b32 %0, %1, %2, %1;" : "=r"(d) : "r"(a), "r"(b));             // SHF.R
+	if (OP == 31) asm volatile("mul.lo.s32 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b));                      // IMUL
 	return d;
 }
 
@@ -121,6 +139,24 @@ int main()
 	run<9>("add.s32", d_out, d_cyc);
 	run<11>("cvt.s32.s16", d_out, d_cyc);
 	run<12>("VIMNMX.S16x2", d_out, d_cyc);
+	run<14>("viaddmax_s16x2 (DPX)", d_out, d_cyc);
+	run<15>("vimax3_s16x2 (DPX)", d_out, d_cyc);
+	run<28>("vsub2", d_out, d_cyc);
+	run<16>("HFMA2", d_out, d_cyc);
+	run<17>("FFMA", d_out, d_cyc);
+	run<18>("SHFL.BFLY + add", d_out, d_cyc);
+	run<19>("MATCH.ANY + add", d_out, d_cyc);
+	run<20>("REDUX.OR + add", d_out, d_cyc);
+	run<29>("REDUX.MAX + add", d_out, d_cyc);
+	run<21>("VOTE.ballot + add", d_out, d_cyc);
+	run<22>("SHF.L.W funnel", d_out, d_cyc);
+	run<30>("SHF.R clamp", d_out, d_cyc);
+	run<23>("FLO(clz) + add", d_out, d_cyc);
+	run<24>("POPC + add", d_out, d_cyc);
+	run<25>("BFE.s32", d_out, d_cyc);
+	run<26>("I2F", d_out, d_cyc);
+	run<27>("F2I", d_out, d_cyc);
+	run<31>("mul.lo", d_out, d_cyc);
 	{
 		const int blocks = 148 * 4, threads = 256;
 		kmix<<<blocks, threads>>>(d_out, 12345, d_cyc);

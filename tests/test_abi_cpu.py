@@ -87,3 +87,15 @@ def test_argument_errors_need_no_device():
                        (b"Ako\x02" + b"\0" * 28, 3), (b"Ako", 15)):
         img2, st2, _ = ako_b200.decode(blob)
         assert img2 is None and st2 == want, (blob[:16], st2)
+
+
+def test_torch_synth_matches_numpy_synth():
+    """bench.py makes its large batches (configs[3], configs[4]) with the torch restatement of SURVEY Appendix C."""
+    import numpy as np
+    from ako_b200.synth import synth_rgba8, synth_rgba8_torch
+    for w, h, seeds in ((300, 200, [1, 2, 1000, 77777]), (520, 391, [5])):
+        got = synth_rgba8_torch(w, h, seeds, device="cpu").numpy()
+        for k, seed in enumerate(seeds):
+            assert np.array_equal(got[k], synth_rgba8(w, h, seed)), (w, h, seed)
+    band = synth_rgba8_torch(300, 50, [9], device="cpu", y0=100).numpy()[0]
+    assert np.array_equal(band, synth_rgba8(300, 200, 9)[100:150])
