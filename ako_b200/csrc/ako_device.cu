@@ -771,13 +771,13 @@ extern "C" int akod_kagari_encode(akodContext* c, uint64_t n_values, const int16
 	uint32_t* blk_own = slots + per_img * n_images * KG_SLOT_WORDS;
 	uint8_t* blk_first = (uint8_t*)(blk_own + per_img * n_images);
 
-	const dim3 grid(nblocks, n_images);
+	const dim3 lgrid((nblocks + KGL_WARPS * KGL_BLOCKS_PER_WARP - 1) / (KGL_WARPS * KGL_BLOCKS_PER_WARP), n_images);
 	AKOD_BYTES(c, 2 * n_values * n_images);
 	AKOD_LAUNCH(c, "kagari_starts", k_kg_starts, dim3((nblocks + KG_STARTS_PER_CTA - 1) / KG_STARTS_PER_CTA, n_images), KG_THREADS,
 	            0, d_in, in_stride, n_values, blk_own, blk_first, nblocks);
 	AKOD_LAUNCH(c, "kagari_scan_max", k_kg_scan_max, n_images, 1024, 0, blk_own, blk_start, nblocks);
 	AKOD_BYTES(c, 2 * n_values * n_images);
-	AKOD_LAUNCH(c, "kagari_lengths", k_kg_lengths, grid, KG_THREADS, 0, d_in, in_stride, n_values, blk_start, blk_bits,
+	AKOD_LAUNCH(c, "kagari_lengths", k_kg_lengths, lgrid, KG_THREADS, 0, d_in, in_stride, n_values, blk_start, blk_bits,
 	            nblocks, slots, blk_own, blk_first);
 	AKOD_LAUNCH(c, "kagari_scan_sum", k_kg_scan_sum, n_images, 1024, 0, blk_bits, blk_off, nblocks, d_bits);
 	const dim3 zgrid((nblocks + 255) / 256, n_images);
@@ -809,13 +809,13 @@ extern "C" int akod_kagari_bits(akodContext* c, uint64_t n_values, const int16_t
 	uint32_t* slots = blk_bits + per_img * n_images;
 	uint32_t* blk_own = slots + per_img * n_images * KG_SLOT_WORDS;
 	uint8_t* blk_first = (uint8_t*)(blk_own + per_img * n_images);
-	const dim3 grid(nblocks, n_images);
+	const dim3 lgrid((nblocks + KGL_WARPS * KGL_BLOCKS_PER_WARP - 1) / (KGL_WARPS * KGL_BLOCKS_PER_WARP), n_images);
 	AKOD_BYTES(c, 2 * n_values * n_images);
 	AKOD_LAUNCH(c, "kagari_starts", k_kg_starts, dim3((nblocks + KG_STARTS_PER_CTA - 1) / KG_STARTS_PER_CTA, n_images), KG_THREADS,
 	            0, d_in, in_stride, n_values, blk_own, blk_first, nblocks);
 	AKOD_LAUNCH(c, "kagari_scan_max", k_kg_scan_max, n_images, 1024, 0, blk_own, blk_start, nblocks);
 	AKOD_BYTES(c, 2 * n_values * n_images);
-	AKOD_LAUNCH(c, "kagari_lengths", k_kg_lengths, grid, KG_THREADS, 0, d_in, in_stride, n_values, blk_start, blk_bits,
+	AKOD_LAUNCH(c, "kagari_lengths", k_kg_lengths, lgrid, KG_THREADS, 0, d_in, in_stride, n_values, blk_start, blk_bits,
 	            nblocks, slots, blk_own, blk_first);
 	AKOD_LAUNCH(c, "kagari_scan_sum", k_kg_scan_sum, n_images, 1024, 0, blk_bits, blk_off, nblocks, d_bits);
 	return AKOD_OK;

@@ -171,6 +171,8 @@ static enum akoStatus head_write(size_t channels, size_t w, size_t h, const stru
 	return AKO_OK;
 }
 
+static enum akoStatus check_sizes(size_t channels, size_t w, size_t h, size_t td);
+
 /* head.c:112-169 */
 static enum akoStatus head_read(const uint8_t in[16], size_t* channels, size_t* w, size_t* h, struct akoSettings* s)
 {
@@ -192,7 +194,9 @@ static enum akoStatus head_read(const uint8_t in[16], size_t* channels, size_t* 
 	if (tiles != 0)
 		tiles = (size_t)1 << (tiles + 2);
 
-	const enum akoStatus st = validate(ch, load_le32(in + 4), load_le32(in + 8), tiles, wrap, wavelet, color, compression);
+	enum akoStatus st = validate(ch, load_le32(in + 4), load_le32(in + 8), tiles, wrap, wavelet, color, compression);
+	if (st == AKO_OK)
+		st = check_sizes(ch, load_le32(in + 4), load_le32(in + 8), tiles);
 	if (st != AKO_OK)
 		return st;
 
@@ -241,6 +245,25 @@ static size_t tiles_count(size_t w, size_t h, size_t tiles) /* akoImageTilesNo, 
 	if (tiles == 0)
 		return 1;
 	return ((w / tiles) + (w % tiles != 0)) * ((h / tiles) + (h % tiles != 0));
+}
+
+/* Sizes that the work areas and the kernels' 32-bit element indices are built on, checked before anything is
+ * allocated or launched: a crafted header (w = h = 2^31 ...) must fail here, not wrap a product. A tile's
+ * coefficient stream has to stay below 2^32 values (Kagari run positions) and a plane below 2^31 samples. */
+static enum akoStatus check_sizes(size_t channels, size_t w, size_t h, size_t td)
+{
+	size_t plane, image, tiles_x, tiles_y, tiles;
+	if (__builtin_mul_overflow(w, h, &plane) || __builtin_mul_overflow(plane, channels, &image) ||
+	    image > ((size_t)1 << 46))
+		return AKO_NO_ENOUGH_MEMORY;
+	const size_t tw = tile_dimension(0, w, td), th = tile_dimension(0, h, td);
+	if (tw * th >= ((size_t)1 << 31) || tile_data_size(tw, th) * channels / 2 >= ((size_t)1 << 32))
+		return AKO_NO_ENOUGH_MEMORY;
+	tiles_x = (td == 0) ? 1 : (w / td) + (w % td != 0);
+	tiles_y = (td == 0) ? 1 : (h / td) + (h % td != 0);
+	if (__builtin_mul_overflow(tiles_x, tiles_y, &tiles) || tiles > ((size_t)1 << 28))
+		return AKO_NO_ENOUGH_MEMORY;
+	return AKO_OK;
 }
 
 AKO_API size_t akoB200StreamSize(size_t channels, size_t tile_w, size_t tile_h)
@@ -877,6 +900,8 @@ static size_t encode_core_ex(akoB200Context* ctx, const struct akoCallbacks* cb,
 		st = AKO_ERROR;
 		goto done;
 	}
+	if ((st = check_sizes(channels, w, h, s.tiles_dimension)) != AKO_OK)
+		goto done;
 	if (!fill && !size_only && out_capacity < akoB200EncodeBound(&s, channels, w, h))
 	{
 		st = AKO_NO_ENOUGH_MEMORY;
@@ -918,7 +943,10 @@ static size_t encode_core_ex(akoB200Context* ctx, const struct akoCallbacks* cb,
 			if (s.compression == AKO_COMPRESSION_NONE)
 				host_cap[t] = data; /* raw copy */
 			else
-				host_cap[t] = (data >= 4) ? ((data - 4) & ~(uint64_t)3) : 0; /* what the packer may write */
+				/* what the packer may write: the reference accepts a block of up to data - 5 bytes (bytes < data - 4,
+				 * compression.c:40-49); the packer stores whole words, and the tile's region (align_up(data, 16)) holds
+				 * the word that byte data - 5 lies in. The exact rule is applied on the host below. */
+				host_cap[t] = (data >= 6) ? align_up(data - 5, 4) : 0;
 			blocks_per_image += align_up(data, 16);
 			tx += td;
 			if (tx >= w)

@@ -393,28 +393,341 @@ __device__ __forceinline__ void kg_put_codes(uint32_t* bitbuf, uint32_t pos, con
 	}
 }
 
-// pass 2: bits emitted by each block (+ the bit string itself into the block's slot when it fits)
-__global__ void __launch_bounds__(KG_THREADS, 8)
+// ------------------------------------------------------------------------------------------------
+// Pass 2 works from bit masks instead of walking the elements. For a thread's 8 values, S = start_mask (bit j: value
+// j starts a run) and c0 = the run counter of value 0 when it continues a run. With no counter overflow inside the
+// thread (c0 + 7 < 65534, all but one thread in 8192 of a long run):
+//     value j emits EV(a[j])            <=>  its counter is <= 2  <=>  a start at j, j-1 or j-2 (or c0 + j <= 2)
+//     value j emits its run's length    <=>  j is the last of its run (a start at j+1, or the end of the stream)
+//                                            and its counter is >= 2 (no start at j nor at j-1)
+// so V and R below name the emitters and only those are looked at: a quantised stream has one emitter per ~16
+// values. The other threads (a counter overflow in reach, or the partial chunk at the end of the stream) take the
+// element-by-element rule of kg_element.
+struct KgMasks
+{
+	uint32_t V, R; // bit j: value j emits its value / the length of its run
+	uint32_t c0;   // run counter of value 0 when it continues a run
+	bool slow;     // take the element-by-element path
+};
+
+__device__ __forceinline__ KgMasks kg_masks(const KgChunk& c, uint64_t base, uint32_t run_start)
+{
+	KgMasks m;
+	const uint32_t S = c.start_mask;
+	const bool cont = (S & 1u) == 0; // value 0 continues the run that starts at run_start - 1
+	uint32_t c0 = 0;
+	if (cont)
+	{
+		const uint32_t k0 = (uint32_t)base + 1u - run_start; // >= 1
+		c0 = (k0 > 65534u) ? ((k0 - 1u) % 65534u) + 1u : k0;
+	}
+	m.c0 = c0;
+	m.slow = c.valid != KG_ITEMS || (cont && c0 + (KG_ITEMS - 1) >= 65534u);
+	uint32_t V = (S | (S << 1) | (S << 2)) & 0xFFu;
+	if (cont)
+		V |= (c0 == 1u) ? 3u : (c0 == 2u) ? 1u : 0u;
+	const uint32_t last = (!c.has_after || c.after != c.v[KG_ITEMS - 1]) ? 0x80u : 0u; // value 7 ends its run
+	uint32_t K2 = ~(S | (S << 1)) & 0xFFu;                                               // counter >= 2
+	if (cont && c0 < 2u)
+		K2 &= ~1u;
+	m.V = V;
+	m.R = ((S >> 1) | last) & K2;
+	return m;
+}
+
+// a bit string under construction in registers: codes are appended at the low end of a 64-bit accumulator and
+// whole 32-bit words leave for the shared buffer as they fill up. The first and the last word of a thread's string
+// are shared with its neighbours (atomicOr); the words in between are its own.
+struct KgSink
+{
+	uint32_t* buf;
+	uint64_t acc;
+	uint32_t n, w; // bits pending in acc (< 32 between calls), next word of buf
+	bool first;
+	__device__ __forceinline__ void open(uint32_t* bitbuf, uint32_t pos)
+	{
+		buf = bitbuf;
+		acc = 0;
+		n = pos & 31u; // the bits before 'pos' in its word belong to the threads before: zeros here
+		w = pos >> 5;
+		first = true;
+	}
+	__device__ __forceinline__ void put(uint32_t code, uint32_t len)
+	{
+		acc = (acc << len) | code;
+		n += len;
+		if (n >= 32u)
+		{
+			n -= 32u;
+			const uint32_t word = (uint32_t)(acc >> n);
+			if (first)
+				atomicOr(&buf[w], word);
+			else
+				buf[w] = word;
+			first = false;
+			w++;
+		}
+	}
+	__device__ __forceinline__ void close()
+	{
+		if (n)
+			atomicOr(&buf[w], (uint32_t)(acc << (32u - n)));
+	}
+};
+
+struct KgCount
+{
+	uint32_t bits;
+	__device__ __forceinline__ void put(uint32_t, uint32_t len) { bits += len; }
+};
+
+// The emitters of a chunk as a list of Elias-gamma arguments ("payloads", 16 bits each: zigzag(value) + 1 for a value,
+// counter - 1 for a run length; 0 stands for the degenerate one-bit code of -32768, kagari.c:38-45 with :214-217), in
+// stream order. PUSH(payload) is called once per code.
+template <typename PUSH>
+__device__ __forceinline__ void kg_emitters(const KgChunk& c, const KgMasks& m, uint64_t n, uint64_t base, uint32_t run_start,
+                                            PUSH push)
+{
+	// the lane's 8 values as two 64-bit words: value j is 16 bits at 16 * (j & 3) of word j >> 2
+	const uint4 q = *reinterpret_cast<const uint4*>(c.v);
+	const uint64_t lo64 = ((uint64_t)q.y << 32) | q.x, hi64 = ((uint64_t)q.w << 32) | q.z;
+	auto value = [&](int j) { return (int16_t)(uint16_t)(((j & 4) ? hi64 : lo64) >> (16 * (j & 3))); };
+	if (m.slow)
+	{
+		// element by element (kg_element's rule): a counter overflow in reach, or the partial chunk at the end
+#pragma unroll 1
+		for (int j = 0; j < c.valid; j++)
+		{
+			if (c.start_mask & (1u << j))
+				run_start = (uint32_t)(base + j) + 1u;
+			const int16_t a = value(j);
+			const bool last = (j + 1 < c.valid) ? (value(j + 1) != a)
+			                                    : ((base + j + 1 >= n) || (j + 1 == KG_ITEMS ? (c.after != a) : true));
+			const uint32_t k = (uint32_t)(base + j) + 1u - run_start;
+			uint32_t cnt = k;
+			if (k > 65534u)
+				cnt = ((k - 1) % 65534u) + 1u;
+			if (cnt <= 2)
+				push(((uint32_t)(((int)a << 1) ^ ((int)a >> 15)) + 1u) & 0xFFFFu);
+			else if (cnt == 65534u)
+			{
+				push(65533u);
+				cnt = 0;
+			}
+			if (last && cnt >= 2)
+				push(cnt - 1u);
+		}
+		return;
+	}
+	uint32_t U = m.V | m.R;
+#pragma unroll 1
+	while (U)
+	{
+		const int j = __ffs(U) - 1;
+		U &= U - 1;
+		if (m.V & (1u << j))
+		{
+			const int a = value(j);
+			push(((uint32_t)((a << 1) ^ (a >> 15)) + 1u) & 0xFFFFu);
+		}
+		if (m.R & (1u << j))
+		{
+			// run counter of value j: distance to the last start at or before j, else c0 + j
+			const uint32_t before = c.start_mask & ((2u << j) - 1u);
+			const uint32_t cj = before ? (uint32_t)j - (31u - (uint32_t)__clz(before)) : m.c0 + (uint32_t)j;
+			push(cj - 1u); // cj >= 2
+		}
+	}
+}
+
+__device__ __forceinline__ uint32_t kg_payload_len(uint32_t p)
+{
+	return p ? 2u * (31u - (uint32_t)__clz(p)) + 1u : 1u;
+}
+
+// pass 2: bits emitted by each block (+ the bit string itself into the block's slot when it fits).
+// A WARP owns a block (and KGL_BLOCKS_PER_WARP consecutive blocks, one after the other): it walks the block's 2048
+// values in eight steps of 256, carrying the run start and the bit position from step to step in registers, so the
+// pass has no __syncthreads and no shared-memory scans at all -- only ballots and shuffles. With one CTA per block the
+// pass was bound by the latency chain of a short-lived CTA (summary words -> values -> three barriers) and by the
+// 300 000 CTAs per step that only find out that their block lies inside a run. The values of step i+1 are fetched
+// before step i is worked on.
+constexpr int KGL_WARPS = KG_THREADS / 32;
+constexpr int KGL_BLOCKS_PER_WARP = 4;
+constexpr int KGL_STEPS = KG_BLOCK / (32 * KG_ITEMS); // 8
+
+// the raw loads of one step: the lane's 8 values and, for the lanes at the warp's edges, the neighbouring values
+struct KgFetch
+{
+	uint4 q;
+	uint32_t before, after; // lane 0 / lane 31 only
+};
+
+__device__ __forceinline__ KgFetch kg_fetch(const int16_t* __restrict__ in, uint64_t n, uint64_t base, int lane)
+{
+	KgFetch f;
+	f.q = make_uint4(0, 0, 0, 0);
+	f.before = f.after = 0;
+	if (base + KG_ITEMS <= n)
+		f.q = __ldg(reinterpret_cast<const uint4*>(in + base));
+	if (lane == 0 && base > 0 && base <= n)
+		f.before = (uint32_t)(uint16_t)__ldg(in + base - 1);
+	if (lane == 31 && base + KG_ITEMS < n)
+		f.after = (uint32_t)(uint16_t)__ldg(in + base + KG_ITEMS);
+	return f;
+}
+
+// kg_load from prefetched registers (full chunks only: the caller sends the end of the stream through kg_load)
+__device__ __forceinline__ KgChunk kg_chunk_from(const KgFetch& f, uint64_t n, uint64_t base, int lane)
+{
+	KgChunk c;
+	const uint32_t w[4] = {f.q.x, f.q.y, f.q.z, f.q.w};
+	uint32_t before = __shfl_up_sync(AKOD_FULL_MASK, w[3], 1) >> 16;
+	uint32_t after = __shfl_down_sync(AKOD_FULL_MASK, w[0], 1) & 0xFFFFu;
+	if (lane == 0)
+		before = f.before;
+	if (lane == 31)
+		after = f.after;
+	c.has_after = base + KG_ITEMS < n;
+	c.after = (int16_t)after;
+	*reinterpret_cast<uint4*>(c.v) = f.q;
+	c.valid = KG_ITEMS;
+	uint32_t mask = 0;
+	uint32_t prev_word = before << 16;
+#pragma unroll
+	for (int i = 0; i < 4; i++)
+	{
+		// halves of d: value 2i against 2i-1, value 2i+1 against 2i; min(d, 1) per half (VIMNMX.U16x2), then both bits
+		const uint32_t d = w[i] ^ __funnelshift_l(prev_word, w[i], 16);
+		const uint32_t ne = __vminu2(d, 0x00010001u);
+		mask |= ((ne | (ne >> 15)) & 3u) << (2 * i);
+		prev_word = w[i];
+	}
+	if (base == 0)
+		mask |= 1u; // element 0 of the stream starts a run
+	c.start_mask = mask;
+	c.last_start = mask ? (uint32_t)base + (31 - __clz(mask)) + 1u : 0u;
+	return c;
+}
+
+// one block by one warp; returns the block's bit count. WHOLE = false: the last, partial block of a stream, whose
+// chunks come through the general loader (kept out of line: it is one block per stream and would only cost the
+// common path registers)
+template <bool WHOLE>
+__device__ __forceinline__ uint32_t kgl_block_body(const int16_t* __restrict__ in, uint64_t n, uint64_t first, uint32_t carry_start,
+                                                   uint32_t* bitbuf, uint16_t* list, KgFetch f, int lane)
+{
+	uint32_t run_carry = carry_start; // (index + 1) of the last run start before the current step
+	uint32_t bitpos = 0;
+	bool overflow = false;
+#pragma unroll 1
+	for (int step = 0; step < KGL_STEPS; step++)
+	{
+		const uint64_t base = first + (uint64_t)step * (32 * KG_ITEMS) + (uint64_t)lane * KG_ITEMS;
+		const KgFetch cur = f;
+		if (WHOLE && step + 1 < KGL_STEPS)
+			f = kg_fetch(in, n, base + 32 * KG_ITEMS, lane);
+		const KgChunk c = WHOLE ? kg_chunk_from(cur, n, base, lane) : kg_load(in, n, base);
+		// run start reaching into this lane: the last start of the lanes before it, else the carry
+		const uint32_t any = __ballot_sync(AKOD_FULL_MASK, c.last_start != 0);
+		const uint32_t lower = any & ((1u << lane) - 1u);
+		const uint32_t from_lower = __shfl_sync(AKOD_FULL_MASK, c.last_start, lower ? 31 - __clz(lower) : 0);
+		const uint32_t warp_last = __shfl_sync(AKOD_FULL_MASK, c.last_start, any ? 31 - __clz(any) : 0);
+		const uint32_t run_start = lower ? from_lower : run_carry;
+		if (any)
+			run_carry = warp_last;
+
+		// ---- the step's emitters, compacted into the warp's list in stream order
+		const KgMasks m = kg_masks(c, base, run_start);
+		uint32_t cnt;
+		if (m.slow)
+		{
+			cnt = 0;
+			kg_emitters(c, m, n, base, run_start, [&](uint32_t) { cnt++; });
+		}
+		else
+			cnt = __popc(m.V) + __popc(m.R);
+		if (__ballot_sync(AKOD_FULL_MASK, cnt != 0) == 0)
+			continue;
+		const uint32_t incl_cnt = warp_incl_sum(cnt);
+		const uint32_t emitters = __shfl_sync(AKOD_FULL_MASK, incl_cnt, 31);
+		if (cnt)
+		{
+			uint32_t at = incl_cnt - cnt;
+			kg_emitters(c, m, n, base, run_start, [&](uint32_t p) { list[at++] = (uint16_t)p; });
+		}
+		__syncwarp();
+
+		// ---- lane l takes the entries [l * per, (l + 1) * per): lengths, a warp scan, then the codes
+		const uint32_t per = (emitters + 31) >> 5;
+		const uint32_t e0 = min((uint32_t)lane * per, emitters), e1 = min(e0 + per, emitters);
+		uint32_t bits = 0;
+		for (uint32_t i = e0; i < e1; i++)
+			bits += kg_payload_len(list[i]);
+		const uint32_t incl = warp_incl_sum(bits);
+		const uint32_t step_total = __shfl_sync(AKOD_FULL_MASK, incl, 31);
+		overflow = overflow || (bitpos + step_total > KG_SLOT_BITS);
+		if (bits && !overflow)
+		{
+			KgSink sink;
+			sink.open(bitbuf, bitpos + incl - bits);
+			for (uint32_t i = e0; i < e1; i++)
+			{
+				const uint32_t p = list[i];
+				sink.put(p, kg_payload_len(p));
+			}
+			sink.close();
+		}
+		bitpos += step_total;
+		__syncwarp(); // the list is rewritten by the next step
+	}
+	return bitpos;
+}
+
+__device__ __noinline__ uint32_t kgl_block_tail(const int16_t* __restrict__ in, uint64_t n, uint64_t first, uint32_t carry_start,
+                                                uint32_t* bitbuf, uint16_t* list, int lane)
+{
+	KgFetch f;
+	f.q = make_uint4(0, 0, 0, 0);
+	f.before = f.after = 0;
+	return kgl_block_body<false>(in, n, first, carry_start, bitbuf, list, f, lane);
+}
+
+__global__ void __launch_bounds__(KG_THREADS, 5)
     k_kg_lengths(const int16_t* __restrict__ in, uint64_t in_stride, uint64_t n, const uint32_t* __restrict__ blk_carry,
                  uint32_t* __restrict__ blk_bits, uint32_t nblocks, uint32_t* __restrict__ slots,
                  const uint32_t* __restrict__ blk_own, const uint8_t* __restrict__ blk_first)
 {
-	__shared__ uint32_t sm_max[33];
-	__shared__ uint32_t sm_sum[33];
-	__shared__ uint32_t bitbuf[KG_SLOT_WORDS + 2];
-	const uint64_t bi = (uint64_t)nblocks * blockIdx.y + blockIdx.x;
-	// the three per-block words of pass 1 are fetched together (independent loads, one round trip), not one after
-	// the other behind short-circuit tests: a CTA lives for a few microseconds and this is its critical path
-	const bool has_next = blockIdx.x + 1 < nblocks;
-	const uint32_t own = __ldg(blk_own + bi);
-	const uint32_t carry_start = __ldg(blk_carry + bi);
-	const uint32_t next_first = __ldg(blk_first + (has_next ? bi + 1 : bi));
+	__shared__ uint32_t bitbuf_all[KGL_WARPS][KG_SLOT_WORDS + 2];
+	__shared__ uint16_t list_all[KGL_WARPS][2 * 32 * KG_ITEMS]; // at most two codes per value
+	const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+	uint32_t* const bitbuf = bitbuf_all[wid];
+	uint16_t* const list = list_all[wid];
+	const uint64_t row = (uint64_t)nblocks * blockIdx.y;
+	in += in_stride * blockIdx.y;
+	for (uint32_t i = lane; i < KG_SLOT_WORDS + 2; i += 32)
+		bitbuf[i] = 0;
+	__syncwarp();
+
+	const uint32_t b_first = (blockIdx.x * KGL_WARPS + wid) * KGL_BLOCKS_PER_WARP;
+	for (uint32_t b = b_first; b < b_first + KGL_BLOCKS_PER_WARP && b < nblocks; b++)
 	{
+		const uint64_t bi = row + b;
+		const bool has_next = b + 1 < nblocks;
+		const uint64_t first = (uint64_t)b * KG_BLOCK;
+		const bool whole = first + KG_BLOCK <= n;
+		// the three per-block words of pass 1, fetched together (independent loads)
+		const uint32_t own = __ldg(blk_own + bi);
+		const uint32_t carry_start = __ldg(blk_carry + bi);
+		const uint32_t next_first = __ldg(blk_first + (has_next ? bi + 1 : bi));
+		// the first step's values are asked for before the summary words are looked at
+		KgFetch f;
+		if (whole)
+			f = kg_fetch(in, n, first + (uint64_t)lane * KG_ITEMS, lane);
 		// A block that lies entirely inside one run which also goes on behind it emits nothing, unless the run
-		// counter passes 1, 2 or 65534 inside it (the same rule as the per-thread fast path of kg_codes). Pass 1
-		// left everything needed to see that without touching the stream: quantised planes are mostly such blocks.
-		const uint64_t first = (uint64_t)blockIdx.x * KG_BLOCK;
-		if (own == 0 && has_next && next_first == 0 && first + KG_BLOCK <= n)
+		// counter passes 1, 2 or 65534 inside it. Pass 1 left everything needed to see that without touching the
+		// stream: quantised planes are mostly such blocks.
+		if (own == 0 && has_next && next_first == 0 && whole)
 		{
 			const uint32_t k0 = (uint32_t)first + 1u - carry_start; // position of the block's first value in its run
 			uint32_t c0 = k0;
@@ -422,33 +735,29 @@ __global__ void __launch_bounds__(KG_THREADS, 8)
 				c0 = ((k0 - 1) % 65534u) + 1u;
 			if (c0 >= 3 && c0 + (KG_BLOCK - 1) < 65534u)
 			{
-				if (threadIdx.x == 0)
+				if (lane == 0)
 					blk_bits[bi] = 0;
-				return;
+				continue;
 			}
 		}
+		const uint32_t bitpos = whole ? kgl_block_body<true>(in, n, first, carry_start, bitbuf, list, f, lane)
+		                              : kgl_block_tail(in, n, first, carry_start, bitbuf, list, lane);
+		if (lane == 0)
+			blk_bits[bi] = bitpos;
+		__syncwarp();
+		// the words this block touched leave for its slot (when the string fits) and are cleared for the next block
+		const uint32_t used = min((bitpos + 31) >> 5, (uint32_t)KG_SLOT_WORDS) + 1;
+		if (bitpos != 0 && bitpos <= KG_SLOT_BITS)
+		{
+			uint32_t* slot = slots + bi * KG_SLOT_WORDS;
+			const uint32_t nwords = (bitpos + 31) >> 5;
+			for (uint32_t i = lane; i < nwords; i += 32)
+				slot[i] = bitbuf[i];
+		}
+		for (uint32_t i = lane; i < used && i < KG_SLOT_WORDS + 2; i += 32)
+			bitbuf[i] = 0;
+		__syncwarp();
 	}
-	in += in_stride * blockIdx.y;
-	const uint64_t base = (uint64_t)blockIdx.x * KG_BLOCK + (uint64_t)threadIdx.x * KG_ITEMS;
-	const KgChunk c = kg_load(in, n, base);
-	KgCode codes[KG_ITEMS];
-	const uint32_t bits = kg_thread_codes<true>(c, n, base, carry_start, sm_max, codes);
-	uint32_t total;
-	const uint32_t excl = block_excl_sum_once<KG_THREADS / 32>(bits, sm_sum, &total);
-	if (threadIdx.x == 0)
-		blk_bits[bi] = total;
-	if (total == 0 || total > KG_SLOT_BITS)
-		return;
-	const uint32_t nwords = (total + 31) >> 5;
-	for (uint32_t i = threadIdx.x; i < nwords + 1; i += KG_THREADS)
-		bitbuf[i] = 0;
-	__syncthreads();
-	if (bits)
-		kg_put_codes(bitbuf, excl, codes);
-	__syncthreads();
-	uint32_t* slot = slots + bi * KG_SLOT_WORDS;
-	for (uint32_t i = threadIdx.x; i < nwords; i += KG_THREADS)
-		slot[i] = bitbuf[i];
 }
 
 // clears the (up to two) 32-bit words each block shares with its neighbours, and the final word

@@ -99,3 +99,13 @@ def test_torch_synth_matches_numpy_synth():
             assert np.array_equal(got[k], synth_rgba8(w, h, seed)), (w, h, seed)
     band = synth_rgba8_torch(300, 50, [9], device="cpu", y0=100).numpy()[0]
     assert np.array_equal(band, synth_rgba8(300, 200, 9)[100:150])
+
+
+def test_crafted_header_sizes_are_refused_before_any_device_work():
+    """A header whose dimensions wrap size_t products, or exceed what the kernels index, must fail in the header
+    checks (no context, no allocation): the reference overflows in the same place (decode.c:87-110)."""
+    import struct
+    for w, h, flags in ((1 << 31, 1 << 31, 3), (0xFFFFFFFF, 0xFFFFFFFF, 15), (1 << 20, 1 << 20, 3)):
+        blob = b"Ako\x02" + struct.pack("<III", w, h, flags) + b"\0" * 64
+        img, st, _ = ako_b200.decode(blob)
+        assert img is None and st == 13, (w, h, st)
