@@ -225,6 +225,58 @@ extern "C" int akod_memset(akodContext* c, void* d, int v, size_t n)
 	return AKOD_OK;
 }
 
+// block j (blockIdx.y, folded over gridDim.z) of 'bytes' bytes from src + off(j) to dst + j*dst_stride
+__global__ void __launch_bounds__(256)
+    k_copy_blocks(uint8_t* __restrict__ dst, uint64_t dst_stride, const uint8_t* __restrict__ src, uint64_t src_stride,
+                  const uint64_t* __restrict__ src_off, uint64_t bytes, uint64_t count)
+{
+	const uint64_t j = (uint64_t)blockIdx.z * gridDim.y + blockIdx.y;
+	if (j >= count)
+		return;
+	uint8_t* d = dst + j * dst_stride;
+	const uint8_t* s = src + (src_off ? src_off[j] : j * src_stride);
+	const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x, stride = (size_t)gridDim.x * blockDim.x;
+	if ((((uintptr_t)d | (uintptr_t)s) & 15) == 0)
+	{
+		const size_t n16 = bytes >> 4;
+		for (size_t i = t; i < n16; i += stride)
+			reinterpret_cast<uint4*>(d)[i] = reinterpret_cast<const uint4*>(s)[i];
+		for (size_t i = (n16 << 4) + t; i < bytes; i += stride)
+			d[i] = s[i];
+	}
+	else
+		for (size_t i = t; i < bytes; i += stride)
+			d[i] = s[i];
+}
+
+static int akod_copy_blocks(akodContext* c, void* d, uint64_t dst_stride, const void* s, uint64_t src_stride,
+                            const uint64_t* d_off, uint64_t bytes, uint64_t count)
+{
+	akod_use(c);
+	if (count == 0 || bytes == 0)
+		return AKOD_OK;
+	const uint64_t per = (bytes / 16 + 255) / 256 + 1;
+	const unsigned gx = (unsigned)(per < 32 ? per : 32);
+	const unsigned gy = (unsigned)(count < 32768 ? count : 32768), gz = (unsigned)((count + gy - 1) / gy);
+	if (gz > 65535)
+		return AKOD_ERROR;
+	AKOD_LAUNCH(c, "copy_blocks", k_copy_blocks, dim3(gx, gy, gz), 256, 0, (uint8_t*)d, dst_stride, (const uint8_t*)s,
+	            src_stride, d_off, bytes, count);
+	return AKOD_OK;
+}
+
+extern "C" int akod_copy_strided(akodContext* c, void* d, uint64_t dst_stride, const void* s, uint64_t src_stride,
+                                 uint64_t bytes, uint64_t count)
+{
+	return akod_copy_blocks(c, d, dst_stride, s, src_stride, nullptr, bytes, count);
+}
+
+extern "C" int akod_gather(akodContext* c, void* d, uint64_t dst_stride, const void* s, const uint64_t* d_off, uint64_t bytes,
+                           uint64_t count)
+{
+	return akod_copy_blocks(c, d, dst_stride, s, 0, d_off, bytes, count);
+}
+
 __global__ void k_fill_words(uint64_t* dst, uint64_t value, size_t count)
 {
 	const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -337,26 +389,51 @@ static inline unsigned akod_stream_grid(akodContext* c, uint64_t items, unsigned
 // ------------------------------------------------------------------------------------------------
 // format
 
+static FmtTiles fmt_tiles(const akodBatch* b)
+{
+	FmtTiles t;
+	memset(&t, 0, sizeof(t));
+	if (b && b->n_real)
+	{
+		t.n_real = b->n_real;
+		t.cols = b->tile_cols ? b->tile_cols : 1;
+		t.first = b->tile_first;
+		t.step = b->tile_step;
+		t.x0 = b->tile_x0;
+		t.y0 = b->tile_y0;
+	}
+	return t;
+}
+
+// the 128-bit path needs every member's first pixel on a 16-byte boundary (4 channels: a multiple of 4 pixels)
+static bool fmt_tiles_aligned(const FmtTiles& t)
+{
+	return t.n_real == 0 || ((t.step % 4) == 0 && (t.x0 % 4) == 0);
+}
+
 extern "C" int akod_format_forward(akodContext* c, int discard, int color, uint32_t channels, uint32_t w, uint32_t h,
                                    uint64_t in_stride_px, const uint8_t* d_in, int16_t* d_planes, const akodBatch* b)
 {
 	akod_use(c);
 	const uint32_t n = b ? b->n : 1;
 	const uint64_t in_is = b ? b->in_stride : 0, pl_is = b ? b->planes_stride : 0;
+	const FmtTiles ft = fmt_tiles(b);
 	const bool fast = channels == 4 && (w % 8) == 0 && (in_stride_px % 4) == 0 && ((uintptr_t)d_in % 16) == 0 &&
-	                  ((uintptr_t)d_planes % 16) == 0 && (in_is % 16) == 0 && (pl_is % 8) == 0;
+	                  ((uintptr_t)d_planes % 16) == 0 && (in_is % 16) == 0 && (pl_is % 8) == 0 && fmt_tiles_aligned(ft);
 	AKOD_BYTES(c, (uint64_t)3 * w * h * channels * n); // u8 in, int16 out
+	// the members of a batch ride in gridDim.y; a member of few pixels gets a grid of few CTAs
+	const unsigned per_sm = n >= 64 ? 1 : 8;
 	if (fast)
 	{
-		const dim3 grid(akod_stream_grid(c, (uint64_t)(w / 8) * h, 256, 8), n);
+		const dim3 grid(akod_stream_grid(c, (uint64_t)(w / 8) * h, 256, per_sm), n);
 		AKOD_LAUNCH(c, "format_fwd_rgba8x8", k_format_fwd_rgba8x8, grid, 256, 0, d_in, d_planes, w, h, in_stride_px, color,
-		            discard, in_is, pl_is);
+		            discard, in_is, pl_is, ft);
 	}
 	else
 	{
-		const dim3 grid(akod_stream_grid(c, (uint64_t)w * h, 256, 8), n);
+		const dim3 grid(akod_stream_grid(c, (uint64_t)w * h, 256, per_sm), n);
 		AKOD_LAUNCH(c, "format_fwd_generic", k_format_fwd_generic, grid, 256, 0, d_in, d_planes, channels, w, h,
-		            in_stride_px, color, discard, in_is, pl_is);
+		            in_stride_px, color, discard, in_is, pl_is, ft);
 	}
 	return AKOD_OK;
 }
@@ -367,20 +444,22 @@ extern "C" int akod_format_inverse(akodContext* c, int color, uint32_t channels,
 	akod_use(c);
 	const uint32_t n = b ? b->n : 1;
 	const uint64_t out_is = b ? b->in_stride : 0, pl_is = b ? b->planes_stride : 0;
+	const FmtTiles ft = fmt_tiles(b);
 	const bool fast = channels == 4 && (w % 8) == 0 && (out_stride_px % 4) == 0 && ((uintptr_t)d_out % 16) == 0 &&
-	                  ((uintptr_t)d_planes % 16) == 0 && (out_is % 16) == 0 && (pl_is % 8) == 0;
+	                  ((uintptr_t)d_planes % 16) == 0 && (out_is % 16) == 0 && (pl_is % 8) == 0 && fmt_tiles_aligned(ft);
 	AKOD_BYTES(c, (uint64_t)3 * w * h * channels * n); // int16 in, u8 out
+	const unsigned per_sm = n >= 64 ? 1 : 8;
 	if (fast)
 	{
-		const dim3 grid(akod_stream_grid(c, (uint64_t)(w / 8) * h, 256, 8), n);
+		const dim3 grid(akod_stream_grid(c, (uint64_t)(w / 8) * h, 256, per_sm), n);
 		AKOD_LAUNCH(c, "format_inv_rgba8x8", k_format_inv_rgba8x8, grid, 256, 0, d_planes, d_out, w, h, out_stride_px, color,
-		            pl_is, out_is);
+		            pl_is, out_is, ft);
 	}
 	else
 	{
-		const dim3 grid(akod_stream_grid(c, (uint64_t)w * h, 256, 8), n);
+		const dim3 grid(akod_stream_grid(c, (uint64_t)w * h, 256, per_sm), n);
 		AKOD_LAUNCH(c, "format_inv_generic", k_format_inv_generic, grid, 256, 0, d_planes, d_out, channels, w, h,
-		            out_stride_px, color, pl_is, out_is);
+		            out_stride_px, color, pl_is, out_is, ft);
 	}
 	return AKOD_OK;
 }
@@ -484,14 +563,19 @@ static int launch_unlift_level(akodContext* c, const UnliftParams& p, uint32_t n
 static int launch_small(akodContext* c, const akodPlan* plan, uint32_t l0, bool forward, int16_t* planes, uint32_t planes_rs,
                         uint64_t planes_ps, uint64_t planes_is, int16_t* stream, uint64_t stream_is, uint32_t n_images)
 {
-	const size_t smem = sizeof(int16_t) * 2 * (size_t)SM_CAP;
 	if (!c->small_attr_done)
 	{
+		const size_t most = sizeof(int16_t) * 2 * (size_t)SM_CAP;
 		AKOD_TRY(cudaSetDevice(c->device));
-		AKOD_TRY(cudaFuncSetAttribute(k_lift_small, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-		AKOD_TRY(cudaFuncSetAttribute(k_unlift_small, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+		AKOD_TRY(cudaFuncSetAttribute(k_lift_small<SM_THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)most));
+		AKOD_TRY(cudaFuncSetAttribute(k_unlift_small<SM_THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)most));
+		AKOD_TRY(cudaFuncSetAttribute(k_lift_small<SM_THREADS_TILE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)most));
+		AKOD_TRY(cudaFuncSetAttribute(k_unlift_small<SM_THREADS_TILE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)most));
 		c->small_attr_done = true;
 	}
+	// shared memory by need: the planes of a tile batch are small and many, several CTAs then share an SM
+	const uint32_t cap = (uint32_t)small_capacity(plan->level[l0].cw, plan->level[l0].ch, plan->levels - l0);
+	const size_t smem = sizeof(int16_t) * 2 * (size_t)cap;
 	SmallParams sp;
 	memset(&sp, 0, sizeof(sp));
 	sp.planes = planes;
@@ -504,6 +588,7 @@ static int launch_small(akodContext* c, const akodPlan* plan, uint32_t l0, bool 
 	sp.ch0 = plan->level[l0].ch;
 	sp.levels = plan->levels - l0;
 	sp.channels = plan->channels;
+	sp.cap = cap;
 	sp.wrap = plan->wrap;
 	sp.wavelet = plan->wavelet;
 	const uint32_t c1 = plan->channels > 1 ? 1 : 0;
@@ -521,10 +606,15 @@ static int launch_small(akodContext* c, const akodPlan* plan, uint32_t l0, bool 
 			samples += (uint64_t)plan->level[l0 + s].cw * plan->level[l0 + s].ch;
 		AKOD_BYTES(c, 4 * samples * plan->channels * n_images);
 	}
-	if (forward)
-		AKOD_LAUNCH(c, "lift_small", k_lift_small, plan->channels * n_images, SM_THREADS, smem, sp);
+	const bool tile_sized = (uint64_t)sp.cw0 * sp.ch0 <= 8192 && n_images > 1;
+	if (forward && tile_sized)
+		AKOD_LAUNCH(c, "lift_small", k_lift_small<SM_THREADS_TILE>, plan->channels * n_images, SM_THREADS_TILE, smem, sp);
+	else if (forward)
+		AKOD_LAUNCH(c, "lift_small", k_lift_small<SM_THREADS>, plan->channels * n_images, SM_THREADS, smem, sp);
+	else if (tile_sized)
+		AKOD_LAUNCH(c, "unlift_small", k_unlift_small<SM_THREADS_TILE>, plan->channels * n_images, SM_THREADS_TILE, smem, sp);
 	else
-		AKOD_LAUNCH(c, "unlift_small", k_unlift_small, plan->channels * n_images, SM_THREADS, smem, sp);
+		AKOD_LAUNCH(c, "unlift_small", k_unlift_small<SM_THREADS>, plan->channels * n_images, SM_THREADS, smem, sp);
 	return AKOD_OK;
 }
 
@@ -978,25 +1068,74 @@ extern "C" int akod_kagari_decode(akodContext* c, uint64_t n_values, const uint8
 // ------------------------------------------------------------------------------------------------
 // container
 
-// one thread per image: byte offset of every tile block inside the blob, and the blob size.
-// bits is [tiles][n_images]. A tile that did not fit its capacity voids the image (total = 0).
-__global__ void k_tile_offsets(const uint64_t* __restrict__ bits, const uint64_t* __restrict__ cap, uint32_t n_tiles,
-                               uint32_t n_images, int with_heads, uint64_t* __restrict__ off,
-                               uint64_t* __restrict__ total)
+struct TileGrid
 {
-	const uint32_t img = blockIdx.x * blockDim.x + threadIdx.x;
-	if (img >= n_images)
-		return;
-	uint64_t o = 16;
-	bool ok = true;
-	for (uint32_t t = 0; t < n_tiles; t++)
+	akodTiles t;
+};
+
+__device__ __forceinline__ void tile_locate(const akodTiles& T, uint32_t t, uint32_t& g, uint32_t& k)
+{
+	const uint32_t ty = t / T.tiles_x, tx = t - ty * T.tiles_x;
+	const uint32_t ex = tx >= T.full_x, ey = ty >= T.full_y;
+	g = ex + 2 * ey;
+	k = (ex && ey) ? 0 : ex ? ty : ey ? tx : ty * T.full_x + tx;
+}
+
+// One CTA per image: byte offset of every tile block inside the blob (an exclusive scan of 4 + block size over
+// the tiles in raster order, compression.c:30-55 / encode.c:170-182) and the blob size. A tile that did not fit
+// its capacity voids the image (total = 0). off is [n_images][n_tiles].
+__global__ void __launch_bounds__(256)
+    k_tile_offsets(const uint64_t* __restrict__ bits, const TileGrid G, int with_heads, uint64_t* __restrict__ off,
+                   uint64_t* __restrict__ total)
+{
+	__shared__ uint64_t warp_sum[8];
+	__shared__ uint64_t carry_sm;
+	__shared__ int bad_sm;
+	const akodTiles& T = G.t;
+	const uint32_t img = blockIdx.x, n_tiles = T.tiles_x * T.tiles_y;
+	const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+	if (threadIdx.x == 0)
 	{
-		const uint64_t bytes = (bits[(uint64_t)t * n_images + img] + 7) >> 3;
-		ok = ok && bytes <= cap[t];
-		off[(uint64_t)t * n_images + img] = o;
-		o += bytes + (with_heads ? 4 : 0);
+		carry_sm = 16;
+		bad_sm = 0;
 	}
-	total[img] = ok ? o : 0;
+	__syncthreads();
+	for (uint32_t t0 = 0; t0 < n_tiles; t0 += 256)
+	{
+		const uint32_t t = t0 + threadIdx.x;
+		uint64_t len = 0;
+		if (t < n_tiles)
+		{
+			uint32_t g, k;
+			tile_locate(T, t, g, k);
+			const uint64_t bytes = (bits[T.bits_base[g] + (uint64_t)k * T.n_images + img] + 7) >> 3;
+			if (bytes > T.group_cap[g])
+				bad_sm = 1;
+			len = bytes + (with_heads ? 4 : 0);
+		}
+		uint64_t incl = len;
+#pragma unroll
+		for (int d = 1; d < 32; d <<= 1)
+		{
+			const uint64_t o = __shfl_up_sync(AKOD_FULL_MASK, incl, d);
+			if (lane >= d)
+				incl += o;
+		}
+		if (lane == 31)
+			warp_sum[wid] = incl;
+		__syncthreads();
+		uint64_t before = carry_sm;
+		for (int w = 0; w < wid; w++)
+			before += warp_sum[w];
+		if (t < n_tiles)
+			off[(uint64_t)img * n_tiles + t] = before + incl - len;
+		__syncthreads();
+		if (threadIdx.x == 255)
+			carry_sm = before + incl;
+		__syncthreads();
+	}
+	if (threadIdx.x == 0)
+		total[img] = bad_sm ? 0 : carry_sm;
 }
 
 struct HeadWords
@@ -1004,42 +1143,48 @@ struct HeadWords
 	uint32_t w[4];
 };
 
-// grid (chunks, tiles, images)
+// blockIdx.x = (image * tiles + tile) * chunks + chunk
 __global__ void __launch_bounds__(256)
-    k_assemble(const HeadWords head, const uint8_t* __restrict__ blocks, uint64_t blocks_stride,
-               const uint64_t* __restrict__ block_off, const uint64_t* __restrict__ bits,
+    k_assemble(const HeadWords head, const uint8_t* __restrict__ blocks, const TileGrid G, const uint64_t* __restrict__ bits,
                const uint64_t* __restrict__ tile_off, const uint64_t* __restrict__ total, int with_heads,
-               uint8_t* __restrict__ out, uint64_t out_stride)
+               uint8_t* __restrict__ out, uint64_t out_stride, uint32_t chunks)
 {
-	const uint32_t t = blockIdx.y, img = blockIdx.z, n_images = gridDim.z;
+	const akodTiles& T = G.t;
+	const uint32_t n_tiles = T.tiles_x * T.tiles_y;
+	const uint32_t chunk = blockIdx.x % chunks;
+	const uint32_t it = blockIdx.x / chunks;
+	const uint32_t img = it / n_tiles, t = it - img * n_tiles;
 	if (total[img] == 0)
 		return;
-	const uint64_t size = (bits[(uint64_t)t * n_images + img] + 7) >> 3;
+	uint32_t g, k;
+	tile_locate(T, t, g, k);
+	const uint64_t member = (uint64_t)k * T.n_images + img;
+	const uint64_t size = (bits[T.bits_base[g] + member] + 7) >> 3;
 	out += out_stride * img;
-	uint8_t* dst = out + tile_off[(uint64_t)t * n_images + img];
-	if (t == 0 && blockIdx.x == 0 && threadIdx.x < 16)
+	uint8_t* dst = out + tile_off[(uint64_t)img * n_tiles + t];
+	if (t == 0 && chunk == 0 && threadIdx.x < 16)
 		out[threadIdx.x] = (uint8_t)(head.w[threadIdx.x >> 2] >> (8 * (threadIdx.x & 3)));
 	if (with_heads)
 	{
-		if (blockIdx.x == 0 && threadIdx.x < 4)
+		if (chunk == 0 && threadIdx.x < 4)
 			dst[threadIdx.x] = (uint8_t)((uint32_t)size >> (8 * threadIdx.x)); // akoBlockHead, compression.c:30-33
 		dst += 4;
 	}
-	const uint8_t* src = blocks + blocks_stride * img + block_off[t];
+	const uint8_t* src = blocks + T.group_base[g] + member * T.group_stride[g];
 	// The block region is 16-byte aligned, its place in the blob is not: every thread produces one 16-byte aligned
 	// chunk of the destination from two aligned 16-byte loads, shifted by the byte misalignment.
 	const uint32_t mis = (uint32_t)((uintptr_t)dst & 15);             // dst = dst_al + mis
 	const uint64_t lead = mis ? min((uint64_t)(16 - mis), size) : 0;  // bytes before the first aligned chunk
 	const uint64_t nchunks = (size - lead) / 16;
-	const uint64_t stride = (uint64_t)gridDim.x * blockDim.x, tid0 = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	const uint64_t stride = (uint64_t)chunks * blockDim.x, tid0 = (uint64_t)chunk * blockDim.x + threadIdx.x;
 	if (tid0 < lead)
 		dst[tid0] = src[tid0];
 	const uint32_t sh = (uint32_t)(lead & 15);                        // chunk k reads src bytes [lead + 16k, +16): offset sh in aligned words
 	const uint4* src4 = reinterpret_cast<const uint4*>(src);
 	uint4* dst4 = reinterpret_cast<uint4*>(dst + lead);
-	for (uint64_t k = tid0; k < nchunks; k += stride)
+	for (uint64_t kk = tid0; kk < nchunks; kk += stride)
 	{
-		const uint64_t s0 = (lead + 16 * k) >> 4;
+		const uint64_t s0 = (lead + 16 * kk) >> 4;
 		const uint4 a = __ldg(src4 + s0);
 		uint4 o = a;
 		if (sh)
@@ -1063,18 +1208,17 @@ __global__ void __launch_bounds__(256)
 			}
 			o = make_uint4(r[0], r[1], r[2], r[3]);
 		}
-		dst4[k] = o;
+		dst4[kk] = o;
 	}
 	for (uint64_t i = lead + 16 * nchunks + tid0; i < size; i += stride)
 		dst[i] = src[i];
 }
 
-extern "C" int akod_assemble(akodContext* c, const uint8_t head16[16], uint32_t n_tiles, uint32_t n_images,
-                             const uint8_t* d_blocks, uint64_t blocks_stride, const uint64_t* d_block_off,
-                             const uint64_t* d_block_cap, const uint64_t* d_bits, int with_heads, uint8_t* d_out,
-                             uint64_t out_stride, uint64_t* d_total)
+extern "C" int akod_assemble(akodContext* c, const uint8_t head16[16], const akodTiles* tiles, const uint8_t* d_blocks,
+                             const uint64_t* d_bits, int with_heads, uint8_t* d_out, uint64_t out_stride, uint64_t* d_total)
 {
 	akod_use(c);
+	const uint64_t n_tiles = (uint64_t)tiles->tiles_x * tiles->tiles_y, n_images = tiles->n_images;
 	void* ws;
 	int rc = akod_workspace(c, AKOD_WS_KAGARI2, sizeof(uint64_t) * (size_t)n_tiles * n_images, &ws);
 	if (rc != AKOD_OK)
@@ -1082,14 +1226,25 @@ extern "C" int akod_assemble(akodContext* c, const uint8_t head16[16], uint32_t 
 	uint64_t* d_tile_off = (uint64_t*)ws;
 	HeadWords hw;
 	memcpy(hw.w, head16, 16);
-	AKOD_LAUNCH(c, "tile_offsets", k_tile_offsets, (n_images + 63) / 64, 64, 0, d_bits, d_block_cap, n_tiles, n_images,
-	            with_heads, d_tile_off, d_total);
-	unsigned chunks = (unsigned)c->sm_count;
-	if ((uint64_t)n_tiles * n_images >= 64)
+	TileGrid G;
+	G.t = *tiles;
+	AKOD_LAUNCH(c, "tile_offsets", k_tile_offsets, (unsigned)n_images, 256, 0, d_bits, G, with_heads, d_tile_off, d_total);
+	// CTAs per block: a lone large block is spread over the GPU, a crowd of blocks gets few CTAs of few threads each
+	uint64_t largest = 0;
+	for (int g = 0; g < 4; g++)
+		largest = tiles->group_cap[g] > largest ? tiles->group_cap[g] : largest;
+	unsigned chunks = (unsigned)c->sm_count, threads = 256;
+	if (n_tiles * n_images >= 64)
 		chunks = 4;
-	const dim3 grid(chunks, n_tiles, n_images);
-	AKOD_LAUNCH(c, "assemble", k_assemble, grid, 256, 0, hw, d_blocks, blocks_stride, d_block_off, d_bits, d_tile_off,
-	            d_total, with_heads, d_out, out_stride);
+	if (largest <= (16u << 10))
+	{
+		chunks = 1;
+		threads = 64;
+	}
+	if (n_tiles * n_images * chunks >= ((uint64_t)1 << 31))
+		return AKOD_ERROR;
+	AKOD_LAUNCH(c, "assemble", k_assemble, (unsigned)(n_tiles * n_images * chunks), threads, 0, hw, d_blocks, G, d_bits,
+	            d_tile_off, d_total, with_heads, d_out, out_stride, chunks);
 	return AKOD_OK;
 }
 

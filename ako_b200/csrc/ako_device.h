@@ -62,7 +62,37 @@ typedef struct
 	uint64_t planes_stride;  /* int16 */
 	uint64_t scratch_stride; /* int16 */
 	uint64_t stream_stride;  /* int16 */
+	/* Tiles as batch members (encode.c:115-205 / decode.c:113-230 make every tile an independent block): with
+	 * n_real != 0 the n members are tiles of n_real images, member v = kk * n_real + i being tile tile_first + kk of
+	 * its shape group in image i. Only the interleaved u8 image is addressed through this: tile k of the group
+	 * starts tile_y0 + (k / tile_cols) * tile_step rows and tile_x0 + (k % tile_cols) * tile_step pixels into
+	 * image i. n_real == 0: a plain batch, member v is image v. */
+	uint32_t n_real, tile_cols, tile_first, tile_step, tile_x0, tile_y0;
 } akodBatch;
+
+/* The tile grid of an image and where each tile's compressed block and bit count live. Tiles come in up to four
+ * shape groups: 0 = full tiles, 1 = the right edge column, 2 = the bottom edge row, 3 = the corner. Tile k of group g
+ * of image i has its bit count at bits_base[g] + k * n_images + i and its block at
+ * group_base[g] + (k * n_images + i) * group_stride[g] (the order a group's members have in a batch). */
+typedef struct
+{
+	uint32_t tiles_x, tiles_y; /* tiles per row / column of the image */
+	uint32_t full_x, full_y;   /* of which full-size */
+	uint32_t n_images;
+	uint64_t group_base[4];
+	uint64_t group_stride[4];
+	uint64_t group_cap[4]; /* bytes a block of the group may hold */
+	uint64_t bits_base[4];
+} akodTiles;
+
+/* raster tile index -> (group, index inside the group) */
+static inline void akod_tile_locate(const akodTiles* T, uint32_t t, uint32_t* g, uint32_t* k)
+{
+	const uint32_t ty = t / T->tiles_x, tx = t - ty * T->tiles_x;
+	const uint32_t ex = tx >= T->full_x, ey = ty >= T->full_y;
+	*g = ex + 2 * ey;
+	*k = (ex && ey) ? 0 : ex ? ty : ey ? tx : ty * T->full_x + tx;
+}
 
 /* ---- context ---- */
 int akod_context_create(int device, akodContext** out);
@@ -79,6 +109,12 @@ int akod_h2d(akodContext*, void* d_dst, const void* src, size_t bytes);
 int akod_d2h(akodContext*, void* dst, const void* d_src, size_t bytes);
 int akod_d2d(akodContext*, void* d_dst, const void* d_src, size_t bytes);
 int akod_memset(akodContext*, void* d_dst, int value, size_t bytes);
+/* count blocks of 'bytes' bytes each: block j from d_src + j*src_stride to d_dst + j*dst_stride (strides in bytes) */
+int akod_copy_strided(akodContext*, void* d_dst, uint64_t dst_stride, const void* d_src, uint64_t src_stride, uint64_t bytes,
+                      uint64_t count);
+/* count blocks of 'bytes' bytes each: block j from d_src + d_off[j] (DEVICE array) to d_dst + j*dst_stride */
+int akod_gather(akodContext*, void* d_dst, uint64_t dst_stride, const void* d_src, const uint64_t* d_off, uint64_t bytes,
+                uint64_t count);
 int akod_fill_words(akodContext*, uint64_t* d_dst, uint64_t value, size_t count);
 /* dst / src: device memory or the context's pinned mailbox (directly addressable by kernels); no copy engine */
 int akod_copy_words(akodContext*, uint64_t* dst, const uint64_t* src, size_t count);
@@ -145,11 +181,10 @@ int akod_kagari_decode(akodContext*, uint64_t n_values, const uint8_t* d_in, con
                        uint64_t out_stride, uint64_t* d_result, uint32_t n_images);
 
 /* Container assembly on the device (encode.c:170-182 without the CPU pass), for n_images same-shape images:
- * out_i = head16 | for each tile t: [u32 size][bytes of tile t]. Sizes come from d_bits ([tiles][n_images] bit
- * counts). Tile t of image i is at d_blocks + i*blocks_stride + d_block_off[t] and may hold d_block_cap[t] bytes;
- * an image with a tile over its capacity gets d_total[i] = 0 and nothing written. d_total[i] = blob size. */
-int akod_assemble(akodContext*, const uint8_t head16[16], uint32_t n_tiles, uint32_t n_images, const uint8_t* d_blocks,
-                  uint64_t blocks_stride, const uint64_t* d_block_off, const uint64_t* d_block_cap,
+ * out_i = head16 | for each tile t in raster order: [u32 size][bytes of tile t]. Sizes come from d_bits, blocks
+ * from d_blocks, both laid out as akodTiles says; an image with a tile over its capacity gets d_total[i] = 0 and
+ * nothing written. d_total[i] = blob size. */
+int akod_assemble(akodContext*, const uint8_t head16[16], const akodTiles* tiles, const uint8_t* d_blocks,
                   const uint64_t* d_bits, int with_heads, uint8_t* d_out, uint64_t out_stride, uint64_t* d_total);
 /* walk the block heads of a device-resident blob: d_off[t] = byte offset of tile t's payload,
  * d_size[t] = its block_size; stops (size 0) if it would run past input_size */

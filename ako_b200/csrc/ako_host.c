@@ -834,6 +834,105 @@ AKO_API size_t akoB200EncodeBound(const struct akoSettings* s_in, size_t channel
 	return bound;
 }
 
+/* ---- tiles as batch members ------------------------------------------------------------------------------
+ * The reference walks the tiles of an image one after the other (encode.c:115-205, decode.c:113-230); every tile is
+ * an independent block. Here the tiles of one shape are members of ONE batch: the full-size tiles (group 0), the
+ * right edge column (1), the bottom edge row (2) and the corner (3) are at most four passes of the batched kernels,
+ * whatever the number of tiles. Member v of a pass = kk * n + i is tile k0 + kk of the group in image i. */
+#define MEMBERS_PER_PASS 32768 /* batch members ride in gridDim.y (<= 65535) */
+
+struct tile_groups
+{
+	akodTiles T;
+	size_t tiles;         /* per image */
+	size_t tw[4], th[4];  /* tile shape of the group */
+	size_t count[4];      /* tiles of the group per image */
+	size_t data[4];       /* bytes of one tile's coefficient stream (all channels): what a block may not reach */
+	uint32_t cols[4], x0[4], y0[4];
+	size_t planes_stride[4], scratch_stride[4], stream_stride[4]; /* int16 elements per member */
+	size_t bits_slots;    /* tiles * n */
+	size_t blocks_bytes;
+};
+
+static void make_groups(struct tile_groups* G, const struct akoSettings* s, size_t channels, size_t w, size_t h, size_t n)
+{
+	const size_t td = s->tiles_dimension;
+	memset(G, 0, sizeof(*G));
+	const size_t full_x = (td == 0) ? 1 : w / td, full_y = (td == 0) ? 1 : h / td;
+	const size_t ex = (td != 0 && w % td != 0), ey = (td != 0 && h % td != 0);
+	G->T.tiles_x = (uint32_t)(full_x + ex);
+	G->T.tiles_y = (uint32_t)(full_y + ey);
+	G->T.full_x = (uint32_t)full_x;
+	G->T.full_y = (uint32_t)full_y;
+	G->T.n_images = (uint32_t)n;
+	G->tiles = (full_x + ex) * (full_y + ey);
+	const size_t fw = (td == 0) ? w : td, fh = (td == 0) ? h : td;
+	const size_t ew = (td == 0) ? 0 : w % td, eh = (td == 0) ? 0 : h % td;
+	const size_t gw[4] = {fw, ew, fw, ew}, gh[4] = {fh, fh, eh, eh};
+	const size_t gc[4] = {full_x * full_y, ex ? full_y : 0, ey ? full_x : 0, (ex && ey) ? 1 : 0};
+	const size_t gcols[4] = {full_x, 1, full_x, 1};
+	const size_t gx0[4] = {0, full_x * td, 0, full_x * td}, gy0[4] = {0, 0, full_y * td, full_y * td};
+	uint64_t blocks = 0, bits = 0;
+	for (int g = 0; g < 4; g++)
+	{
+		G->tw[g] = gw[g];
+		G->th[g] = gh[g];
+		G->count[g] = gc[g];
+		G->cols[g] = (uint32_t)(gcols[g] ? gcols[g] : 1);
+		G->x0[g] = (uint32_t)gx0[g];
+		G->y0[g] = (uint32_t)gy0[g];
+		if (gc[g] == 0)
+			continue;
+		const size_t data = (s->wavelet != AKO_WAVELET_NONE) ? tile_data_size(gw[g], gh[g]) * channels
+		                                                     : gw[g] * gh[g] * channels * 2;
+		G->data[g] = data;
+		G->planes_stride[g] = align_up(gw[g] * gh[g] * channels, 8);
+		G->scratch_stride[g] = align_up(half_up(gw[g]) * half_up(gh[g]) * channels, 8);
+		G->stream_stride[g] = align_up(data / 2, 8);
+		/* what the packer may write: the reference accepts a block of up to data - 5 bytes (bytes < data - 4,
+		 * compression.c:40-49); the packer stores whole words, and the tile's region (align_up(data, 16)) holds
+		 * the word that byte data - 5 lies in. The exact rule is applied on the host from the bit counts. */
+		G->T.group_cap[g] = (s->compression == AKO_COMPRESSION_NONE) ? data : (data >= 6) ? align_up(data - 5, 4) : 0;
+		G->T.group_stride[g] = align_up(data, 16);
+		G->T.group_base[g] = blocks;
+		G->T.bits_base[g] = bits;
+		blocks += (uint64_t)gc[g] * n * G->T.group_stride[g];
+		bits += (uint64_t)gc[g] * n;
+	}
+	G->bits_slots = (size_t)bits;
+	G->blocks_bytes = (size_t)blocks;
+}
+
+/* most members one pass of group g may take */
+static size_t group_pass_tiles(const struct tile_groups* G, int g, size_t n, int tile_by_tile)
+{
+	if (tile_by_tile)
+		return 1;
+	size_t kc = MEMBERS_PER_PASS / n;
+	kc = (kc < 1) ? 1 : kc;
+	return (kc > G->count[g]) ? G->count[g] : kc;
+}
+
+static void group_batch(akodBatch* b, const struct tile_groups* G, int g, size_t k0, size_t kc, size_t n, size_t image_stride,
+                        size_t td)
+{
+	memset(b, 0, sizeof(*b));
+	b->n = (uint32_t)(kc * n);
+	b->in_stride = image_stride;
+	b->planes_stride = G->planes_stride[g];
+	b->scratch_stride = G->scratch_stride[g];
+	b->stream_stride = G->stream_stride[g];
+	if (td != 0)
+	{
+		b->n_real = (uint32_t)n;
+		b->tile_cols = G->cols[g];
+		b->tile_first = (uint32_t)k0;
+		b->tile_step = (uint32_t)td;
+		b->tile_x0 = G->x0[g];
+		b->tile_y0 = G->y0[g];
+	}
+}
+
 /* Same-shape batch core. n images at d_in + i*in_stride -> n blobs at d_out + i*out_stride.
  * 'cb' only for events (may be NULL). */
 /* Ratio search support (akoB200EncodeRatio): the UNQUANTISED coefficient stream of every tile of ONE image is kept
@@ -866,7 +965,6 @@ static size_t encode_core_ex(akoB200Context* ctx, const struct akoCallbacks* cb,
 	enum akoStatus st = AKO_OK;
 	struct akoSettings s = (s_in != NULL) ? *s_in : akoDefaultSettings();
 	size_t done = 0;
-	uint64_t* host_off = NULL;
 	const int fill = (sc != NULL && sc->mode == SC_FILL);
 	const int use = (sc != NULL && sc->mode == SC_USE);
 	const int size_only = (sc != NULL && sc->size_only);
@@ -909,132 +1007,126 @@ static size_t encode_core_ex(akoB200Context* ctx, const struct akoCallbacks* cb,
 	}
 
 	const size_t td = s.tiles_dimension;
-	const size_t tiles = tiles_count(w, h, td);
-	const size_t max_w = tile_dimension(0, w, td), max_h = tile_dimension(0, h, td);
-	const size_t planes_stride = align_up(max_w * max_h * channels, 8);
-	const size_t stream_cap = align_up(
-	    (s.wavelet != AKO_WAVELET_NONE ? tile_data_size(max_w, max_h) * channels : max_w * max_h * channels * 2) / 2, 8);
+	struct tile_groups G;
+	make_groups(&G, &s, channels, w, h, n);
+	const size_t tiles = G.tiles;
+	/* a caller's stopwatch (events) and the ratio search's per-tile cache see the tiles one after the other, as the
+	 * reference does them; everybody else gets one pass per tile shape */
+	const int tile_by_tile = (cb != NULL && cb->events != NULL) || sc != NULL;
+	if (n > MEMBERS_PER_PASS)
+	{
+		st = AKO_ERROR; /* the batch entry points split larger batches */
+		goto done;
+	}
 
 	void *planes, *scratch, *stream, *blocks, *small;
-	size_t scratch_stride;
-	if ((st = from_dev(akod_workspace(ctx->dev, AKOD_WS_PLANES, planes_stride * n * 2 + 64, &planes))) != AKO_OK ||
-	    (st = scratch_for(ctx, channels, max_w, max_h, n, (int16_t**)&scratch, &scratch_stride)) != AKO_OK ||
-	    (st = from_dev(akod_workspace(ctx->dev, AKOD_WS_STREAM, stream_cap * n * 2 + 64, &stream))) != AKO_OK)
-		goto done;
-
-	/* every tile's compressed block gets its own 16-byte aligned region, image-major */
-	host_off = malloc(sizeof(uint64_t) * tiles * 3); /* [off | cap | data] : off and cap are uploaded together */
-	if (host_off == NULL)
 	{
-		st = AKO_NO_ENOUGH_MEMORY;
-		goto done;
-	}
-	uint64_t* host_cap = host_off + tiles;
-	uint64_t* host_data = host_cap + tiles;
-	size_t blocks_per_image = 0;
-	{
-		size_t tx = 0, ty = 0;
-		for (size_t t = 0; t < tiles; t++)
-		{
-			const size_t tw = tile_dimension(tx, w, td), th = tile_dimension(ty, h, td);
-			const size_t data = (s.wavelet != AKO_WAVELET_NONE) ? tile_data_size(tw, th) * channels : tw * th * channels * 2;
-			host_off[t] = blocks_per_image;
-			host_data[t] = data;
-			if (s.compression == AKO_COMPRESSION_NONE)
-				host_cap[t] = data; /* raw copy */
-			else
-				/* what the packer may write: the reference accepts a block of up to data - 5 bytes (bytes < data - 4,
-				 * compression.c:40-49); the packer stores whole words, and the tile's region (align_up(data, 16)) holds
-				 * the word that byte data - 5 lies in. The exact rule is applied on the host below. */
-				host_cap[t] = (data >= 6) ? align_up(data - 5, 4) : 0;
-			blocks_per_image += align_up(data, 16);
-			tx += td;
-			if (tx >= w)
+		size_t need_planes = 0, need_scratch = 0, need_stream = 0;
+		for (int g = 0; g < 4; g++)
+			if (G.count[g] != 0)
 			{
-				tx = 0;
-				ty += td;
+				const size_t members = group_pass_tiles(&G, g, n, tile_by_tile) * n;
+				need_planes = (G.planes_stride[g] * members > need_planes) ? G.planes_stride[g] * members : need_planes;
+				need_scratch = (G.scratch_stride[g] * members > need_scratch) ? G.scratch_stride[g] * members : need_scratch;
+				need_stream = (G.stream_stride[g] * members > need_stream) ? G.stream_stride[g] * members : need_stream;
 			}
-		}
+		if ((st = from_dev(akod_workspace(ctx->dev, AKOD_WS_PLANES, need_planes * 2 + 64, &planes))) != AKO_OK ||
+		    (st = from_dev(akod_workspace(ctx->dev, AKOD_WS_SCRATCH, need_scratch * 2 + 64, &scratch))) != AKO_OK ||
+		    (st = from_dev(akod_workspace(ctx->dev, AKOD_WS_STREAM, need_stream * 2 + 64, &stream))) != AKO_OK ||
+		    (st = from_dev(akod_workspace(ctx->dev, AKOD_WS_BLOCKS, G.blocks_bytes + 64, &blocks))) != AKO_OK ||
+		    (st = from_dev(akod_workspace(ctx->dev, AKOD_WS_SMALL, sizeof(uint64_t) * (G.bits_slots + n) + 64, &small))) != AKO_OK)
+			goto done;
 	}
-	if ((st = from_dev(akod_workspace(ctx->dev, AKOD_WS_BLOCKS, blocks_per_image * n + 64, &blocks))) != AKO_OK ||
-	    (st = from_dev(akod_workspace(ctx->dev, AKOD_WS_SMALL, sizeof(uint64_t) * ((tiles + 1) * n + 2 * tiles) + 64,
-	                                  &small))) != AKO_OK)
-		goto done;
-	uint64_t* d_bits = small;                    /* [tiles][n] */
-	uint64_t* d_total = d_bits + tiles * n;      /* [n] */
-	uint64_t* d_block_off = d_total + n;         /* [tiles] */
-	uint64_t* d_block_cap = d_block_off + tiles; /* [tiles] */
-	if ((st = upload_words(ctx, d_block_off, host_off, tiles * 2)) != AKO_OK)
-		goto done;
+	uint64_t* d_bits = small;              /* laid out as akodTiles says */
+	uint64_t* d_total = d_bits + G.bits_slots; /* [n] */
 
-	akodBatch batch;
-	batch.n = (uint32_t)n;
-	batch.in_stride = in_stride;
-	batch.planes_stride = planes_stride;
-	batch.scratch_stride = scratch_stride;
-	batch.stream_stride = stream_cap;
-
-	size_t tx = 0, ty = 0;
-	size_t cache_cursor = 0; /* elements */
-	for (size_t t = 0; t < tiles && st == AKO_OK; t++)
+	size_t cache_cursor = 0; /* elements; the search cache keeps the tiles in raster order */
+	/* work list: per-tile mode walks the tiles in raster order, one tile of all n images per pass; otherwise every
+	 * shape group is cut into passes of at most MEMBERS_PER_PASS members */
+	for (size_t item = 0; st == AKO_OK; item++)
 	{
-		const size_t tw = tile_dimension(tx, w, td), th = tile_dimension(ty, h, td);
-		const uint8_t* tile_in = d_in + (w * ty + tx) * channels;
+		uint32_t g = 0, k0 = 0;
+		size_t kc = 0, t_event = 0;
+		if (tile_by_tile)
+		{
+			if (item >= tiles)
+				break;
+			akod_tile_locate(&G.T, (uint32_t)item, &g, &k0);
+			kc = 1;
+			t_event = item;
+		}
+		else
+		{
+			/* item enumerates (group, pass) pairs */
+			size_t left = item;
+			int found = 0;
+			for (int gg = 0; gg < 4 && !found; gg++)
+			{
+				if (G.count[gg] == 0)
+					continue;
+				const size_t per = group_pass_tiles(&G, gg, n, 0);
+				const size_t passes = (G.count[gg] + per - 1) / per;
+				if (left < passes)
+				{
+					g = (uint32_t)gg;
+					k0 = (uint32_t)(left * per);
+					kc = (G.count[gg] - k0 < per) ? G.count[gg] - k0 : per;
+					found = 1;
+				}
+				else
+					left -= passes;
+			}
+			if (!found)
+				break;
+		}
+		const size_t tw = G.tw[g], th = G.th[g];
+		const size_t members = kc * n;
+		akodBatch batch;
+		group_batch(&batch, &G, (int)g, k0, kc, n, in_stride, td);
 		int16_t* cached = (sc != NULL && sc->d_raw != NULL) ? sc->d_raw + cache_cursor : NULL;
-		cache_cursor += align_up(host_data[t] / 2, 8);
+		cache_cursor += align_up(G.data[g] / 2, 8);
 
 		if (!use)
 		{
-			fire(cb, ctx, t, tiles, AKO_EVENT_FORMAT_START);
+			fire(cb, ctx, t_event, tiles, AKO_EVENT_FORMAT_START);
 			st = from_dev(akod_format_forward(ctx->dev, s.discard_non_visible, (int)s.color, (uint32_t)channels,
-			                                  (uint32_t)tw, (uint32_t)th, w, tile_in, planes, &batch));
-			fire(cb, ctx, t, tiles, AKO_EVENT_FORMAT_END);
+			                                  (uint32_t)tw, (uint32_t)th, w, d_in, planes, &batch));
+			fire(cb, ctx, t_event, tiles, AKO_EVENT_FORMAT_END);
 		}
 
 		const int16_t* data = planes;
-		uint64_t data_stride = planes_stride;
+		uint64_t data_stride = G.planes_stride[g];
 		if (st == AKO_OK && s.wavelet != AKO_WAVELET_NONE)
 		{
-			fire(cb, ctx, t, tiles, AKO_EVENT_WAVELET_START);
+			fire(cb, ctx, t_event, tiles, AKO_EVENT_WAVELET_START);
 			if (use)
 				st = from_dev(akod_requantize(ctx->dev, get_plan(ctx, &s, channels, tw, th), cached, stream));
 			else
 				st = from_dev(akod_lift(ctx->dev, get_plan(ctx, &s, channels, tw, th), planes, scratch,
 				                        fill ? cached : stream, &batch));
-			fire(cb, ctx, t, tiles, AKO_EVENT_WAVELET_END);
+			fire(cb, ctx, t_event, tiles, AKO_EVENT_WAVELET_END);
 			data = stream;
-			data_stride = stream_cap;
+			data_stride = G.stream_stride[g];
 		}
 		if (fill)
-			goto next_tile;
+			continue;
 
-		fire(cb, ctx, t, tiles, AKO_EVENT_COMPRESSION_START);
+		uint64_t* bits_at = d_bits + G.T.bits_base[g] + (uint64_t)k0 * n;
+		uint8_t* blocks_at = (uint8_t*)blocks + G.T.group_base[g] + (uint64_t)k0 * n * G.T.group_stride[g];
+		fire(cb, ctx, t_event, tiles, AKO_EVENT_COMPRESSION_START);
 		if (st == AKO_OK && size_only)
-			st = from_dev(akod_kagari_bits(ctx->dev, host_data[t] / 2, data, data_stride, d_bits + t * n, (uint32_t)n));
+			st = from_dev(akod_kagari_bits(ctx->dev, G.data[g] / 2, data, data_stride, bits_at, (uint32_t)members));
 		else if (st == AKO_OK && s.compression != AKO_COMPRESSION_NONE)
-		{
-			/* capacity = what the reference hands to akoKagariEncode (compression.c:40-45), rounded down to words */
-			st = from_dev(akod_kagari_encode(ctx->dev, host_data[t] / 2, data, data_stride, (uint8_t*)blocks + host_off[t],
-			                                 blocks_per_image, host_cap[t], d_bits + t * n, (uint32_t)n));
-		}
+			st = from_dev(akod_kagari_encode(ctx->dev, G.data[g] / 2, data, data_stride, blocks_at, G.T.group_stride[g],
+			                                 G.T.group_cap[g], bits_at, (uint32_t)members));
 		else if (st == AKO_OK)
 		{
 			/* no compression: the block is the raw int16 data (encode.c:151-153) */
-			for (size_t i = 0; i < n && st == AKO_OK; i++)
-				st = from_dev(akod_d2d(ctx->dev, (uint8_t*)blocks + blocks_per_image * i + host_off[t],
-				                       data + data_stride * i, host_data[t]));
+			st = from_dev(akod_copy_strided(ctx->dev, blocks_at, G.T.group_stride[g], data, data_stride * 2, G.data[g], members));
 			if (st == AKO_OK)
-				st = from_dev(akod_fill_words(ctx->dev, d_bits + t * n, (uint64_t)host_data[t] * 8, n));
+				st = from_dev(akod_fill_words(ctx->dev, bits_at, (uint64_t)G.data[g] * 8, members));
 		}
-		fire(cb, ctx, t, tiles, AKO_EVENT_COMPRESSION_END);
-
-	next_tile:
-		tx += td;
-		if (tx >= w)
-		{
-			tx = 0;
-			ty += td;
-		}
+		fire(cb, ctx, t_event, tiles, AKO_EVENT_COMPRESSION_END);
 	}
 	if (st != AKO_OK)
 		goto done;
@@ -1047,13 +1139,12 @@ static size_t encode_core_ex(akoB200Context* ctx, const struct akoCallbacks* cb,
 	/* container assembly on the device, then one small read-back of sizes */
 	if (size_only)
 		st = from_dev(akod_fill_words(ctx->dev, d_total, 1, n)); /* the host adds the sizes up below */
-	else if ((st = from_dev(akod_assemble(ctx->dev, head, (uint32_t)tiles, (uint32_t)n, blocks, blocks_per_image, d_block_off,
-	                                 d_block_cap, d_bits, s.compression != AKO_COMPRESSION_NONE, d_out, out_stride,
-	                                 d_total))) != AKO_OK)
+	else if ((st = from_dev(akod_assemble(ctx->dev, head, &G.T, blocks, d_bits, s.compression != AKO_COMPRESSION_NONE, d_out,
+	                                      out_stride, d_total))) != AKO_OK)
 		goto done;
 
 	{
-		const size_t words = (tiles + 1) * n;
+		const size_t words = G.bits_slots + n;
 		uint64_t* all = malloc(sizeof(uint64_t) * words);
 		if (all == NULL)
 		{
@@ -1063,30 +1154,26 @@ static size_t encode_core_ex(akoB200Context* ctx, const struct akoCallbacks* cb,
 		st = download_words(ctx, all, small, words);
 		for (size_t i = 0; i < n && st == AKO_OK; i++)
 		{
-			if (s.compression != AKO_COMPRESSION_NONE)
-				for (size_t t = 0; t < tiles; t++)
+			uint64_t total = 16;
+			for (int g = 0; g < 4; g++)
+				for (size_t k = 0; k < G.count[g]; k++)
 				{
 					/* akoKagariEncode succeeds iff its bytes are < the capacity it was given, which is the tile's
 					 * stream size minus the block head (compression.c:40-49; kagari.c:65-68, :93-107). A failure
 					 * makes akoEncodeExt return AKO_ERROR (encode.c:159-164). */
-					const uint64_t bytes = (all[t * n + i] + 7) / 8;
-					if (bytes == 0 || bytes >= host_data[t] - 4)
+					const uint64_t bytes = (all[G.T.bits_base[g] + k * n + i] + 7) / 8;
+					if (s.compression != AKO_COMPRESSION_NONE && (bytes == 0 || bytes >= G.data[g] - 4))
 						st = AKO_ERROR;
+					total += 4 + bytes; /* head + per tile [u32 block_size][Kagari bytes] (encode.c:170-182) */
 				}
-			if (st == AKO_OK && all[tiles * n + i] == 0)
+			if (st == AKO_OK && all[G.bits_slots + i] == 0)
 				st = AKO_ERROR;
 			if (st == AKO_OK && size_only)
-			{
-				/* head + per tile [u32 block_size][Kagari bytes] (encode.c:170-182) */
-				uint64_t total = 16;
-				for (size_t t = 0; t < tiles; t++)
-					total += 4 + (all[t * n + i] + 7) / 8;
-				all[tiles * n + i] = total;
-			}
+				all[G.bits_slots + i] = total;
 			if (st == AKO_OK)
 			{
 				if (out_sizes != NULL)
-					out_sizes[i] = (size_t)all[tiles * n + i];
+					out_sizes[i] = (size_t)all[G.bits_slots + i];
 				done = i + 1;
 			}
 		}
@@ -1094,7 +1181,6 @@ static size_t encode_core_ex(akoB200Context* ctx, const struct akoCallbacks* cb,
 	}
 
 done:
-	free(host_off);
 	if (out_status != NULL)
 		*out_status = st;
 	return done;
@@ -1119,8 +1205,22 @@ AKO_API size_t akoB200EncodeBatchDevice(akoB200Context* ctx, const struct akoSet
 			*out_status = AKO_OK;
 		return 0;
 	}
-	return encode_core(ctx, NULL, s, channels, w, h, n_images, d_in, in_stride, d_out, out_stride, out_stride, out_sizes,
-	                   out_status);
+	/* batch members ride in a grid dimension: larger batches go through in pieces */
+	size_t done = 0;
+	enum akoStatus st = AKO_OK;
+	while (done < n_images && st == AKO_OK)
+	{
+		const size_t m = (n_images - done < MEMBERS_PER_PASS) ? n_images - done : MEMBERS_PER_PASS;
+		const size_t ok = encode_core(ctx, NULL, s, channels, w, h, m, (const uint8_t*)d_in + in_stride * done, in_stride,
+		                              (uint8_t*)d_out + out_stride * done, out_stride, out_stride,
+		                              (out_sizes != NULL) ? out_sizes + done : NULL, &st);
+		done += ok;
+		if (ok != m)
+			break;
+	}
+	if (out_status != NULL)
+		*out_status = st;
+	return done;
 }
 
 AKO_API size_t akoB200EncodeDevice(akoB200Context* ctx, const struct akoSettings* s, size_t channels, size_t w, size_t h,
@@ -1449,90 +1549,132 @@ static enum akoStatus decode_core(akoB200Context* ctx, const struct akoCallbacks
 {
 	enum akoStatus st = AKO_OK;
 	const size_t td = s->tiles_dimension;
-	const size_t tiles = tiles_count(w, h, td);
-	const size_t max_w = tile_dimension(0, w, td), max_h = tile_dimension(0, h, td);
-	const size_t planes_stride = align_up(max_w * max_h * channels, 8);
-	const size_t stream_cap = align_up(
-	    (s->wavelet != AKO_WAVELET_NONE ? tile_data_size(max_w, max_h) * channels : max_w * max_h * channels * 2) / 2, 8);
+	struct tile_groups G;
+	make_groups(&G, s, channels, w, h, n);
+	const size_t tiles = G.tiles;
+	const int tile_by_tile = (cb != NULL && cb->events != NULL);
 	uint64_t* off_abs = NULL;
 	*done_out = 0;
+	if (n > MEMBERS_PER_PASS)
+		return AKO_ERROR; /* the batch entry points split larger batches */
 
 	void *planes, *scratch, *stream, *small;
-	size_t scratch_stride;
-	if ((st = from_dev(akod_workspace(ctx->dev, AKOD_WS_PLANES, planes_stride * n * 2 + 64, &planes))) != AKO_OK ||
-	    (st = scratch_for(ctx, channels, max_w, max_h, n, (int16_t**)&scratch, &scratch_stride)) != AKO_OK ||
-	    (st = from_dev(akod_workspace(ctx->dev, AKOD_WS_STREAM, stream_cap * n * 2 + 64, &stream))) != AKO_OK ||
-	    (st = from_dev(akod_workspace(ctx->dev, AKOD_WS_SMALL, sizeof(uint64_t) * tiles * n * 3 + 64, &small))) != AKO_OK)
-		return st;
-	uint64_t* d_result = small;            /* [tiles][n] */
-	uint64_t* d_off = d_result + tiles * n; /* [tiles][n] absolute byte offsets into d_in */
-	uint64_t* d_size = d_off + tiles * n;   /* [tiles][n] */
+	{
+		size_t need_planes = 0, need_scratch = 0, need_stream = 0;
+		for (int g = 0; g < 4; g++)
+			if (G.count[g] != 0)
+			{
+				const size_t members = group_pass_tiles(&G, g, n, tile_by_tile) * n;
+				need_planes = (G.planes_stride[g] * members > need_planes) ? G.planes_stride[g] * members : need_planes;
+				need_scratch = (G.scratch_stride[g] * members > need_scratch) ? G.scratch_stride[g] * members : need_scratch;
+				need_stream = (G.stream_stride[g] * members > need_stream) ? G.stream_stride[g] * members : need_stream;
+			}
+		if ((st = from_dev(akod_workspace(ctx->dev, AKOD_WS_PLANES, need_planes * 2 + 64, &planes))) != AKO_OK ||
+		    (st = from_dev(akod_workspace(ctx->dev, AKOD_WS_SCRATCH, need_scratch * 2 + 64, &scratch))) != AKO_OK ||
+		    (st = from_dev(akod_workspace(ctx->dev, AKOD_WS_STREAM, need_stream * 2 + 64, &stream))) != AKO_OK ||
+		    (st = from_dev(akod_workspace(ctx->dev, AKOD_WS_SMALL, sizeof(uint64_t) * G.bits_slots * 3 + 64, &small))) != AKO_OK)
+			return st;
+	}
+	const size_t slots = G.bits_slots;
+	uint64_t* d_result = small;        /* all three laid out as akodTiles says */
+	uint64_t* d_off = d_result + slots; /* absolute byte offsets into d_in */
+	uint64_t* d_size = d_off + slots;
 
-	off_abs = malloc(sizeof(uint64_t) * tiles * n * 3);
+	off_abs = malloc(sizeof(uint64_t) * slots * 3);
 	if (off_abs == NULL)
 		return AKO_NO_ENOUGH_MEMORY;
-	uint64_t* size_abs = off_abs + tiles * n;
-	uint64_t* results = size_abs + tiles * n;
+	uint64_t* size_abs = off_abs + slots;
+	uint64_t* results = size_abs + slots;
+	uint64_t largest[4] = {0, 0, 0, 0};
 	for (size_t t = 0; t < tiles; t++)
+	{
+		uint32_t g, k;
+		akod_tile_locate(&G.T, (uint32_t)t, &g, &k);
 		for (size_t i = 0; i < n; i++)
 		{
-			off_abs[t * n + i] = in_stride * i + blk_off[tiles * i + t];
-			size_abs[t * n + i] = blk_size[tiles * i + t];
+			const size_t at = (size_t)G.T.bits_base[g] + (size_t)k * n + i;
+			off_abs[at] = in_stride * i + blk_off[tiles * i + t];
+			size_abs[at] = blk_size[tiles * i + t];
+			largest[g] = (size_abs[at] > largest[g]) ? size_abs[at] : largest[g];
 		}
-	if ((st = upload_words(ctx, d_off, off_abs, tiles * n * 2)) != AKO_OK)
+	}
+	if (slots * 2 <= MAILBOX_WORDS)
+		st = upload_words(ctx, d_off, off_abs, slots * 2);
+	else
+	{
+		st = from_dev(akod_h2d(ctx->dev, d_off, off_abs, sizeof(uint64_t) * slots * 2));
+		if (st == AKO_OK)
+			st = from_dev(akod_sync(ctx->dev)); /* pageable source: off_abs may be reused only after the copy */
+	}
+	if (st != AKO_OK)
 	{
 		free(off_abs);
 		return st;
 	}
 
-	akodBatch batch;
-	batch.n = (uint32_t)n;
-	batch.in_stride = out_stride; /* format_inverse uses in_stride as the u8 image stride */
-	batch.planes_stride = planes_stride;
-	batch.scratch_stride = scratch_stride;
-	batch.stream_stride = stream_cap;
-
-	size_t tx = 0, ty = 0;
-	for (size_t t = 0; t < tiles && st == AKO_OK; t++)
+	for (size_t item = 0; st == AKO_OK; item++)
 	{
-		const size_t tw = tile_dimension(tx, w, td), th = tile_dimension(ty, h, td);
-		const size_t data = (s->wavelet != AKO_WAVELET_NONE) ? tile_data_size(tw, th) * channels : tw * th * channels * 2;
-		int16_t* target = (s->wavelet != AKO_WAVELET_NONE) ? stream : planes;
-		const uint64_t target_stride = (s->wavelet != AKO_WAVELET_NONE) ? stream_cap : planes_stride;
-
-		fire(cb, ctx, t, tiles, AKO_EVENT_COMPRESSION_START);
-		if (s->compression != AKO_COMPRESSION_NONE)
+		uint32_t g = 0, k0 = 0;
+		size_t kc = 0, t_event = 0;
+		if (tile_by_tile)
 		{
-			uint64_t largest = 0;
-			for (size_t i = 0; i < n; i++)
-				largest = (size_abs[t * n + i] > largest) ? size_abs[t * n + i] : largest;
-			st = from_dev(akod_kagari_decode(ctx->dev, data / 2, d_in, d_off + t * n, d_size + t * n, largest, target,
-			                                 target_stride, d_result + t * n, (uint32_t)n));
+			if (item >= tiles)
+				break;
+			akod_tile_locate(&G.T, (uint32_t)item, &g, &k0);
+			kc = 1;
+			t_event = item;
 		}
 		else
-			for (size_t i = 0; i < n && st == AKO_OK; i++)
-				st = from_dev(akod_d2d(ctx->dev, target + target_stride * i, d_in + off_abs[t * n + i], data));
-		fire(cb, ctx, t, tiles, AKO_EVENT_COMPRESSION_END);
+		{
+			size_t left = item;
+			int found = 0;
+			for (int gg = 0; gg < 4 && !found; gg++)
+			{
+				if (G.count[gg] == 0)
+					continue;
+				const size_t per = group_pass_tiles(&G, gg, n, 0);
+				const size_t passes = (G.count[gg] + per - 1) / per;
+				if (left < passes)
+				{
+					g = (uint32_t)gg;
+					k0 = (uint32_t)(left * per);
+					kc = (G.count[gg] - k0 < per) ? G.count[gg] - k0 : per;
+					found = 1;
+				}
+				else
+					left -= passes;
+			}
+			if (!found)
+				break;
+		}
+		const size_t tw = G.tw[g], th = G.th[g];
+		const size_t members = kc * n;
+		const size_t at = (size_t)G.T.bits_base[g] + (size_t)k0 * n;
+		akodBatch batch;
+		group_batch(&batch, &G, (int)g, k0, kc, n, out_stride, td); /* format_inverse reads in_stride as the u8 image stride */
+		int16_t* target = (s->wavelet != AKO_WAVELET_NONE) ? stream : planes;
+		const uint64_t target_stride = (s->wavelet != AKO_WAVELET_NONE) ? G.stream_stride[g] : G.planes_stride[g];
+
+		fire(cb, ctx, t_event, tiles, AKO_EVENT_COMPRESSION_START);
+		if (s->compression != AKO_COMPRESSION_NONE)
+			st = from_dev(akod_kagari_decode(ctx->dev, G.data[g] / 2, d_in, d_off + at, d_size + at, largest[g], target,
+			                                 target_stride, d_result + at, (uint32_t)members));
+		else
+			st = from_dev(akod_gather(ctx->dev, target, target_stride * 2, d_in, d_off + at, G.data[g], members));
+		fire(cb, ctx, t_event, tiles, AKO_EVENT_COMPRESSION_END);
 
 		if (st == AKO_OK && s->wavelet != AKO_WAVELET_NONE)
 		{
-			fire(cb, ctx, t, tiles, AKO_EVENT_WAVELET_START);
+			fire(cb, ctx, t_event, tiles, AKO_EVENT_WAVELET_START);
 			st = from_dev(akod_unlift(ctx->dev, get_plan(ctx, s, channels, tw, th), stream, planes, scratch, &batch));
-			fire(cb, ctx, t, tiles, AKO_EVENT_WAVELET_END);
+			fire(cb, ctx, t_event, tiles, AKO_EVENT_WAVELET_END);
 		}
 		if (st == AKO_OK)
 		{
-			fire(cb, ctx, t, tiles, AKO_EVENT_FORMAT_START);
+			fire(cb, ctx, t_event, tiles, AKO_EVENT_FORMAT_START);
 			st = from_dev(akod_format_inverse(ctx->dev, (int)s->color, (uint32_t)channels, (uint32_t)tw, (uint32_t)th, w,
-			                                  planes, d_out + (w * ty + tx) * channels, &batch));
-			fire(cb, ctx, t, tiles, AKO_EVENT_FORMAT_END);
-		}
-
-		tx += td;
-		if (tx >= w)
-		{
-			tx = 0;
-			ty += td;
+			                                  planes, d_out, &batch));
+			fire(cb, ctx, t_event, tiles, AKO_EVENT_FORMAT_END);
 		}
 	}
 
@@ -1540,11 +1682,22 @@ static enum akoStatus decode_core(akoB200Context* ctx, const struct akoCallbacks
 	{
 		/* compression.c:69-70, decode.c:152-156: every block must have been consumed exactly */
 		size_t first_bad = n;
-		st = download_words(ctx, results, d_result, tiles * n);
-		for (size_t k = 0; k < tiles * n && st == AKO_OK; k++)
-			if (results[k] == 0 || results[k] != size_abs[k])
-				if (k % n < first_bad)
-					first_bad = k % n;
+		if (slots <= MAILBOX_WORDS)
+			st = download_words(ctx, results, d_result, slots);
+		else
+		{
+			st = from_dev(akod_d2h(ctx->dev, results, d_result, sizeof(uint64_t) * slots));
+			if (st == AKO_OK)
+				st = from_dev(akod_sync(ctx->dev));
+		}
+		/* slot = bits_base[g] + k * n + i: the image of a slot is (slot - bits_base[g]) % n */
+		for (int g = 0; g < 4 && st == AKO_OK; g++)
+			for (size_t j = 0; j < G.count[g] * n; j++)
+			{
+				const size_t at = (size_t)G.T.bits_base[g] + j;
+				if ((results[at] == 0 || results[at] != size_abs[at]) && j % n < first_bad)
+					first_bad = j % n;
+			}
 		if (st == AKO_OK)
 		{
 			*done_out = first_bad;
@@ -1878,8 +2031,16 @@ AKO_API size_t akoB200DecodeBatchDevice(akoB200Context* ctx, size_t n_images, co
 		}
 		free(sizes64);
 	}
-	if (st == AKO_OK)
-		st = decode_core(ctx, NULL, &s, channels, w, h, n_images, d_in, in_stride, off, size, d_out, out_stride, &ok);
+	while (st == AKO_OK && ok < n_images)
+	{
+		const size_t m = (n_images - ok < MEMBERS_PER_PASS) ? n_images - ok : MEMBERS_PER_PASS;
+		size_t part = 0;
+		st = decode_core(ctx, NULL, &s, channels, w, h, m, (const uint8_t*)d_in + in_stride * ok, in_stride, off + tiles * ok,
+		                 size + tiles * ok, (uint8_t*)d_out + out_stride * ok, out_stride, &part);
+		ok += part;
+		if (part != m)
+			break;
+	}
 
 done:
 	free(blk);

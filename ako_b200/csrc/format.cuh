@@ -74,17 +74,34 @@ __device__ __forceinline__ void color_inverse(int color, int16_t p0, int16_t u, 
 	}
 }
 
+// Batch member -> its interleaved u8 image (see akodBatch): a plain batch, or tiles of n_real images.
+struct FmtTiles
+{
+	uint32_t n_real, cols, first, step, x0, y0;
+};
+
+__device__ __forceinline__ uint64_t fmt_member_offset(const FmtTiles& t, uint32_t v, uint64_t img_stride, uint64_t stride_px,
+                                                      uint32_t channels)
+{
+	if (t.n_real == 0)
+		return img_stride * v;
+	const uint32_t kk = v / t.n_real, i = v - kk * t.n_real;
+	const uint32_t k = t.first + kk;
+	const uint32_t ky = k / t.cols, kx = k - ky * t.cols;
+	return img_stride * i + ((uint64_t)(t.y0 + ky * t.step) * stride_px + (t.x0 + kx * t.step)) * channels;
+}
+
 // ---- 4 channels, rows whose width is a multiple of 8 and 16-byte aligned: 8 pixels per thread,
 //      two 128-bit loads in, four 128-bit stores out.
 __global__ void __launch_bounds__(256)
     k_format_fwd_rgba8x8(const uint8_t* __restrict__ in, int16_t* __restrict__ planes, uint32_t w, uint32_t h,
                          uint64_t in_stride_px, int color, int discard, uint64_t in_img_stride,
-                         uint64_t planes_img_stride)
+                         uint64_t planes_img_stride, const FmtTiles tiles)
 {
 	const uint32_t groups_per_row = w >> 3;
 	const uint64_t total = (uint64_t)groups_per_row * h;
 	const uint64_t plane = (uint64_t)w * h;
-	in += in_img_stride * blockIdx.y;
+	in += fmt_member_offset(tiles, blockIdx.y, in_img_stride, in_stride_px, 4);
 	planes += planes_img_stride * blockIdx.y;
 
 	for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (uint64_t)gridDim.x * blockDim.x)
@@ -117,10 +134,10 @@ __global__ void __launch_bounds__(256)
 __global__ void __launch_bounds__(256)
     k_format_fwd_generic(const uint8_t* __restrict__ in, int16_t* __restrict__ planes, uint32_t channels, uint32_t w,
                          uint32_t h, uint64_t in_stride_px, int color, int discard, uint64_t in_img_stride,
-                         uint64_t planes_img_stride)
+                         uint64_t planes_img_stride, const FmtTiles tiles)
 {
 	const uint64_t plane = (uint64_t)w * h;
-	in += in_img_stride * blockIdx.y;
+	in += fmt_member_offset(tiles, blockIdx.y, in_img_stride, in_stride_px, channels);
 	planes += planes_img_stride * blockIdx.y;
 	// discard_non_visible is only honoured for 2 and 4 channels (format.c:74-83)
 	const bool use_discard = discard && (channels == 2 || channels == 4);
@@ -154,13 +171,14 @@ __global__ void __launch_bounds__(256)
 
 __global__ void __launch_bounds__(256)
     k_format_inv_rgba8x8(const int16_t* __restrict__ planes, uint8_t* __restrict__ out, uint32_t w, uint32_t h,
-                         uint64_t out_stride_px, int color, uint64_t planes_img_stride, uint64_t out_img_stride)
+                         uint64_t out_stride_px, int color, uint64_t planes_img_stride, uint64_t out_img_stride,
+                         const FmtTiles tiles)
 {
 	const uint32_t groups_per_row = w >> 3;
 	const uint64_t total = (uint64_t)groups_per_row * h;
 	const uint64_t plane = (uint64_t)w * h;
 	planes += planes_img_stride * blockIdx.y;
-	out += out_img_stride * blockIdx.y;
+	out += fmt_member_offset(tiles, blockIdx.y, out_img_stride, out_stride_px, 4);
 
 	for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (uint64_t)gridDim.x * blockDim.x)
 	{
@@ -189,11 +207,11 @@ __global__ void __launch_bounds__(256)
 __global__ void __launch_bounds__(256)
     k_format_inv_generic(const int16_t* __restrict__ planes, uint8_t* __restrict__ out, uint32_t channels, uint32_t w,
                          uint32_t h, uint64_t out_stride_px, int color, uint64_t planes_img_stride,
-                         uint64_t out_img_stride)
+                         uint64_t out_img_stride, const FmtTiles tiles)
 {
 	const uint64_t plane = (uint64_t)w * h;
 	planes += planes_img_stride * blockIdx.y;
-	out += out_img_stride * blockIdx.y;
+	out += fmt_member_offset(tiles, blockIdx.y, out_img_stride, out_stride_px, channels);
 
 	for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < plane; i += (uint64_t)gridDim.x * blockDim.x)
 	{

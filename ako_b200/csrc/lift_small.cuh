@@ -12,7 +12,8 @@
 
 #include "lift.cuh"
 
-constexpr int SM_THREADS = 1024;
+constexpr int SM_THREADS = 1024;      // planes of up to 32 768 samples
+constexpr int SM_THREADS_TILE = 256;  // planes of up to 8 192 samples (tile batches): several CTAs share an SM
 constexpr int SM_MAX_LEVELS = 16;
 constexpr uint32_t SM_MAX_SAMPLES = 32768;      // plane size at which the small kernels take over
 constexpr uint32_t SM_CAP = 34816;              // elements per shared buffer (two buffers, 136 KiB)
@@ -33,6 +34,7 @@ struct SmallParams
 	uint32_t cw0, ch0;   // dimensions of the first (finest) small level's plane
 	uint32_t levels;     // how many levels the kernel runs (all that remain)
 	uint32_t channels;
+	uint32_t cap;        // elements per shared buffer (small_capacity): a 64 x 64 tile does not ask for 136 KiB
 	int32_t wrap, wavelet; // wavelet = the settings' wavelet; the per-level fallback is applied here
 	SmallLevelQ lq[SM_MAX_LEVELS]; // [0] = finest small level
 };
@@ -51,9 +53,10 @@ __device__ __forceinline__ int sm_level_wavelet(int wavelet, int tw, int th) // 
 	return AKOD_DD137;
 }
 
-// Walks a rows x cols index space with all SM_THREADS threads, element by element (row-major), without a division
+// Walks a rows x cols index space with all NT threads of the CTA, element by element (row-major), without a division
 // per element: the small levels have fewer columns than a warp has lanes, so a (warp = row, lane = column)
 // mapping would leave most lanes idle.
+template <int NT>
 struct SmWalk
 {
 	int row, col, dq, dr, cols;
@@ -61,8 +64,8 @@ struct SmWalk
 	{
 		row = (int)threadIdx.x / cols;
 		col = (int)threadIdx.x - row * cols;
-		dq = SM_THREADS / cols;
-		dr = SM_THREADS - dq * cols;
+		dq = NT / cols;
+		dr = NT - dq * cols;
 	}
 	__device__ __forceinline__ void next()
 	{
@@ -110,14 +113,14 @@ __device__ __forceinline__ void sm_offsets(const SmallParams& p, uint32_t chn, u
 // ------------------------------------------------------------------------------------------------
 // forward
 
-template <int WL, bool CLAMP>
+template <int WL, bool CLAMP, int NT>
 __device__ __forceinline__ void sm_forward_level(int16_t* A, int16_t* Bf, int cw, int ch, int tw, int th, int wrap,
                                                  int q, int g, uint32_t magic, int16_t* out_c, int16_t* ll_next)
 {
 	const int bw = 2 * tw; // row pitch of the H-pass output [L | H]
 
 	// ---- H pass, highpass: Bf[y][tw + c]
-	for (SmWalk it(tw); it.row < ch; it.next())
+	for (SmWalk<NT> it(tw); it.row < ch; it.next())
 	{
 		const int y = it.row, c = it.col;
 		const int16_t* row = A + y * cw;
@@ -139,7 +142,7 @@ __device__ __forceinline__ void sm_forward_level(int16_t* A, int16_t* Bf, int cw
 	}
 	__syncthreads();
 	// ---- H pass, lowpass: Bf[y][c]
-	for (SmWalk it(tw); it.row < ch; it.next())
+	for (SmWalk<NT> it(tw); it.row < ch; it.next())
 	{
 		const int y = it.row, c = it.col;
 		const int16_t* row = A + y * cw;
@@ -163,7 +166,7 @@ __device__ __forceinline__ void sm_forward_level(int16_t* A, int16_t* Bf, int cw
 	__syncthreads();
 	// ---- V pass, highpass of every column of [L | H]: HV[r][col] overwrites A (dead now)
 	int16_t* HV = A;
-	for (SmWalk it(bw); it.row < th; it.next())
+	for (SmWalk<NT> it(bw); it.row < th; it.next())
 	{
 		const int r = it.row, col = it.col;
 		{
@@ -187,7 +190,7 @@ __device__ __forceinline__ void sm_forward_level(int16_t* A, int16_t* Bf, int cw
 	// ---- V pass, lowpass + gate/quantise + stores. LL goes to ll_next (shared), C/B/D to the stream.
 	int16_t* out_b = out_c + tw * th;
 	int16_t* out_d = out_b + tw * th;
-	for (SmWalk it(bw); it.row < th; it.next())
+	for (SmWalk<NT> it(bw); it.row < th; it.next())
 	{
 		const int r = it.row, col = it.col;
 		{
@@ -220,11 +223,12 @@ __device__ __forceinline__ void sm_forward_level(int16_t* A, int16_t* Bf, int cw
 	__syncthreads();
 }
 
-__global__ void __launch_bounds__(SM_THREADS, 1) k_lift_small(const SmallParams p)
+template <int NT>
+__global__ void __launch_bounds__(NT, (NT <= 256) ? 4 : 1) k_lift_small(const SmallParams p)
 {
 	extern __shared__ __align__(16) int16_t sm_buf[];
 	int16_t* A = sm_buf;
-	int16_t* Bf = sm_buf + SM_CAP;
+	int16_t* Bf = sm_buf + p.cap;
 	__shared__ uint32_t off_c[SM_MAX_LEVELS], lw[SM_MAX_LEVELS + 1], lh[SM_MAX_LEVELS + 1];
 
 	const uint32_t img = blockIdx.x / p.channels, chn = blockIdx.x - img * p.channels;
@@ -232,7 +236,7 @@ __global__ void __launch_bounds__(SM_THREADS, 1) k_lift_small(const SmallParams 
 		sm_offsets(p, chn, off_c, lw, lh);
 	const int16_t* in = p.planes + p.planes_is * img + p.planes_ps * chn;
 	int16_t* stream = p.stream + p.stream_is * img;
-	for (SmWalk it((int)p.cw0); it.row < (int)p.ch0; it.next())
+	for (SmWalk<NT> it((int)p.cw0); it.row < (int)p.ch0; it.next())
 		A[it.row * (int)p.cw0 + it.col] = __ldg(in + (uint64_t)it.row * p.planes_rs + it.col);
 	__syncthreads();
 
@@ -251,27 +255,27 @@ __global__ void __launch_bounds__(SM_THREADS, 1) k_lift_small(const SmallParams 
 		int16_t* ll_next = cur + th * 2 * tw; // behind the V-highpass scratch that overwrites 'cur'
 		const bool clamp = p.wrap == AKOD_WRAP_CLAMP;
 		if (wl == AKOD_DD137 && clamp)
-			sm_forward_level<AKOD_DD137, true>(cur, Bf, cw, ch, tw, th, p.wrap, q, g, magic, out_c, ll_next);
+			sm_forward_level<AKOD_DD137, true, NT>(cur, Bf, cw, ch, tw, th, p.wrap, q, g, magic, out_c, ll_next);
 		else if (wl == AKOD_DD137)
-			sm_forward_level<AKOD_DD137, false>(cur, Bf, cw, ch, tw, th, p.wrap, q, g, magic, out_c, ll_next);
+			sm_forward_level<AKOD_DD137, false, NT>(cur, Bf, cw, ch, tw, th, p.wrap, q, g, magic, out_c, ll_next);
 		else if (wl == AKOD_CDF53 && clamp)
-			sm_forward_level<AKOD_CDF53, true>(cur, Bf, cw, ch, tw, th, p.wrap, q, g, magic, out_c, ll_next);
+			sm_forward_level<AKOD_CDF53, true, NT>(cur, Bf, cw, ch, tw, th, p.wrap, q, g, magic, out_c, ll_next);
 		else if (wl == AKOD_CDF53)
-			sm_forward_level<AKOD_CDF53, false>(cur, Bf, cw, ch, tw, th, p.wrap, q, g, magic, out_c, ll_next);
+			sm_forward_level<AKOD_CDF53, false, NT>(cur, Bf, cw, ch, tw, th, p.wrap, q, g, magic, out_c, ll_next);
 		else
-			sm_forward_level<AKOD_HAAR, true>(cur, Bf, cw, ch, tw, th, p.wrap, q, g, magic, out_c, ll_next);
+			sm_forward_level<AKOD_HAAR, true, NT>(cur, Bf, cw, ch, tw, th, p.wrap, q, g, magic, out_c, ll_next);
 		cur = ll_next;
 	}
 	// lowpass section (lifting.c:280-291)
 	const uint32_t lpn = lw[p.levels] * lh[p.levels];
-	for (uint32_t i = threadIdx.x; i < lpn; i += SM_THREADS)
+	for (uint32_t i = threadIdx.x; i < lpn; i += NT)
 		stream[chn * lpn + i] = cur[i];
 }
 
 // ------------------------------------------------------------------------------------------------
 // inverse
 
-template <int WL, bool CLAMP>
+template <int WL, bool CLAMP, int NT>
 __device__ __forceinline__ void sm_inverse_level(int16_t* R, int16_t* T, int hw, int hh, int tw, int th, int wrap, int q,
                                                  const int16_t* __restrict__ in_c)
 {
@@ -282,14 +286,14 @@ __device__ __forceinline__ void sm_inverse_level(int16_t* R, int16_t* T, int hw,
 	int16_t* HC = R + band; // C, then B, then D
 
 	// lifting.c:30-40: coefficient * q narrowed to int16, skipped when q <= 1
-	for (int i = threadIdx.x; i < 3 * band; i += SM_THREADS)
+	for (int i = threadIdx.x; i < 3 * band; i += NT)
 	{
 		const int v = __ldg(in_c + i);
 		HC[i] = (int16_t)((q > 1) ? v * q : v);
 	}
 	__syncthreads();
 	// ---- V pass, even rows: T[2r][col]
-	for (SmWalk it(bw); it.row < hh; it.next())
+	for (SmWalk<NT> it(bw); it.row < hh; it.next())
 	{
 		const int r = it.row, col = it.col;
 		{
@@ -314,7 +318,7 @@ __device__ __forceinline__ void sm_inverse_level(int16_t* R, int16_t* T, int hw,
 	}
 	__syncthreads();
 	// ---- V pass, odd rows: T[2r+1][col]
-	for (SmWalk it(bw); it.row < hh; it.next())
+	for (SmWalk<NT> it(bw); it.row < hh; it.next())
 	{
 		const int r = it.row, col = it.col;
 		{
@@ -340,7 +344,7 @@ __device__ __forceinline__ void sm_inverse_level(int16_t* R, int16_t* T, int hw,
 	__syncthreads();
 	// ---- H pass, even samples of the th real rows: R[y][2c]  (LL and the staged subbands are dead now)
 	const int hwt = (tw + 1) / 2; // == hw
-	for (SmWalk it(hwt); it.row < th; it.next())
+	for (SmWalk<NT> it(hwt); it.row < th; it.next())
 	{
 		const int y = it.row, c = it.col;
 		const int16_t* lrow = T + y * bw;
@@ -362,7 +366,7 @@ __device__ __forceinline__ void sm_inverse_level(int16_t* R, int16_t* T, int hw,
 	}
 	__syncthreads();
 	// ---- H pass, odd samples (a last odd column dropped by the plus-one rule is not written)
-	for (SmWalk it(hwt); it.row < th; it.next())
+	for (SmWalk<NT> it(hwt); it.row < th; it.next())
 	{
 		const int y = it.row, c = it.col;
 		const int16_t* hrow = T + y * bw + hw;
@@ -387,11 +391,12 @@ __device__ __forceinline__ void sm_inverse_level(int16_t* R, int16_t* T, int hw,
 	__syncthreads();
 }
 
-__global__ void __launch_bounds__(SM_THREADS, 1) k_unlift_small(const SmallParams p)
+template <int NT>
+__global__ void __launch_bounds__(NT, (NT <= 256) ? 4 : 1) k_unlift_small(const SmallParams p)
 {
 	extern __shared__ __align__(16) int16_t sm_buf[];
 	int16_t* R = sm_buf;
-	int16_t* T = sm_buf + SM_CAP;
+	int16_t* T = sm_buf + p.cap;
 	__shared__ uint32_t off_c[SM_MAX_LEVELS], lw[SM_MAX_LEVELS + 1], lh[SM_MAX_LEVELS + 1];
 
 	const uint32_t img = blockIdx.x / p.channels, chn = blockIdx.x - img * p.channels;
@@ -400,7 +405,7 @@ __global__ void __launch_bounds__(SM_THREADS, 1) k_unlift_small(const SmallParam
 	__syncthreads();
 	const int16_t* stream = p.stream + p.stream_is * img;
 	const uint32_t lpn = lw[p.levels] * lh[p.levels];
-	for (uint32_t i = threadIdx.x; i < lpn; i += SM_THREADS)
+	for (uint32_t i = threadIdx.x; i < lpn; i += NT)
 		R[i] = __ldg(stream + chn * lpn + i);
 	__syncthreads();
 
@@ -412,38 +417,46 @@ __global__ void __launch_bounds__(SM_THREADS, 1) k_unlift_small(const SmallParam
 		const int q = (int)__ldg(in_c - 1); // the decoder learns q from the lift head (misc.c:262-268)
 		const bool clamp = p.wrap == AKOD_WRAP_CLAMP;
 		if (wl == AKOD_DD137 && clamp)
-			sm_inverse_level<AKOD_DD137, true>(R, T, hw, hh, tw, th, p.wrap, q, in_c);
+			sm_inverse_level<AKOD_DD137, true, NT>(R, T, hw, hh, tw, th, p.wrap, q, in_c);
 		else if (wl == AKOD_DD137)
-			sm_inverse_level<AKOD_DD137, false>(R, T, hw, hh, tw, th, p.wrap, q, in_c);
+			sm_inverse_level<AKOD_DD137, false, NT>(R, T, hw, hh, tw, th, p.wrap, q, in_c);
 		else if (wl == AKOD_CDF53 && clamp)
-			sm_inverse_level<AKOD_CDF53, true>(R, T, hw, hh, tw, th, p.wrap, q, in_c);
+			sm_inverse_level<AKOD_CDF53, true, NT>(R, T, hw, hh, tw, th, p.wrap, q, in_c);
 		else if (wl == AKOD_CDF53)
-			sm_inverse_level<AKOD_CDF53, false>(R, T, hw, hh, tw, th, p.wrap, q, in_c);
+			sm_inverse_level<AKOD_CDF53, false, NT>(R, T, hw, hh, tw, th, p.wrap, q, in_c);
 		else
-			sm_inverse_level<AKOD_HAAR, true>(R, T, hw, hh, tw, th, p.wrap, q, in_c);
+			sm_inverse_level<AKOD_HAAR, true, NT>(R, T, hw, hh, tw, th, p.wrap, q, in_c);
 	}
 
 	int16_t* out = p.planes + p.planes_is * img + p.planes_ps * chn;
-	for (SmWalk it((int)p.cw0); it.row < (int)p.ch0; it.next())
+	for (SmWalk<NT> it((int)p.cw0); it.row < (int)p.ch0; it.next())
 		out[(uint64_t)it.row * p.planes_rs + it.col] = R[it.row * (int)p.cw0 + it.col];
 }
 
-// host side: can the small kernels take the pyramid from a cw x ch plane downwards?
-static inline bool small_eligible(uint32_t cw, uint32_t ch, uint32_t levels)
+// host side: elements each of the two shared buffers must hold for the pyramid from a cw x ch plane downwards.
+// forward: 'cur' walks forward through buffer A (each level's V-highpass scratch th*2tw, then the next LL); the
+// H-pass buffer holds ch rows of 2tw. inverse: R holds the 4 subbands (4*hw*hh), T 2hh rows of 2hw.
+static inline uint64_t small_capacity(uint32_t cw, uint32_t ch, uint32_t levels)
 {
-	if (levels == 0 || levels > SM_MAX_LEVELS || (uint64_t)cw * ch > SM_MAX_SAMPLES)
-		return false;
-	// forward: 'cur' walks forward through buffer A (each level's V-highpass scratch th*2tw, then the next LL);
-	// the H-pass buffer holds ch rows of 2tw. inverse: R holds the 4 subbands (4*hw*hh), T 2hh rows of 2hw.
-	uint64_t at = 0;
+	uint64_t at = 0, cap = 0;
 	for (uint32_t s = 0; s < levels; s++)
 	{
 		const uint32_t tw = sm_half(cw), th = sm_half(ch);
-		if ((uint64_t)ch * 2 * tw > SM_CAP || at + (uint64_t)th * 3 * tw > SM_CAP || (uint64_t)4 * tw * th > SM_CAP)
-			return false;
+		const uint64_t a = (uint64_t)ch * 2 * tw, b = at + (uint64_t)th * 3 * tw, c = (uint64_t)4 * tw * th;
+		cap = a > cap ? a : cap;
+		cap = b > cap ? b : cap;
+		cap = c > cap ? c : cap;
 		at += (uint64_t)th * 2 * tw;
 		cw = tw;
 		ch = th;
 	}
-	return true;
+	return (cap + 7) & ~(uint64_t)7;
+}
+
+// can the small kernels take the pyramid from a cw x ch plane downwards?
+static inline bool small_eligible(uint32_t cw, uint32_t ch, uint32_t levels)
+{
+	if (levels == 0 || levels > SM_MAX_LEVELS || (uint64_t)cw * ch > SM_MAX_SAMPLES)
+		return false;
+	return small_capacity(cw, ch, levels) <= SM_CAP;
 }

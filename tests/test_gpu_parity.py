@@ -196,6 +196,30 @@ def test_end_to_end_tiles(orc, tiles):
             _e2e(orc, img, wavelet=wavelet, tiles=tiles, q=16, g=4)
 
 
+def test_more_tiles_than_a_grid_dimension(orc):
+    """2048 x 2056 with tiles_dimension = 8 is 65 792 tiles (a grid dimension holds 65 535); all four tile shape
+    groups with every wavelet at a smaller size, through events (tile by tile) and without (one pass per shape)."""
+    from ako_b200 import lib as akolib
+    img = ol.synth(orc, 2048, 2056, 3)
+    _e2e(orc, img, wavelet=W_CDF53, tiles=8, q=0)
+    img = ol.synth(orc, 333, 222, 4)[..., :3].copy()
+    seen = []
+    cb = ako_b200.load().akoDefaultCallbacks()
+    fn = akolib.EVENTS_FN(lambda t, n, e, d: seen.append((t, n, e)))
+    cb.events = C.cast(fn, C.c_void_p)
+    for wavelet in (W_DD137, W_CDF53, W_HAAR):
+        for tiles in (16, 64):
+            want = _e2e(orc, img, wavelet=wavelet, tiles=tiles, q=16, g=8)
+            del seen[:]
+            got, st = ako_b200.encode(img, S(wavelet=wavelet, tiles=tiles, q=16, g=8), cb)
+            assert st == 0 and got == want
+            n_tiles = -(-333 // tiles) * -(-222 // tiles)
+            assert len(seen) == 6 * n_tiles and [t for t, _, _ in seen] == sorted(t for t, _, _ in seen)
+            px, st, _ = ako_b200.decode(want, cb)
+            want_px, _ = ol.orc_decode(orc, want)
+            assert st == 0 and np.array_equal(px, want_px)
+
+
 with open(os.path.join(os.path.dirname(__file__), "golden", "golden.json")) as f:
     GOLDEN = json.load(f)
 
