@@ -1043,7 +1043,11 @@ extern "C" int akod_kagari_decode(akodContext* c, uint64_t n_values, const uint8
 	AKOD_LAUNCH(c, "kagari_dec_scan", k_kd_scan_counts, n_images, 1024, 0, blk_count, blk_base, nblk1, info);
 	AKOD_LAUNCH(c, "kagari_dec_extract", k_kd_extract, grid1, KD_THREADS, 0, d_in, d_off, d_size, nblk1, sub, blk_base, tokens,
 	            token_cap, token_cap);
-	const dim3 grid2(nblk2, n_images);
+	// grid-stride over the token blocks that exist: enough CTAs to fill the GPU a few times over, not one per possible block
+	uint32_t gx2 = (uint32_t)c->sm_count * 16 / n_images;
+	gx2 = gx2 < 8 ? 8 : gx2;
+	gx2 = gx2 > nblk2 ? nblk2 : gx2;
+	const dim3 grid2(gx2, n_images);
 	AKOD_LAUNCH(c, "kagari_dec_spans", k_kt_spans, grid2, KT_SPAN_THREADS, 0, tokens, token_cap, token_cap, info, blk_span, nblk2);
 	AKOD_LAUNCH(c, "kagari_dec_resolve", k_kt_resolve, n_images, KR_THREADS, 0, blk_span, nblk2, blk_state, blk_out, info, n_values,
 	            token_cap, d_result);

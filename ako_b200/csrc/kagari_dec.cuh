@@ -187,37 +187,51 @@ __device__ __forceinline__ uint32_t kd_peek(const uint32_t* sm, uint32_t pos)
 // walks codewords from 'start' (relative to the CTA) until the first boundary >= limit.
 // Returns that boundary (or KD_STOP if the chain ends), counts codewords starting before 'limit'.
 // If stop_at != nullptr and the chain ends, *stop_at receives the relative position where it ended.
-template <bool EMIT>
-__device__ __forceinline__ uint32_t kd_walk(const uint32_t* sm, uint32_t start, uint32_t limit, uint64_t bits_left,
-                                            uint32_t& count, uint32_t* stop_at, uint16_t* __restrict__ tokens,
-                                            uint64_t token_base, uint64_t token_cap)
+// bits_left: codewords may not reach past this CTA-relative position (the end of the stream, clamped to 32 bits).
+// The two words under the cursor ride in registers and one shared load follows per word crossed, instead of two
+// per codeword (a lossless stream averages 3.4 bits per codeword).
+// EMIT: token j of the walk goes to emit(j, raw codeword value).
+template <bool EMIT, typename F>
+__device__ __forceinline__ uint32_t kd_walk(const uint32_t* sm, uint32_t start, uint32_t limit, uint32_t bits_left,
+                                            uint32_t& count, uint32_t* stop_at, F emit)
 {
 	count = 0;
 	if (start == KD_STOP)
 		return KD_STOP;
 	uint32_t p = start;
-	while (p < limit)
+	if (p >= limit)
+		return p;
+	uint32_t idx = p >> 5;
+	uint32_t hi = sm[idx], lo = sm[idx + 1];
+	do
 	{
-		const uint32_t w = kd_peek(sm, p);
+		const uint32_t w = __funnelshift_l(lo, hi, p & 31);
 		const int z = __clz(w); // 32 for w == 0
 		const uint32_t len = 2 * z + 1;
-		if (z > 15 || (uint64_t)p + len > bits_left)
+		if (w < 0x10000u || p + len > bits_left) // more than 15 leading zeros, or past the end of the stream
 		{
 			if (stop_at)
 				*stop_at = p;
 			return KD_STOP;
 		}
 		if (EMIT)
-		{
-			const uint64_t t = token_base + count;
-			if (t < token_cap)
-				tokens[t] = (uint16_t)(w >> (31 - 2 * z));
-		}
+			emit(count, w >> (31 - 2 * z));
 		count++;
 		p += len;
-	}
+		if ((p >> 5) != idx) // len <= 31: at most one word further
+		{
+			idx++;
+			hi = lo;
+			lo = sm[idx + 1];
+		}
+	} while (p < limit);
 	return p;
 }
+
+struct KdNoEmit
+{
+	__device__ __forceinline__ void operator()(uint32_t, uint32_t) const {}
+};
 
 // One synchronisation run. run == 0: every CTA assumes it starts on a boundary.
 // run > 0: CTA b starts where CTA b-1 ended in the previous run (ends_prev).
@@ -269,7 +283,8 @@ __global__ void __launch_bounds__(KD_THREADS)
 	kd_stage_bits(sm, in_base + off, size, cta_bit0 >> 3);
 	__syncthreads();
 
-	const uint64_t bits_left = total_bits - cta_bit0; // codewords may not cross this (relative) position
+	// codewords may not cross this (relative) position
+	const uint32_t bits_left = (uint32_t)min(total_bits - cta_bit0, (uint64_t)0xFFFFFFFFu);
 	uint32_t start;
 	if (t == 0)
 	{
@@ -283,7 +298,7 @@ __global__ void __launch_bounds__(KD_THREADS)
 	const uint32_t limit = (t + 1) * KD_SUB_BITS;
 
 	uint32_t count, stop_rel = KD_STOP;
-	uint32_t end = kd_walk<false>(sm, start, limit, bits_left, count, &stop_rel, nullptr, 0, 0);
+	uint32_t end = kd_walk<false>(sm, start, limit, bits_left, count, &stop_rel, KdNoEmit());
 	for (;;)
 	{
 		sm_end[t] = end;
@@ -296,7 +311,7 @@ __global__ void __launch_bounds__(KD_THREADS)
 			{
 				start = real_start;
 				stop_rel = KD_STOP;
-				end = kd_walk<false>(sm, start, limit, bits_left, count, &stop_rel, nullptr, 0, 0);
+				end = kd_walk<false>(sm, start, limit, bits_left, count, &stop_rel, KdNoEmit());
 				moved = true;
 			}
 		}
@@ -345,7 +360,12 @@ __global__ void __launch_bounds__(1024)
 		info[blockIdx.x].tokens = carry;
 }
 
-// re-walks every subsequence from its final start and stores the raw codeword values
+// re-walks every subsequence from its final start and stores the raw codeword values. A CTA's tokens are one
+// contiguous piece of the token buffer: they are collected in shared memory and leave in 16-byte rows (a thread
+// storing its own tokens one by one touched a 32-byte sector per 2-byte store). What does not fit the stage
+// (more than KD_STAGE tokens in 32 Kibit: codewords under 3.2 bits on average) goes out directly.
+constexpr uint32_t KD_STAGE = 10240;
+
 __global__ void __launch_bounds__(KD_THREADS)
     k_kd_extract(const uint8_t* __restrict__ in_base, const uint64_t* __restrict__ in_off,
                  const uint64_t* __restrict__ in_size, uint32_t nblk, const KdSubState* __restrict__ sub,
@@ -354,6 +374,7 @@ __global__ void __launch_bounds__(KD_THREADS)
 {
 	__shared__ uint32_t sm[KD_CTA_WORDS + 2];
 	__shared__ uint32_t sm_sum[33];
+	__shared__ __align__(16) uint16_t stage[KD_STAGE];
 	const uint32_t img = blockIdx.y, b = blockIdx.x, t = threadIdx.x;
 	const uint64_t size = __ldg(in_size + img);
 	const uint64_t off = __ldg(in_off + img);
@@ -366,9 +387,38 @@ __global__ void __launch_bounds__(KD_THREADS)
 	kd_stage_bits(sm, in_base + off, size, cta_bit0 >> 3);
 	uint32_t total;
 	const uint32_t excl = block_excl_sum(s.count, sm_sum, &total); // syncs: sm is staged after it
+	uint16_t* const tok = tokens + token_stride * img;
 	uint32_t count;
-	kd_walk<true>(sm, s.start, (t + 1) * KD_SUB_BITS, total_bits - cta_bit0, count, nullptr,
-	              tokens + token_stride * img, tok0 + excl, token_cap);
+	kd_walk<true>(sm, s.start, (t + 1) * KD_SUB_BITS, (uint32_t)min(total_bits - cta_bit0, (uint64_t)0xFFFFFFFFu), count, nullptr,
+	              [&](uint32_t j, uint32_t u) {
+		              const uint32_t at = excl + j;
+		              if (at < KD_STAGE)
+			              stage[at] = (uint16_t)u;
+		              else if (tok0 + at < token_cap)
+			              tok[tok0 + at] = (uint16_t)u;
+	              });
+	__syncthreads();
+	// staged tokens [0, n) -> tok[tok0 .. tok0 + n), clipped to the buffer: 16-byte rows of the destination
+	const uint64_t room = (tok0 < token_cap) ? token_cap - tok0 : 0;
+	const uint32_t n = (uint32_t)min((uint64_t)min(total, KD_STAGE), room);
+	const uint32_t head = min(n, (uint32_t)((8 - (tok0 & 7)) & 7)); // tokens before the first 16-byte boundary
+	if (t < head)
+		tok[tok0 + t] = stage[t];
+	const uint32_t rows = (n - head) >> 3;
+	uint4* const dst = reinterpret_cast<uint4*>(tok + tok0 + head);
+	for (uint32_t r = t; r < rows; r += KD_THREADS)
+	{
+		const uint16_t* src = stage + head + 8 * r;
+		uint4 v;
+		v.x = (uint32_t)src[0] | ((uint32_t)src[1] << 16);
+		v.y = (uint32_t)src[2] | ((uint32_t)src[3] << 16);
+		v.z = (uint32_t)src[4] | ((uint32_t)src[5] << 16);
+		v.w = (uint32_t)src[6] | ((uint32_t)src[7] << 16);
+		dst[r] = v;
+	}
+	const uint32_t tail0 = head + 8 * rows;
+	if (tail0 + t < n)
+		tok[tok0 + tail0 + t] = stage[tail0 + t];
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -406,15 +456,20 @@ __device__ __forceinline__ KtSpan kt_identity()
 	return s;
 }
 
+// the four transition functions as packed maps (2 bits per entry state, V A S R from the low end):
+//   e1 e2    V  A  S  R
+//   0  0  -> V  V  V  A    0x40
+//   1  0  -> S  V  R  A    0x72
+//   0  1  -> V  S  V  A    0x48
+//   1  1  -> S  S  R  A    0x7A
+__device__ __forceinline__ uint32_t kt_step_map(bool e1, bool e2)
+{
+	return e1 ? (e2 ? 0x7Au : 0x72u) : (e2 ? 0x48u : 0x40u);
+}
+
 __device__ __forceinline__ uint32_t kt_next(uint32_t state, bool e1, bool e2)
 {
-	switch (state)
-	{
-	case ST_V: return e1 ? ST_S : ST_V;
-	case ST_A: return e2 ? ST_S : ST_V;
-	case ST_S: return e1 ? ST_R : ST_V;
-	default: return ST_A;
-	}
+	return (kt_step_map(e1, e2) >> (2 * state)) & 3u;
 }
 
 // a then b
@@ -451,13 +506,18 @@ __device__ __forceinline__ int kt_load(const uint16_t* __restrict__ tok, uint64_
 	u[1] = (base >= 1 && base - 1 < m) ? tok[base - 1] : 0x20000u;
 	if (base + ITEMS <= m)
 	{
-		uint16_t tmp[ITEMS];
 #pragma unroll
 		for (int k = 0; k < ITEMS; k += 8)
-			*reinterpret_cast<uint4*>(tmp + k) = __ldg(reinterpret_cast<const uint4*>(tok + base + k));
+		{
+			const uint4 q = __ldg(reinterpret_cast<const uint4*>(tok + base + k));
+			const uint32_t w[4] = {q.x, q.y, q.z, q.w};
 #pragma unroll
-		for (int j = 0; j < ITEMS; j++)
-			u[j + 2] = tmp[j];
+			for (int i = 0; i < 4; i++)
+			{
+				u[k + 2 * i + 2] = w[i] & 0xFFFFu;
+				u[k + 2 * i + 3] = w[i] >> 16;
+			}
+		}
 		valid = ITEMS;
 	}
 	else
@@ -476,23 +536,65 @@ __device__ __forceinline__ int kt_load(const uint16_t* __restrict__ tok, uint64_
 	return valid;
 }
 
+// The span of a thread's ITEMS tokens. The four entry states are simulated side by side only until they agree:
+// two tokens in a row that differ from both their predecessors send every state to V (see the table above), so in
+// anything but a run of repeats the states have merged after three tokens and one simulation finishes the job.
 template <int ITEMS>
 __device__ __forceinline__ KtSpan kt_thread_span(const uint32_t u[ITEMS + 2], int valid)
 {
-	// simulate the four entry states side by side
+	constexpr int PRE = (ITEMS < 3) ? ITEMS : 3;
 	uint32_t st[4] = {ST_V, ST_A, ST_S, ST_R};
 	uint32_t out[4] = {0, 0, 0, 0};
 #pragma unroll
-	for (int j = 0; j < ITEMS; j++)
+	for (int j = 0; j < PRE; j++)
 	{
 		if (j < valid)
 		{
-			const bool e1 = u[j + 2] == u[j + 1], e2 = u[j + 2] == u[j];
+			const uint32_t m = kt_step_map(u[j + 2] == u[j + 1], u[j + 2] == u[j]);
 #pragma unroll
 			for (int s = 0; s < 4; s++)
 			{
 				out[s] += (st[s] == ST_R) ? (u[j + 2] - 1u) : 1u;
-				st[s] = kt_next(st[s], e1, e2);
+				st[s] = (m >> (2 * st[s])) & 3u;
+			}
+		}
+	}
+	if (ITEMS > PRE)
+	{
+		if (st[0] == st[1] && st[1] == st[2] && st[2] == st[3])
+		{
+			uint32_t s1 = st[0], o1 = 0;
+#pragma unroll
+			for (int j = PRE; j < ITEMS; j++)
+			{
+				if (j < valid)
+				{
+					o1 += (s1 == ST_R) ? (u[j + 2] - 1u) : 1u;
+					s1 = kt_next(s1, u[j + 2] == u[j + 1], u[j + 2] == u[j]);
+				}
+			}
+#pragma unroll
+			for (int s = 0; s < 4; s++)
+			{
+				out[s] += o1;
+				st[s] = s1;
+			}
+		}
+		else
+		{
+#pragma unroll
+			for (int j = PRE; j < ITEMS; j++)
+			{
+				if (j < valid)
+				{
+					const uint32_t m = kt_step_map(u[j + 2] == u[j + 1], u[j + 2] == u[j]);
+#pragma unroll
+					for (int s = 0; s < 4; s++)
+					{
+						out[s] += (st[s] == ST_R) ? (u[j + 2] - 1u) : 1u;
+						st[s] = (m >> (2 * st[s])) & 3u;
+					}
+				}
 			}
 		}
 	}
@@ -504,11 +606,43 @@ __device__ __forceinline__ KtSpan kt_thread_span(const uint32_t u[ITEMS + 2], in
 	return r;
 }
 
-// Block-wide exclusive scan of spans. sm must hold 33 KtSpan. Returns the span of everything before this thread;
-// *total = span of the whole CTA.
-__device__ __forceinline__ KtSpan kt_block_excl_scan(KtSpan v, KtSpan* sm, KtSpan* total)
+// a span whose exit state does not depend on the entry state
+__device__ __forceinline__ bool kt_is_const(uint32_t map)
 {
-	const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+	return ((map ^ (map >> 2)) & 0x3Fu) == 0;
+}
+
+// Exclusive scan of the 32 spans of a warp; *total = all 32 composed. When every lane's span has a constant exit
+// state (the rule, see kt_thread_span) lane l is entered in lane l-1's exit state whatever came before, and the scan
+// is one shuffle for the states and an integer prefix sum for the counts; otherwise the generic composition runs.
+// Lanes >= n_active hold nothing (the caller passes identities there).
+__device__ __forceinline__ KtSpan kt_warp_excl_scan(const KtSpan& v, KtSpan* total, int n_active = 32)
+{
+	const int lane = threadIdx.x & 31;
+	if (__all_sync(AKOD_FULL_MASK, kt_is_const(v.map) || lane >= n_active))
+	{
+		const uint32_t exit_state = v.map & 3u;
+		const uint32_t prev_exit = __shfl_up_sync(AKOD_FULL_MASK, exit_state, 1);
+		// what lane l >= 1 contributes, entered in lane l-1's exit state
+		const uint32_t c = (lane == 0 || lane >= n_active)
+		                       ? 0u
+		                       : (prev_exit == 0 ? v.out[0] : prev_exit == 1 ? v.out[1] : prev_exit == 2 ? v.out[2] : v.out[3]);
+		const uint32_t incl = warp_incl_sum(c);
+		const uint32_t before = incl - c; // lanes 1 .. l-1
+		const uint32_t all = __shfl_sync(AKOD_FULL_MASK, incl, 31);
+		const uint32_t last_exit = __shfl_sync(AKOD_FULL_MASK, exit_state, n_active - 1);
+		KtSpan r;
+		r.map = (lane == 0) ? kt_identity().map : prev_exit * 0x55u;
+		total->map = last_exit * 0x55u;
+#pragma unroll
+		for (int s = 0; s < 4; s++)
+		{
+			const uint32_t first = __shfl_sync(AKOD_FULL_MASK, v.out[s], 0); // lane 0 entered in state s
+			r.out[s] = (lane == 0) ? 0u : first + before;
+			total->out[s] = first + all;
+		}
+		return r;
+	}
 	KtSpan incl = v;
 #pragma unroll
 	for (int d = 1; d < 32; d <<= 1)
@@ -520,26 +654,31 @@ __device__ __forceinline__ KtSpan kt_block_excl_scan(KtSpan v, KtSpan* sm, KtSpa
 	KtSpan excl = kt_shfl_up(incl, 1);
 	if (lane == 0)
 		excl = kt_identity();
-	if (lane == 31)
-		sm[wid] = incl;
+	total->map = __shfl_sync(AKOD_FULL_MASK, incl.map, 31);
+#pragma unroll
+	for (int s = 0; s < 4; s++)
+		total->out[s] = __shfl_sync(AKOD_FULL_MASK, incl.out[s], 31);
+	return excl;
+}
+
+// Block-wide exclusive scan of spans. sm must hold 33 KtSpan. Returns the span of everything before this thread;
+// *total = span of the whole CTA.
+__device__ __forceinline__ KtSpan kt_block_excl_scan(KtSpan v, KtSpan* sm, KtSpan* total)
+{
+	const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+	KtSpan warp_total;
+	const KtSpan excl = kt_warp_excl_scan(v, &warp_total);
+	if (lane == 0)
+		sm[wid] = warp_total;
 	__syncthreads();
 	if (wid == 0)
 	{
-		KtSpan w = (lane < nw) ? sm[lane] : kt_identity();
-		KtSpan wi = w;
-#pragma unroll
-		for (int d = 1; d < 32; d <<= 1)
-		{
-			const KtSpan o = kt_shfl_up(wi, d);
-			if (lane >= d)
-				wi = kt_compose(o, wi);
-		}
-		KtSpan we = kt_shfl_up(wi, 1);
-		if (lane == 0)
-			we = kt_identity();
+		const KtSpan w = (lane < nw) ? sm[lane] : kt_identity();
+		KtSpan all;
+		const KtSpan we = kt_warp_excl_scan(w, &all, nw);
 		sm[lane] = we;
-		if (lane == 31)
-			sm[32] = wi;
+		if (lane == 0)
+			sm[32] = all;
 	}
 	__syncthreads();
 	const KtSpan r = kt_compose(sm[wid], excl);
@@ -548,7 +687,9 @@ __device__ __forceinline__ KtSpan kt_block_excl_scan(KtSpan v, KtSpan* sm, KtSpa
 	return r;
 }
 
-// pass A: the span of every CTA's tokens
+// pass A: the span of every block of KT_BLOCK tokens. The grid is sized for the most tokens a stream of this length
+// could hold, a quantised image has a small fraction of that: CTAs walk the blocks that exist with a grid stride
+// (one CTA per possible block was ~10 000 CTAs per image that only found out they had nothing to do).
 __global__ void __launch_bounds__(KT_SPAN_THREADS)
     k_kt_spans(const uint16_t* __restrict__ tokens, uint64_t token_stride, uint64_t token_cap,
                const KdImage* __restrict__ info, KtSpan* __restrict__ blk_span, uint32_t nblk)
@@ -556,13 +697,17 @@ __global__ void __launch_bounds__(KT_SPAN_THREADS)
 	__shared__ KtSpan sm[33];
 	const uint32_t img = blockIdx.y;
 	const uint64_t m = min(info[img].tokens, token_cap);
-	const uint64_t base = (uint64_t)blockIdx.x * KT_BLOCK + (uint64_t)threadIdx.x * KT_SPAN_ITEMS;
-	uint32_t u[KT_SPAN_ITEMS + 2];
-	const int valid = (base < m) ? kt_load<KT_SPAN_ITEMS>(tokens + token_stride * img, m, base, u) : 0;
-	KtSpan total;
-	kt_block_excl_scan(kt_thread_span<KT_SPAN_ITEMS>(u, valid), sm, &total);
-	if (threadIdx.x == 0)
-		blk_span[(uint64_t)nblk * img + blockIdx.x] = total;
+	const uint32_t used = (uint32_t)((m + KT_BLOCK - 1) / KT_BLOCK);
+	for (uint32_t blk = blockIdx.x; blk < used; blk += gridDim.x)
+	{
+		const uint64_t base = (uint64_t)blk * KT_BLOCK + (uint64_t)threadIdx.x * KT_SPAN_ITEMS;
+		uint32_t u[KT_SPAN_ITEMS + 2];
+		const int valid = (base < m) ? kt_load<KT_SPAN_ITEMS>(tokens + token_stride * img, m, base, u) : 0;
+		KtSpan total;
+		kt_block_excl_scan(kt_thread_span<KT_SPAN_ITEMS>(u, valid), sm, &total);
+		if (threadIdx.x == 0)
+			blk_span[(uint64_t)nblk * img + blk] = total;
+	}
 }
 
 // pass B: one CTA per image resolves every expand-CTA's entry state and output base, and validates the block.
@@ -711,6 +856,8 @@ constexpr uint32_t KT_PIECE = 4096; // ... in pieces of at most this many values
 // pass C: classify every token and write what it expands to. Quantised planes are mostly a few very long
 // runs; whichever CTA meets their tokens would have to write megabytes alone, so those runs are only
 // recorded here (big_list, at most n_values / KT_BIG pieces per image) and written by k_kt_fill.
+// (Collecting a block's values in shared memory and storing them in 16-byte rows was tried: the kernel is bound by
+// its instruction count, not by its 2-byte stores, and the extra barriers and registers cost 10-20 %.)
 __global__ void __launch_bounds__(KT_THREADS)
     k_kt_expand(const uint16_t* __restrict__ tokens, uint64_t token_stride, uint64_t token_cap,
                 const KdImage* __restrict__ info, const uint32_t* __restrict__ blk_state,
@@ -722,81 +869,85 @@ __global__ void __launch_bounds__(KT_THREADS)
 	__shared__ uint32_t queue_len;
 
 	const uint32_t img = blockIdx.y;
-	// the three per-CTA words are fetched together: behind the scan's barriers they would be a second round trip
 	const uint64_t m_all = __ldg(&info[img].tokens);
-	const uint32_t entry = __ldg(blk_state + (uint64_t)nblk * img + blockIdx.x);
-	const uint64_t out0 = __ldg(blk_out + (uint64_t)nblk * img + blockIdx.x);
 	const uint64_t m = min(m_all, token_cap);
-	const uint64_t cta_base = (uint64_t)blockIdx.x * KT_BLOCK;
-	if (cta_base >= m)
-		return;
+	const uint32_t used = (uint32_t)((m + KT_BLOCK - 1) / KT_BLOCK);
 	int16_t* out = out_base + out_stride * img;
-	const uint64_t base = cta_base + (uint64_t)threadIdx.x * KT_ITEMS;
-	uint32_t u[KT_ITEMS + 2];
-	const int valid = (base < m) ? kt_load<KT_ITEMS>(tokens + token_stride * img, m, base, u) : 0;
-	if (threadIdx.x == 0)
-		queue_len = 0;
+	// grid stride over the token blocks that exist (see k_kt_spans)
+	for (uint32_t blk = blockIdx.x; blk < used; blk += gridDim.x)
+	{
+		// the per-block words are fetched together: behind the scan's barriers they would be a second round trip
+		const uint32_t entry = __ldg(blk_state + (uint64_t)nblk * img + blk);
+		const uint64_t out0 = __ldg(blk_out + (uint64_t)nblk * img + blk);
+		const uint64_t cta_base = (uint64_t)blk * KT_BLOCK;
+		const uint64_t base = cta_base + (uint64_t)threadIdx.x * KT_ITEMS;
+		uint32_t u[KT_ITEMS + 2];
+		const int valid = (base < m) ? kt_load<KT_ITEMS>(tokens + token_stride * img, m, base, u) : 0;
+		if (threadIdx.x == 0)
+			queue_len = 0;
 
-	KtSpan total;
-	const KtSpan before = kt_block_excl_scan(kt_thread_span<KT_ITEMS>(u, valid), sm, &total);
-	uint32_t state = (before.map >> (2 * entry)) & 3u;
-	uint64_t pos = out0 + before.out[entry];
+		KtSpan total;
+		const KtSpan before = kt_block_excl_scan(kt_thread_span<KT_ITEMS>(u, valid), sm, &total);
+		uint32_t state = (before.map >> (2 * entry)) & 3u;
+		uint64_t pos = out0 + before.out[entry];
 
 #pragma unroll
-	for (int j = 0; j < KT_ITEMS; j++)
-	{
-		if (j < valid)
+		for (int j = 0; j < KT_ITEMS; j++)
 		{
-			const uint32_t cur = u[j + 2];
-			if (state == ST_R)
+			if (j < valid)
 			{
-				// an RLE count: (cur - 1) more copies of the value before it (kagari.c:342-354)
-				const uint32_t count = cur - 1u;
-				const int16_t v = kt_value(u[j + 1]);
-				if (pos + count <= n_values)
+				const uint32_t cur = u[j + 2];
+				if (state == ST_R)
 				{
-					if (count >= KT_BIG)
+					// an RLE count: (cur - 1) more copies of the value before it (kagari.c:342-354)
+					const uint32_t count = cur - 1u;
+					const int16_t v = kt_value(u[j + 1]);
+					if (pos + count <= n_values)
 					{
-						const uint32_t pieces = (count + KT_PIECE - 1) / KT_PIECE;
-						const uint32_t first = atomicAdd(&big_count[img], pieces);
-						for (uint32_t k = 0; k < pieces; k++)
-							if (first + k < big_cap) // cannot overflow for a stream that expands to n_values
-							{
-								KtRun r;
-								r.pos = pos + (uint64_t)k * KT_PIECE;
-								r.count = min(KT_PIECE, count - k * KT_PIECE);
-								r.value = v;
-								big_list[(uint64_t)big_cap * img + first + k] = r;
-							}
+						if (count >= KT_BIG)
+						{
+							const uint32_t pieces = (count + KT_PIECE - 1) / KT_PIECE;
+							const uint32_t first = atomicAdd(&big_count[img], pieces);
+							for (uint32_t k = 0; k < pieces; k++)
+								if (first + k < big_cap) // cannot overflow for a stream that expands to n_values
+								{
+									KtRun r;
+									r.pos = pos + (uint64_t)k * KT_PIECE;
+									r.count = min(KT_PIECE, count - k * KT_PIECE);
+									r.value = v;
+									big_list[(uint64_t)big_cap * img + first + k] = r;
+								}
+						}
+						else if (count >= KT_LONG)
+						{
+							const uint32_t slot = atomicAdd(&queue_len, 1u);
+							queue[slot].pos = pos;
+							queue[slot].count = count;
+							queue[slot].value = v;
+						}
+						else
+							for (uint32_t k = 0; k < count; k++)
+								out[pos + k] = v;
 					}
-					else if (count >= KT_LONG)
-					{
-						const uint32_t slot = atomicAdd(&queue_len, 1u);
-						queue[slot].pos = pos;
-						queue[slot].count = count;
-						queue[slot].value = v;
-					}
-					else
-						for (uint32_t k = 0; k < count; k++)
-							out[pos + k] = v;
+					pos += count;
+					state = ST_A;
 				}
-				pos += count;
-				state = ST_A;
-			}
-			else
-			{
-				if (pos < n_values)
-					out[pos] = kt_value(cur);
-				pos += 1;
-				state = kt_next(state, cur == u[j + 1], cur == u[j]);
+				else
+				{
+					if (pos < n_values)
+						out[pos] = kt_value(cur);
+					pos += 1;
+					state = kt_next(state, cur == u[j + 1], cur == u[j]);
+				}
 			}
 		}
+		__syncthreads();
+		const uint32_t nq = queue_len;
+		const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+		for (uint32_t i = wid; i < nq; i += KT_THREADS / 32)
+			kt_fill_warp(out, queue[i].pos, queue[i].count, queue[i].value, lane);
+		__syncthreads(); // the queue is reused by the next block
 	}
-	__syncthreads();
-	const uint32_t nq = queue_len;
-	const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-	for (uint32_t i = wid; i < nq; i += KT_THREADS / 32)
-		kt_fill_warp(out, queue[i].pos, queue[i].count, queue[i].value, lane);
 }
 
 // pass D: the big runs, one warp per piece, spread over the whole GPU

@@ -147,12 +147,12 @@ struct StripQuant
 	int shift;
 };
 
+// q == 1 goes through the same expression (m = 2^15 + 1, s = 15: floor(v * m / 2^15) = v for v >= 0, v - 1 for v < 0):
+// a channel's q is uniform per CTA, but a branch on it in the store loop costs two instructions per value.
 template <bool GATE>
 __device__ __forceinline__ int strip_quant(int x_hi, const StripQuant& sq)
 {
 	const int v = x_hi >> 16;
-	if (sq.q <= 1)
-		return GATE ? (((uint32_t)(v + sq.g) > (uint32_t)(2 * sq.g)) ? v : 0) : v;
 	int d = (v * (int)sq.mul) >> sq.shift; // |v| * m <= 2^31, exact in 32 bits
 	d += (int)((uint32_t)v >> 31);
 	if (GATE)
@@ -570,8 +570,11 @@ __global__ void __launch_bounds__(FS_THREADS, 6) k_lift_strip(const StripParams 
 			int16_t* const row_hi = out_hi + (int64_t)i0 * (int64_t)hi_rs;
 			int16_t* const row_lo = out_lo + (int64_t)i0 * (int64_t)lo_rs;
 
-			auto vstep = [&](auto edge_tag) {
+			// EDGE: a boundary rule or the CTA's row range cuts this step. ODD: the channel's subbands start at an odd
+			// int16 offset of the stream (uniform per CTA; as a tag it costs no branch per row).
+			auto vstep = [&](auto edge_tag, auto odd_tag) {
 				constexpr bool EDGE = decltype(edge_tag)::value;
+				constexpr bool ODD = decltype(odd_tag)::value;
 #pragma unroll
 				for (int k = 0; k < FS_STEP; k++)
 				{
@@ -591,15 +594,14 @@ __global__ void __launch_bounds__(FS_THREADS, 6) k_lift_strip(const StripParams 
 							wlo = pair_hi((uint32_t)la, (uint32_t)lb);
 						else
 							wlo = pack2(strip_quant<GATE>(la, sq), strip_quant<GATE>(lb, sq));
-						// odd_offset is uniform per CTA: the branches below do not diverge
-						if (odd_offset)
+						if (ODD)
 						{
 							dh[0] = (int16_t)whi;
 							dh[1] = (int16_t)(whi >> 16);
 						}
 						else
 							*reinterpret_cast<uint32_t*>(dh) = whi;
-						if (odd_offset && right_half)
+						if (ODD && right_half)
 						{
 							dl[0] = (int16_t)wlo;
 							dl[1] = (int16_t)(wlo >> 16);
@@ -609,10 +611,16 @@ __global__ void __launch_bounds__(FS_THREADS, 6) k_lift_strip(const StripParams 
 					}
 				}
 			};
+			auto vstep_o = [&](auto edge_tag) {
+				if (odd_offset)
+					vstep(edge_tag, std::true_type{});
+				else
+					vstep(edge_tag, std::false_type{});
+			};
 			if (interior)
-				vstep(std::false_type{});
+				vstep_o(std::false_type{});
 			else
-				vstep(std::true_type{});
+				vstep_o(std::true_type{});
 		}
 		// No barrier here: the next step's H pass writes the other HB buffer; this one is rewritten two steps on,
 		// behind the next step's barrier. X[buf] is reloaded by the issue() at the top of the next step -- every
