@@ -42,6 +42,8 @@ extern "C" int akod_context_create(int device, akodContext** out)
 	c->next_bytes = 0;
 	c->small_attr_done = false;
 	c->mailbox = nullptr;
+	c->sync_event = nullptr;
+	c->blocking_sync = false;
 	for (int i = 0; i < AKOD_WS_COUNT; i++)
 	{
 		c->ws[i] = nullptr;
@@ -55,6 +57,7 @@ extern "C" int akod_context_create(int device, akodContext** out)
 	}
 	c->sm_count = prop.multiProcessorCount;
 	if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess ||
+	    cudaEventCreateWithFlags(&c->sync_event, cudaEventBlockingSync | cudaEventDisableTiming) != cudaSuccess ||
 	    cudaHostAlloc(&c->mailbox, 1 << 16, cudaHostAllocMapped | cudaHostAllocPortable) != cudaSuccess)
 	{
 		delete c;
@@ -94,6 +97,8 @@ extern "C" void akod_context_destroy(akodContext* c)
 			cudaFree(c->ws[i]);
 	if (c->mailbox)
 		cudaFreeHost(c->mailbox);
+	if (c->sync_event)
+		cudaEventDestroy(c->sync_event);
 	cudaStreamDestroy(c->stream);
 	delete c;
 }
@@ -111,8 +116,19 @@ extern "C" void* akod_stream(akodContext* c)
 extern "C" int akod_sync(akodContext* c)
 {
 	akod_use(c);
+	if (c->blocking_sync)
+	{
+		AKOD_TRY(cudaEventRecord(c->sync_event, c->stream));
+		AKOD_TRY(cudaEventSynchronize(c->sync_event));
+		return AKOD_OK;
+	}
 	AKOD_TRY(cudaStreamSynchronize(c->stream));
 	return AKOD_OK;
+}
+
+extern "C" void akod_set_blocking_sync(akodContext* c, int blocking)
+{
+	c->blocking_sync = blocking != 0;
 }
 
 extern "C" void* akod_alloc(akodContext* c, size_t bytes)

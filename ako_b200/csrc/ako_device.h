@@ -100,6 +100,10 @@ void akod_context_destroy(akodContext*);
 int akod_device_index(akodContext*);
 void* akod_stream(akodContext*);
 int akod_sync(akodContext*);
+/* blocking != 0: akod_sync sleeps on an event (cudaEventBlockingSync) instead of spinning in the driver. For callers
+ * whose waits are milliseconds of PCIe copies and who are many per core (the host-pointer API); a context that
+ * serves device-resident calls keeps the spin, whose wake-up is tens of microseconds faster. */
+void akod_set_blocking_sync(akodContext*, int blocking);
 
 void* akod_alloc(akodContext*, size_t bytes);
 void akod_free(akodContext*, void* d_ptr);

@@ -403,6 +403,31 @@ static int env_device(void)
 	return (e != NULL && *e != '\0') ? atoi(e) : 0;
 }
 
+/* The devices the host-pointer API spreads its work over: $AKO_CUDA_DEVICES = "0,1,..." (one process, several
+ * GPUs: images and chunks of a batch are independent), else the single $AKO_CUDA_DEVICE (default 0). */
+#define MAX_DEVICES 16
+static int env_devices(int list[MAX_DEVICES])
+{
+	const char* e = getenv("AKO_CUDA_DEVICES");
+	int n = 0;
+	if (e != NULL)
+		while (*e != '\0' && n < MAX_DEVICES)
+		{
+			char* end = NULL;
+			const long d = strtol(e, &end, 10);
+			if (end == e)
+				break;
+			if (d >= 0 && d < 1024)
+				list[n++] = (int)d;
+			e = (*end == ',') ? end + 1 : end;
+			if (*end != ',' && *end != '\0')
+				break;
+		}
+	if (n == 0)
+		list[n++] = env_device();
+	return n;
+}
+
 AKO_API akoB200Context* akoB200ContextCreate(int device, enum akoStatus* out_status)
 {
 	akoB200Context* ctx = calloc(1, sizeof(*ctx));
@@ -614,9 +639,8 @@ static pthread_mutex_t g_pool_lock = PTHREAD_MUTEX_INITIALIZER;
 static akoB200Context* g_pool[POOL_MAX];
 static int g_pool_len = 0;
 
-static akoB200Context* pool_acquire(enum akoStatus* st)
+static akoB200Context* pool_acquire_on(int device, enum akoStatus* st)
 {
-	const int device = env_device();
 	akoB200Context* ctx = NULL;
 	pthread_mutex_lock(&g_pool_lock);
 	for (int i = 0; i < g_pool_len; i++)
@@ -628,8 +652,23 @@ static akoB200Context* pool_acquire(enum akoStatus* st)
 		}
 	pthread_mutex_unlock(&g_pool_lock);
 	if (ctx == NULL)
+	{
 		ctx = akoB200ContextCreate(device, st);
+		/* the pool serves host-pointer calls: their waits are PCIe copies, and their callers may outnumber the cores */
+		if (ctx != NULL && getenv("AKO_B200_SPIN_SYNC") == NULL)
+			akod_set_blocking_sync(ctx->dev, 1);
+	}
 	return ctx;
+}
+
+/* single-image calls: concurrent callers are dealt over the listed devices in turn */
+static akoB200Context* pool_acquire(enum akoStatus* st)
+{
+	static unsigned next = 0;
+	int list[MAX_DEVICES];
+	const int n = env_devices(list);
+	const unsigned turn = (n > 1) ? __atomic_fetch_add(&next, 1u, __ATOMIC_RELAXED) : 0u;
+	return pool_acquire_on(list[turn % (unsigned)n], st);
 }
 
 static void pool_release(akoB200Context* ctx)
@@ -2057,7 +2096,7 @@ done:
  * images. A few worker threads (the caller is one of them) take chunks as they come, so the copies of one chunk
  * overlap the kernels of another and the read-backs of a third: PCIe stays busy in both directions. */
 #define HOST_BATCH_CHUNK 8    /* most images per chunk ($AKO_B200_BATCH_CHUNK lowers it) */
-#define HOST_BATCH_WORKERS 8  /* most worker threads ($AKO_B200_BATCH_WORKERS picks 1..8, default 2) */
+#define HOST_BATCH_WORKERS 32 /* most worker threads ($AKO_B200_BATCH_WORKERS; default two per device) */
 
 static size_t env_size(const char* name, size_t fallback, size_t lo, size_t hi)
 {
@@ -2074,6 +2113,8 @@ struct host_batch
 	struct akoCallbacks cb;
 	struct akoSettings s; /* encode: the caller's; decode: what blob 0's head says */
 	size_t channels, w, h, n, chunk, workers;
+	int devices[MAX_DEVICES];
+	int n_devices;
 	const void* const* in;
 	const size_t* in_sizes;
 	void** out;
@@ -2096,10 +2137,10 @@ static void host_batch_fail(struct host_batch* b, size_t image, enum akoStatus s
 	pthread_mutex_unlock(&b->lock);
 }
 
-static void host_batch_encode_chunk(struct host_batch* b, size_t first, size_t count)
+static void host_batch_encode_chunk(struct host_batch* b, size_t first, size_t count, int device)
 {
 	enum akoStatus st = AKO_OK;
-	akoB200Context* ctx = pool_acquire(&st);
+	akoB200Context* ctx = pool_acquire_on(device, &st);
 	if (ctx == NULL)
 	{
 		host_batch_fail(b, first, st);
@@ -2155,7 +2196,7 @@ static void host_batch_encode_chunk(struct host_batch* b, size_t first, size_t c
 	pool_release(ctx);
 }
 
-static void host_batch_decode_chunk(struct host_batch* b, size_t first, size_t count)
+static void host_batch_decode_chunk(struct host_batch* b, size_t first, size_t count, int device)
 {
 	enum akoStatus st = AKO_OK;
 	const size_t tiles = tiles_count(b->w, b->h, b->s.tiles_dimension);
@@ -2197,7 +2238,7 @@ static void host_batch_decode_chunk(struct host_batch* b, size_t first, size_t c
 		}
 		largest = (size > largest) ? size : largest;
 	}
-	if (usable == 0 || (ctx = pool_acquire(&st)) == NULL)
+	if (usable == 0 || (ctx = pool_acquire_on(device, &st)) == NULL)
 	{
 		if (usable != 0)
 			host_batch_fail(b, first, st);
@@ -2253,9 +2294,16 @@ static void host_batch_decode_chunk(struct host_batch* b, size_t first, size_t c
 	free(blk);
 }
 
+struct host_batch_arg
+{
+	struct host_batch* b;
+	int device;
+};
+
 static void* host_batch_worker(void* raw)
 {
-	struct host_batch* b = raw;
+	struct host_batch_arg* a = raw;
+	struct host_batch* b = a->b;
 	for (;;)
 	{
 		pthread_mutex_lock(&b->lock);
@@ -2266,9 +2314,9 @@ static void* host_batch_worker(void* raw)
 			break;
 		const size_t count = (b->n - first < b->chunk) ? b->n - first : b->chunk;
 		if (b->decode)
-			host_batch_decode_chunk(b, first, count);
+			host_batch_decode_chunk(b, first, count, a->device);
 		else
-			host_batch_encode_chunk(b, first, count);
+			host_batch_encode_chunk(b, first, count, a->device);
 	}
 	return NULL;
 }
@@ -2278,16 +2326,23 @@ static void* host_batch_worker(void* raw)
 static size_t host_batch_run(struct host_batch* b, enum akoStatus* out_status)
 {
 	pthread_t helpers[HOST_BATCH_WORKERS];
+	struct host_batch_arg args[HOST_BATCH_WORKERS];
 	size_t started = 0;
 	const size_t chunks = (b->n + b->chunk - 1) / b->chunk;
 	pthread_mutex_init(&b->lock, NULL);
 	b->next_chunk = 0;
 	b->first_failed = b->n;
 	b->st = AKO_OK;
+	/* worker k works on device k mod n_devices (the caller is worker 0) */
+	for (size_t k = 0; k < b->workers; k++)
+	{
+		args[k].b = b;
+		args[k].device = b->devices[k % (size_t)b->n_devices];
+	}
 	for (size_t k = 1; k < b->workers && k < chunks; k++)
-		if (pthread_create(&helpers[started], NULL, host_batch_worker, b) == 0)
+		if (pthread_create(&helpers[started], NULL, host_batch_worker, &args[k]) == 0)
 			started++;
-	host_batch_worker(b);
+	host_batch_worker(&args[0]);
 	for (size_t k = 0; k < started; k++)
 		pthread_join(helpers[k], NULL);
 	pthread_mutex_destroy(&b->lock);
@@ -2298,9 +2353,10 @@ static size_t host_batch_run(struct host_batch* b, enum akoStatus* out_status)
 
 static void host_batch_geometry(struct host_batch* b)
 {
-	/* two chunks per worker when the batch allows it (one in its copy phase while the other computes), at most
-	 * HOST_BATCH_CHUNK images each */
-	b->workers = env_size("AKO_B200_BATCH_WORKERS", 2, 1, HOST_BATCH_WORKERS);
+	/* two workers per device (one chunk in its copy phase while the other computes), two chunks per worker when
+	 * the batch allows it, at most HOST_BATCH_CHUNK images each */
+	b->n_devices = env_devices(b->devices);
+	b->workers = env_size("AKO_B200_BATCH_WORKERS", 2 * (size_t)b->n_devices, 1, HOST_BATCH_WORKERS);
 	const size_t most = env_size("AKO_B200_BATCH_CHUNK", HOST_BATCH_CHUNK, 1, HOST_BATCH_CHUNK);
 	size_t chunk = (b->n + 2 * b->workers - 1) / (2 * b->workers);
 	chunk = (chunk > most) ? most : chunk;

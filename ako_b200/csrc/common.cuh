@@ -32,6 +32,8 @@ struct akodContext
 	void* ws[AKOD_WS_COUNT];
 	size_t ws_size[AKOD_WS_COUNT];
 	void* mailbox; // pinned host, 64 KiB
+	cudaEvent_t sync_event; // blocking-sync event (cudaEventBlockingSync), see akod_sync
+	bool blocking_sync;     // wait for the stream by sleeping on sync_event instead of spinning in the driver
 	// accounting
 	bool profiling;
 	uint64_t launch_count;

@@ -858,7 +858,7 @@ constexpr uint32_t KT_PIECE = 4096; // ... in pieces of at most this many values
 // recorded here (big_list, at most n_values / KT_BIG pieces per image) and written by k_kt_fill.
 // (Collecting a block's values in shared memory and storing them in 16-byte rows was tried: the kernel is bound by
 // its instruction count, not by its 2-byte stores, and the extra barriers and registers cost 10-20 %.)
-__global__ void __launch_bounds__(KT_THREADS)
+__global__ void __launch_bounds__(KT_THREADS, 5)
     k_kt_expand(const uint16_t* __restrict__ tokens, uint64_t token_stride, uint64_t token_cap,
                 const KdImage* __restrict__ info, const uint32_t* __restrict__ blk_state,
                 const uint64_t* __restrict__ blk_out, uint32_t nblk, int16_t* __restrict__ out_base, uint64_t out_stride,

@@ -480,6 +480,25 @@ def run_ours(args, rank, world):
                     "api": f"akoEncodeExt + akoDecodeExt per image, NULL callbacks, pageable buffers, {host_threads} caller threads"}
     except Exception as e:  # noqa: BLE001
         pageable = {"error": repr(e)}
+    # one PROCESS, all GPUs of the box through the C API ($AKO_CUDA_DEVICES): rank 0 alone, the other ranks wait
+    one_process = None
+    if world > 1:
+        barrier()
+        if rank == 0:
+            try:
+                os.environ["AKO_CUDA_DEVICES"] = ",".join(str(d) for d in range(world))
+                run_batch(2)
+                t0 = time.perf_counter()
+                run_batch(e2e_steps * world)
+                leg_s = time.perf_counter() - t0
+                one_process = {"value": round(px * B * e2e_steps * world / leg_s / 1e6, 1), "unit": "MPix/s",
+                               "api": f"akoB200EncodeBatch + akoB200DecodeBatch from ONE process with AKO_CUDA_DEVICES="
+                                      f"{os.environ['AKO_CUDA_DEVICES']} (chunks dealt over the GPUs by the library's workers)"}
+            except Exception as e:  # noqa: BLE001
+                one_process = {"error": repr(e)}
+            finally:
+                os.environ.pop("AKO_CUDA_DEVICES", None)
+        barrier()
     pool_exec.shutdown()
     e2e_api = {"batch": "akoB200EncodeBatch + akoB200DecodeBatch (host pointer arrays, pinned buffers via "
                         "akoB200PinnedCallbacks; encode of step i+1 overlaps decode of step i)",
@@ -630,7 +649,7 @@ def run_ours(args, rank, world):
             "e2e": {"value": round(e2e_value, 1), "unit": "MPix/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "api": e2e_api[best_leg], "steps": e2e_steps, "repetitions": e2e_all[best_leg],
                     "repetition_rule": f"best of {E2E_REPS} repetitions of the same {e2e_steps} steps",
-                    "copy_ceiling": ceiling, "pageable_drop_in": pageable,
+                    "copy_ceiling": ceiling, "pageable_drop_in": pageable, "one_process_all_gpus": one_process,
                     "other_api": {k: {"value": round(px * B * world * e2e_steps / v[0] / 1e6, 1), "api": e2e_api[k],
                                       "repetitions": e2e_all[k]}
                                   for k, v in e2e_legs.items() if k != best_leg}},

@@ -451,6 +451,32 @@ def test_host_batch_api_failures(orc):
         assert done == 12
 
 
+def test_one_process_spreads_a_batch_over_the_listed_devices(orc):
+    """$AKO_CUDA_DEVICES = "0,1": akoB200EncodeBatch / akoB200DecodeBatch deal their chunks over both GPUs, and
+    concurrent akoEncodeExt callers are dealt over them in turn; every result is what one GPU gives. Needs two GPUs."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    old = os.environ.get("AKO_CUDA_DEVICES")
+    os.environ["AKO_CUDA_DEVICES"] = "0,1"
+    try:
+        imgs = [ol.synth(orc, 200, 136, 90 + i) for i in range(37)]
+        want = [ol.orc_encode(orc, im, wavelet=1, q=16, g=4)[0] for im in imgs]
+        s = S(wavelet=1, quantization=16, gate=4)
+        blobs, st, done = ako_b200.encode_batch(imgs, s)
+        assert (st, done) == (0, 37) and blobs == want
+        px, st, done = ako_b200.decode_batch(blobs)
+        assert (st, done) == (0, 37)
+        assert all(np.array_equal(px[i], ol.orc_decode(orc, want[i])[0]) for i in range(37))
+        for i in range(6):  # single calls alternate between the devices
+            assert ako_b200.encode(imgs[i], s)[0] == want[i]
+    finally:
+        if old is None:
+            os.environ.pop("AKO_CUDA_DEVICES", None)
+        else:
+            os.environ["AKO_CUDA_DEVICES"] = old
+
+
 def test_pooled_contexts_follow_the_device_not_the_thread(orc):
     """CUDA's current device is per thread; pooled contexts are not. With $AKO_CUDA_DEVICE naming a device other than
     0, calls from fresh threads (whose current device is 0) and the library's own worker threads must still run on the
