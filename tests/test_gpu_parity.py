@@ -122,6 +122,54 @@ def test_kagari_stage(orc, ctx):
         assert used == wn and np.array_equal(back, v), n
 
 
+def test_kagari_minus_32768_encoder_bits(orc, ctx):
+    """The reference's encoder emits a single zero bit for -32768 (kagari.c:214-217 with :38-45; undecodable, SURVEY
+    7.3 "replicate encoder bits anyway"): the CUDA encoder must produce the same bytes; nothing is decoded back."""
+    rs = np.random.RandomState(32768)
+    vectors = [np.array([-32768], np.int16), np.array([-32768, -32768], np.int16), np.full(9, -32768, np.int16),
+               np.array([5, -32768, 5, 5, 5, -32768, -32768, -32768, -32768, 7], np.int16),
+               np.concatenate([np.array([1], np.int16), np.full(70000, -32768, np.int16), np.array([2], np.int16)])]
+    for n in (100, 5000, 9000):
+        v = rs.randint(-40, 41, size=n).astype(np.int16)
+        v[rs.rand(n) < 0.1] = -32768
+        vectors.append(v)
+    for v in vectors:
+        n = len(v)
+        cap = n * 4 + 64
+        want = np.zeros(cap, np.uint8)
+        wn = orc.orc_kagari_encode(n, P(v, i16p), cap, P(want, u8p))
+        got = ctx.kagari_encode(v, cap)
+        assert got is not None and len(got) == wn and np.array_equal(want[:wn], got), n
+
+
+def test_strip_kernels_full_amplitude(orc, ctx):
+    """+-32767 planes through several strips and row splits (2064 x 1100), all three wavelets: the hi-domain
+    arithmetic of the strip kernels (|n| < 2^26, lift_strip.cuh hi_step) at the largest tap sums, lossless and
+    quantised, forward and inverse."""
+    rs = np.random.RandomState(77)
+    w, h = 2064, 1100
+    for wavelet in (W_DD137, W_CDF53, W_HAAR):
+        planes = rs.randint(-32767, 32768, size=(1, h, w)).astype(np.int16)
+        planes[0, ::97, ::53] = 32767
+        planes[0, 5::89, 7::61] = -32767
+        for q, g in ((0, 0), (9, 13)):
+            n = orc.orc_tile_data_size(w, h) // 2
+            want = np.zeros(n, np.int16)
+            tmp = planes.copy()
+            os_ = OS(wavelet=wavelet, q=q, g=g)
+            orc.orc_lift(C.byref(os_), 1, w, h, P(tmp, i16p), P(want, i16p))
+            s = S(wavelet=wavelet, q=q, g=g)
+            got = ctx.lift(planes, s)
+            assert np.array_equal(want, got), (wavelet, q, int(np.argmax(want != got)))
+            back_want = np.zeros((1, h, w), np.int16)
+            st = want.copy()
+            orc.orc_unlift(C.byref(os_), 1, w, h, P(st, i16p), P(back_want, i16p))
+            back = ctx.unlift(want, s, 1, w, h)
+            assert np.array_equal(back_want, back), (wavelet, q)
+            if q == 0:
+                assert np.array_equal(back, planes)
+
+
 def test_kagari_capacity_rule(orc, ctx):
     rs = np.random.RandomState(11)
     for n in (7, 64, 300, 3000):

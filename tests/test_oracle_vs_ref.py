@@ -200,6 +200,29 @@ def test_kagari_vs_reference(orc, ref):
         assert used2 == wn and np.array_equal(back2[:n], v)
 
 
+def test_kagari_minus_32768_encoder_bits(orc, ref):
+    """-32768 zig-zags to 0xFFFF and +1 wraps the uint16 parameter of akoEliasEncodeStep to 0 (kagari.c:214-217 with
+    :38-45): the reference emits ONE zero bit for it, which no decoder can read back. SURVEY 7.3: replicate the
+    encoder's bits anyway (a 16-bit image cannot produce the value, a raw stage call can)."""
+    rs = np.random.RandomState(32768)
+    vectors = [np.array([-32768], np.int16), np.array([-32768, -32768], np.int16), np.full(9, -32768, np.int16),
+               np.array([5, -32768, 5, 5, 5, -32768, -32768, -32768, -32768, 7], np.int16),
+               np.concatenate([np.array([1], np.int16), np.full(70000, -32768, np.int16), np.array([2], np.int16)])]
+    for n in (100, 5000):
+        v = rs.randint(-40, 41, size=n).astype(np.int16)
+        v[rs.rand(n) < 0.1] = -32768
+        vectors.append(v)
+    for v in vectors:
+        n = len(v)
+        cap = n * 4 + 64
+        want = np.zeros(cap, np.uint8)
+        wn = ref.akoKagariEncode(n * 2, cap, v.ctypes.data, want.ctypes.data)
+        got = np.zeros(cap, np.uint8)
+        gn = orc.orc_kagari_encode(n, P(v, i16p), cap, P(got, u8p))
+        assert wn == gn and wn > 0 and np.array_equal(want[:wn], got[:gn]), n
+        assert (orc.orc_kagari_bits(n, P(v, i16p)) + 7) // 8 == wn
+
+
 def test_kagari_capacity_rule(orc, ref):
     """Success iff ceil(bits/8) < capacity (derived from kagari.c:65-68, :93-107)."""
     rs = np.random.RandomState(11)

@@ -77,3 +77,41 @@ def test_tools_benchmark_output(tools, tmp_path, orc):
     lines = run(os.path.join(tools, "akodec"), "-i", ako, "-b").splitlines()
     assert [l.split(":")[0] for l in lines[1:5]] == [" - Compression", " - Wavelet transformation", " - Format", " - Total"]
     assert run(os.path.join(tools, "akoenc"), "-i", png, "-quiet") == ""
+
+
+LIB = os.path.join(ROOT, "ako_b200", "libako_b200.so")
+
+
+@pytest.mark.parametrize("flags", [[], ["-q", "0", "-w", "CDF53"], ["-q", "30", "-g", "10", "-w", "HAAR"], ["-dev-r", "12"],
+                                   ["-wr", "MIRROR", "-c", "SUBTRACT-G", "-q", "8"]], ids=lambda f: "".join(f) or "defaults")
+def test_reference_tools_preloaded_with_libako_b200(tools, tmp_path, orc, flags):
+    """The drop-in claim of INTEGRATION.md section 1 on the reference's OWN callers: its akoenc / akodec binaries
+    (tools/akoenc.cpp:118-213, tools/akodec.cpp:139), unmodified, with LD_PRELOAD=libako_b200.so so that every
+    library/ako.h symbol resolves to the CUDA implementation: same .ako bytes, same pixels, same summary lines as
+    the same binaries on their own library; -b shows the stages timed through the events callback."""
+    img = ol.synth(orc, 520, 384, 31)
+    png = str(tmp_path / "in.png")
+    Image.fromarray(img, "RGBA").save(png)
+    env = dict(os.environ, LD_PRELOAD=LIB)
+
+    def run_env(env_, *cmd):
+        r = subprocess.run(list(cmd), capture_output=True, text=True, env=env_)
+        assert r.returncode == 0, (cmd, r.stdout, r.stderr)
+        return r.stdout
+
+    a_ref, a_pre = str(tmp_path / "ref.ako"), str(tmp_path / "pre.ako")
+    out_ref = run_env(os.environ, os.path.join(REF, "akoenc"), "-i", png, "-o", a_ref, "-ch", *flags)
+    out_pre = run_env(env, os.path.join(REF, "akoenc"), "-i", png, "-o", a_pre, "-ch", *flags)
+    assert open(a_ref, "rb").read() == open(a_pre, "rb").read()
+    assert out_ref.strip().splitlines()[-1] == out_pre.strip().splitlines()[-1]
+    p_ref, p_pre = str(tmp_path / "ref.png"), str(tmp_path / "pre.png")
+    out_ref = run_env(os.environ, os.path.join(REF, "akodec"), "-i", a_ref, "-o", p_ref, "-ch")
+    out_pre = run_env(env, os.path.join(REF, "akodec"), "-i", a_ref, "-o", p_pre, "-ch")
+    assert out_ref.strip().splitlines()[-1] == out_pre.strip().splitlines()[-1]
+    assert np.array_equal(np.asarray(Image.open(p_ref)), np.asarray(Image.open(p_pre)))
+    # the preloaded library really is the one at work: its events drive the tool's stopwatches, and the loader maps it
+    bench = run_env(env, os.path.join(REF, "akoenc"), "-i", png, "-o", a_pre, "-b", *flags)
+    assert "Benchmark" in bench
+    maps = subprocess.run(["bash", "-c", f"LD_PRELOAD={LIB} LD_DEBUG=libs {os.path.join(REF, 'akodec')} -i {a_ref} -o {p_pre} 2>&1 | grep -c libako_b200"],
+                          capture_output=True, text=True)
+    assert int(maps.stdout.strip() or 0) > 0
