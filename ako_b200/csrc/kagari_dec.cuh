@@ -342,18 +342,31 @@ __global__ void __launch_bounds__(1024)
     k_kd_scan_counts(const uint32_t* __restrict__ blk_count, uint64_t* __restrict__ blk_base, uint32_t nblk,
                      KdImage* __restrict__ info)
 {
+	constexpr int ITEMS = 16;
 	__shared__ uint32_t sm[33];
 	blk_count += (uint64_t)nblk * blockIdx.x;
 	blk_base += (uint64_t)nblk * blockIdx.x;
 	uint64_t carry = 0;
-	for (uint32_t b0 = 0; b0 < nblk; b0 += 1024)
+	for (uint32_t b0 = 0; b0 < nblk; b0 += 1024 * ITEMS)
 	{
-		const uint32_t b = b0 + threadIdx.x;
-		const uint32_t v = (b < nblk) ? blk_count[b] : 0; // <= 65536 each
+		const uint32_t first = b0 + threadIdx.x * ITEMS;
+		uint32_t v[ITEMS];
+		uint32_t mine = 0; // <= 32768 each
+#pragma unroll
+		for (int i = 0; i < ITEMS; i++)
+		{
+			v[i] = (first + i < nblk) ? blk_count[first + i] : 0;
+			mine += v[i];
+		}
 		uint32_t tot;
-		const uint32_t ex = block_excl_sum(v, sm, &tot);
-		if (b < nblk)
-			blk_base[b] = carry + ex;
+		uint64_t at = carry + block_excl_sum(mine, sm, &tot);
+#pragma unroll
+		for (int i = 0; i < ITEMS; i++)
+		{
+			if (first + i < nblk)
+				blk_base[first + i] = at;
+			at += v[i];
+		}
 		carry += tot;
 	}
 	if (threadIdx.x == 0)
@@ -737,9 +750,18 @@ __global__ void __launch_bounds__(KR_THREADS)
 	const uint32_t b0 = min(t * chunk, used), b1 = min(b0 + chunk, used);
 
 	// a thread's chunk expands to fewer than 2^32 values for any stream that can be valid (n_values < 2^32)
+	// (the loads of eight spans are in flight together: one at a time this loop was a chain of L2 round trips)
 	KtSpan mine = kt_identity();
-	for (uint32_t b = b0; b < b1; b++)
-		mine = kt_compose(mine, blk_span[b]);
+	for (uint32_t b = b0; b < b1; b += 8)
+	{
+		KtSpan sp[8];
+#pragma unroll
+		for (int i = 0; i < 8; i++)
+			sp[i] = (b + i < b1) ? blk_span[b + i] : kt_identity();
+#pragma unroll
+		for (int i = 0; i < 8; i++)
+			mine = kt_compose(mine, sp[i]);
+	}
 	s_map[t] = mine.map;
 #pragma unroll
 	for (int k = 0; k < 4; k++)
@@ -794,13 +816,21 @@ __global__ void __launch_bounds__(KR_THREADS)
 
 	uint32_t state = s_state[t];
 	uint64_t base = s_base[t];
-	for (uint32_t b = b0; b < b1; b++)
+	for (uint32_t b = b0; b < b1; b += 8)
 	{
-		blk_state[b] = state;
-		blk_out[b] = base;
-		const KtSpan sp = blk_span[b];
-		base += sp.out[state];
-		state = (sp.map >> (2 * state)) & 3u;
+		KtSpan sp[8];
+#pragma unroll
+		for (int i = 0; i < 8; i++)
+			sp[i] = (b + i < b1) ? blk_span[b + i] : kt_identity();
+#pragma unroll
+		for (int i = 0; i < 8; i++)
+			if (b + i < b1)
+			{
+				blk_state[b + i] = state;
+				blk_out[b + i] = base;
+				base += state == 0 ? sp[i].out[0] : state == 1 ? sp[i].out[1] : state == 2 ? sp[i].out[2] : sp[i].out[3];
+				state = (sp[i].map >> (2 * state)) & 3u;
+			}
 	}
 	if (t == 0)
 	{

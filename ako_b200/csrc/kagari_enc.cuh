@@ -262,6 +262,11 @@ __global__ void __launch_bounds__(KG_THREADS)
 	}
 }
 
+// The two scans over the blocks of an image run in one CTA per image; a thread takes KG_SCAN_ITEMS consecutive
+// blocks per round, so that a 16384 x 16384 image (half a million blocks) is 32 rounds of one block-wide scan each
+// instead of 512.
+constexpr int KG_SCAN_ITEMS = 16;
+
 // exclusive max-scan over the blocks of one image (one CTA per image); identity 0
 __global__ void __launch_bounds__(1024)
     k_kg_scan_max(const uint32_t* __restrict__ blk, uint32_t* __restrict__ blk_carry, uint32_t nblocks)
@@ -270,14 +275,26 @@ __global__ void __launch_bounds__(1024)
 	blk += (uint64_t)nblocks * blockIdx.x;
 	blk_carry += (uint64_t)nblocks * blockIdx.x;
 	uint32_t carry = 0;
-	for (uint32_t b0 = 0; b0 < nblocks; b0 += 1024)
+	for (uint32_t b0 = 0; b0 < nblocks; b0 += 1024 * KG_SCAN_ITEMS)
 	{
-		const uint32_t b = b0 + threadIdx.x;
-		const uint32_t v = (b < nblocks) ? blk[b] : 0;
+		const uint32_t first = b0 + threadIdx.x * KG_SCAN_ITEMS;
+		uint32_t v[KG_SCAN_ITEMS];
+		uint32_t last = 0; // last nonzero of this thread's blocks (run starts are increasing: "last nonzero" = max)
+#pragma unroll
+		for (int i = 0; i < KG_SCAN_ITEMS; i++)
+		{
+			v[i] = (first + i < nblocks) ? blk[first + i] : 0;
+			last = v[i] ? v[i] : last;
+		}
 		uint32_t total;
-		const uint32_t ex = block_excl_last_start(v, sm, &total);
-		if (b < nblocks)
-			blk_carry[b] = max(carry, ex);
+		uint32_t run = max(carry, block_excl_last_start(last, sm, &total));
+#pragma unroll
+		for (int i = 0; i < KG_SCAN_ITEMS; i++)
+		{
+			if (first + i < nblocks)
+				blk_carry[first + i] = run;
+			run = v[i] ? v[i] : run;
+		}
 		carry = max(carry, total);
 	}
 }
@@ -291,14 +308,26 @@ __global__ void __launch_bounds__(1024)
 	blk_bits += (uint64_t)nblocks * blockIdx.x;
 	blk_off += (uint64_t)nblocks * blockIdx.x;
 	uint64_t carry = 0;
-	for (uint32_t b0 = 0; b0 < nblocks; b0 += 1024)
+	for (uint32_t b0 = 0; b0 < nblocks; b0 += 1024 * KG_SCAN_ITEMS)
 	{
-		const uint32_t b = b0 + threadIdx.x;
-		const uint32_t v = (b < nblocks) ? blk_bits[b] : 0; // <= 65536 each, 1024 of them fit in 32 bits
+		const uint32_t first = b0 + threadIdx.x * KG_SCAN_ITEMS;
+		uint32_t v[KG_SCAN_ITEMS];
+		uint32_t mine = 0; // <= 65536 each, 16384 of them fit in 32 bits
+#pragma unroll
+		for (int i = 0; i < KG_SCAN_ITEMS; i++)
+		{
+			v[i] = (first + i < nblocks) ? blk_bits[first + i] : 0;
+			mine += v[i];
+		}
 		uint32_t tot;
-		const uint32_t ex = block_excl_sum(v, sm, &tot);
-		if (b < nblocks)
-			blk_off[b] = carry + ex;
+		uint64_t at = carry + block_excl_sum(mine, sm, &tot);
+#pragma unroll
+		for (int i = 0; i < KG_SCAN_ITEMS; i++)
+		{
+			if (first + i < nblocks)
+				blk_off[first + i] = at;
+			at += v[i];
+		}
 		carry += tot;
 	}
 	if (threadIdx.x == 0)
