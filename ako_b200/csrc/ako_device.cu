@@ -1002,11 +1002,6 @@ extern "C" int akod_kagari_decode(akodContext* c, uint64_t n_values, const uint8
 	// geometry shared by all images of the batch (sized for the largest block)
 	const uint64_t max_bits = max_in_size * 8;
 	const uint32_t nblk1 = (uint32_t)(max_bits / KD_CTA_BITS) + 1;
-	uint64_t token_cap = n_values + n_values / 2 + 64; // a well-formed block never has more codewords (2 values per count)
-	if (token_cap > max_bits)
-		token_cap = max_bits;
-	token_cap = (token_cap + 15) & ~(uint64_t)15;
-	const uint32_t nblk2 = (uint32_t)((token_cap + KT_BLOCK - 1) / KT_BLOCK);
 
 	// workspace carve-up
 	size_t bytes = 0;
@@ -1019,15 +1014,14 @@ extern "C" int akod_kagari_decode(akodContext* c, uint64_t n_values, const uint8
 	const size_t o_ends_a = carve(sizeof(uint64_t) * nblk1 * n_images);
 	const size_t o_ends_b = carve(sizeof(uint64_t) * nblk1 * n_images);
 	const size_t o_sub = carve(sizeof(KdSubState) * (size_t)nblk1 * KD_THREADS * n_images);
-	const size_t o_cnt = carve(sizeof(uint32_t) * nblk1 * n_images);
-	const size_t o_base = carve(sizeof(uint64_t) * nblk1 * n_images);
-	const size_t o_tok = carve(sizeof(uint16_t) * token_cap * n_images);
-	const size_t o_span = carve(sizeof(KtSpan) * nblk2 * n_images);
-	const size_t o_state = carve(sizeof(uint32_t) * nblk2 * n_images);
-	const size_t o_out = carve(sizeof(uint64_t) * nblk2 * n_images);
+	// zeroed before every decode: look-back records, inclusive prefixes, CTA tickets, big-run counters
+	const size_t o_look = carve(sizeof(KfLook) * (size_t)nblk1 * n_images);
+	const size_t o_prefix = carve(sizeof(uint64_t) * (size_t)nblk1 * n_images);
+	const size_t o_ticket = carve(sizeof(uint32_t) * n_images);
+	const size_t o_bigc = carve(sizeof(uint32_t) * n_images);
+	const size_t o_zero_end = bytes;
 	const uint32_t big_cap = (uint32_t)(n_values / KT_BIG) + 16;
 	const size_t o_big = carve(sizeof(KtRun) * (size_t)big_cap * n_images);
-	const size_t o_bigc = carve(sizeof(uint32_t) * n_images);
 	void* ws;
 	int rc = akod_workspace(c, AKOD_WS_KAGARI, bytes, &ws);
 	if (rc != AKOD_OK)
@@ -1037,46 +1031,33 @@ extern "C" int akod_kagari_decode(akodContext* c, uint64_t n_values, const uint8
 	uint64_t* ends_a = (uint64_t*)(w8 + o_ends_a);
 	uint64_t* ends_b = (uint64_t*)(w8 + o_ends_b);
 	KdSubState* sub = (KdSubState*)(w8 + o_sub);
-	uint32_t* blk_count = (uint32_t*)(w8 + o_cnt);
-	uint64_t* blk_base = (uint64_t*)(w8 + o_base);
-	uint16_t* tokens = (uint16_t*)(w8 + o_tok);
-	KtSpan* blk_span = (KtSpan*)(w8 + o_span);
-	uint32_t* blk_state = (uint32_t*)(w8 + o_state);
-	uint64_t* blk_out = (uint64_t*)(w8 + o_out);
+	KfLook* look = (KfLook*)(w8 + o_look);
+	uint64_t* prefix = (uint64_t*)(w8 + o_prefix);
+	uint32_t* ticket = (uint32_t*)(w8 + o_ticket);
 	KtRun* big_list = (KtRun*)(w8 + o_big);
 	uint32_t* big_count = (uint32_t*)(w8 + o_bigc);
 
-	AKOD_TRY(cudaMemsetAsync(big_count, 0, sizeof(uint32_t) * n_images, c->stream));
+	AKOD_TRY(cudaMemsetAsync(w8 + o_look, 0, o_zero_end - o_look, c->stream));
 	AKOD_LAUNCH(c, "kagari_dec_init", k_kd_init, (n_images + 63) / 64, 64, 0, info, n_images);
 	const dim3 grid1(nblk1, n_images);
 	for (int run = 0; run < KD_MAX_RUNS; run++)
 	{
 		uint64_t* prev = (run & 1) ? ends_a : ends_b;
 		uint64_t* next = (run & 1) ? ends_b : ends_a;
-		AKOD_LAUNCH(c, "kagari_dec_sync", k_kd_sync, grid1, KD_THREADS, 0, d_in, d_off, d_size, nblk1, run, prev, next, sub,
-		            blk_count, info);
+		AKOD_LAUNCH(c, "kagari_dec_sync", k_kd_sync, grid1, KD_THREADS, 0, d_in, d_off, d_size, nblk1, run, prev, next, sub, info);
 	}
-	AKOD_LAUNCH(c, "kagari_dec_scan", k_kd_scan_counts, n_images, 1024, 0, blk_count, blk_base, nblk1, info);
-	AKOD_LAUNCH(c, "kagari_dec_extract", k_kd_extract, grid1, KD_THREADS, 0, d_in, d_off, d_size, nblk1, sub, blk_base, tokens,
-	            token_cap, token_cap);
-	// grid-stride over the token blocks that exist: enough CTAs to fill the GPU a few times over, not one per possible block
-	uint32_t gx2 = (uint32_t)c->sm_count * 16 / n_images;
-	gx2 = gx2 < 8 ? 8 : gx2;
-	gx2 = gx2 > nblk2 ? nblk2 : gx2;
-	const dim3 grid2(gx2, n_images);
-	AKOD_LAUNCH(c, "kagari_dec_spans", k_kt_spans, grid2, KT_SPAN_THREADS, 0, tokens, token_cap, token_cap, info, blk_span, nblk2);
-	AKOD_LAUNCH(c, "kagari_dec_resolve", k_kt_resolve, n_images, KR_THREADS, 0, blk_span, nblk2, blk_state, blk_out, info, n_values,
-	            token_cap, d_result);
+	static_assert((KD_MAX_RUNS & 1) == 0, "the last run writes ends_b");
 	AKOD_BYTES(c, 2 * n_values * n_images); // the decoded values, written by this kernel and k_kt_fill together
-	AKOD_LAUNCH(c, "kagari_dec_expand", k_kt_expand, grid2, KT_THREADS, 0, tokens, token_cap, token_cap, info, blk_state,
-	            blk_out, nblk2, d_out, out_stride, n_values, big_list, big_count, big_cap);
+	AKOD_LAUNCH(c, "kagari_dec_expand", k_kd_decode, grid1, KD_THREADS, 0, d_in, d_off, d_size, nblk1, sub, ends_b, look, prefix,
+	            ticket, info, d_out, out_stride, n_values, big_list, big_count, big_cap);
 	{
 		// enough warps to saturate HBM with stores, whatever the number of big runs turns out to be
 		const uint64_t pieces_max = (uint64_t)big_cap;
 		const uint32_t want = (uint32_t)c->sm_count * 8;
 		const uint32_t gx = (uint32_t)((pieces_max + 7) / 8 < want ? (pieces_max + 7) / 8 : want);
 		const dim3 gridf(gx ? gx : 1, n_images);
-		AKOD_LAUNCH(c, "kagari_dec_fill", k_kt_fill, gridf, 256, 0, big_list, big_count, big_cap, d_out, out_stride);
+		AKOD_LAUNCH(c, "kagari_dec_fill", k_kt_fill, gridf, 256, 0, big_list, big_count, big_cap, d_out, out_stride, info,
+		            n_values, d_result);
 	}
 	// Streams that did not self-synchronise within KD_MAX_RUNS (adversarial input) are decoded by one thread
 	// on the device; a no-op for every other image.

@@ -234,16 +234,19 @@ struct KdNoEmit
 };
 
 // One synchronisation run. run == 0: every CTA assumes it starts on a boundary.
-// run > 0: CTA b starts where CTA b-1 ended in the previous run (ends_prev).
+// run > 0: CTA b starts where CTA b-1 ended in the previous run (ends_prev). Only thread 0's start can differ from
+// the previous run then, and Elias gamma codes resynchronise within a few codewords: thread 0 alone re-walks its
+// 128 bits (six words fetched by lanes 0-5) and, when it lands on the boundary thread 1 started from, nothing else
+// in the CTA changes -- the whole CTA restages and re-walks only when it does not (fast path: a 458 MB lossless
+// stream spent as long in run 1 as in run 0 before).
 __global__ void __launch_bounds__(KD_THREADS)
     k_kd_sync(const uint8_t* __restrict__ in_base, const uint64_t* __restrict__ in_off,
               const uint64_t* __restrict__ in_size, uint32_t nblk, int run, const uint64_t* __restrict__ ends_prev,
-              uint64_t* __restrict__ ends_new, KdSubState* __restrict__ sub, uint32_t* __restrict__ blk_count,
-              KdImage* __restrict__ info)
+              uint64_t* __restrict__ ends_new, KdSubState* __restrict__ sub, KdImage* __restrict__ info)
 {
 	__shared__ uint32_t sm[KD_CTA_WORDS + 2];
 	__shared__ uint32_t sm_end[KD_THREADS];
-	__shared__ uint32_t sm_sum[33];
+	__shared__ uint32_t sm_fast;
 
 	const uint32_t img = blockIdx.y, b = blockIdx.x, t = threadIdx.x;
 	const uint64_t size = __ldg(in_size + img);
@@ -253,7 +256,6 @@ __global__ void __launch_bounds__(KD_THREADS)
 	ends_prev += (uint64_t)nblk * img;
 	ends_new += (uint64_t)nblk * img;
 	sub += (uint64_t)nblk * KD_THREADS * img;
-	blk_count += (uint64_t)nblk * img;
 
 	if (run >= 2 && info[img].changed[run - 1] == 0)
 	{
@@ -271,11 +273,67 @@ __global__ void __launch_bounds__(KD_THREADS)
 			if (run > 0 && ends_prev[b] != KD_STOP64)
 				atomicAdd((unsigned long long*)&info[img].changed[run], 1ull);
 			ends_new[b] = KD_STOP64;
-			blk_count[b] = 0;
 		}
 		sub[(uint64_t)b * KD_THREADS + t] = KdSubState{KD_STOP, 0};
 		return;
 	}
+	// codewords may not cross this (relative) position
+	const uint32_t bits_left = (uint32_t)min(total_bits - cta_bit0, (uint64_t)0xFFFFFFFFu);
+
+	if (run > 0)
+	{
+		if (t < 32)
+		{
+			uint32_t new_start = 0, old_next = 0;
+			uint64_t e_old = 0;
+			KdSubState old0 = KdSubState{0, 0};
+			if (t == 0)
+			{
+				const uint64_t e_prev = b ? ends_prev[b - 1] : 0;
+				new_start = (e_prev == KD_STOP64) ? KD_STOP : (uint32_t)(e_prev - cta_bit0);
+				old0 = sub[(uint64_t)b * KD_THREADS];
+				old_next = sub[(uint64_t)b * KD_THREADS + 1].start;
+				e_old = ends_prev[b];
+			}
+			if (t < 6) // bits [0, 192) of the CTA: the first subsequence and the look-ahead of its last codeword
+			{
+				const uint8_t* in = in_base + off;
+				const uint64_t at = (cta_bit0 >> 3) + (uint64_t)t * 4;
+				uint32_t w = 0;
+#pragma unroll
+				for (int k = 0; k < 4; k++)
+					w = (w << 8) | (uint32_t)((at + k < size) ? in[at + k] : 0);
+				sm[t] = w;
+			}
+			__syncwarp();
+			if (t == 0)
+			{
+				uint32_t fast = 0;
+				if (new_start == old0.start)
+				{
+					ends_new[b] = e_old; // same start as in the previous run: same everything
+					fast = 1;
+				}
+				else if (new_start != KD_STOP)
+				{
+					uint32_t count, stop_rel;
+					const uint32_t end0 = kd_walk<false>(sm, new_start, KD_SUB_BITS, bits_left, count, &stop_rel, KdNoEmit());
+					if (end0 != KD_STOP && end0 == old_next)
+					{
+						sub[(uint64_t)b * KD_THREADS] = KdSubState{new_start, count};
+						ends_new[b] = e_old;
+						fast = 1;
+					}
+				}
+				sm_fast = fast;
+			}
+		}
+		__syncthreads();
+		if (sm_fast)
+			return;
+		__syncthreads(); // sm[0..5] are restaged below
+	}
+
 	// where the previous CTA's chain ended in the previous run: asked for before the staging barrier
 	uint64_t e_prev = 0;
 	if (t == 0 && run != 0 && b != 0)
@@ -283,8 +341,6 @@ __global__ void __launch_bounds__(KD_THREADS)
 	kd_stage_bits(sm, in_base + off, size, cta_bit0 >> 3);
 	__syncthreads();
 
-	// codewords may not cross this (relative) position
-	const uint32_t bits_left = (uint32_t)min(total_bits - cta_bit0, (uint64_t)0xFFFFFFFFu);
 	uint32_t start;
 	if (t == 0)
 	{
@@ -320,12 +376,6 @@ __global__ void __launch_bounds__(KD_THREADS)
 	}
 
 	sub[(uint64_t)b * KD_THREADS + t] = KdSubState{start, count};
-	// the one thread of the consistent chain that ran into the end of the stream records where
-	if (start != KD_STOP && end == KD_STOP)
-		info[img].stop_pos = cta_bit0 + stop_rel;
-
-	uint32_t total;
-	block_excl_sum(count, sm_sum, &total);
 	if (t == KD_THREADS - 1)
 	{
 		const uint64_t e = (end == KD_STOP) ? KD_STOP64 : cta_bit0 + end;
@@ -333,105 +383,6 @@ __global__ void __launch_bounds__(KD_THREADS)
 			atomicAdd((unsigned long long*)&info[img].changed[run], 1ull);
 		ends_new[b] = e;
 	}
-	if (t == 0)
-		blk_count[b] = total;
-}
-
-// exclusive sum over CTAs of codeword counts (one CTA per image) -> first token index of every CTA
-__global__ void __launch_bounds__(1024)
-    k_kd_scan_counts(const uint32_t* __restrict__ blk_count, uint64_t* __restrict__ blk_base, uint32_t nblk,
-                     KdImage* __restrict__ info)
-{
-	constexpr int ITEMS = 16;
-	__shared__ uint32_t sm[33];
-	blk_count += (uint64_t)nblk * blockIdx.x;
-	blk_base += (uint64_t)nblk * blockIdx.x;
-	uint64_t carry = 0;
-	for (uint32_t b0 = 0; b0 < nblk; b0 += 1024 * ITEMS)
-	{
-		const uint32_t first = b0 + threadIdx.x * ITEMS;
-		uint32_t v[ITEMS];
-		uint32_t mine = 0; // <= 32768 each
-#pragma unroll
-		for (int i = 0; i < ITEMS; i++)
-		{
-			v[i] = (first + i < nblk) ? blk_count[first + i] : 0;
-			mine += v[i];
-		}
-		uint32_t tot;
-		uint64_t at = carry + block_excl_sum(mine, sm, &tot);
-#pragma unroll
-		for (int i = 0; i < ITEMS; i++)
-		{
-			if (first + i < nblk)
-				blk_base[first + i] = at;
-			at += v[i];
-		}
-		carry += tot;
-	}
-	if (threadIdx.x == 0)
-		info[blockIdx.x].tokens = carry;
-}
-
-// re-walks every subsequence from its final start and stores the raw codeword values. A CTA's tokens are one
-// contiguous piece of the token buffer: they are collected in shared memory and leave in 16-byte rows (a thread
-// storing its own tokens one by one touched a 32-byte sector per 2-byte store). What does not fit the stage
-// (more than KD_STAGE tokens in 32 Kibit: codewords under 3.2 bits on average) goes out directly.
-constexpr uint32_t KD_STAGE = 10240;
-
-__global__ void __launch_bounds__(KD_THREADS)
-    k_kd_extract(const uint8_t* __restrict__ in_base, const uint64_t* __restrict__ in_off,
-                 const uint64_t* __restrict__ in_size, uint32_t nblk, const KdSubState* __restrict__ sub,
-                 const uint64_t* __restrict__ blk_base, uint16_t* __restrict__ tokens, uint64_t token_stride,
-                 uint64_t token_cap)
-{
-	__shared__ uint32_t sm[KD_CTA_WORDS + 2];
-	__shared__ uint32_t sm_sum[33];
-	__shared__ __align__(16) uint16_t stage[KD_STAGE];
-	const uint32_t img = blockIdx.y, b = blockIdx.x, t = threadIdx.x;
-	const uint64_t size = __ldg(in_size + img);
-	const uint64_t off = __ldg(in_off + img);
-	const uint64_t tok0 = __ldg(blk_base + (uint64_t)nblk * img + b); // independent loads: one round trip
-	const uint64_t total_bits = size * 8;
-	const uint64_t cta_bit0 = (uint64_t)b * KD_CTA_BITS;
-	if (cta_bit0 > total_bits)
-		return;
-	const KdSubState s = sub[((uint64_t)nblk * img + b) * KD_THREADS + t];
-	kd_stage_bits(sm, in_base + off, size, cta_bit0 >> 3);
-	uint32_t total;
-	const uint32_t excl = block_excl_sum(s.count, sm_sum, &total); // syncs: sm is staged after it
-	uint16_t* const tok = tokens + token_stride * img;
-	uint32_t count;
-	kd_walk<true>(sm, s.start, (t + 1) * KD_SUB_BITS, (uint32_t)min(total_bits - cta_bit0, (uint64_t)0xFFFFFFFFu), count, nullptr,
-	              [&](uint32_t j, uint32_t u) {
-		              const uint32_t at = excl + j;
-		              if (at < KD_STAGE)
-			              stage[at] = (uint16_t)u;
-		              else if (tok0 + at < token_cap)
-			              tok[tok0 + at] = (uint16_t)u;
-	              });
-	__syncthreads();
-	// staged tokens [0, n) -> tok[tok0 .. tok0 + n), clipped to the buffer: 16-byte rows of the destination
-	const uint64_t room = (tok0 < token_cap) ? token_cap - tok0 : 0;
-	const uint32_t n = (uint32_t)min((uint64_t)min(total, KD_STAGE), room);
-	const uint32_t head = min(n, (uint32_t)((8 - (tok0 & 7)) & 7)); // tokens before the first 16-byte boundary
-	if (t < head)
-		tok[tok0 + t] = stage[t];
-	const uint32_t rows = (n - head) >> 3;
-	uint4* const dst = reinterpret_cast<uint4*>(tok + tok0 + head);
-	for (uint32_t r = t; r < rows; r += KD_THREADS)
-	{
-		const uint16_t* src = stage + head + 8 * r;
-		uint4 v;
-		v.x = (uint32_t)src[0] | ((uint32_t)src[1] << 16);
-		v.y = (uint32_t)src[2] | ((uint32_t)src[3] << 16);
-		v.z = (uint32_t)src[4] | ((uint32_t)src[5] << 16);
-		v.w = (uint32_t)src[6] | ((uint32_t)src[7] << 16);
-		dst[r] = v;
-	}
-	const uint32_t tail0 = head + 8 * rows;
-	if (tail0 + t < n)
-		tok[tok0 + tail0 + t] = stage[tail0 + t];
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -507,115 +458,6 @@ __device__ __forceinline__ KtSpan kt_shfl_up(const KtSpan& v, int d)
 #pragma unroll
 	for (int s = 0; s < 4; s++)
 		r.out[s] = __shfl_up_sync(AKOD_FULL_MASK, v.out[s], d);
-	return r;
-}
-
-// loads this thread's ITEMS tokens plus the two before them
-template <int ITEMS>
-__device__ __forceinline__ int kt_load(const uint16_t* __restrict__ tok, uint64_t m, uint64_t base, uint32_t u[ITEMS + 2])
-{
-	int valid = 0;
-	u[0] = (base >= 2 && base - 2 < m) ? tok[base - 2] : 0x10000u; // sentinels never compare equal
-	u[1] = (base >= 1 && base - 1 < m) ? tok[base - 1] : 0x20000u;
-	if (base + ITEMS <= m)
-	{
-#pragma unroll
-		for (int k = 0; k < ITEMS; k += 8)
-		{
-			const uint4 q = __ldg(reinterpret_cast<const uint4*>(tok + base + k));
-			const uint32_t w[4] = {q.x, q.y, q.z, q.w};
-#pragma unroll
-			for (int i = 0; i < 4; i++)
-			{
-				u[k + 2 * i + 2] = w[i] & 0xFFFFu;
-				u[k + 2 * i + 3] = w[i] >> 16;
-			}
-		}
-		valid = ITEMS;
-	}
-	else
-	{
-#pragma unroll
-		for (int j = 0; j < ITEMS; j++)
-		{
-			u[j + 2] = 0x30000u;
-			if (base + j < m)
-			{
-				u[j + 2] = tok[base + j];
-				valid = j + 1;
-			}
-		}
-	}
-	return valid;
-}
-
-// The span of a thread's ITEMS tokens. The four entry states are simulated side by side only until they agree:
-// two tokens in a row that differ from both their predecessors send every state to V (see the table above), so in
-// anything but a run of repeats the states have merged after three tokens and one simulation finishes the job.
-template <int ITEMS>
-__device__ __forceinline__ KtSpan kt_thread_span(const uint32_t u[ITEMS + 2], int valid)
-{
-	constexpr int PRE = (ITEMS < 3) ? ITEMS : 3;
-	uint32_t st[4] = {ST_V, ST_A, ST_S, ST_R};
-	uint32_t out[4] = {0, 0, 0, 0};
-#pragma unroll
-	for (int j = 0; j < PRE; j++)
-	{
-		if (j < valid)
-		{
-			const uint32_t m = kt_step_map(u[j + 2] == u[j + 1], u[j + 2] == u[j]);
-#pragma unroll
-			for (int s = 0; s < 4; s++)
-			{
-				out[s] += (st[s] == ST_R) ? (u[j + 2] - 1u) : 1u;
-				st[s] = (m >> (2 * st[s])) & 3u;
-			}
-		}
-	}
-	if (ITEMS > PRE)
-	{
-		if (st[0] == st[1] && st[1] == st[2] && st[2] == st[3])
-		{
-			uint32_t s1 = st[0], o1 = 0;
-#pragma unroll
-			for (int j = PRE; j < ITEMS; j++)
-			{
-				if (j < valid)
-				{
-					o1 += (s1 == ST_R) ? (u[j + 2] - 1u) : 1u;
-					s1 = kt_next(s1, u[j + 2] == u[j + 1], u[j + 2] == u[j]);
-				}
-			}
-#pragma unroll
-			for (int s = 0; s < 4; s++)
-			{
-				out[s] += o1;
-				st[s] = s1;
-			}
-		}
-		else
-		{
-#pragma unroll
-			for (int j = PRE; j < ITEMS; j++)
-			{
-				if (j < valid)
-				{
-					const uint32_t m = kt_step_map(u[j + 2] == u[j + 1], u[j + 2] == u[j]);
-#pragma unroll
-					for (int s = 0; s < 4; s++)
-					{
-						out[s] += (st[s] == ST_R) ? (u[j + 2] - 1u) : 1u;
-						st[s] = (m >> (2 * st[s])) & 3u;
-					}
-				}
-			}
-		}
-	}
-	KtSpan r;
-	r.map = st[0] | (st[1] << 2) | (st[2] << 4) | (st[3] << 6);
-#pragma unroll
-	for (int s = 0; s < 4; s++)
-		r.out[s] = out[s];
 	return r;
 }
 
@@ -700,148 +542,6 @@ __device__ __forceinline__ KtSpan kt_block_excl_scan(KtSpan v, KtSpan* sm, KtSpa
 	return r;
 }
 
-// pass A: the span of every block of KT_BLOCK tokens. The grid is sized for the most tokens a stream of this length
-// could hold, a quantised image has a small fraction of that: CTAs walk the blocks that exist with a grid stride
-// (one CTA per possible block was ~10 000 CTAs per image that only found out they had nothing to do).
-__global__ void __launch_bounds__(KT_SPAN_THREADS)
-    k_kt_spans(const uint16_t* __restrict__ tokens, uint64_t token_stride, uint64_t token_cap,
-               const KdImage* __restrict__ info, KtSpan* __restrict__ blk_span, uint32_t nblk)
-{
-	__shared__ KtSpan sm[33];
-	const uint32_t img = blockIdx.y;
-	const uint64_t m = min(info[img].tokens, token_cap);
-	const uint32_t used = (uint32_t)((m + KT_BLOCK - 1) / KT_BLOCK);
-	for (uint32_t blk = blockIdx.x; blk < used; blk += gridDim.x)
-	{
-		const uint64_t base = (uint64_t)blk * KT_BLOCK + (uint64_t)threadIdx.x * KT_SPAN_ITEMS;
-		uint32_t u[KT_SPAN_ITEMS + 2];
-		const int valid = (base < m) ? kt_load<KT_SPAN_ITEMS>(tokens + token_stride * img, m, base, u) : 0;
-		KtSpan total;
-		kt_block_excl_scan(kt_thread_span<KT_SPAN_ITEMS>(u, valid), sm, &total);
-		if (threadIdx.x == 0)
-			blk_span[(uint64_t)nblk * img + blk] = total;
-	}
-}
-
-// pass B: one CTA per image resolves every expand-CTA's entry state and output base, and validates the block.
-// Three levels: every thread composes the spans of its own chunk of CTAs; warp 0 chains the 1024 thread
-// composites (32 per lane, then the 32 lanes in order) with 64-bit output counts; every thread then walks its
-// chunk again from its resolved (state, base). A 458 MB lossless block has ~150 000 spans.
-constexpr int KR_THREADS = 1024;
-
-__global__ void __launch_bounds__(KR_THREADS)
-    k_kt_resolve(const KtSpan* __restrict__ blk_span, uint32_t nblk, uint32_t* __restrict__ blk_state,
-                 uint64_t* __restrict__ blk_out, KdImage* __restrict__ info, uint64_t n_values, uint64_t token_cap,
-                 uint64_t* __restrict__ result)
-{
-	__shared__ uint32_t s_map[KR_THREADS];
-	__shared__ uint32_t s_out[KR_THREADS][4];
-	__shared__ uint32_t s_state[KR_THREADS];
-	__shared__ uint64_t s_base[KR_THREADS];
-	__shared__ uint64_t s_grand;
-
-	const uint32_t img = blockIdx.x, t = threadIdx.x;
-	blk_span += (uint64_t)nblk * img;
-	blk_state += (uint64_t)nblk * img;
-	blk_out += (uint64_t)nblk * img;
-	const uint64_t m = min(info[img].tokens, token_cap);
-	const uint32_t used = (uint32_t)((m + KT_BLOCK - 1) / KT_BLOCK);
-	const uint32_t chunk = (used + KR_THREADS - 1) / KR_THREADS;
-	const uint32_t b0 = min(t * chunk, used), b1 = min(b0 + chunk, used);
-
-	// a thread's chunk expands to fewer than 2^32 values for any stream that can be valid (n_values < 2^32)
-	// (the loads of eight spans are in flight together: one at a time this loop was a chain of L2 round trips)
-	KtSpan mine = kt_identity();
-	for (uint32_t b = b0; b < b1; b += 8)
-	{
-		KtSpan sp[8];
-#pragma unroll
-		for (int i = 0; i < 8; i++)
-			sp[i] = (b + i < b1) ? blk_span[b + i] : kt_identity();
-#pragma unroll
-		for (int i = 0; i < 8; i++)
-			mine = kt_compose(mine, sp[i]);
-	}
-	s_map[t] = mine.map;
-#pragma unroll
-	for (int k = 0; k < 4; k++)
-		s_out[t][k] = mine.out[k];
-	__syncthreads();
-
-	if (t < 32)
-	{
-		// lane composite over its 32 thread composites, 64-bit counts
-		uint32_t lmap = (ST_V) | (ST_A << 2) | (ST_S << 4) | (ST_R << 6);
-		uint64_t lout[4] = {0, 0, 0, 0};
-		for (int i = 0; i < 32; i++)
-		{
-			const uint32_t c = t * 32 + i, cmap = s_map[c];
-			uint32_t nmap = 0;
-#pragma unroll
-			for (int st = 0; st < 4; st++)
-			{
-				const uint32_t mid = (lmap >> (2 * st)) & 3u;
-				nmap |= ((cmap >> (2 * mid)) & 3u) << (2 * st);
-				lout[st] += s_out[c][mid];
-			}
-			lmap = nmap;
-		}
-		// entry (state, base) of each lane: the 32 lanes in order
-		uint32_t state = ST_V;
-		uint64_t base = 0;
-		for (int l = 0; l < 32; l++)
-		{
-			const uint32_t map_l = __shfl_sync(AKOD_FULL_MASK, lmap, l);
-			const uint64_t o0 = __shfl_sync(AKOD_FULL_MASK, lout[0], l), o1 = __shfl_sync(AKOD_FULL_MASK, lout[1], l);
-			const uint64_t o2 = __shfl_sync(AKOD_FULL_MASK, lout[2], l), o3 = __shfl_sync(AKOD_FULL_MASK, lout[3], l);
-			if ((int)t > l)
-			{
-				base += state == 0 ? o0 : state == 1 ? o1 : state == 2 ? o2 : o3;
-				state = (map_l >> (2 * state)) & 3u;
-			}
-		}
-		// entry (state, base) of each of the lane's 32 threads
-		for (int i = 0; i < 32; i++)
-		{
-			const uint32_t c = t * 32 + i;
-			s_state[c] = state;
-			s_base[c] = base;
-			base += s_out[c][state];
-			state = (s_map[c] >> (2 * state)) & 3u;
-		}
-		if (t == 31)
-			s_grand = base;
-	}
-	__syncthreads();
-
-	uint32_t state = s_state[t];
-	uint64_t base = s_base[t];
-	for (uint32_t b = b0; b < b1; b += 8)
-	{
-		KtSpan sp[8];
-#pragma unroll
-		for (int i = 0; i < 8; i++)
-			sp[i] = (b + i < b1) ? blk_span[b + i] : kt_identity();
-#pragma unroll
-		for (int i = 0; i < 8; i++)
-			if (b + i < b1)
-			{
-				blk_state[b + i] = state;
-				blk_out[b + i] = base;
-				base += state == 0 ? sp[i].out[0] : state == 1 ? sp[i].out[1] : state == 2 ? sp[i].out[2] : sp[i].out[3];
-				state = (sp[i].map >> (2 * state)) & 3u;
-			}
-	}
-	if (t == 0)
-	{
-		const uint64_t grand = s_grand;
-		info[img].outputs = grand;
-		const bool ok = grand == n_values && info[img].tokens <= token_cap && !kd_needs_rescue(info, img) &&
-		                info[img].stop_pos != KD_STOP64;
-		result[img] = ok ? ((info[img].stop_pos + 7) >> 3) : 0;
-	}
-}
-
 __device__ __forceinline__ int16_t kt_value(uint32_t u)
 {
 	const uint32_t z = (u - 1u) & 0xFFFFu;
@@ -883,59 +583,395 @@ struct KtRun
 constexpr uint32_t KT_BIG = 2048;   // runs at least this long leave the CTA: they go to a list that k_kt_fill spreads over the GPU
 constexpr uint32_t KT_PIECE = 4096; // ... in pieces of at most this many values (one warp each)
 
-// pass C: classify every token and write what it expands to. Quantised planes are mostly a few very long
-// runs; whichever CTA meets their tokens would have to write megabytes alone, so those runs are only
-// recorded here (big_list, at most n_values / KT_BIG pieces per image) and written by k_kt_fill.
-// (Collecting a block's values in shared memory and storing them in 16-byte rows was tried: the kernel is bound by
-// its instruction count, not by its 2-byte stores, and the extra barriers and registers cost 10-20 %.)
-__global__ void __launch_bounds__(KT_THREADS, 5)
-    k_kt_expand(const uint16_t* __restrict__ tokens, uint64_t token_stride, uint64_t token_cap,
-                const KdImage* __restrict__ info, const uint32_t* __restrict__ blk_state,
-                const uint64_t* __restrict__ blk_out, uint32_t nblk, int16_t* __restrict__ out_base, uint64_t out_stride,
-                uint64_t n_values, KtRun* __restrict__ big_list, uint32_t* __restrict__ big_count, uint32_t big_cap)
+// ------------------------------------------------------------------------------------------------
+// The fused pass: classification and expansion straight from the bit stream, one launch after the boundary search.
+//
+// A CTA takes the same 4 KiB of stream as in k_kd_sync and its 256 final (start, count) pairs. There is no token
+// buffer: every thread walks its 128 bits twice from shared memory,
+//   walk 1  builds the span of its codewords (4-state function + the number of values per entry state) as they are
+//           decoded; the first two codewords of a subsequence are compared against the previous thread's last two
+//           (handed over in shared memory, from the previous CTA through its look-back record) after the walk;
+//   scan    one block-wide scan of the 256 spans; the CTA's own span is published and a decoupled look-back over the
+//           preceding CTAs' spans (CTA indices are tickets, so every predecessor is running or done) yields the state
+//           the CTA is entered in and its first output position, with 64-bit counts;
+//   walk 2  decodes again, now knowing state and position, and writes. A warp whose values fit KF_WIN collects them
+//           in shared memory and stores 16-byte rows (a thread's ~38 values lie 76 bytes from its neighbour's: direct
+//           2-byte stores would cost a 32-byte sector each); other warps store directly, runs of KT_LONG..KT_BIG-1
+//           values are filled by the warp together, longer ones go to big_list for k_kt_fill.
+// This replaces five kernels (token extraction, two token passes, the single-CTA resolve pass, the token count scan)
+// and 6 bytes of HBM traffic per codeword.
+
+constexpr uint32_t KF_WIN = 2048;              // values a warp stages
+constexpr uint32_t KF_PITCH = KF_WIN + 8 + 8;  // + misalignment of its first value, rounded to whole 16-byte rows
+constexpr uint64_t KF_VALID = (uint64_t)1 << 63;
+constexpr uint64_t KF_COUNT_MASK = ((uint64_t)1 << 60) - 1;
+
+struct KfLook // look-back record of one CTA
 {
-	__shared__ KtSpan sm[33];
-	__shared__ KtRun queue[KT_BLOCK / 3 + 1]; // an RLE count follows at least two value tokens
-	__shared__ uint32_t queue_len;
+	uint32_t flag;    // 1 once map / out are readable
+	uint32_t map;
+	uint32_t out[4];
+	uint64_t tail;    // KF_VALID | last two codewords (second to last in bits 0-15, last in bits 16-31)
+};
 
-	const uint32_t img = blockIdx.y;
-	const uint64_t m_all = __ldg(&info[img].tokens);
-	const uint64_t m = min(m_all, token_cap);
-	const uint32_t used = (uint32_t)((m + KT_BLOCK - 1) / KT_BLOCK);
-	int16_t* out = out_base + out_stride * img;
-	// grid stride over the token blocks that exist (see k_kt_spans)
-	for (uint32_t blk = blockIdx.x; blk < used; blk += gridDim.x)
-	{
-		// the per-block words are fetched together: behind the scan's barriers they would be a second round trip
-		const uint32_t entry = __ldg(blk_state + (uint64_t)nblk * img + blk);
-		const uint64_t out0 = __ldg(blk_out + (uint64_t)nblk * img + blk);
-		const uint64_t cta_base = (uint64_t)blk * KT_BLOCK;
-		const uint64_t base = cta_base + (uint64_t)threadIdx.x * KT_ITEMS;
-		uint32_t u[KT_ITEMS + 2];
-		const int valid = (base < m) ? kt_load<KT_ITEMS>(tokens + token_stride * img, m, base, u) : 0;
-		if (threadIdx.x == 0)
-			queue_len = 0;
+struct KfSpan64
+{
+	uint32_t map;
+	uint64_t out[4];
+};
 
-		KtSpan total;
-		const KtSpan before = kt_block_excl_scan(kt_thread_span<KT_ITEMS>(u, valid), sm, &total);
-		uint32_t state = (before.map >> (2 * entry)) & 3u;
-		uint64_t pos = out0 + before.out[entry];
-
+// a then b
+__device__ __forceinline__ KfSpan64 kf_compose(const KfSpan64& a, const KfSpan64& b)
+{
+	KfSpan64 r;
+	r.map = 0;
 #pragma unroll
-		for (int j = 0; j < KT_ITEMS; j++)
+	for (int s = 0; s < 4; s++)
+	{
+		const uint32_t mid = (a.map >> (2 * s)) & 3u;
+		r.map |= ((b.map >> (2 * mid)) & 3u) << (2 * s);
+		r.out[s] = a.out[s] + (mid == 0 ? b.out[0] : mid == 1 ? b.out[1] : mid == 2 ? b.out[2] : b.out[3]);
+	}
+	return r;
+}
+
+__device__ __forceinline__ uint32_t kf_pick(const uint32_t (&o)[4], uint32_t s)
+{
+	return s == 0 ? o[0] : s == 1 ? o[1] : s == 2 ? o[2] : o[3];
+}
+
+struct KfCursor
+{
+	uint32_t p, idx, hi, lo;
+};
+
+__device__ __forceinline__ void kf_open(const uint32_t* sm, uint32_t start, KfCursor& c)
+{
+	c.p = start;
+	c.idx = start >> 5;
+	c.hi = sm[c.idx];
+	c.lo = sm[c.idx + 1];
+}
+
+// next codeword (the boundary search has validated it: at most 15 leading zeros, inside the stream)
+__device__ __forceinline__ uint32_t kf_next(const uint32_t* sm, KfCursor& c)
+{
+	const uint32_t w = __funnelshift_l(c.lo, c.hi, c.p & 31);
+	const int z = __clz(w | 0x10000u);
+	const uint32_t u = w >> (31 - 2 * z);
+	c.p += 2 * z + 1;
+	if ((c.p >> 5) != c.idx)
+	{
+		c.idx++;
+		c.hi = c.lo;
+		c.lo = sm[c.idx + 1];
+	}
+	return u;
+}
+
+// fills dst[off, off + count) of a 16-byte aligned shared array, by the 32 lanes of a warp
+__device__ __forceinline__ void kf_fill_stage(int16_t* dst, uint32_t off, uint32_t count, int16_t v, int lane)
+{
+	int16_t* const o = dst + off;
+	const uint32_t head = (8u - (off & 7u)) & 7u;
+	if (count < head + 8u)
+	{
+		for (uint32_t i = (uint32_t)lane; i < count; i += 32)
+			o[i] = v;
+		return;
+	}
+	if ((uint32_t)lane < head)
+		o[lane] = v;
+	const uint32_t vv = (uint32_t)(uint16_t)v * 0x10001u;
+	const uint4 q = make_uint4(vv, vv, vv, vv);
+	uint4* const body = reinterpret_cast<uint4*>(o + head);
+	const uint32_t nq = (count - head) >> 3, tail0 = head + (nq << 3);
+	for (uint32_t i = (uint32_t)lane; i < nq; i += 32)
+		body[i] = q;
+	if (tail0 + (uint32_t)lane < count)
+		o[tail0 + lane] = v;
+}
+
+__global__ void __launch_bounds__(KD_THREADS, 4)
+    k_kd_decode(const uint8_t* __restrict__ in_base, const uint64_t* __restrict__ in_off,
+                const uint64_t* __restrict__ in_size, uint32_t nblk, const KdSubState* __restrict__ sub,
+                const uint64_t* __restrict__ ends_final, KfLook* __restrict__ look, uint64_t* __restrict__ prefix,
+                uint32_t* __restrict__ ticket, KdImage* __restrict__ info, int16_t* __restrict__ out_base,
+                uint64_t out_stride, uint64_t n_values, KtRun* __restrict__ big_list, uint32_t* __restrict__ big_count,
+                uint32_t big_cap)
+{
+	__shared__ uint32_t sm[KD_CTA_WORDS + 2];
+	__shared__ KtSpan sm_scan[33];
+	__shared__ uint32_t sm_last[KD_THREADS];
+	__shared__ uint32_t sm_b, sm_entry;
+	__shared__ uint64_t sm_base;
+	__shared__ __align__(16) int16_t stage[KD_THREADS / 32][KF_PITCH];
+
+	const uint32_t img = blockIdx.y, t = threadIdx.x;
+	const int lane = t & 31, wid = t >> 5;
+	if (kd_needs_rescue(info, img))
+		return; // no fixed point within KD_MAX_RUNS: the sequential kernel decodes this image
+	if (t == 0)
+		sm_b = atomicAdd(&ticket[img], 1u);
+	__syncthreads();
+	const uint32_t b = sm_b;
+	const uint64_t size = __ldg(in_size + img);
+	const uint64_t off = __ldg(in_off + img);
+	const uint64_t total_bits = size * 8;
+	const uint64_t cta_bit0 = (uint64_t)b * KD_CTA_BITS;
+	if (cta_bit0 > total_bits)
+		return;
+	const bool last_cta = cta_bit0 + KD_CTA_BITS > total_bits; // the next CTA has nothing
+	sub += ((uint64_t)nblk * img + b) * KD_THREADS;
+	look += (uint64_t)nblk * img;
+	prefix += (uint64_t)nblk * img;
+	int16_t* const out = out_base + out_stride * img;
+
+	const KdSubState s = sub[t];
+	// where the next subsequence starts: KD_STOP there and not here = the chain ends in this one
+	uint32_t next_start;
+	if (t + 1 < KD_THREADS)
+		next_start = sub[t + 1].start;
+	else
+		next_start = (ends_final[(uint64_t)nblk * img + b] == KD_STOP64) ? KD_STOP : 0u;
+	kd_stage_bits(sm, in_base + off, size, cta_bit0 >> 3);
+	__syncthreads();
+
+	// ---------------- walk 1: the span of this subsequence
+	const uint32_t K = (s.start == KD_STOP) ? 0u : s.count;
+	uint32_t f0 = 0, f1 = 0, p1 = 0, p2 = 0;
+	KtSpan rest = kt_identity();
+	{
+		KfCursor c;
+		kf_open(sm, (s.start != KD_STOP) ? s.start : 0u, c);
+		if (K > 0)
+			p1 = f0 = kf_next(sm, c);
+		if (K > 1)
 		{
-			if (j < valid)
+			p2 = p1;
+			p1 = f1 = kf_next(sm, c);
+		}
+		// codewords 2..K-1: the four entry states side by side until they agree (two codewords in a row that differ
+		// from both their predecessors send every state to V), one state and one common count afterwards
+		uint32_t map = rest.map, o[4] = {0, 0, 0, 0}, x = 0, common = 0;
+		bool merged = false;
+		for (uint32_t j = 2; j < K; j++)
+		{
+			const uint32_t u = kf_next(sm, c);
+			const uint32_t m = kt_step_map(u == p1, u == p2);
+			if (merged)
 			{
-				const uint32_t cur = u[j + 2];
+				common += (x == ST_R) ? (u - 1u) : 1u;
+				x = (m >> (2 * x)) & 3u;
+			}
+			else
+			{
+				uint32_t nmap = 0;
+#pragma unroll
+				for (int k = 0; k < 4; k++)
+				{
+					const uint32_t st = (map >> (2 * k)) & 3u;
+					o[k] += (st == ST_R) ? (u - 1u) : 1u;
+					nmap |= ((m >> (2 * st)) & 3u) << (2 * k);
+				}
+				map = nmap;
+				merged = kt_is_const(map);
+				x = map & 3u;
+			}
+			p2 = p1;
+			p1 = u;
+		}
+		rest.map = merged ? x * 0x55u : map;
+#pragma unroll
+		for (int k = 0; k < 4; k++)
+			rest.out[k] = o[k] + common;
+		// the one thread whose chain ends here records where (the boundary search has left that to this kernel)
+		if (s.start != KD_STOP && next_start == KD_STOP)
+			info[img].stop_pos = cta_bit0 + c.p;
+	}
+	sm_last[t] = (p2 & 0xFFFFu) | (p1 << 16);
+	if (t == KD_THREADS - 1)
+		*(volatile uint64_t*)&look[b].tail = KF_VALID | (uint64_t)((p2 & 0xFFFFu) | (p1 << 16));
+	__syncthreads();
+
+	// ---------------- the two codewords before this subsequence
+	uint32_t q1, q2; // q1 = the one right before
+	if (t > 0)
+	{
+		const uint32_t l = sm_last[t - 1];
+		q2 = l & 0xFFFFu;
+		q1 = l >> 16;
+	}
+	else if (b == 0)
+	{
+		q2 = 0x10000u; // sentinels never compare equal
+		q1 = 0x20000u;
+	}
+	else
+	{
+		uint64_t tl;
+		do
+			tl = *(volatile const uint64_t*)&look[b - 1].tail;
+		while (!(tl & KF_VALID));
+		q2 = (uint32_t)tl & 0xFFFFu;
+		q1 = ((uint32_t)tl >> 16) & 0xFFFFu;
+	}
+	KtSpan mine = rest;
+	if (K > 0)
+	{
+		const uint32_t m0 = kt_step_map(f0 == q1, f0 == q2);
+		const uint32_t m1 = kt_step_map(f1 == f0, f1 == q1);
+		mine.map = 0;
+#pragma unroll
+		for (int k = 0; k < 4; k++)
+		{
+			uint32_t st = (uint32_t)k;
+			uint32_t n = (st == ST_R) ? (f0 - 1u) : 1u;
+			st = (m0 >> (2 * st)) & 3u;
+			if (K > 1)
+			{
+				n += (st == ST_R) ? (f1 - 1u) : 1u;
+				st = (m1 >> (2 * st)) & 3u;
+			}
+			n += kf_pick(rest.out, st);
+			mine.map |= ((rest.map >> (2 * st)) & 3u) << (2 * k);
+			mine.out[k] = n;
+		}
+	}
+
+	KtSpan total;
+	const KtSpan before = kt_block_excl_scan(mine, sm_scan, &total);
+
+	// ---------------- look-back (warp 0): entry state and first output position of this CTA
+	if (wid == 0)
+	{
+		uint32_t entry = ST_V;
+		uint64_t base = 0;
+		if (b != 0)
+		{
+			if (lane == 0)
+			{
+				look[b].map = total.map;
+#pragma unroll
+				for (int k = 0; k < 4; k++)
+					look[b].out[k] = total.out[k];
+				__threadfence();
+				*(volatile uint32_t*)&look[b].flag = 1u;
+			}
+			KfSpan64 F; // everything between the window under examination and this CTA
+			F.map = kt_identity().map;
+			F.out[0] = F.out[1] = F.out[2] = F.out[3] = 0;
+			for (int64_t cur = (int64_t)b - 1;; cur -= 32)
+			{
+				const int64_t p = cur - lane;
+				KfSpan64 A;
+				A.map = kt_identity().map;
+				A.out[0] = A.out[1] = A.out[2] = A.out[3] = 0;
+				uint64_t pv = KF_VALID; // before the first CTA: state V, nothing written
+				if (p >= 0)
+				{
+					for (;;)
+					{
+						pv = *(volatile const uint64_t*)&prefix[p];
+						if (pv & KF_VALID)
+							break;
+						if (*(volatile const uint32_t*)&look[p].flag)
+						{
+							__threadfence();
+							A.map = *(volatile const uint32_t*)&look[p].map;
+#pragma unroll
+							for (int k = 0; k < 4; k++)
+								A.out[k] = *(volatile const uint32_t*)&look[p].out[k];
+							break;
+						}
+					}
+				}
+				const uint32_t pm = __ballot_sync(AKOD_FULL_MASK, (pv & KF_VALID) != 0);
+				const int first = pm ? __ffs(pm) - 1 : 32;
+				if (lane >= first)
+				{
+					A.map = kt_identity().map;
+					A.out[0] = A.out[1] = A.out[2] = A.out[3] = 0;
+				}
+				// ordered fold: higher lanes are older CTAs and apply first
+#pragma unroll
+				for (int d = 1; d < 32; d <<= 1)
+				{
+					KfSpan64 O;
+					O.map = __shfl_down_sync(AKOD_FULL_MASK, A.map, d);
+#pragma unroll
+					for (int k = 0; k < 4; k++)
+						O.out[k] = __shfl_down_sync(AKOD_FULL_MASK, A.out[k], d);
+					if (lane + d < 32)
+						A = kf_compose(O, A);
+				}
+				KfSpan64 G;
+				G.map = __shfl_sync(AKOD_FULL_MASK, A.map, 0);
+#pragma unroll
+				for (int k = 0; k < 4; k++)
+					G.out[k] = __shfl_sync(AKOD_FULL_MASK, A.out[k], 0);
+				F = kf_compose(G, F);
+				if (first < 32)
+				{
+					const uint64_t pf = __shfl_sync(AKOD_FULL_MASK, pv, first);
+					const uint32_t st = (uint32_t)(pf >> 60) & 3u;
+					entry = (F.map >> (2 * st)) & 3u;
+					base = (pf & KF_COUNT_MASK) + (st == 0 ? F.out[0] : st == 1 ? F.out[1] : st == 2 ? F.out[2] : F.out[3]);
+					break;
+				}
+			}
+		}
+		if (lane == 0)
+		{
+			const uint32_t exit_state = (total.map >> (2 * entry)) & 3u;
+			const uint64_t incl = (base + kf_pick(total.out, entry)) & KF_COUNT_MASK;
+			*(volatile uint64_t*)&prefix[b] = KF_VALID | ((uint64_t)exit_state << 60) | incl;
+			sm_entry = entry;
+			sm_base = base;
+			if (last_cta)
+				info[img].outputs = incl;
+		}
+	}
+	__syncthreads();
+
+	// ---------------- walk 2: write
+	const uint32_t entry = sm_entry;
+	const uint64_t cta_base = sm_base;
+	uint32_t state = (before.map >> (2 * entry)) & 3u;
+	uint32_t rel = kf_pick(before.out, entry);           // position relative to the CTA's first value
+	const uint32_t len = kf_pick(mine.out, state);       // values this thread writes
+	const uint32_t w_rel0 = __shfl_sync(AKOD_FULL_MASK, rel, 0);
+	const uint32_t w_len = __shfl_sync(AKOD_FULL_MASK, rel + len, 31) - w_rel0;
+	const bool staged = w_len < KF_WIN; // uniform per warp; no run of KT_BIG values fits
+	const uint64_t w_pos0 = cta_base + w_rel0;
+	const uint32_t mis = (uint32_t)w_pos0 & 7u;
+	int16_t* const wst = stage[wid];
+	const uint32_t Kmax = __reduce_max_sync(AKOD_FULL_MASK, K);
+	{
+		KfCursor c;
+		kf_open(sm, K ? s.start : 0u, c);
+		p1 = q1;
+		p2 = q2;
+		for (uint32_t j = 0; j < Kmax; j++)
+		{
+			bool coop = false;
+			uint32_t count = 0;
+			int16_t v = 0;
+			if (j < K)
+			{
+				const uint32_t u = kf_next(sm, c);
 				if (state == ST_R)
 				{
-					// an RLE count: (cur - 1) more copies of the value before it (kagari.c:342-354)
-					const uint32_t count = cur - 1u;
-					const int16_t v = kt_value(u[j + 1]);
-					if (pos + count <= n_values)
+					// an RLE count: (u - 1) more copies of the value before it (kagari.c:342-354)
+					count = u - 1u;
+					v = kt_value(p1);
+					const uint64_t pos = cta_base + rel;
+					const bool fits = pos + count <= n_values;
+					if (staged || fits)
 					{
 						if (count >= KT_BIG)
 						{
+							// (never in a staged warp: its values would not fit KF_WIN, so 'fits' holds here)
 							const uint32_t pieces = (count + KT_PIECE - 1) / KT_PIECE;
 							const uint32_t first = atomicAdd(&big_count[img], pieces);
 							for (uint32_t k = 0; k < pieces; k++)
@@ -949,43 +985,95 @@ __global__ void __launch_bounds__(KT_THREADS, 5)
 								}
 						}
 						else if (count >= KT_LONG)
+							coop = true;
+						else if (staged)
 						{
-							const uint32_t slot = atomicAdd(&queue_len, 1u);
-							queue[slot].pos = pos;
-							queue[slot].count = count;
-							queue[slot].value = v;
+							int16_t* d = wst + (rel - w_rel0 + mis);
+							for (uint32_t k = 0; k < count; k++)
+								d[k] = v;
 						}
 						else
+						{
+							int16_t* d = out + pos;
 							for (uint32_t k = 0; k < count; k++)
-								out[pos + k] = v;
+								d[k] = v;
+						}
 					}
-					pos += count;
+					if (!coop)
+						rel += count;
 					state = ST_A;
 				}
 				else
 				{
-					if (pos < n_values)
-						out[pos] = kt_value(cur);
-					pos += 1;
-					state = kt_next(state, cur == u[j + 1], cur == u[j]);
+					if (staged)
+						wst[rel - w_rel0 + mis] = kt_value(u);
+					else if (cta_base + rel < n_values)
+						out[cta_base + rel] = kt_value(u);
+					rel += 1;
+					state = kt_next(state, u == p1, u == p2);
 				}
+				p2 = p1;
+				p1 = u;
 			}
+			// runs of KT_LONG .. KT_BIG-1 values: the warp fills them together
+			uint32_t todo = __ballot_sync(AKOD_FULL_MASK, coop);
+			while (todo)
+			{
+				const int src = __ffs(todo) - 1;
+				todo &= todo - 1;
+				const uint32_t r_rel = __shfl_sync(AKOD_FULL_MASK, rel, src);
+				const uint32_t r_count = __shfl_sync(AKOD_FULL_MASK, count, src);
+				const int16_t r_v = (int16_t)__shfl_sync(AKOD_FULL_MASK, (int)v, src);
+				if (staged)
+					kf_fill_stage(wst, r_rel - w_rel0 + mis, r_count, r_v, lane);
+				else
+					kt_fill_warp(out, cta_base + r_rel, r_count, r_v, lane);
+			}
+			if (coop)
+				rel += count;
 		}
-		__syncthreads();
-		const uint32_t nq = queue_len;
-		const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-		for (uint32_t i = wid; i < nq; i += KT_THREADS / 32)
-			kt_fill_warp(out, queue[i].pos, queue[i].count, queue[i].value, lane);
-		__syncthreads(); // the queue is reused by the next block
+	}
+	if (staged)
+	{
+		__syncwarp();
+		// stage[i] is value w_pos0 - mis + i: rows of eight are 16-byte aligned on both sides
+		uint64_t room = (w_pos0 < n_values) ? n_values - w_pos0 : 0; // (a broken stream may expand past the plane)
+		const uint32_t n = (uint32_t)min((uint64_t)w_len, room);
+		const uint32_t lo = mis, hi = mis + n;
+		const uint32_t row0 = (lo + 7) >> 3, row1 = hi >> 3;
+		int16_t* const g = out + (w_pos0 - mis);
+		if (row0 >= row1)
+		{
+			for (uint32_t i = lo + lane; i < hi; i += 32)
+				g[i] = wst[i];
+		}
+		else
+		{
+			if (lo + lane < row0 * 8)
+				g[lo + lane] = wst[lo + lane];
+			const uint4* src = reinterpret_cast<const uint4*>(wst);
+			uint4* dst = reinterpret_cast<uint4*>(g);
+			for (uint32_t r = row0 + lane; r < row1; r += 32)
+				dst[r] = src[r];
+			if (row1 * 8 + lane < hi)
+				g[row1 * 8 + lane] = wst[row1 * 8 + lane];
+		}
 	}
 }
 
-// pass D: the big runs, one warp per piece, spread over the whole GPU
+// the big runs, one warp per piece, spread over the whole GPU; the first thread of each image also gives the verdict:
+// bytes consumed = ceil(end of the last codeword / 8) when exactly n values came out, else 0
 __global__ void __launch_bounds__(256)
     k_kt_fill(const KtRun* __restrict__ big_list, const uint32_t* __restrict__ big_count, uint32_t big_cap,
-              int16_t* __restrict__ out_base, uint64_t out_stride)
+              int16_t* __restrict__ out_base, uint64_t out_stride, const KdImage* __restrict__ info, uint64_t n_values,
+              uint64_t* __restrict__ result)
 {
 	const uint32_t img = blockIdx.y;
+	if (blockIdx.x == 0 && threadIdx.x == 0)
+	{
+		const bool ok = info[img].outputs == n_values && !kd_needs_rescue(info, img) && info[img].stop_pos != KD_STOP64;
+		result[img] = ok ? ((info[img].stop_pos + 7) >> 3) : 0;
+	}
 	const uint32_t n = min(big_count[img], big_cap);
 	const uint32_t warps = gridDim.x * (blockDim.x >> 5);
 	const int lane = threadIdx.x & 31;
