@@ -159,16 +159,23 @@ struct KdSubState
 	uint32_t count; // codewords that start in it
 };
 
-// stages one CTA's worth (+ 2 words look-ahead) of the stream as big-endian words; bytes past 'size' read as zero
+// stages one CTA's worth (+ 2 words look-ahead) of the stream as big-endian words; bytes past 'size' read as zero.
+// A block sits at any byte offset of the blob: words are assembled from the two aligned 32-bit words that hold them
+// (two loads instead of four byte loads and their shifts); only the words at the very end of the stream go by bytes.
 __device__ __forceinline__ void kd_stage_bits(uint32_t* sm, const uint8_t* __restrict__ in, uint64_t size,
                                               uint64_t first_byte)
 {
+	const uint32_t a = (uint32_t)((uintptr_t)(in + first_byte) & 3u);
+	const uint32_t* __restrict__ wp = reinterpret_cast<const uint32_t*>(in + first_byte - a);
 	for (int i = threadIdx.x; i < KD_CTA_WORDS + 2; i += KD_THREADS)
 	{
 		const uint64_t b = first_byte + (uint64_t)i * 4;
 		uint32_t w = 0;
-		if (b + 4 <= size)
-			w = ((uint32_t)in[b] << 24) | ((uint32_t)in[b + 1] << 16) | ((uint32_t)in[b + 2] << 8) | (uint32_t)in[b + 3];
+		if (b + 8 <= size) // both aligned words end inside the stream
+		{
+			const uint32_t v = __funnelshift_r(__ldg(wp + i), __ldg(wp + i + 1), 8 * a);
+			w = __byte_perm(v, 0, 0x0123);
+		}
 		else
 		{
 #pragma unroll
@@ -188,8 +195,8 @@ __device__ __forceinline__ uint32_t kd_peek(const uint32_t* sm, uint32_t pos)
 // Returns that boundary (or KD_STOP if the chain ends), counts codewords starting before 'limit'.
 // If stop_at != nullptr and the chain ends, *stop_at receives the relative position where it ended.
 // bits_left: codewords may not reach past this CTA-relative position (the end of the stream, clamped to 32 bits).
-// The two words under the cursor ride in registers and one shared load follows per word crossed, instead of two
-// per codeword (a lossless stream averages 3.4 bits per codeword).
+// Both words under the cursor are fetched for every codeword (two LDS off one address): carrying them in registers
+// and reloading on a word crossing is a branch that some lane takes at nearly every codeword.
 // EMIT: token j of the walk goes to emit(j, raw codeword value).
 template <bool EMIT, typename F>
 __device__ __forceinline__ uint32_t kd_walk(const uint32_t* sm, uint32_t start, uint32_t limit, uint32_t bits_left,
@@ -201,11 +208,10 @@ __device__ __forceinline__ uint32_t kd_walk(const uint32_t* sm, uint32_t start, 
 	uint32_t p = start;
 	if (p >= limit)
 		return p;
-	uint32_t idx = p >> 5;
-	uint32_t hi = sm[idx], lo = sm[idx + 1];
 	do
 	{
-		const uint32_t w = __funnelshift_l(lo, hi, p & 31);
+		const uint32_t* at = sm + (p >> 5);
+		const uint32_t w = __funnelshift_l(at[1], at[0], p & 31);
 		const int z = __clz(w); // 32 for w == 0
 		const uint32_t len = 2 * z + 1;
 		if (w < 0x10000u || p + len > bits_left) // more than 15 leading zeros, or past the end of the stream
@@ -218,12 +224,6 @@ __device__ __forceinline__ uint32_t kd_walk(const uint32_t* sm, uint32_t start, 
 			emit(count, w >> (31 - 2 * z));
 		count++;
 		p += len;
-		if ((p >> 5) != idx) // len <= 31: at most one word further
-		{
-			idx++;
-			hi = lo;
-			lo = sm[idx + 1];
-		}
 	} while (p < limit);
 	return p;
 }
@@ -606,11 +606,15 @@ constexpr uint32_t KF_PITCH = KF_WIN + 8 + 8;  // + misalignment of its first va
 constexpr uint64_t KF_VALID = (uint64_t)1 << 63;
 constexpr uint64_t KF_COUNT_MASK = ((uint64_t)1 << 60) - 1;
 
-struct KfLook // look-back record of one CTA
+// Look-back record of one CTA, one 32-byte sector. Every word validates itself (top bit), so a record needs neither a
+// flag nor a fence: a reader fetches all of it together with the CTA's prefix word in ONE round trip and simply looks
+// again when a word is still empty. (A CTA's span maps at most 32768 codewords of at most 65534 values: < 2^31.)
+constexpr uint32_t KF_W = 0x80000000u;
+struct __align__(32) KfLook
 {
-	uint32_t flag;    // 1 once map / out are readable
-	uint32_t map;
-	uint32_t out[4];
+	uint32_t out[4];  // KF_W | values the CTA expands to, per entry state
+	uint32_t map;     // KF_W | exit states
+	uint32_t pad;
 	uint64_t tail;    // KF_VALID | last two codewords (second to last in bits 0-15, last in bits 16-31)
 };
 
@@ -640,32 +644,27 @@ __device__ __forceinline__ uint32_t kf_pick(const uint32_t (&o)[4], uint32_t s)
 	return s == 0 ? o[0] : s == 1 ? o[1] : s == 2 ? o[2] : o[3];
 }
 
+// Cursor of a walk. Every codeword fetches the two words under it again (two LDS off one address): keeping them in
+// registers and reloading on a word crossing was a branch that some lane of the warp takes at nearly every codeword,
+// i.e. more instructions than the loads it saved.
 struct KfCursor
 {
-	uint32_t p, idx, hi, lo;
+	uint32_t p;
 };
 
-__device__ __forceinline__ void kf_open(const uint32_t* sm, uint32_t start, KfCursor& c)
+__device__ __forceinline__ void kf_open(const uint32_t*, uint32_t start, KfCursor& c)
 {
 	c.p = start;
-	c.idx = start >> 5;
-	c.hi = sm[c.idx];
-	c.lo = sm[c.idx + 1];
 }
 
 // next codeword (the boundary search has validated it: at most 15 leading zeros, inside the stream)
 __device__ __forceinline__ uint32_t kf_next(const uint32_t* sm, KfCursor& c)
 {
-	const uint32_t w = __funnelshift_l(c.lo, c.hi, c.p & 31);
-	const int z = __clz(w | 0x10000u);
-	const uint32_t u = w >> (31 - 2 * z);
-	c.p += 2 * z + 1;
-	if ((c.p >> 5) != c.idx)
-	{
-		c.idx++;
-		c.hi = c.lo;
-		c.lo = sm[c.idx + 1];
-	}
+	const uint32_t* at = sm + (c.p >> 5);
+	const uint32_t w = __funnelshift_l(at[1], at[0], c.p & 31);
+	const int top = 31 - __clz(w | 0x10000u); // position of the leading one: 31 - zeros
+	const uint32_t u = w >> (2 * top - 31);
+	c.p += 63 - 2 * top;
 	return u;
 }
 
@@ -692,7 +691,10 @@ __device__ __forceinline__ void kf_fill_stage(int16_t* dst, uint32_t off, uint32
 		o[tail0 + lane] = v;
 }
 
-__global__ void __launch_bounds__(KD_THREADS, 4)
+#ifndef KF_CTAS
+#define KF_CTAS 4
+#endif
+__global__ void __launch_bounds__(KD_THREADS, KF_CTAS)
     k_kd_decode(const uint8_t* __restrict__ in_base, const uint64_t* __restrict__ in_off,
                 const uint64_t* __restrict__ in_size, uint32_t nblk, const KdSubState* __restrict__ sub,
                 const uint64_t* __restrict__ ends_final, KfLook* __restrict__ look, uint64_t* __restrict__ prefix,
@@ -701,8 +703,8 @@ __global__ void __launch_bounds__(KD_THREADS, 4)
                 uint32_t big_cap)
 {
 	__shared__ uint32_t sm[KD_CTA_WORDS + 2];
-	__shared__ KtSpan sm_scan[33];
-	__shared__ uint32_t sm_last[KD_THREADS];
+	__shared__ KtSpan sm_scan[KD_THREADS / 32];
+	__shared__ uint64_t sm_last[KD_THREADS / 32]; // KF_VALID | the last two codewords of the warp below
 	__shared__ uint32_t sm_b, sm_entry;
 	__shared__ uint64_t sm_base;
 	__shared__ __align__(16) int16_t stage[KD_THREADS / 32][KF_PITCH];
@@ -713,6 +715,8 @@ __global__ void __launch_bounds__(KD_THREADS, 4)
 		return; // no fixed point within KD_MAX_RUNS: the sequential kernel decodes this image
 	if (t == 0)
 		sm_b = atomicAdd(&ticket[img], 1u);
+	if (t < KD_THREADS / 32)
+		sm_last[t] = 0;
 	__syncthreads();
 	const uint32_t b = sm_b;
 	const uint64_t size = __ldg(in_size + img);
@@ -740,6 +744,7 @@ __global__ void __launch_bounds__(KD_THREADS, 4)
 	// ---------------- walk 1: the span of this subsequence
 	const uint32_t K = (s.start == KD_STOP) ? 0u : s.count;
 	uint32_t f0 = 0, f1 = 0, p1 = 0, p2 = 0;
+	uint32_t coop_mask = 0; // bit k: entered in state k, codewords 2.. hold a run of KT_LONG values or more
 	KtSpan rest = kt_identity();
 	{
 		KfCursor c;
@@ -761,7 +766,13 @@ __global__ void __launch_bounds__(KD_THREADS, 4)
 			const uint32_t m = kt_step_map(u == p1, u == p2);
 			if (merged)
 			{
-				common += (x == ST_R) ? (u - 1u) : 1u;
+				if (x == ST_R)
+				{
+					common += u - 1u;
+					coop_mask = (u > KT_LONG) ? 0xFu : coop_mask;
+				}
+				else
+					common += 1u;
 				x = (m >> (2 * x)) & 3u;
 			}
 			else
@@ -772,6 +783,7 @@ __global__ void __launch_bounds__(KD_THREADS, 4)
 				{
 					const uint32_t st = (map >> (2 * k)) & 3u;
 					o[k] += (st == ST_R) ? (u - 1u) : 1u;
+					coop_mask |= (uint32_t)(st == ST_R && u > KT_LONG) << k;
 					nmap |= ((m >> (2 * st)) & 3u) << (2 * k);
 				}
 				map = nmap;
@@ -789,38 +801,48 @@ __global__ void __launch_bounds__(KD_THREADS, 4)
 		if (s.start != KD_STOP && next_start == KD_STOP)
 			info[img].stop_pos = cta_bit0 + c.p;
 	}
-	sm_last[t] = (p2 & 0xFFFFu) | (p1 << 16);
-	if (t == KD_THREADS - 1)
-		*(volatile uint64_t*)&look[b].tail = KF_VALID | (uint64_t)((p2 & 0xFFFFu) | (p1 << 16));
-	__syncthreads();
 
-	// ---------------- the two codewords before this subsequence
-	uint32_t q1, q2; // q1 = the one right before
-	if (t > 0)
+	// ---------------- the two codewords before this subsequence: from the lane below, the warp below (shared memory,
+	// point to point: no barrier) or the CTA below (its look-back record)
+	const uint32_t my_last = (p2 & 0xFFFFu) | (p1 << 16);
+	if (lane == 31)
 	{
-		const uint32_t l = sm_last[t - 1];
-		q2 = l & 0xFFFFu;
-		q1 = l >> 16;
+		if (wid == KD_THREADS / 32 - 1)
+			*(volatile uint64_t*)&look[b].tail = KF_VALID | (uint64_t)my_last;
+		else
+			*(volatile uint64_t*)&sm_last[wid + 1] = KF_VALID | (uint64_t)my_last;
 	}
-	else if (b == 0)
+	uint32_t prev_last = __shfl_up_sync(AKOD_FULL_MASK, my_last, 1);
+	uint32_t q1, q2; // q1 = the codeword right before this subsequence, q2 the one before that
+	if (lane == 0)
+	{
+		uint64_t tl = KF_VALID;
+		if (wid > 0)
+		{
+			do
+				tl = *(volatile const uint64_t*)&sm_last[wid];
+			while (!(tl & KF_VALID));
+		}
+		else if (b != 0)
+		{
+			do
+				tl = *(volatile const uint64_t*)&look[b - 1].tail;
+			while (!(tl & KF_VALID));
+		}
+		prev_last = (uint32_t)tl;
+	}
+	q2 = prev_last & 0xFFFFu;
+	q1 = prev_last >> 16;
+	if (t == 0 && b == 0)
 	{
 		q2 = 0x10000u; // sentinels never compare equal
 		q1 = 0x20000u;
 	}
-	else
-	{
-		uint64_t tl;
-		do
-			tl = *(volatile const uint64_t*)&look[b - 1].tail;
-		while (!(tl & KF_VALID));
-		q2 = (uint32_t)tl & 0xFFFFu;
-		q1 = ((uint32_t)tl >> 16) & 0xFFFFu;
-	}
 	KtSpan mine = rest;
+	const uint32_t m0 = kt_step_map(f0 == q1, f0 == q2);
+	const uint32_t m1 = kt_step_map(f1 == f0, f1 == q1);
 	if (K > 0)
 	{
-		const uint32_t m0 = kt_step_map(f0 == q1, f0 == q2);
-		const uint32_t m1 = kt_step_map(f1 == f0, f1 == q1);
 		mine.map = 0;
 #pragma unroll
 		for (int k = 0; k < 4; k++)
@@ -839,25 +861,32 @@ __global__ void __launch_bounds__(KD_THREADS, 4)
 		}
 	}
 
-	KtSpan total;
-	const KtSpan before = kt_block_excl_scan(mine, sm_scan, &total);
+	// ---------------- block scan of the spans with ONE barrier: warps scan themselves, then fold the totals below them
+	KtSpan warp_total;
+	KtSpan before = kt_warp_excl_scan(mine, &warp_total);
+	if (lane == 0)
+		sm_scan[wid] = warp_total;
+	__syncthreads();
+	{
+		KtSpan carry = kt_identity();
+		for (int w = 0; w < wid; w++)
+			carry = kt_compose(carry, sm_scan[w]);
+		before = kt_compose(carry, before);
+	}
 
 	// ---------------- look-back (warp 0): entry state and first output position of this CTA
 	if (wid == 0)
 	{
+		KtSpan total = sm_scan[0];
+#pragma unroll
+		for (int w = 1; w < KD_THREADS / 32; w++)
+			total = kt_compose(total, sm_scan[w]);
 		uint32_t entry = ST_V;
 		uint64_t base = 0;
 		if (b != 0)
 		{
-			if (lane == 0)
-			{
-				look[b].map = total.map;
-#pragma unroll
-				for (int k = 0; k < 4; k++)
-					look[b].out[k] = total.out[k];
-				__threadfence();
-				*(volatile uint32_t*)&look[b].flag = 1u;
-			}
+			if (lane < 5)
+				*(volatile uint32_t*)(&look[b].out[0] + lane) = KF_W | (lane < 4 ? kf_pick(total.out, (uint32_t)lane) : total.map);
 			KfSpan64 F; // everything between the window under examination and this CTA
 			F.map = kt_identity().map;
 			F.out[0] = F.out[1] = F.out[2] = F.out[3] = 0;
@@ -872,16 +901,22 @@ __global__ void __launch_bounds__(KD_THREADS, 4)
 				{
 					for (;;)
 					{
+						// prefix and record together: one round trip
 						pv = *(volatile const uint64_t*)&prefix[p];
+						uint32_t r0, r1, r2, r3;
+						asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];"
+						             : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3)
+						             : "l"(&look[p].out[0]));
+						const uint32_t rm = *(volatile const uint32_t*)&look[p].map;
 						if (pv & KF_VALID)
 							break;
-						if (*(volatile const uint32_t*)&look[p].flag)
+						if (r0 & r1 & r2 & r3 & rm & KF_W)
 						{
-							__threadfence();
-							A.map = *(volatile const uint32_t*)&look[p].map;
-#pragma unroll
-							for (int k = 0; k < 4; k++)
-								A.out[k] = *(volatile const uint32_t*)&look[p].out[k];
+							A.map = rm & 0xFFu;
+							A.out[0] = r0 & ~KF_W;
+							A.out[1] = r1 & ~KF_W;
+							A.out[2] = r2 & ~KF_W;
+							A.out[3] = r3 & ~KF_W;
 							break;
 						}
 					}
@@ -893,23 +928,51 @@ __global__ void __launch_bounds__(KD_THREADS, 4)
 					A.map = kt_identity().map;
 					A.out[0] = A.out[1] = A.out[2] = A.out[3] = 0;
 				}
-				// ordered fold: higher lanes are older CTAs and apply first
-#pragma unroll
-				for (int d = 1; d < 32; d <<= 1)
+				// Fold of the window's records in CTA order (higher lanes are older and apply first). A window costs its
+				// round trip plus this fold, and that must stay below the time in which 32 newer CTAs start, or the
+				// look-back of every CTA grows to the depth of all resident CTAs (measured: a fifth of the kernel's warp
+				// time sat at the barrier below). Records nearly always have a constant exit state: lane l is then entered
+				// in lane l+1's exit state whatever came before, and the fold is one shuffle and two warp reductions.
+				KfSpan64 G;
+				if (first == 0)
 				{
-					KfSpan64 O;
-					O.map = __shfl_down_sync(AKOD_FULL_MASK, A.map, d);
+					G.map = kt_identity().map;
+					G.out[0] = G.out[1] = G.out[2] = G.out[3] = 0;
+				}
+				else if (__all_sync(AKOD_FULL_MASK, lane >= first || kt_is_const(A.map)))
+				{
+					const uint32_t exit_state = A.map & 3u;
+					const uint32_t entered = __shfl_down_sync(AKOD_FULL_MASK, exit_state, 1);
+					const uint32_t c = (lane + 1 < first) ? (uint32_t)(entered == 0   ? A.out[0]
+					                                                   : entered == 1 ? A.out[1]
+					                                                   : entered == 2 ? A.out[2]
+					                                                                  : A.out[3])
+					                                      : 0u; // < 2^31 each
+					const uint64_t sum = (uint64_t)__reduce_add_sync(AKOD_FULL_MASK, c & 0xFFFFu) +
+					                     ((uint64_t)__reduce_add_sync(AKOD_FULL_MASK, c >> 16) << 16);
+					G.map = __shfl_sync(AKOD_FULL_MASK, exit_state, 0) * 0x55u;
 #pragma unroll
 					for (int k = 0; k < 4; k++)
-						O.out[k] = __shfl_down_sync(AKOD_FULL_MASK, A.out[k], d);
-					if (lane + d < 32)
-						A = kf_compose(O, A);
+						G.out[k] = (uint64_t)__shfl_sync(AKOD_FULL_MASK, (uint32_t)A.out[k], first - 1) + sum; // the oldest record
 				}
-				KfSpan64 G;
-				G.map = __shfl_sync(AKOD_FULL_MASK, A.map, 0);
+				else
+				{
 #pragma unroll
-				for (int k = 0; k < 4; k++)
-					G.out[k] = __shfl_sync(AKOD_FULL_MASK, A.out[k], 0);
+					for (int d = 1; d < 32; d <<= 1)
+					{
+						KfSpan64 O;
+						O.map = __shfl_down_sync(AKOD_FULL_MASK, A.map, d);
+#pragma unroll
+						for (int k = 0; k < 4; k++)
+							O.out[k] = __shfl_down_sync(AKOD_FULL_MASK, A.out[k], d);
+						if (lane + d < 32)
+							A = kf_compose(O, A);
+					}
+					G.map = __shfl_sync(AKOD_FULL_MASK, A.map, 0);
+#pragma unroll
+					for (int k = 0; k < 4; k++)
+						G.out[k] = __shfl_sync(AKOD_FULL_MASK, A.out[k], 0);
+				}
 				F = kf_compose(G, F);
 				if (first < 32)
 				{
@@ -946,12 +1009,75 @@ __global__ void __launch_bounds__(KD_THREADS, 4)
 	const uint64_t w_pos0 = cta_base + w_rel0;
 	const uint32_t mis = (uint32_t)w_pos0 & 7u;
 	int16_t* const wst = stage[wid];
-	const uint32_t Kmax = __reduce_max_sync(AKOD_FULL_MASK, K);
+	// does any thread of the warp meet a run that the warp should fill together? (exact: the first two codewords are
+	// classified with the entry state now known, the others were recorded per entry state in walk 1)
+	bool any_coop;
 	{
+		bool mine_coop = false;
+		uint32_t st = state;
+		if (K > 0)
+		{
+			mine_coop = (st == ST_R) && f0 > KT_LONG;
+			st = (m0 >> (2 * st)) & 3u;
+		}
+		if (K > 1)
+		{
+			mine_coop |= (st == ST_R) && f1 > KT_LONG;
+			st = (m1 >> (2 * st)) & 3u;
+		}
+		mine_coop |= ((coop_mask >> st) & 1u) != 0;
+		any_coop = __any_sync(AKOD_FULL_MASK, mine_coop);
+	}
+	p1 = q1;
+	p2 = q2;
+	auto emit_literal = [&](uint32_t u) {
+		if (staged)
+			wst[rel - w_rel0 + mis] = kt_value(u);
+		else if (cta_base + rel < n_values)
+			out[cta_base + rel] = kt_value(u);
+		rel += 1;
+		state = kt_next(state, u == p1, u == p2);
+	};
+	if (!any_coop)
+	{
+		// every run of this warp is shorter than KT_LONG: threads go their own way
 		KfCursor c;
 		kf_open(sm, K ? s.start : 0u, c);
-		p1 = q1;
-		p2 = q2;
+		for (uint32_t j = 0; j < K; j++)
+		{
+			const uint32_t u = kf_next(sm, c);
+			if (state == ST_R)
+			{
+				// an RLE count: (u - 1) more copies of the value before it (kagari.c:342-354)
+				const uint32_t count = u - 1u;
+				const int16_t v = kt_value(p1);
+				const uint64_t pos = cta_base + rel;
+				if (staged)
+				{
+					int16_t* d = wst + (rel - w_rel0 + mis);
+					for (uint32_t k = 0; k < count; k++)
+						d[k] = v;
+				}
+				else if (pos + count <= n_values)
+				{
+					int16_t* d = out + pos;
+					for (uint32_t k = 0; k < count; k++)
+						d[k] = v;
+				}
+				rel += count;
+				state = ST_A;
+			}
+			else
+				emit_literal(u);
+			p2 = p1;
+			p1 = u;
+		}
+	}
+	else
+	{
+		const uint32_t Kmax = __reduce_max_sync(AKOD_FULL_MASK, K);
+		KfCursor c;
+		kf_open(sm, K ? s.start : 0u, c);
 		for (uint32_t j = 0; j < Kmax; j++)
 		{
 			bool coop = false;
@@ -962,7 +1088,6 @@ __global__ void __launch_bounds__(KD_THREADS, 4)
 				const uint32_t u = kf_next(sm, c);
 				if (state == ST_R)
 				{
-					// an RLE count: (u - 1) more copies of the value before it (kagari.c:342-354)
 					count = u - 1u;
 					v = kt_value(p1);
 					const uint64_t pos = cta_base + rel;
@@ -1004,14 +1129,7 @@ __global__ void __launch_bounds__(KD_THREADS, 4)
 					state = ST_A;
 				}
 				else
-				{
-					if (staged)
-						wst[rel - w_rel0 + mis] = kt_value(u);
-					else if (cta_base + rel < n_values)
-						out[cta_base + rel] = kt_value(u);
-					rel += 1;
-					state = kt_next(state, u == p1, u == p2);
-				}
+					emit_literal(u);
 				p2 = p1;
 				p1 = u;
 			}

@@ -42,7 +42,8 @@ EVENTS_FN = C.CFUNCTYPE(None, c_size_t, c_size_t, c_int, c_void_p)
 
 
 def lib_path():
-    return os.path.join(HERE, "libako_b200.so")
+    # AKO_B200_LIB: another build of the same library (A/B experiments of kernel variants)
+    return os.environ.get("AKO_B200_LIB") or os.path.join(HERE, "libako_b200.so")
 
 
 def build(verbose=False):

@@ -18,5 +18,5 @@ for r in rows:
 tot = sum(cnt.values()); ts = sum(samples.values()) or 1
 print("total", tot)
 for k in sorted(cnt):
-    if cnt[k] * 200 >= tot:
+    if cnt[k] * 200 >= tot or samples[k] * 100 >= ts:
         print(f"{k[0]}:{k[1]:4d} {100*cnt[k]/tot:5.1f}% inst {100*samples[k]/ts:5.1f}% samples | {text.get(k,'')[:110]}")
