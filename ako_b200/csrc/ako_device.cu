@@ -11,6 +11,7 @@
 #include "lift.cuh"
 #include "lift_small.cuh"
 #include "lift_strip.cuh"
+#include "lift_strip4.cuh"
 #include "unlift_strip.cuh"
 
 // ------------------------------------------------------------------------------------------------
@@ -41,6 +42,7 @@ extern "C" int akod_context_create(int device, akodContext** out)
 	c->launch_count = 0;
 	c->next_bytes = 0;
 	c->small_attr_done = false;
+	c->strip4_attr_done = 0;
 	c->mailbox = nullptr;
 	c->sync_event = nullptr;
 	c->blocking_sync = false;
@@ -544,6 +546,48 @@ static int launch_lift_strip(akodContext* c, const LiftParams& p, uint32_t n_ima
 	return AKOD_OK;
 }
 
+// level 0 straight from the interleaved RGBA8 image (lift_strip4.cuh)
+template <int WL>
+static int launch_lift_strip4(akodContext* c, const LiftParams& p, uint32_t n_images, const uint8_t* rgba, uint64_t rgba_is,
+                              uint64_t rgba_rs, int color, int discard)
+{
+	constexpr int LAT = StripGeom<WL>::LAT;
+	if (!(c->strip4_attr_done & (1u << WL)))
+	{
+		AKOD_TRY(cudaSetDevice(c->device));
+		AKOD_TRY(cudaFuncSetAttribute(k_lift_strip4<WL, FS_PLAIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)F4_SMEM));
+		AKOD_TRY(cudaFuncSetAttribute(k_lift_strip4<WL, FS_QUANT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)F4_SMEM));
+		AKOD_TRY(cudaFuncSetAttribute(k_lift_strip4<WL, FS_GATE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)F4_SMEM));
+		c->strip4_attr_done |= 1u << WL;
+	}
+	const uint32_t strips = (p.tw + F4_TW - 1) / F4_TW;
+	const uint32_t split = strip_split(p.th, (uint64_t)strips * n_images, (uint64_t)c->sm_count * F4_CTAS, LAT);
+	Strip4Params sp;
+	sp.p = p;
+	sp.rgba = rgba;
+	sp.rgba_is = rgba_is;
+	sp.rgba_rs = (uint32_t)rgba_rs;
+	sp.color = color;
+	sp.discard = discard;
+	sp.split = split;
+	bool plain = true, gate = false;
+	for (uint32_t ch = 0; ch < p.channels; ch++)
+	{
+		plain = plain && p.q[ch] <= 1 && p.g[ch] == 0;
+		gate = gate || p.g[ch] >= p.q[ch];
+	}
+	const dim3 grid(strips, (p.th + split - 1) / split, n_images);
+	static const char* const names[3] = {"lift_strip4_dd137", "lift_strip4_cdf53", "lift_strip4_haar"};
+	AKOD_BYTES(c, (uint64_t)3 * p.cw * p.ch * p.channels * n_images); // every u8 sample read once, every int16 coefficient written once
+	if (plain)
+		AKOD_LAUNCH(c, names[WL], (k_lift_strip4<WL, FS_PLAIN>), grid, F4_THREADS, F4_SMEM, sp);
+	else if (!gate)
+		AKOD_LAUNCH(c, names[WL], (k_lift_strip4<WL, FS_QUANT>), grid, F4_THREADS, F4_SMEM, sp);
+	else
+		AKOD_LAUNCH(c, names[WL], (k_lift_strip4<WL, FS_GATE>), grid, F4_THREADS, F4_SMEM, sp);
+	return AKOD_OK;
+}
+
 template <int WL>
 static int launch_unlift_strip(akodContext* c, const UnliftParams& p, uint32_t n_images, bool v1)
 {
@@ -634,10 +678,20 @@ static int launch_small(akodContext* c, const akodPlan* plan, uint32_t l0, bool 
 	return AKOD_OK;
 }
 
-extern "C" int akod_lift(akodContext* c, const akodPlan* plan, int16_t* d_planes, int16_t* d_scratch, int16_t* d_stream,
-                         const akodBatch* b)
+// u8: when not NULL, level 0 may read the interleaved RGBA8 image itself (the colour/format pass fused into the
+// lifting kernel); *fused tells whether it did -- if not, the caller's planes must hold the formatted image.
+struct LiftRgba
 {
-	akod_use(c);
+	const uint8_t* rgba;
+	uint64_t rgba_is, rgba_rs;
+	int color, discard;
+};
+
+static int lift_pyramid(akodContext* c, const akodPlan* plan, int16_t* d_planes, int16_t* d_scratch, int16_t* d_stream,
+                        const akodBatch* b, const LiftRgba* u8, bool probe_only, bool* fused)
+{
+	if (fused)
+		*fused = false;
 	const uint32_t n = b ? b->n : 1;
 	const uint64_t planes_is = b ? b->planes_stride : 0, scratch_is = b ? b->scratch_stride : 0;
 	const uint64_t stream_is = b ? b->stream_stride : 0;
@@ -697,7 +751,24 @@ extern "C" int akod_lift(akodContext* c, const akodPlan* plan, int16_t* d_planes
 		}
 		int rc;
 		static const bool no_strip = getenv("AKO_B200_NO_STRIP") != nullptr;
-		if (!no_strip && lift_strip_eligible(p))
+		static const bool no_fuse = getenv("AKO_B200_NO_FUSE") != nullptr;
+		if (l == 0 && fused)
+		{
+			*fused = u8 != nullptr && !no_strip && !no_fuse &&
+			         lift_strip4_eligible(p, u8->rgba, u8->rgba_is, u8->rgba_rs);
+			if (probe_only)
+				return AKOD_OK;
+		}
+		if (l == 0 && fused && *fused)
+		{
+			if (L->wavelet == AKOD_DD137)
+				rc = launch_lift_strip4<AKOD_DD137>(c, p, n, u8->rgba, u8->rgba_is, u8->rgba_rs, u8->color, u8->discard);
+			else if (L->wavelet == AKOD_CDF53)
+				rc = launch_lift_strip4<AKOD_CDF53>(c, p, n, u8->rgba, u8->rgba_is, u8->rgba_rs, u8->color, u8->discard);
+			else
+				rc = launch_lift_strip4<AKOD_HAAR>(c, p, n, u8->rgba, u8->rgba_is, u8->rgba_rs, u8->color, u8->discard);
+		}
+		else if (!no_strip && lift_strip_eligible(p))
 		{
 			if (L->wavelet == AKOD_DD137)
 				rc = launch_lift_strip<AKOD_DD137>(c, p, n);
@@ -734,6 +805,57 @@ extern "C" int akod_lift(akodContext* c, const akodPlan* plan, int16_t* d_planes
 			                         sizeof(int16_t) * plan->stream_len, cudaMemcpyDeviceToDevice, c->stream));
 	}
 	return AKOD_OK;
+}
+
+extern "C" int akod_lift(akodContext* c, const akodPlan* plan, int16_t* d_planes, int16_t* d_scratch, int16_t* d_stream,
+                         const akodBatch* b)
+{
+	akod_use(c);
+	return lift_pyramid(c, plan, d_planes, d_scratch, d_stream, b, nullptr, false, nullptr);
+}
+
+// Will akod_format_lift run the colour/format pass inside the level-0 lifting kernel? (4-channel CLAMP images whose
+// level 0 takes the strip kernel: lift_strip4.cuh.) The host asks so that its FORMAT / WAVELET events bracket what
+// they name.
+extern "C" int akod_format_lift_fuses(akodContext* c, uint32_t channels, uint32_t w, uint32_t h, uint64_t in_stride_px,
+                                      const uint8_t* d_in, const akodPlan* plan, int16_t* d_planes, int16_t* d_scratch,
+                                      int16_t* d_stream, const akodBatch* b)
+{
+	if (channels != 4 || (b && b->n_real) || plan->w != w || plan->h != h || plan->levels == 0)
+		return 0;
+	LiftRgba u8;
+	u8.rgba = d_in;
+	u8.rgba_is = b ? b->in_stride : 0;
+	u8.rgba_rs = in_stride_px * 4;
+	u8.color = u8.discard = 0;
+	bool fused = false;
+	if (lift_pyramid(c, plan, d_planes, d_scratch, d_stream, b, &u8, true, &fused) != AKOD_OK)
+		return 0;
+	return fused ? 1 : 0;
+}
+
+// akod_format_forward + akod_lift; when akod_format_lift_fuses() says so, level 0 reads the RGBA8 image itself and
+// d_planes is only a ping-pong buffer of the coarser levels
+extern "C" int akod_format_lift(akodContext* c, int discard, int color, uint32_t channels, uint32_t w, uint32_t h,
+                                uint64_t in_stride_px, const uint8_t* d_in, const akodPlan* plan, int16_t* d_planes,
+                                int16_t* d_scratch, int16_t* d_stream, const akodBatch* b)
+{
+	akod_use(c);
+	if (akod_format_lift_fuses(c, channels, w, h, in_stride_px, d_in, plan, d_planes, d_scratch, d_stream, b))
+	{
+		LiftRgba u8;
+		u8.rgba = d_in;
+		u8.rgba_is = b ? b->in_stride : 0;
+		u8.rgba_rs = in_stride_px * 4;
+		u8.color = color;
+		u8.discard = discard;
+		bool fused = false;
+		return lift_pyramid(c, plan, d_planes, d_scratch, d_stream, b, &u8, false, &fused);
+	}
+	const int rc = akod_format_forward(c, discard, color, channels, w, h, in_stride_px, d_in, d_planes, b);
+	if (rc != AKOD_OK)
+		return rc;
+	return lift_pyramid(c, plan, d_planes, d_scratch, d_stream, b, nullptr, false, nullptr);
 }
 
 extern "C" int akod_unlift(akodContext* c, const akodPlan* plan, const int16_t* d_stream, int16_t* d_planes,

@@ -162,6 +162,14 @@ int akod_format_inverse(akodContext*, int color, uint32_t channels, uint32_t w, 
 /* full pyramid; d_planes (channels*w*h) is destroyed; d_scratch needs channels*ceil(w/2)*ceil(h/2) */
 int akod_lift(akodContext*, const akodPlan*, int16_t* d_planes, int16_t* d_scratch, int16_t* d_stream,
               const akodBatch*);
+/* akod_format_forward followed by akod_lift; the two are one kernel on level 0 when the image allows (lift_strip4.cuh):
+ * akod_format_lift_fuses() tells (1 / 0) */
+int akod_format_lift_fuses(akodContext*, uint32_t channels, uint32_t w, uint32_t h, uint64_t in_stride_px,
+                           const uint8_t* d_in, const akodPlan*, int16_t* d_planes, int16_t* d_scratch, int16_t* d_stream,
+                           const akodBatch*);
+int akod_format_lift(akodContext*, int discard, int color, uint32_t channels, uint32_t w, uint32_t h,
+                     uint64_t in_stride_px, const uint8_t* d_in, const akodPlan*, int16_t* d_planes, int16_t* d_scratch,
+                     int16_t* d_stream, const akodBatch*);
 /* full inverse pyramid into d_planes; d_scratch as above; d_stream untouched */
 int akod_unlift(akodContext*, const akodPlan*, const int16_t* d_stream, int16_t* d_planes, int16_t* d_scratch,
                 const akodBatch*);

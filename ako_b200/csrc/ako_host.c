@@ -1125,11 +1125,17 @@ static size_t encode_core_ex(akoB200Context* ctx, const struct akoCallbacks* cb,
 		int16_t* cached = (sc != NULL && sc->d_raw != NULL) ? sc->d_raw + cache_cursor : NULL;
 		cache_cursor += align_up(G.data[g] / 2, 8);
 
+		/* level 0 of the lifting may read the RGBA8 image itself (colour/format fused into the kernel) */
+		int fuse = 0;
+		if (!use && s.wavelet != AKO_WAVELET_NONE)
+			fuse = akod_format_lift_fuses(ctx->dev, (uint32_t)channels, (uint32_t)tw, (uint32_t)th, w, d_in,
+			                              get_plan(ctx, &s, channels, tw, th), planes, scratch, fill ? cached : stream, &batch);
 		if (!use)
 		{
 			fire(cb, ctx, t_event, tiles, AKO_EVENT_FORMAT_START);
-			st = from_dev(akod_format_forward(ctx->dev, s.discard_non_visible, (int)s.color, (uint32_t)channels,
-			                                  (uint32_t)tw, (uint32_t)th, w, d_in, planes, &batch));
+			if (!fuse)
+				st = from_dev(akod_format_forward(ctx->dev, s.discard_non_visible, (int)s.color, (uint32_t)channels,
+				                                  (uint32_t)tw, (uint32_t)th, w, d_in, planes, &batch));
 			fire(cb, ctx, t_event, tiles, AKO_EVENT_FORMAT_END);
 		}
 
@@ -1140,6 +1146,10 @@ static size_t encode_core_ex(akoB200Context* ctx, const struct akoCallbacks* cb,
 			fire(cb, ctx, t_event, tiles, AKO_EVENT_WAVELET_START);
 			if (use)
 				st = from_dev(akod_requantize(ctx->dev, get_plan(ctx, &s, channels, tw, th), cached, stream));
+			else if (fuse)
+				st = from_dev(akod_format_lift(ctx->dev, s.discard_non_visible, (int)s.color, (uint32_t)channels, (uint32_t)tw,
+				                               (uint32_t)th, w, d_in, get_plan(ctx, &s, channels, tw, th), planes, scratch,
+				                               fill ? cached : stream, &batch));
 			else
 				st = from_dev(akod_lift(ctx->dev, get_plan(ctx, &s, channels, tw, th), planes, scratch,
 				                        fill ? cached : stream, &batch));

@@ -39,6 +39,7 @@ struct akodContext
 	uint64_t launch_count;
 	uint64_t next_bytes; // algorithmic bytes of the next launch (consumed by AKOD_LAUNCH)
 	bool small_attr_done; // cudaFuncSetAttribute for the small-pyramid kernels done on this device
+	uint32_t strip4_attr_done; // ... for the fused level-0 kernels, one bit per wavelet
 	std::vector<akodProfEntry> prof;
 	std::vector<akodPending> pending;
 	std::vector<cudaEvent_t> event_pool;

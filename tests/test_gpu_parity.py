@@ -233,6 +233,25 @@ def test_end_to_end_options(orc):
     _e2e(orc, img, wavelet=W_NONE, compression=2, q=0)
 
 
+@pytest.mark.parametrize("wavelet", [W_DD137, W_CDF53, W_HAAR])
+def test_end_to_end_rgba_level0_fused(orc, wavelet):
+    """4-channel CLAMP images whose level 0 runs in the fused colour + lifting kernel (lift_strip4.cuh): noise RGBA
+    with transparent pixels, one / several / partial 64-column strips, several row splits, odd heights, every colour
+    model with and without alpha discard, every quantiser mode -- .ako bytes against the oracle's."""
+    rs = np.random.RandomState(7 + wavelet)
+    for (w, h) in [(64, 16), (72, 17), (136, 72), (200, 151), (1032, 530), (2064, 1100)]:
+        img = noise_image(w, h, 4, w + h)
+        img[rs.rand(h, w) < 0.3, 3] = 0
+        big = w * h > 100000
+        for color in ((C_YCOCG,) if big else (C_YCOCG, C_SUBG, C_NONE)):
+            for discard in ((1,) if big else (0, 1)):
+                for q, g in [(0, 0), (16, 0), (5, 12)]:
+                    _e2e(orc, img, wavelet=wavelet, color=color, discard=discard, q=q, g=g)
+    # smooth content as well (the quantised planes of noise are all escapes)
+    img = ol.synth(orc, 1632, 616, 3)
+    _e2e(orc, img, wavelet=wavelet, q=16, g=16)
+
+
 @pytest.mark.parametrize("tiles", [8, 32, 64, 256])
 def test_end_to_end_tiles(orc, tiles):
     for (w, h) in [(200, 150), (256, 256), (67, 131)]:
