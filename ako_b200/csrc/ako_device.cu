@@ -999,14 +999,19 @@ extern "C" int akod_kagari_encode(akodContext* c, uint64_t n_values, const int16
 	uint32_t* blk_own = slots + per_img * n_images * KG_SLOT_WORDS;
 	uint8_t* blk_first = (uint8_t*)(blk_own + per_img * n_images);
 
-	const dim3 lgrid((nblocks + KGL_WARPS * KGL_BLOCKS_PER_WARP - 1) / (KGL_WARPS * KGL_BLOCKS_PER_WARP), n_images);
+	// blocks per warp: four when that still gives every SM its five CTAs, fewer for a small batch (one image alone was
+	// 246 CTAs of 32 blocks each: a latency chain on 1.7 CTAs per SM)
+	uint32_t bpw = KGL_BLOCKS_PER_WARP;
+	while (bpw > 1 && (uint64_t)((nblocks + KGL_WARPS * bpw - 1) / (KGL_WARPS * bpw)) * n_images < (uint64_t)c->sm_count * 5)
+		bpw >>= 1;
+	const dim3 lgrid((nblocks + KGL_WARPS * bpw - 1) / (KGL_WARPS * bpw), n_images);
 	AKOD_BYTES(c, 2 * n_values * n_images);
 	AKOD_LAUNCH(c, "kagari_starts", k_kg_starts, dim3((nblocks + KG_STARTS_PER_CTA - 1) / KG_STARTS_PER_CTA, n_images), KG_THREADS,
 	            0, d_in, in_stride, n_values, blk_own, blk_first, nblocks);
 	AKOD_LAUNCH(c, "kagari_scan_max", k_kg_scan_max, n_images, 1024, 0, blk_own, blk_start, nblocks);
 	AKOD_BYTES(c, 2 * n_values * n_images);
 	AKOD_LAUNCH(c, "kagari_lengths", k_kg_lengths, lgrid, KG_THREADS, 0, d_in, in_stride, n_values, blk_start, blk_bits,
-	            nblocks, slots, blk_own, blk_first);
+	            nblocks, slots, blk_own, blk_first, bpw);
 	AKOD_LAUNCH(c, "kagari_scan_sum", k_kg_scan_sum, n_images, 1024, 0, blk_bits, blk_off, nblocks, d_bits);
 	const dim3 zgrid((nblocks + 255) / 256, n_images);
 	AKOD_LAUNCH(c, "kagari_zero_edges", k_kg_zero_edges, zgrid, 256, 0, blk_off, blk_bits, nblocks, d_out, out_stride,
@@ -1037,14 +1042,19 @@ extern "C" int akod_kagari_bits(akodContext* c, uint64_t n_values, const int16_t
 	uint32_t* slots = blk_bits + per_img * n_images;
 	uint32_t* blk_own = slots + per_img * n_images * KG_SLOT_WORDS;
 	uint8_t* blk_first = (uint8_t*)(blk_own + per_img * n_images);
-	const dim3 lgrid((nblocks + KGL_WARPS * KGL_BLOCKS_PER_WARP - 1) / (KGL_WARPS * KGL_BLOCKS_PER_WARP), n_images);
+	// blocks per warp: four when that still gives every SM its five CTAs, fewer for a small batch (one image alone was
+	// 246 CTAs of 32 blocks each: a latency chain on 1.7 CTAs per SM)
+	uint32_t bpw = KGL_BLOCKS_PER_WARP;
+	while (bpw > 1 && (uint64_t)((nblocks + KGL_WARPS * bpw - 1) / (KGL_WARPS * bpw)) * n_images < (uint64_t)c->sm_count * 5)
+		bpw >>= 1;
+	const dim3 lgrid((nblocks + KGL_WARPS * bpw - 1) / (KGL_WARPS * bpw), n_images);
 	AKOD_BYTES(c, 2 * n_values * n_images);
 	AKOD_LAUNCH(c, "kagari_starts", k_kg_starts, dim3((nblocks + KG_STARTS_PER_CTA - 1) / KG_STARTS_PER_CTA, n_images), KG_THREADS,
 	            0, d_in, in_stride, n_values, blk_own, blk_first, nblocks);
 	AKOD_LAUNCH(c, "kagari_scan_max", k_kg_scan_max, n_images, 1024, 0, blk_own, blk_start, nblocks);
 	AKOD_BYTES(c, 2 * n_values * n_images);
 	AKOD_LAUNCH(c, "kagari_lengths", k_kg_lengths, lgrid, KG_THREADS, 0, d_in, in_stride, n_values, blk_start, blk_bits,
-	            nblocks, slots, blk_own, blk_first);
+	            nblocks, slots, blk_own, blk_first, bpw);
 	AKOD_LAUNCH(c, "kagari_scan_sum", k_kg_scan_sum, n_images, 1024, 0, blk_bits, blk_off, nblocks, d_bits);
 	return AKOD_OK;
 }

@@ -1280,6 +1280,225 @@ AKO_API size_t akoB200EncodeDevice(akoB200Context* ctx, const struct akoSettings
 	return ok ? size : 0;
 }
 
+/* ---- one tiled image over several GPUs: tiles are independent blocks (encode.c:115-205,
+ * decode.c:113-230), so the tile rows are cut into one band per device of $AKO_CUDA_DEVICES. A band is encoded or
+ * decoded as the image it is (same width, same tiles_dimension: its tiles have the sizes they have in the whole
+ * image, and a tile's block does not depend on where the tile lies); the host concatenates the bands' blocks in raster
+ * order behind the one head, or cuts the blob at the block heads it has walked. Events are tile-ordered callbacks
+ * and keep such calls on one device. */
+#define BANDS_MIN_PIXELS ((size_t)8 << 20)
+static size_t env_size(const char* name, size_t fallback, size_t lo, size_t hi);
+
+struct band_job
+{
+	int device;
+	size_t y0, bh;          /* image rows of the band */
+	size_t t0, tn;          /* its tiles (raster order) */
+	akoB200Context* ctx;
+	enum akoStatus st;
+	/* encode */
+	const struct akoSettings* s;
+	size_t channels, w;
+	const uint8_t* in;
+	uint8_t* d_out;
+	size_t size;
+	/* decode */
+	const uint8_t* blob;
+	const uint64_t *off, *bsz;
+	uint8_t* image;
+	pthread_t thread;
+};
+
+static int bands_wanted(const struct akoCallbacks* cb, const struct akoSettings* s, size_t w, size_t h, int devices[MAX_DEVICES])
+{
+	const size_t td = s->tiles_dimension;
+	if (td == 0 || (cb != NULL && cb->events != NULL) || w * h < env_size("AKO_B200_BANDS_MIN_PIXELS", BANDS_MIN_PIXELS, 1, (size_t)1 << 40))
+		return 0;
+	const int nd = env_devices(devices);
+	const size_t rows = (h / td) + (h % td != 0);
+	if (nd < 2 || rows < 2)
+		return 0;
+	return (rows < (size_t)nd) ? (int)rows : nd;
+}
+
+static void bands_cut(struct band_job* jobs, int nb, const int* devices, size_t w, size_t h, size_t td)
+{
+	const size_t rows = (h / td) + (h % td != 0), tiles_x = (w / td) + (w % td != 0);
+	for (int k = 0; k < nb; k++)
+	{
+		const size_t r0 = rows * (size_t)k / (size_t)nb, r1 = rows * (size_t)(k + 1) / (size_t)nb;
+		memset(&jobs[k], 0, sizeof(jobs[k]));
+		jobs[k].device = devices[k];
+		jobs[k].y0 = r0 * td;
+		jobs[k].bh = ((r1 * td < h) ? r1 * td : h) - r0 * td;
+		jobs[k].t0 = r0 * tiles_x;
+		jobs[k].tn = (r1 - r0) * tiles_x;
+		jobs[k].st = AKO_OK;
+	}
+}
+
+static void* band_encode_worker(void* raw)
+{
+	struct band_job* j = raw;
+	const struct akoCallbacks quiet = akoDefaultCallbacks();
+	if ((j->ctx = pool_acquire_on(j->device, &j->st)) == NULL)
+		return NULL;
+	const size_t bytes = j->w * j->bh * j->channels;
+	const size_t bound = akoB200EncodeBound(j->s, j->channels, j->w, j->bh);
+	void *d_in, *d_out;
+	if ((j->st = from_dev(akod_workspace(j->ctx->dev, AKOD_WS_INPUT, bytes + 64, &d_in))) != AKO_OK ||
+	    (j->st = from_dev(akod_workspace(j->ctx->dev, AKOD_WS_OUTPUT, bound + 64, &d_out))) != AKO_OK ||
+	    (j->st = from_dev(akod_h2d(j->ctx->dev, d_in, j->in + j->y0 * j->w * j->channels, bytes))) != AKO_OK)
+		return NULL;
+	if (encode_core(j->ctx, &quiet, j->s, j->channels, j->w, j->bh, 1, d_in, 0, d_out, 0, bound, &j->size, &j->st) != 1)
+		j->size = 0;
+	j->d_out = d_out;
+	return NULL;
+}
+
+static size_t encode_bands(const struct akoCallbacks* cb, const struct akoSettings* s, size_t channels, size_t w, size_t h,
+                           const void* in, const uint8_t head[16], const int* devices, int nb, void** out,
+                           enum akoStatus* out_status)
+{
+	struct band_job jobs[MAX_DEVICES];
+	enum akoStatus st = AKO_OK;
+	uint8_t* blob = NULL;
+	size_t total = 16;
+	bands_cut(jobs, nb, devices, w, h, s->tiles_dimension);
+	for (int k = 0; k < nb; k++)
+	{
+		jobs[k].s = s;
+		jobs[k].channels = channels;
+		jobs[k].w = w;
+		jobs[k].in = in;
+	}
+	for (int k = 1; k < nb; k++)
+		if (pthread_create(&jobs[k].thread, NULL, band_encode_worker, &jobs[k]) != 0)
+		{
+			jobs[k].st = AKO_ERROR;
+			jobs[k].thread = 0;
+		}
+	band_encode_worker(&jobs[0]);
+	for (int k = 1; k < nb; k++)
+		if (jobs[k].thread != 0)
+			pthread_join(jobs[k].thread, NULL);
+	for (int k = 0; k < nb && st == AKO_OK; k++)
+	{
+		st = jobs[k].st;
+		if (st == AKO_OK && jobs[k].size <= 16)
+			st = AKO_ERROR;
+		total += jobs[k].size - 16;
+	}
+	if (st == AKO_OK && (blob = cb->malloc(total)) == NULL)
+		st = AKO_NO_ENOUGH_MEMORY;
+	if (st == AKO_OK)
+	{
+		/* the bands' blocks, in raster order, behind the head of the whole image */
+		size_t at = 16;
+		memcpy(blob, head, 16);
+		for (int k = 0; k < nb && st == AKO_OK; k++)
+		{
+			st = from_dev(akod_d2h(jobs[k].ctx->dev, blob + at, jobs[k].d_out + 16, jobs[k].size - 16));
+			at += jobs[k].size - 16;
+		}
+		for (int k = 0; k < nb; k++)
+		{
+			const enum akoStatus w_st = from_dev(akod_sync(jobs[k].ctx->dev));
+			if (st == AKO_OK)
+				st = w_st;
+		}
+	}
+	for (int k = 0; k < nb; k++)
+		if (jobs[k].ctx != NULL)
+			pool_release(jobs[k].ctx);
+	if (st != AKO_OK)
+	{
+		if (blob != NULL)
+			cb->free(blob);
+		blob = NULL;
+		total = 0;
+	}
+	if (out != NULL)
+		*out = blob;
+	else if (blob != NULL)
+		cb->free(blob);
+	if (out_status != NULL)
+		*out_status = st;
+	return total;
+}
+
+static enum akoStatus decode_core(akoB200Context* ctx, const struct akoCallbacks* cb, const struct akoSettings* s,
+                                  size_t channels, size_t w, size_t h, size_t n, const uint8_t* d_in, size_t in_stride,
+                                  const uint64_t* blk_off, const uint64_t* blk_size, uint8_t* d_out, size_t out_stride,
+                                  size_t* done_out);
+
+static void* band_decode_worker(void* raw)
+{
+	struct band_job* j = raw;
+	const struct akoCallbacks quiet = akoDefaultCallbacks();
+	uint64_t* off = NULL;
+	if ((j->ctx = pool_acquire_on(j->device, &j->st)) == NULL)
+		return NULL;
+	/* the bytes of the band's blocks, block heads included */
+	const size_t head_bytes = (j->s->compression != AKO_COMPRESSION_NONE) ? 4 : 0;
+	const size_t first = (size_t)j->off[j->t0] - head_bytes;
+	const size_t last = (size_t)(j->off[j->t0 + j->tn - 1] + j->bsz[j->t0 + j->tn - 1]);
+	const size_t image_bytes = j->w * j->bh * j->channels;
+	void *d_in, *d_out;
+	size_t ok = 0;
+	if ((off = malloc(sizeof(uint64_t) * j->tn)) == NULL)
+	{
+		j->st = AKO_NO_ENOUGH_MEMORY;
+		return NULL;
+	}
+	for (size_t t = 0; t < j->tn; t++)
+		off[t] = j->off[j->t0 + t] - first;
+	if ((j->st = from_dev(akod_workspace(j->ctx->dev, AKOD_WS_INPUT, last - first + 64, &d_in))) == AKO_OK &&
+	    (j->st = from_dev(akod_workspace(j->ctx->dev, AKOD_WS_OUTPUT, image_bytes + 64, &d_out))) == AKO_OK &&
+	    (j->st = from_dev(akod_h2d(j->ctx->dev, d_in, j->blob + first, last - first))) == AKO_OK &&
+	    (j->st = decode_core(j->ctx, &quiet, j->s, j->channels, j->w, j->bh, 1, d_in, 0, off, j->bsz + j->t0, d_out, 0, &ok)) == AKO_OK &&
+	    (j->st = from_dev(akod_d2h(j->ctx->dev, j->image + j->y0 * j->w * j->channels, d_out, image_bytes))) == AKO_OK)
+		j->st = from_dev(akod_sync(j->ctx->dev));
+	free(off);
+	return NULL;
+}
+
+static enum akoStatus decode_bands(const struct akoSettings* s, size_t channels, size_t w, size_t h, const uint8_t* blob,
+                                   const uint64_t* off, const uint64_t* bsz, uint8_t* image, const int* devices, int nb)
+{
+	struct band_job jobs[MAX_DEVICES];
+	enum akoStatus st = AKO_OK;
+	bands_cut(jobs, nb, devices, w, h, s->tiles_dimension);
+	for (int k = 0; k < nb; k++)
+	{
+		jobs[k].s = s;
+		jobs[k].channels = channels;
+		jobs[k].w = w;
+		jobs[k].blob = blob;
+		jobs[k].off = off;
+		jobs[k].bsz = bsz;
+		jobs[k].image = image;
+	}
+	for (int k = 1; k < nb; k++)
+		if (pthread_create(&jobs[k].thread, NULL, band_decode_worker, &jobs[k]) != 0)
+		{
+			jobs[k].st = AKO_ERROR;
+			jobs[k].thread = 0;
+		}
+	band_decode_worker(&jobs[0]);
+	for (int k = 1; k < nb; k++)
+		if (jobs[k].thread != 0)
+			pthread_join(jobs[k].thread, NULL);
+	for (int k = 0; k < nb; k++)
+	{
+		if (st == AKO_OK)
+			st = jobs[k].st;
+		if (jobs[k].ctx != NULL)
+			pool_release(jobs[k].ctx);
+	}
+	return st;
+}
+
 AKO_API size_t akoEncodeExt(const struct akoCallbacks* c, const struct akoSettings* s, size_t channels, size_t w,
                             size_t h, const void* in, void** out, enum akoStatus* out_status)
 {
@@ -1305,10 +1524,14 @@ AKO_API size_t akoEncodeExt(const struct akoCallbacks* c, const struct akoSettin
 		/* validate before touching the device so that bad arguments never cost a context */
 		struct akoSettings v = checked;
 		uint8_t head[16];
+		int devices[MAX_DEVICES];
 		if (v.color == AKO_COLOR_YCOCG && (v.quantization > 0 || v.gate > 0))
 			v.color = AKO_COLOR_YCOCG_Q;
 		if ((st = head_write(channels, w, h, &v, head)) != AKO_OK)
 			goto done;
+		const int nb = bands_wanted(&cb, &checked, w, h, devices);
+		if (nb > 1) /* a tiled image and several GPUs: one band of tile rows per device */
+			return encode_bands(&cb, &checked, channels, w, h, in, head, devices, nb, out, out_status);
 	}
 	if ((ctx = pool_acquire(&st)) == NULL)
 		goto done;
@@ -1847,6 +2070,32 @@ AKO_API uint8_t* akoDecodeExt(const struct akoCallbacks* c, size_t input_size, c
 	}
 	if ((st = walk_blocks_host(in, input_size, &s, channels, w, h, blk, blk + tiles)) != AKO_OK)
 		goto done;
+	{
+		int devices[MAX_DEVICES];
+		const int nb = bands_wanted(&cb, &s, w, h, devices);
+		if (nb > 1) /* a tiled image and several GPUs: one band of tile rows per device */
+		{
+			if ((image = cb.malloc(w * h * channels)) == NULL)
+				st = AKO_NO_ENOUGH_MEMORY;
+			else if ((st = decode_bands(&s, channels, w, h, in, blk, blk + tiles, image, devices, nb)) != AKO_OK)
+			{
+				cb.free(image);
+				image = NULL;
+			}
+			if (st == AKO_OK)
+			{
+				if (out_s != NULL)
+					*out_s = s;
+				if (out_channels != NULL)
+					*out_channels = channels;
+				if (out_w != NULL)
+					*out_w = w;
+				if (out_h != NULL)
+					*out_h = h;
+			}
+			goto done;
+		}
+	}
 	if ((ctx = pool_acquire(&st)) == NULL)
 		goto done;
 

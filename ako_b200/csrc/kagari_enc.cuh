@@ -582,7 +582,7 @@ __device__ __forceinline__ uint32_t kg_payload_len(uint32_t p)
 // 300 000 CTAs per step that only find out that their block lies inside a run. The values of step i+1 are fetched
 // before step i is worked on.
 constexpr int KGL_WARPS = KG_THREADS / 32;
-constexpr int KGL_BLOCKS_PER_WARP = 4;
+constexpr int KGL_BLOCKS_PER_WARP = 4; // at most: the launcher takes fewer when the batch is too small to fill the GPU so
 constexpr int KGL_STEPS = KG_BLOCK / (32 * KG_ITEMS); // 8
 
 // the raw loads of one step: the lane's 8 values and, for the lanes at the warp's edges, the neighbouring values
@@ -725,7 +725,7 @@ __device__ __noinline__ uint32_t kgl_block_tail(const int16_t* __restrict__ in, 
 __global__ void __launch_bounds__(KG_THREADS, 5)
     k_kg_lengths(const int16_t* __restrict__ in, uint64_t in_stride, uint64_t n, const uint32_t* __restrict__ blk_carry,
                  uint32_t* __restrict__ blk_bits, uint32_t nblocks, uint32_t* __restrict__ slots,
-                 const uint32_t* __restrict__ blk_own, const uint8_t* __restrict__ blk_first)
+                 const uint32_t* __restrict__ blk_own, const uint8_t* __restrict__ blk_first, uint32_t blocks_per_warp)
 {
 	__shared__ uint32_t bitbuf_all[KGL_WARPS][KG_SLOT_WORDS + 2];
 	__shared__ uint16_t list_all[KGL_WARPS][2 * 32 * KG_ITEMS]; // at most two codes per value
@@ -738,8 +738,8 @@ __global__ void __launch_bounds__(KG_THREADS, 5)
 		bitbuf[i] = 0;
 	__syncwarp();
 
-	const uint32_t b_first = (blockIdx.x * KGL_WARPS + wid) * KGL_BLOCKS_PER_WARP;
-	for (uint32_t b = b_first; b < b_first + KGL_BLOCKS_PER_WARP && b < nblocks; b++)
+	const uint32_t b_first = (blockIdx.x * KGL_WARPS + wid) * blocks_per_warp;
+	for (uint32_t b = b_first; b < b_first + blocks_per_warp && b < nblocks; b++)
 	{
 		const uint64_t bi = row + b;
 		const bool has_next = b + 1 < nblocks;

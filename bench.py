@@ -621,6 +621,8 @@ def run_ours(args, rank, world):
             attempt("c5", lambda: secondary_c5(env, args.c5_size), False)
         if "shapes" in want:
             attempt("shapes", lambda: secondary_shapes(env, 5), False)
+        if "tiled" in want:
+            attempt("tiled", lambda: secondary_tiled(env, world, args.tiled_size), False)
 
     line = None
     if rank == 0:
@@ -896,6 +898,74 @@ def secondary_c5(env, size=16384):
             "kernels_ms": {k: round(v[1], 3) for k, v in sorted(prof.items(), key=lambda kv: -kv[1][1])[:10]}}
 
 
+def secondary_tiled(env, world, size=16384, tiles=512):
+    """One tiled image through the reference's own entry points (akoEncodeExt / akoDecodeExt, page-locked host buffers),
+    from ONE process: on one device, and -- when the job has several GPUs -- cut into bands of tile rows over all of
+    them with AKO_CUDA_DEVICES (tiles are independent blocks: encode.c:115-205, decode.c:113-230). Same bytes both ways."""
+    import ctypes as C
+    torch, ako, local = env["torch"], env["ako"], env["local"]
+    from ako_b200.synth import synth_rgba8_torch
+    from ako_b200 import lib as akolib
+    L = akolib.load()
+    w = h = size
+    host = torch.empty((h, w, CHANNELS), dtype=torch.uint8, pin_memory=True)
+    for y0 in range(0, h, 1024):
+        host[y0:y0 + 1024] = synth_rgba8_torch(w, min(1024, h - y0), [5], device=f"cuda:{local}", y0=y0)[0].cpu()
+    torch.cuda.synchronize()
+    s = ako.default_settings(wavelet=0, quantization=16, gate=16, tiles_dimension=tiles)
+    cb = L.akoB200PinnedCallbacks()
+    free = C.CFUNCTYPE(None, C.c_void_p)(cb.free)
+
+    def run():
+        out, st = C.c_void_p(), C.c_int(0)
+        t0 = time.perf_counter()
+        n = L.akoEncodeExt(C.byref(cb), C.byref(s), CHANNELS, w, h, host.data_ptr(), C.byref(out), C.byref(st))
+        t1 = time.perf_counter()
+        if n == 0:
+            raise RuntimeError("tiled encode: " + ako.status_string(st.value))
+        so = akolib.AkoSettings()
+        ch_, w_, h_ = C.c_size_t(), C.c_size_t(), C.c_size_t()
+        t2 = time.perf_counter()
+        px = L.akoDecodeExt(C.byref(cb), n, out, C.byref(so), C.byref(ch_), C.byref(w_), C.byref(h_), C.byref(st))
+        t3 = time.perf_counter()
+        if not px:
+            raise RuntimeError("tiled decode: " + ako.status_string(st.value))
+        blob = np.ctypeslib.as_array(C.cast(out, C.POINTER(C.c_uint8)), shape=(n,)).copy()
+        img = np.ctypeslib.as_array(C.cast(px, C.POINTER(C.c_uint8)), shape=(h * w * CHANNELS,))
+        digest = (int(img[::4097].astype(np.uint64).sum()), hash(img[:1 << 20].tobytes()))
+        free(out)
+        free(px)
+        return (t1 - t0) * 1e3, (t3 - t2) * 1e3, blob, digest
+
+    def best(reps):
+        runs = [run() for _ in range(reps)]
+        return min(r[0] for r in runs), min(r[1] for r in runs), runs[-1][2], runs[-1][3]
+
+    os.environ.pop("AKO_CUDA_DEVICES", None)
+    os.environ["AKO_CUDA_DEVICE"] = str(local)
+    run()
+    e1, d1, blob1, dig1 = best(3)
+    px = w * h
+    res = {"workload": f"DD137 -q16 -g16 tiles_dimension={tiles}: akoEncodeExt / akoDecodeExt of one synthetic {w}x{h} RGBA8 "
+                       "image, page-locked host buffers, wall time of the call",
+           "blob_bytes": int(blob1.size),
+           "one_device": {"encode_ms": round(e1, 2), "decode_ms": round(d1, 2),
+                          "encode_MPix_s": round(px / e1 / 1e3, 1), "decode_MPix_s": round(px / d1 / 1e3, 1)}}
+    if world > 1:
+        os.environ["AKO_CUDA_DEVICES"] = ",".join(str(d) for d in range(world))
+        try:
+            run()
+            eN, dN, blobN, digN = best(3)
+            res["all_devices"] = {"devices": world, "encode_ms": round(eN, 2), "decode_ms": round(dN, 2),
+                                  "encode_MPix_s": round(px / eN / 1e3, 1), "decode_MPix_s": round(px / dN / 1e3, 1),
+                                  "same_bytes_as_one_device": bool(np.array_equal(blob1, blobN) and dig1 == digN),
+                                  "how": "bands of tile rows, one per device of AKO_CUDA_DEVICES, blocks concatenated "
+                                         "in raster order by the host"}
+        finally:
+            os.environ.pop("AKO_CUDA_DEVICES", None)
+    return res
+
+
 SHAPES = {
     # name: (w, h, channels, wavelet, q, g, tiles, images per step)
     "aligned_rgba_1024x1024": (1024, 1024, 4, 0, 16, 0, 0, 64),
@@ -1084,7 +1154,8 @@ def main():
     ap.add_argument("--dwt-wavelets", default="cdf53,dd137,haar")
     ap.add_argument("--skip-cpu", action="store_true", help="profiling runs: do not time the CPU reference")
     ap.add_argument("--no-secondary", action="store_true", help="headline config only (profiling runs)")
-    ap.add_argument("--secondaries", default="dwt,c1,c4,c5,shapes", help="which secondary measurements to run")
+    ap.add_argument("--secondaries", default="dwt,c1,c4,c5,shapes,tiled", help="which secondary measurements to run")
+    ap.add_argument("--tiled-size", type=int, default=16384, help="edge of the image of the 'tiled' secondary")
     ap.add_argument("--c4-images", type=int, default=4096, help="size of the fixed configs[3] batch")
     ap.add_argument("--c5-size", type=int, default=16384, help="side of the configs[4] image")
     args = ap.parse_args()

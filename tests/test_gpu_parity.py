@@ -491,6 +491,28 @@ def test_host_batch_api(orc, n):
             assert np.array_equal(px[i], ol.orc_decode(orc, want[i])[0])
 
 
+@pytest.mark.parametrize("bands", [2, 3, 7])
+def test_tiled_image_over_devices(orc, bands, monkeypatch):
+    """One tiled image cut into bands of tile rows, one per entry of AKO_CUDA_DEVICES (akoEncodeExt / akoDecodeExt;
+    encode.c:115-205, decode.c:113-230: tiles are independent blocks): the same .ako bytes and pixels as from one
+    device. On a one-GPU box the bands share device 0 (one pooled context each); with more GPUs they spread."""
+    import torch
+    ndev = max(1, torch.cuda.device_count())
+    monkeypatch.setenv("AKO_CUDA_DEVICES", ",".join(str(i % ndev) for i in range(bands)))
+    monkeypatch.setenv("AKO_B200_BANDS_MIN_PIXELS", "1")
+    made = 0
+    for (w, h, ch, tiles) in [(600, 500, 4, 64), (333, 222, 3, 32), (256, 1024, 4, 128), (200, 130, 1, 64)]:
+        img = ol.synth(orc, w, h, 11 + w)[..., :ch].copy()
+        for kw in (dict(wavelet=W_DD137, q=16, g=16), dict(wavelet=W_CDF53, q=0, g=0), dict(wavelet=W_HAAR, q=4, g=0, compression=2)):
+            made += _e2e(orc, img, tiles=tiles, **kw) is not None  # (an incompressible tile fails both encoders alike)
+    assert made >= 9
+    # a blob whose last band is cut short: the same refusal as from one device
+    img = ol.synth(orc, 600, 500, 3)
+    blob, _ = ol.orc_encode(orc, img, wavelet=W_CDF53, q=8, tiles=64)
+    px, st, _ = ako_b200.decode(blob[:len(blob) - 40])
+    assert px is None and st == 15
+
+
 def test_host_batch_api_failures(orc):
     imgs = [ol.synth(orc, 96, 80, 60 + i) for i in range(12)]
     blobs, st, done = ako_b200.encode_batch(imgs, S(wavelet=1, q=8))
