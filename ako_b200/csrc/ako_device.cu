@@ -436,7 +436,8 @@ extern "C" int akod_format_forward(akodContext* c, int discard, int color, uint3
 	const uint32_t n = b ? b->n : 1;
 	const uint64_t in_is = b ? b->in_stride : 0, pl_is = b ? b->planes_stride : 0;
 	const FmtTiles ft = fmt_tiles(b);
-	const bool fast = channels == 4 && (w % 8) == 0 && (in_stride_px % 4) == 0 && ((uintptr_t)d_in % 16) == 0 &&
+	const uint32_t pitch = (b && b->planes_pitch) ? b->planes_pitch : w;
+	const bool fast = channels == 4 && (w % 8) == 0 && (pitch % 8) == 0 && (in_stride_px % 4) == 0 && ((uintptr_t)d_in % 16) == 0 &&
 	                  ((uintptr_t)d_planes % 16) == 0 && (in_is % 16) == 0 && (pl_is % 8) == 0 && fmt_tiles_aligned(ft);
 	AKOD_BYTES(c, (uint64_t)3 * w * h * channels * n); // u8 in, int16 out
 	// the members of a batch ride in gridDim.y; a member of few pixels gets a grid of few CTAs
@@ -445,13 +446,13 @@ extern "C" int akod_format_forward(akodContext* c, int discard, int color, uint3
 	{
 		const dim3 grid(akod_stream_grid(c, (uint64_t)(w / 8) * h, 256, per_sm), n);
 		AKOD_LAUNCH(c, "format_fwd_rgba8x8", k_format_fwd_rgba8x8, grid, 256, 0, d_in, d_planes, w, h, in_stride_px, color,
-		            discard, in_is, pl_is, ft);
+		            discard, in_is, pl_is, ft, pitch);
 	}
 	else
 	{
 		const dim3 grid(akod_stream_grid(c, (uint64_t)w * h, 256, per_sm), n);
 		AKOD_LAUNCH(c, "format_fwd_generic", k_format_fwd_generic, grid, 256, 0, d_in, d_planes, channels, w, h,
-		            in_stride_px, color, discard, in_is, pl_is, ft);
+		            in_stride_px, color, discard, in_is, pl_is, ft, pitch);
 	}
 	return AKOD_OK;
 }
@@ -463,7 +464,8 @@ extern "C" int akod_format_inverse(akodContext* c, int color, uint32_t channels,
 	const uint32_t n = b ? b->n : 1;
 	const uint64_t out_is = b ? b->in_stride : 0, pl_is = b ? b->planes_stride : 0;
 	const FmtTiles ft = fmt_tiles(b);
-	const bool fast = channels == 4 && (w % 8) == 0 && (out_stride_px % 4) == 0 && ((uintptr_t)d_out % 16) == 0 &&
+	const uint32_t pitch = (b && b->planes_pitch) ? b->planes_pitch : w;
+	const bool fast = channels == 4 && (w % 8) == 0 && (pitch % 8) == 0 && (out_stride_px % 4) == 0 && ((uintptr_t)d_out % 16) == 0 &&
 	                  ((uintptr_t)d_planes % 16) == 0 && (out_is % 16) == 0 && (pl_is % 8) == 0 && fmt_tiles_aligned(ft);
 	AKOD_BYTES(c, (uint64_t)3 * w * h * channels * n); // int16 in, u8 out
 	const unsigned per_sm = n >= 64 ? 1 : 8;
@@ -471,13 +473,13 @@ extern "C" int akod_format_inverse(akodContext* c, int color, uint32_t channels,
 	{
 		const dim3 grid(akod_stream_grid(c, (uint64_t)(w / 8) * h, 256, per_sm), n);
 		AKOD_LAUNCH(c, "format_inv_rgba8x8", k_format_inv_rgba8x8, grid, 256, 0, d_planes, d_out, w, h, out_stride_px, color,
-		            pl_is, out_is, ft);
+		            pl_is, out_is, ft, pitch);
 	}
 	else
 	{
 		const dim3 grid(akod_stream_grid(c, (uint64_t)w * h, 256, per_sm), n);
 		AKOD_LAUNCH(c, "format_inv_generic", k_format_inv_generic, grid, 256, 0, d_planes, d_out, channels, w, h,
-		            out_stride_px, color, pl_is, out_is, ft);
+		            out_stride_px, color, pl_is, out_is, ft, pitch);
 	}
 	return AKOD_OK;
 }
@@ -678,6 +680,11 @@ static int launch_small(akodContext* c, const akodPlan* plan, uint32_t l0, bool 
 	return AKOD_OK;
 }
 
+static inline uint32_t akod_pad8(uint32_t v)
+{
+	return (v + 7u) & ~7u;
+}
+
 // u8: when not NULL, level 0 may read the interleaved RGBA8 image itself (the colour/format pass fused into the
 // lifting kernel); *fused tells whether it did -- if not, the caller's planes must hold the formatted image.
 struct LiftRgba
@@ -696,22 +703,26 @@ static int lift_pyramid(akodContext* c, const akodPlan* plan, int16_t* d_planes,
 	const uint64_t planes_is = b ? b->planes_stride : 0, scratch_is = b ? b->scratch_stride : 0;
 	const uint64_t stream_is = b ? b->stream_stride : 0;
 
-	// ping-pong: level l reads 'src' (dense cw x ch planes) and writes the next LL densely into 'dst'
+	// ping-pong: level l reads 'src' (cw x ch planes, rows src_rs apart) and writes the next LL into 'dst'. Rows of
+	// the intermediate planes are padded to a multiple of 8 elements, so that every row starts on a 16-byte boundary
+	// whatever the width (the strip kernels fetch rows with the TMA engine); the caller says how the level-0 planes
+	// are laid out (akodBatch.planes_pitch, dense when 0).
 	int16_t* src = d_planes;
 	int16_t* dst = d_scratch;
 	uint64_t src_is = planes_is, dst_is = scratch_is;
-	uint64_t src_ps = (uint64_t)plan->w * plan->h; // level 0 planes keep the full-image plane stride
+	uint32_t src_rs = (b && b->planes_pitch) ? b->planes_pitch : plan->w;
+	uint64_t src_ps = (uint64_t)src_rs * plan->h;
 
 	static const bool no_small = getenv("AKO_B200_NO_SMALL") != nullptr;
 	for (uint32_t l = 0; l < plan->levels; l++)
 	{
 		const akodLevel* L = &plan->level[l];
 		if (!no_small && small_eligible(L->cw, L->ch, plan->levels - l))
-			return launch_small(c, plan, l, true, src, L->cw, src_ps, src_is, d_stream, stream_is, n);
+			return launch_small(c, plan, l, true, src, src_rs, src_ps, src_is, d_stream, stream_is, n);
 		LiftParams p;
 		memset(&p, 0, sizeof(p));
 		p.in = src;
-		p.in_rs = L->cw;
+		p.in_rs = src_rs;
 		p.in_ps = src_ps;
 		p.in_is = src_is;
 		p.cw = L->cw;
@@ -733,8 +744,8 @@ static int lift_pyramid(akodContext* c, const akodPlan* plan, int16_t* d_planes,
 		else
 		{
 			p.ll = dst;
-			p.ll_rs = L->tw;
-			p.ll_ps = (uint64_t)L->tw * L->th;
+			p.ll_rs = akod_pad8(L->tw);
+			p.ll_ps = (uint64_t)p.ll_rs * L->th;
 			p.ll_is = dst_is;
 		}
 		for (uint32_t ch = 0; ch < plan->channels; ch++)
@@ -793,7 +804,8 @@ static int lift_pyramid(akodContext* c, const akodPlan* plan, int16_t* d_planes,
 		const uint64_t ti = src_is;
 		src_is = dst_is;
 		dst_is = ti;
-		src_ps = (uint64_t)L->tw * L->th;
+		src_rs = p.ll_rs;
+		src_ps = p.ll_ps;
 	}
 
 	if (plan->levels == 0)
@@ -875,7 +887,9 @@ extern "C" int akod_unlift(akodContext* c, const akodPlan* plan, const int16_t* 
 	}
 
 	// The finest level must land in d_planes; alternate buffers backwards from there.
-	// level index l (0 = finest) writes to planes if l is even, scratch if odd.
+	// level index l (0 = finest) writes to planes if l is even, scratch if odd. Rows of the intermediate planes are
+	// padded to a multiple of 8 elements (see lift_pyramid); the level-0 planes as the caller says.
+	const uint32_t pitch0 = (b && b->planes_pitch) ? b->planes_pitch : plan->w;
 	static const bool no_small = getenv("AKO_B200_NO_SMALL") != nullptr;
 	uint32_t l_top = plan->levels; // levels l_top .. levels-1 are done by the small kernel
 	if (!no_small)
@@ -889,7 +903,8 @@ extern "C" int akod_unlift(akodContext* c, const akodPlan* plan, const int16_t* 
 	{
 		const akodLevel* L = &plan->level[l_top];
 		const bool to_planes = (l_top % 2) == 0;
-		int rc = launch_small(c, plan, l_top, false, to_planes ? d_planes : d_scratch, L->cw, (uint64_t)L->cw * L->ch,
+		const uint32_t rs = (l_top == 0) ? pitch0 : akod_pad8(L->cw);
+		int rc = launch_small(c, plan, l_top, false, to_planes ? d_planes : d_scratch, rs, (uint64_t)rs * L->ch,
 		                      to_planes ? planes_is : scratch_is, const_cast<int16_t*>(d_stream), stream_is, n);
 		if (rc != AKOD_OK)
 			return rc;
@@ -918,14 +933,14 @@ extern "C" int akod_unlift(akodContext* c, const akodPlan* plan, const int16_t* 
 		{
 			const bool from_planes = ((l + 1) % 2) == 0;
 			p.ll = from_planes ? d_planes : d_scratch;
-			p.ll_rs = L->tw;
-			p.ll_ps = (uint64_t)L->tw * L->th;
+			p.ll_rs = akod_pad8(L->tw);
+			p.ll_ps = (uint64_t)p.ll_rs * L->th;
 			p.ll_is = from_planes ? planes_is : scratch_is;
 		}
 		const bool to_planes = (l % 2) == 0;
 		p.out = to_planes ? d_planes : d_scratch;
-		p.out_rs = L->cw;
-		p.out_ps = (uint64_t)L->cw * L->ch;
+		p.out_rs = (l == 0) ? pitch0 : akod_pad8(L->cw);
+		p.out_ps = (uint64_t)p.out_rs * L->ch;
 		p.out_is = to_planes ? planes_is : scratch_is;
 		for (uint32_t ch = 0; ch < plan->channels; ch++)
 			p.off_c[ch] = L->off_c[ch];

@@ -62,6 +62,8 @@ typedef struct
 	uint64_t planes_stride;  /* int16 */
 	uint64_t scratch_stride; /* int16 */
 	uint64_t stream_stride;  /* int16 */
+	uint32_t planes_pitch;   /* int16 elements between the rows of a full-size plane (0: dense, = the width); the cores
+	                          * pad it to a multiple of 8 so that every row starts on a 16-byte boundary (TMA row copies) */
 	/* Tiles as batch members (encode.c:115-205 / decode.c:113-230 make every tile an independent block): with
 	 * n_real != 0 the n members are tiles of n_real images, member v = kk * n_real + i being tile tile_first + kk of
 	 * its shape group in image i. Only the interleaved u8 image is addressed through this: tile k of the group

@@ -734,7 +734,7 @@ static enum akoStatus scratch_for(akoB200Context* ctx, size_t channels, size_t w
                                   size_t* stride)
 {
 	void* p = NULL;
-	*stride = align_up(half_up(w) * half_up(h) * channels, 8);
+	*stride = align_up(align_up(half_up(w), 8) * half_up(h) * channels, 8); /* rows padded to 8 elements (akod_lift) */
 	const enum akoStatus st = from_dev(akod_workspace(ctx->dev, AKOD_WS_SCRATCH, *stride * n * sizeof(int16_t) + 64, &p));
 	*out = p;
 	return st;
@@ -889,6 +889,7 @@ struct tile_groups
 	size_t data[4];       /* bytes of one tile's coefficient stream (all channels): what a block may not reach */
 	uint32_t cols[4], x0[4], y0[4];
 	size_t planes_stride[4], scratch_stride[4], stream_stride[4]; /* int16 elements per member */
+	uint32_t planes_pitch[4];                                     /* row pitch of the planes, 0 = dense */
 	size_t bits_slots;    /* tiles * n */
 	size_t blocks_bytes;
 };
@@ -925,8 +926,11 @@ static void make_groups(struct tile_groups* G, const struct akoSettings* s, size
 		const size_t data = (s->wavelet != AKO_WAVELET_NONE) ? tile_data_size(gw[g], gh[g]) * channels
 		                                                     : gw[g] * gh[g] * channels * 2;
 		G->data[g] = data;
-		G->planes_stride[g] = align_up(gw[g] * gh[g] * channels, 8);
-		G->scratch_stride[g] = align_up(half_up(gw[g]) * half_up(gh[g]) * channels, 8);
+		/* planes that feed the lifting have their rows padded to 8 elements (every row on a 16-byte boundary: the strip
+		 * kernels fetch rows with the TMA engine); without a wavelet the planes ARE the tile's data and stay dense */
+		G->planes_pitch[g] = (s->wavelet != AKO_WAVELET_NONE) ? (uint32_t)align_up(gw[g], 8) : 0;
+		G->planes_stride[g] = align_up((G->planes_pitch[g] ? G->planes_pitch[g] : gw[g]) * gh[g] * channels, 8);
+		G->scratch_stride[g] = align_up(align_up(half_up(gw[g]), 8) * half_up(gh[g]) * channels, 8);
 		G->stream_stride[g] = align_up(data / 2, 8);
 		/* what the packer may write: the reference accepts a block of up to data - 5 bytes (bytes < data - 4,
 		 * compression.c:40-49); the packer stores whole words, and the tile's region (align_up(data, 16)) holds
@@ -959,6 +963,7 @@ static void group_batch(akodBatch* b, const struct tile_groups* G, int g, size_t
 	b->n = (uint32_t)(kc * n);
 	b->in_stride = image_stride;
 	b->planes_stride = G->planes_stride[g];
+	b->planes_pitch = G->planes_pitch[g];
 	b->scratch_stride = G->scratch_stride[g];
 	b->stream_stride = G->stream_stride[g];
 	if (td != 0)

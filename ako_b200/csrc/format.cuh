@@ -96,11 +96,11 @@ __device__ __forceinline__ uint64_t fmt_member_offset(const FmtTiles& t, uint32_
 __global__ void __launch_bounds__(256)
     k_format_fwd_rgba8x8(const uint8_t* __restrict__ in, int16_t* __restrict__ planes, uint32_t w, uint32_t h,
                          uint64_t in_stride_px, int color, int discard, uint64_t in_img_stride,
-                         uint64_t planes_img_stride, const FmtTiles tiles)
+                         uint64_t planes_img_stride, const FmtTiles tiles, uint32_t pitch)
 {
 	const uint32_t groups_per_row = w >> 3;
 	const uint64_t total = (uint64_t)groups_per_row * h;
-	const uint64_t plane = (uint64_t)w * h;
+	const uint64_t plane = (uint64_t)pitch * h;
 	in += fmt_member_offset(tiles, blockIdx.y, in_img_stride, in_stride_px, 4);
 	planes += planes_img_stride * blockIdx.y;
 
@@ -122,7 +122,7 @@ __global__ void __launch_bounds__(256)
 			color_forward(color, r, g, bl, o0[k], o1[k], o2[k]);
 			o3[k] = (int16_t)al;
 		}
-		const uint64_t o = (uint64_t)y * w + x;
+		const uint64_t o = (uint64_t)y * pitch + x;
 		*reinterpret_cast<uint4*>(planes + o) = *reinterpret_cast<const uint4*>(o0);
 		*reinterpret_cast<uint4*>(planes + plane + o) = *reinterpret_cast<const uint4*>(o1);
 		*reinterpret_cast<uint4*>(planes + plane * 2 + o) = *reinterpret_cast<const uint4*>(o2);
@@ -134,18 +134,19 @@ __global__ void __launch_bounds__(256)
 __global__ void __launch_bounds__(256)
     k_format_fwd_generic(const uint8_t* __restrict__ in, int16_t* __restrict__ planes, uint32_t channels, uint32_t w,
                          uint32_t h, uint64_t in_stride_px, int color, int discard, uint64_t in_img_stride,
-                         uint64_t planes_img_stride, const FmtTiles tiles)
+                         uint64_t planes_img_stride, const FmtTiles tiles, uint32_t pitch)
 {
-	const uint64_t plane = (uint64_t)w * h;
+	const uint64_t plane = (uint64_t)pitch * h, pixels = (uint64_t)w * h;
 	in += fmt_member_offset(tiles, blockIdx.y, in_img_stride, in_stride_px, channels);
 	planes += planes_img_stride * blockIdx.y;
 	// discard_non_visible is only honoured for 2 and 4 channels (format.c:74-83)
 	const bool use_discard = discard && (channels == 2 || channels == 4);
 
-	for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < plane; i += (uint64_t)gridDim.x * blockDim.x)
+	for (uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; j < pixels; j += (uint64_t)gridDim.x * blockDim.x)
 	{
-		const uint32_t y = (uint32_t)(i / w);
-		const uint32_t x = (uint32_t)(i - (uint64_t)y * w);
+		const uint32_t y = (uint32_t)(j / w);
+		const uint32_t x = (uint32_t)(j - (uint64_t)y * w);
+		const uint64_t i = (uint64_t)y * pitch + x;
 		const uint8_t* px = in + ((uint64_t)y * in_stride_px + x) * channels;
 		const bool visible = !use_discard || px[channels - 1] != 0;
 		if (channels >= 3)
@@ -172,11 +173,11 @@ __global__ void __launch_bounds__(256)
 __global__ void __launch_bounds__(256)
     k_format_inv_rgba8x8(const int16_t* __restrict__ planes, uint8_t* __restrict__ out, uint32_t w, uint32_t h,
                          uint64_t out_stride_px, int color, uint64_t planes_img_stride, uint64_t out_img_stride,
-                         const FmtTiles tiles)
+                         const FmtTiles tiles, uint32_t pitch)
 {
 	const uint32_t groups_per_row = w >> 3;
 	const uint64_t total = (uint64_t)groups_per_row * h;
-	const uint64_t plane = (uint64_t)w * h;
+	const uint64_t plane = (uint64_t)pitch * h;
 	planes += planes_img_stride * blockIdx.y;
 	out += fmt_member_offset(tiles, blockIdx.y, out_img_stride, out_stride_px, 4);
 
@@ -184,7 +185,7 @@ __global__ void __launch_bounds__(256)
 	{
 		const uint32_t y = (uint32_t)(i / groups_per_row);
 		const uint32_t x = (uint32_t)(i - (uint64_t)y * groups_per_row) << 3;
-		const uint64_t o = (uint64_t)y * w + x;
+		const uint64_t o = (uint64_t)y * pitch + x;
 		int16_t p0[8], p1[8], p2[8], p3[8];
 		*reinterpret_cast<uint4*>(p0) = __ldg(reinterpret_cast<const uint4*>(planes + o));
 		*reinterpret_cast<uint4*>(p1) = __ldg(reinterpret_cast<const uint4*>(planes + plane + o));
@@ -207,16 +208,17 @@ __global__ void __launch_bounds__(256)
 __global__ void __launch_bounds__(256)
     k_format_inv_generic(const int16_t* __restrict__ planes, uint8_t* __restrict__ out, uint32_t channels, uint32_t w,
                          uint32_t h, uint64_t out_stride_px, int color, uint64_t planes_img_stride,
-                         uint64_t out_img_stride, const FmtTiles tiles)
+                         uint64_t out_img_stride, const FmtTiles tiles, uint32_t pitch)
 {
-	const uint64_t plane = (uint64_t)w * h;
+	const uint64_t plane = (uint64_t)pitch * h, pixels = (uint64_t)w * h;
 	planes += planes_img_stride * blockIdx.y;
 	out += fmt_member_offset(tiles, blockIdx.y, out_img_stride, out_stride_px, channels);
 
-	for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < plane; i += (uint64_t)gridDim.x * blockDim.x)
+	for (uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; j < pixels; j += (uint64_t)gridDim.x * blockDim.x)
 	{
-		const uint32_t y = (uint32_t)(i / w);
-		const uint32_t x = (uint32_t)(i - (uint64_t)y * w);
+		const uint32_t y = (uint32_t)(j / w);
+		const uint32_t x = (uint32_t)(j - (uint64_t)y * w);
+		const uint64_t i = (uint64_t)y * pitch + x;
 		uint8_t* px = out + ((uint64_t)y * out_stride_px + x) * channels;
 		uint32_t first = 0;
 		if (channels >= 3)

@@ -12,12 +12,14 @@ WANT = {
     "_Z12k_lift_stripILi1ELi0EEv11StripParams": "k_lift_strip_cdf53_plain",
     "_Z14k_unlift_stripILi0EEv13UnstripParams": "k_unlift_strip_dd137",
     "_Z14k_unlift_stripILi1EEv13UnstripParams": "k_unlift_strip_cdf53",
-    "_Z12k_kg_lengthsPKsmmPKjPjjS3_S2_PKh": "k_kg_lengths",
+    "_Z13k_lift_strip4ILi0ELi2EEv12Strip4Params": "k_lift_strip4_dd137_gate",
+    "_Z12k_kg_lengthsPKsmmPKjPjjS3_S2_PKhj": "k_kg_lengths",
     "_Z11k_kg_startsPKsmmPjPhj": "k_kg_starts",
     "_Z9k_kg_packPKsmmPKjPKmS2_jPhmmS2_": "k_kg_pack",
-    "_Z11k_kt_expandPKtmmPK7KdImagePKjPKmjPsmmP5KtRunPjj": "k_kt_expand",
-    "_Z20k_format_fwd_rgba8x8PKhPsjjmiimm": "k_format_fwd_rgba8x8",
-    "_Z20k_format_inv_rgba8x8PKsPhjjmimm": "k_format_inv_rgba8x8",
+    "_Z11k_kd_decodePKhPKmS2_jPK10KdSubStateS2_P6KfLookPmPjP7KdImagePsmmP5KtRunS9_j": "k_kd_decode",
+    "_Z9k_kd_syncPKhPKmS2_jiS2_PmP10KdSubStateP7KdImage": "k_kd_sync",
+    "_Z20k_format_fwd_rgba8x8PKhPsjjmiimm8FmtTiles": "k_format_fwd_rgba8x8",
+    "_Z20k_format_inv_rgba8x8PKsPhjjmimm8FmtTiles": "k_format_inv_rgba8x8",
 }
 text = subprocess.run(["cuobjdump", "-sass", obj], capture_output=True, text=True).stdout
 cur, funcs = None, collections.OrderedDict()
