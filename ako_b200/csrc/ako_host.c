@@ -764,6 +764,22 @@ AKO_API enum akoStatus akoB200Lift(akoB200Context* ctx, const struct akoSettings
 	const enum akoStatus st = scratch_for(ctx, channels, w, h, 1, &scratch, &stride);
 	if (st != AKO_OK)
 		return st;
+	if (w % 8 != 0)
+	{
+		/* the cores feed the lifting planes whose rows are padded to 8 elements: so does the stage (same kernels) */
+		const size_t pitch = align_up(w, 8);
+		void* padded;
+		akodBatch b;
+		memset(&b, 0, sizeof(b));
+		b.n = 1;
+		b.planes_pitch = (uint32_t)pitch;
+		enum akoStatus st2 = from_dev(akod_workspace(ctx->dev, AKOD_WS_PLANES, pitch * h * channels * 2 + 64, &padded));
+		if (st2 == AKO_OK)
+			st2 = from_dev(akod_copy_strided(ctx->dev, padded, pitch * 2, d_planes, w * 2, w * 2, h * channels));
+		if (st2 != AKO_OK)
+			return st2;
+		return from_dev(akod_lift(ctx->dev, get_plan(ctx, s, channels, w, h), padded, scratch, d_stream, &b));
+	}
 	return from_dev(akod_lift(ctx->dev, get_plan(ctx, s, channels, w, h), d_planes, scratch, d_stream, NULL));
 }
 
@@ -777,6 +793,21 @@ AKO_API enum akoStatus akoB200Unlift(akoB200Context* ctx, const struct akoSettin
 	const enum akoStatus st = scratch_for(ctx, channels, w, h, 1, &scratch, &stride);
 	if (st != AKO_OK)
 		return st;
+	if (w % 8 != 0)
+	{
+		const size_t pitch = align_up(w, 8);
+		void* padded;
+		akodBatch b;
+		memset(&b, 0, sizeof(b));
+		b.n = 1;
+		b.planes_pitch = (uint32_t)pitch;
+		enum akoStatus st2 = from_dev(akod_workspace(ctx->dev, AKOD_WS_PLANES, pitch * h * channels * 2 + 64, &padded));
+		if (st2 == AKO_OK)
+			st2 = from_dev(akod_unlift(ctx->dev, get_plan(ctx, s, channels, w, h), d_stream, padded, scratch, &b));
+		if (st2 == AKO_OK)
+			st2 = from_dev(akod_copy_strided(ctx->dev, d_planes, w * 2, padded, pitch * 2, w * 2, h * channels));
+		return st2;
+	}
 	return from_dev(akod_unlift(ctx->dev, get_plan(ctx, s, channels, w, h), d_stream, d_planes, scratch, NULL));
 }
 

@@ -1,6 +1,7 @@
-// lift_strip.cuh -- the fast forward-lifting kernel ("strip marching"), used for the large, aligned,
-// CLAMP-wrapped levels that carry nearly all the bytes. Same results as k_lift_level (lift.cuh), which stays
-// the general kernel for every other case (other wrap modes, odd widths, tiny levels).
+// lift_strip.cuh -- the fast forward-lifting kernel ("strip marching"), used for the large CLAMP-wrapped levels
+// (any width from 64 samples, any height from 8 coefficient rows; rows 16-byte aligned) that carry nearly all the
+// bytes. Same results as k_lift_level (lift.cuh), which stays the general kernel for every other case (other wrap
+// modes, tiny levels).
 //
 // Structure. A CTA owns a strip of 128 coefficient columns (256 samples + 8 halo each side) and MARCHES down
 // it, 16 input rows (8 coefficient rows) per step:
@@ -271,15 +272,18 @@ __device__ __forceinline__ void strip_hpass(const uint32_t (&w)[24], bool left_e
 		}
 		if (left_edge)
 			H[2] = H[3] = H[4]; // H(-1) = H(-2) = H(0)
-		// H(t) = H(t-1); t is 4, 8, 12 or 16 columns into an edge chunk
-		if (rem == 4)
-			H[8] = H[7];
-		if (rem == 8)
-			H[12] = H[11];
-		if (rem == 12)
-			H[16] = H[15];
-		if (rem == 16)
-			H[20] = H[19];
+		// H(t) = H(t-1); t is 'rem' columns into the chunk of the right edge (any width: 1 .. 16)
+		if (rem <= 16)
+		{
+			// (bit selects on static indices: the compiler turns a chain of conditional moves into an indexed store,
+			// which sends H[] to local memory)
+#pragma unroll
+			for (int k = 20; k >= 5; k--)
+			{
+				const int take = -(int)(rem + 4 == k);
+				H[k] = (H[k - 1] & take) | (H[k] & ~take);
+			}
+		}
 		// L(k) = e(k) + (-H(k-2) + 9 H(k-1) + 9 H(k) - H(k+1)) / 32                k = 4..19
 		uint32_t TH[24];
 #pragma unroll
@@ -444,13 +448,17 @@ __global__ void __launch_bounds__(FS_THREADS, 6) k_lift_strip(const StripParams 
 	if (blockIdx.x == 0 && blockIdx.y == 0 && tid == 0)
 		out_c[-1] = (int16_t)sq.q; // akoLiftHead
 
-	// ---- loader geometry: staged sample x of a row is input sample xs0 + x; [xa, xb) is inside the row
+	// ---- loader geometry: staged sample x of a row is input sample xs0 + x; [xa, xb) is inside the row. Rows start on
+	// 16-byte boundaries (in_rs % 8 == 0) and xs0 is a multiple of 8, so the TMA copy takes [xa, xb8), xb8 = xb rounded
+	// down to 8 samples; a width that is no multiple of 8 leaves up to 7 samples of the last strip to the fill threads.
 	const int xs0 = 2 * c0 - 8;
 	const int xa = (xs0 < 0) ? 8 : 0;                       // first staged sample that exists
 	const int xb = min(FS_XW, cw - xs0);                    // one past the last
+	const int xb8 = xb & ~7;
 	const int in_rs = (int)p.in_rs, last_row = (int)p.ch - 1;
-	const uint32_t row_bytes = (uint32_t)(xb - xa) * 2;
+	const uint32_t row_bytes = (uint32_t)(xb8 - xa) * 2;
 	const bool edge_strip = (xa != 0) || (xb != FS_XW);
+	const int x_last_even = (cw - 1) & ~1;                  // CLAMP source on the right (the "fake last" odd sample too)
 
 	// One warp issues the step's row copies. (Spreading them over the four warps, as the inverse kernel does with
 	// its 32 copies per step, gained 1 % on 8192^2 planes and lost 2 % on the 816-column C2 planes, where 2 of 7
@@ -471,8 +479,9 @@ __global__ void __launch_bounds__(FS_THREADS, 6) k_lift_strip(const StripParams 
 		}
 		else if (edge_strip)
 		{
-			// CLAMP: every sample outside the row is the first / last even sample, 8 samples per store
-			const int nleft = xa >> 3, nright = (FS_XW - xb) >> 3;
+			// CLAMP: every sample outside the row is the first / last even sample, 8 samples per store; the group that
+			// straddles the end of a row whose width is no multiple of 8 also carries the row's last samples
+			const int nleft = xa >> 3, nright = (FS_XW - xb8) >> 3;
 			for (int i = tid - 32; i < FS_ROWS * (nleft + nright); i += FS_THREADS - 32)
 			{
 				const int r = i / (nleft + nright), v = i - r * (nleft + nright);
@@ -480,10 +489,23 @@ __global__ void __launch_bounds__(FS_THREADS, 6) k_lift_strip(const StripParams 
 				const int y = min(2 * j + (r & 1), last_row);
 				const int16_t* row = in + (uint32_t)(y * in_rs);
 				const bool left = v < nleft;
-				const uint32_t e = (uint16_t)__ldg(row + (left ? 0 : cw - 2));
+				const uint32_t e = (uint16_t)__ldg(row + (left ? 0 : x_last_even));
 				const uint32_t w = e * 0x10001u;
-				const int x = left ? 8 * v : xb + 8 * (v - nleft);
-				*reinterpret_cast<uint4*>(dstbuf + r * FS_XP + x) = make_uint4(w, w, w, w);
+				const int x = left ? 8 * v : xb8 + 8 * (v - nleft);
+				uint4 q = make_uint4(w, w, w, w);
+				if (!left && x < xb)
+				{
+					uint32_t m[4];
+#pragma unroll
+					for (int k = 0; k < 4; k++)
+					{
+						const uint32_t lo = (x + 2 * k < xb) ? (uint32_t)(uint16_t)__ldg(row + xs0 + x + 2 * k) : e;
+						const uint32_t hi = (x + 2 * k + 1 < xb) ? (uint32_t)(uint16_t)__ldg(row + xs0 + x + 2 * k + 1) : e;
+						m[k] = lo | (hi << 16);
+					}
+					q = make_uint4(m[0], m[1], m[2], m[3]);
+				}
+				*reinterpret_cast<uint4*>(dstbuf + r * FS_XP + x) = q;
 			}
 		}
 	};
@@ -508,7 +530,10 @@ __global__ void __launch_bounds__(FS_THREADS, 6) k_lift_strip(const StripParams 
 	// The C/B/D subbands of a channel start at an odd or even int16 offset of the stream (a 2-byte lift head
 	// precedes each channel's block, so the parity alternates from channel to channel): pairs are stored with
 	// one 32-bit store when aligned, two 16-bit stores otherwise. Uniform per CTA.
-	const bool odd_offset = (p.off_c[chn] & 1) != 0;
+	// ... or the level has an odd number of coefficient columns, so that the parity alternates from row to row; the
+	// last thread of such a level owns one column only.
+	const bool odd_offset = ((p.off_c[chn] | p.tw) & 1) != 0;
+	const bool vsingle = vcol + 1 >= tw;
 	StripV<WL> vs;
 	vs.init();
 
@@ -597,14 +622,16 @@ __global__ void __launch_bounds__(FS_THREADS, 6) k_lift_strip(const StripParams 
 						if (ODD)
 						{
 							dh[0] = (int16_t)whi;
-							dh[1] = (int16_t)(whi >> 16);
+							if (!vsingle)
+								dh[1] = (int16_t)(whi >> 16);
 						}
 						else
 							*reinterpret_cast<uint32_t*>(dh) = whi;
-						if (ODD && right_half)
+						if (ODD && (right_half || vsingle))
 						{
 							dl[0] = (int16_t)wlo;
-							dl[1] = (int16_t)(wlo >> 16);
+							if (!vsingle)
+								dl[1] = (int16_t)(wlo >> 16);
 						}
 						else
 							*reinterpret_cast<uint32_t*>(dl) = wlo;
@@ -638,7 +665,7 @@ __global__ void __launch_bounds__(FS_THREADS, 6) k_lift_strip(const StripParams 
 // host-side eligibility of a level for the strip kernel
 static inline bool lift_strip_eligible(const LiftParams& p)
 {
-	return p.wrap == AKOD_WRAP_CLAMP && (p.cw % 8) == 0 && p.cw >= 64 && p.th >= 8 && (p.in_rs % 8) == 0 &&
+	return p.wrap == AKOD_WRAP_CLAMP && p.cw >= 64 && p.th >= 8 && (p.in_rs % 8) == 0 &&
 	       (p.in_ps % 8) == 0 && (p.in_is % 8) == 0 && ((uintptr_t)p.in % 16) == 0 && (p.ll_rs % 2) == 0 &&
 	       (p.ll_ps % 2) == 0 && (p.ll_is % 2) == 0 && ((uintptr_t)p.ll % 4) == 0 && (p.stream_is % 2) == 0 &&
 	       ((uintptr_t)p.stream % 4) == 0 && (uint64_t)p.cw * p.ch < ((uint64_t)1 << 31);

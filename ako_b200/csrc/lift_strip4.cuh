@@ -180,7 +180,8 @@ __global__ void __launch_bounds__(F4_THREADS, F4_CTAS) k_lift_strip4(const Strip
 	int16_t* const out_hi = (right_half ? out_c + 2 * (uint64_t)band : out_c) + vcol;
 	int16_t* const out_lo = right_half ? (out_c + band + vcol) : (ll + vcol);
 	const uint32_t hi_rs = (uint32_t)tw, lo_rs = right_half ? (uint32_t)tw : p.ll_rs;
-	const bool odd_offset = (p.off_c[chn] & 1) != 0;
+	const bool odd_offset = ((p.off_c[chn] | p.tw) & 1) != 0;
+	const bool vsingle = vcol + 1 >= tw;
 	StripV<WL> vs;
 	vs.init();
 	const int color = sp.color;
@@ -317,14 +318,16 @@ __global__ void __launch_bounds__(F4_THREADS, F4_CTAS) k_lift_strip4(const Strip
 						if (ODD)
 						{
 							dh[0] = (int16_t)whi;
-							dh[1] = (int16_t)(whi >> 16);
+							if (!vsingle)
+								dh[1] = (int16_t)(whi >> 16);
 						}
 						else
 							*reinterpret_cast<uint32_t*>(dh) = whi;
-						if (ODD && right_half)
+						if (ODD && (right_half || vsingle))
 						{
 							dl[0] = (int16_t)wlo;
-							dl[1] = (int16_t)(wlo >> 16);
+							if (!vsingle)
+								dl[1] = (int16_t)(wlo >> 16);
 						}
 						else
 							*reinterpret_cast<uint32_t*>(dl) = wlo;
@@ -355,7 +358,7 @@ __global__ void __launch_bounds__(F4_THREADS, F4_CTAS) k_lift_strip4(const Strip
 // host-side eligibility of level 0 for the fused kernel (p as akod_lift builds it, without p.in)
 static inline bool lift_strip4_eligible(const LiftParams& p, const uint8_t* rgba, uint64_t rgba_is, uint64_t rgba_rs)
 {
-	return p.channels == 4 && p.wrap == AKOD_WRAP_CLAMP && (p.cw % 8) == 0 && p.cw >= 64 && p.th >= 8 &&
+	return p.channels == 4 && p.wrap == AKOD_WRAP_CLAMP && (p.cw % 4) == 0 && p.cw >= 64 && p.th >= 8 &&
 	       ((uintptr_t)rgba % 16) == 0 && (rgba_is % 16) == 0 && (rgba_rs % 16) == 0 && rgba_rs < ((uint64_t)1 << 32) &&
 	       (p.ll_rs % 2) == 0 && (p.ll_ps % 2) == 0 && (p.ll_is % 2) == 0 && ((uintptr_t)p.ll % 4) == 0 &&
 	       (p.stream_is % 2) == 0 && ((uintptr_t)p.stream % 4) == 0 && (uint64_t)p.cw * p.ch < ((uint64_t)1 << 31);
