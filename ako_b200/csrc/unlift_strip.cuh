@@ -178,11 +178,22 @@ __device__ __forceinline__ void unstrip_hpass(const uint32_t (&lw)[8], uint32_t 
 		return;
 	}
 
-	// highpass clamps on the inputs: H(-1) = H(-2) = H(0) (column 0 is k = 4), H(t) = H(t-1) (column t is k = rem + 4)
+	// highpass clamps on the inputs: H(-1) = H(-2) = H(0) (column 0 is k = 4), H(t) = H(t-1) (column t is k = rem + 4,
+	// hw[m] holds H(2m), H(2m+1)). The chunk computes E up to k = 13 from H up to k = 14, so the rule also reaches the
+	// chunk before a right edge that lies one or two columns into the next chunk (rem = 9, 10)
 	if (left_edge)
 		hw[1] = pair_lo(hw[2], hw[2]);
-	if (rem == 8)
-		hw[6] = pair_hi(hw[5], hw[5]);
+	if (rem <= 10)
+	{
+#pragma unroll
+		for (int k = 5; k <= 14; k++)
+		{
+			// (bit selects on static indices keep hw[] in registers)
+			const uint32_t take = 0u - (uint32_t)(rem + 4 == k);
+			const uint32_t v = (k & 1) ? pair_lo(hw[k >> 1], hw[k >> 1]) : pair_hi(hw[(k >> 1) - 1], hw[k >> 1]);
+			hw[k >> 1] = (v & take) | (hw[k >> 1] & ~take);
+		}
+	}
 
 	int e[16];
 	if (WL == AKOD_CDF53)
@@ -199,8 +210,15 @@ __device__ __forceinline__ void unstrip_hpass(const uint32_t (&lw)[8], uint32_t 
 				n = dp2_lo(__byte_perm(hw[(k >> 1) - 1], hw[k >> 1], 0x5432), KM, 0); // (H(k-1), H(k))
 			e[k] = hi_step<2>(n, lbase(k));
 		}
-		if (rem == 8)
-			e[12] = e[11]; // E(t) = E(t-1)
+		if (rem <= 8) // E(t) = E(t-1)
+		{
+#pragma unroll
+			for (int k = 12; k >= 5; k--)
+			{
+				const int take = -(int)(rem + 4 == k);
+				e[k] = (e[k - 1] & take) | (e[k] & ~take);
+			}
+		}
 		// O(k) = H(k) + (E(k) + E(k+1)) / 2                                       k = 4..11
 		constexpr uint32_t KP = dpw(1, 1, 0, 0);
 #pragma unroll
@@ -230,8 +248,15 @@ __device__ __forceinline__ void unstrip_hpass(const uint32_t (&lw)[8], uint32_t 
 		}
 		if (left_edge)
 			e[3] = e[4]; // E(-1) = E(0)
-		if (rem == 8)
-			e[12] = e[13] = e[11]; // E(t) = E(t+1) = E(t-1)
+		if (rem <= 9) // E(t) = E(t+1) = E(t-1); E(13) is column t when the edge lies one column into the next chunk
+		{
+#pragma unroll
+			for (int k = 13; k >= 5; k--)
+			{
+				const int take1 = -(int)(rem + 4 == k), take2 = (k >= 6) ? -(int)(rem + 5 == k) : 0;
+				e[k] = (e[k - 1] & take1) | ((k >= 6 ? e[k - 2] : 0) & take2) | (e[k] & ~(take1 | take2));
+			}
+		}
 		// O(k) = H(k) - (E(k-1) - 9 E(k) - 9 E(k+1) + E(k+2)) / 16                k = 4..11
 		constexpr uint32_t KL = dpw(-1, 9, 9, -1);
 		uint32_t te[16]; // te[k] = (E(k), E(k+1))
@@ -271,15 +296,20 @@ __global__ void __launch_bounds__(UT_THREADS, 6) k_unlift_strip(const UnstripPar
 	const int q = (int)__ldg(in_c - 1); // lift head: the decoder learns q from the stream (misc.c:262-268)
 	int16_t* __restrict__ out = p.out + p.out_is * img + p.out_ps * chn;
 
-	// ---- loader geometry. Staged column index x <-> level column c0 - 8 + x. Subband rows start at element
-	// offset off_c + band*b + j*hw of the stream: hw % 8 == 0 and band % 8 == 0, so the misalignment sh (in
-	// elements) of a row against 16 bytes is the same for every row of the three subbands.
-	const int sh = (int)((p.stream_is * img + p.off_c[chn]) & 7);
+	// ---- loader geometry. Staged column index x <-> level column c0 - 8 + x. A subband row starts at element
+	// off_c + band*b + j*hw of the stream, anywhere against 16 bytes: the copy starts at the 16-byte boundary below the
+	// first wanted element and the V pass reads with the row's shift (0..7 elements). With hw % 8 == 0 (and then
+	// band % 8 == 0) the shift is the same for every row of the three subbands (ALIGNED); otherwise it changes from
+	// row to row and band to band and is recomputed where it is needed. Copies take whole 16-byte groups up to the end
+	// of the strip or of the row: what they bring in beyond the level's last column is garbage that the H pass
+	// overrides (see above), and the rows of the LL plane are padded to 8 elements.
+	const uint64_t base_el = p.stream_is * img + p.off_c[chn]; // element offset of the channel's first subband
+	const bool aligned = (hw & 7) == 0;
+	const int hwm = hw & 7;
+	const int sh = (int)(base_el & 7);                          // ALIGNED: the shift of every subband row
 	const int x0 = (c0 == 0) ? 8 : 0;                        // first staged column that exists (left edge: columns < 0 do not)
-	const int ll_x1 = min(UT_LLW, hw - (c0 - 8));            // one past the last LL column staged (a multiple of 8)
-	const int hp_x1 = min(UT_HPW, (hw - (c0 - 8) + sh) & ~7); // same for the shifted subband window
-	const int hp_tail = min(UT_HPW, hw - (c0 - 8) + sh) - hp_x1; // 0..7 row-end elements the 16-byte copies cannot reach
-	const uint32_t ll_bytes = (uint32_t)(ll_x1 - x0) * 2, hp_bytes = (uint32_t)(hp_x1 - x0) * 2;
+	const int col_end = min(UT_LLW, hw - (c0 - 8));          // one past the last staged column the level has
+	const uint32_t ll_bytes = (uint32_t)(((col_end - x0) + 7) & ~7) * 2;
 
 	// Warp b issues the 8 row copies of band b (0 = LL, 1..3 = C, B, D) and arrives on the barrier with that band's
 	// bytes: with one issuing warp that warp reached the step's __syncthreads late, every step, and the others waited.
@@ -288,28 +318,28 @@ __global__ void __launch_bounds__(UT_THREADS, 6) k_unlift_strip(const UnstripPar
 		const int lane = tid & 31, b = tid >> 5;
 		if (lane < UT_STEP)
 		{
-			if (lane == 0)
-				mbar_expect_tx(&bars[buf], UT_STEP * (b == 0 ? ll_bytes : hp_bytes));
-			__syncwarp((1u << UT_STEP) - 1u);
 			const int r = lane;
 			const int j = min(max(js + r, 0), hh - 1);
 			int16_t* dst = dstbuf + (b * UT_STEP + r) * UT_SP + x0;
+			const int16_t* src;
+			uint32_t bytes;
 			if (b == 0)
-				bulk_g2s(dst, in_ll + (uint32_t)(j * (int)p.ll_rs) + (c0 - 8 + x0), ll_bytes, &bars[buf]);
-			else
-				bulk_g2s(dst, in_c + (uint64_t)(b - 1) * band + (uint32_t)(j * hw) + (c0 - 8 + x0 - sh), hp_bytes, &bars[buf]);
-		}
-		else if (hp_tail > 0)
-		{
-			// right-edge strip: the last (< 8) elements of each subband row, element by element
-			for (int i = b * (32 - UT_STEP) + lane - UT_STEP; i < 3 * UT_STEP * hp_tail; i += (UT_THREADS / 32) * (32 - UT_STEP))
 			{
-				const int e = i % hp_tail, rb = i / hp_tail;
-				const int bb = rb >> 3, r = rb & 7;
-				const int j = min(max(js + r, 0), hh - 1);
-				dstbuf[((bb + 1) * UT_STEP + r) * UT_SP + hp_x1 + e] =
-				    __ldg(in_c + (uint64_t)bb * band + (uint32_t)(j * hw) + (c0 - 8 - sh + hp_x1 + e));
+				src = in_ll + (uint32_t)(j * (int)p.ll_rs) + (c0 - 8 + x0);
+				bytes = ll_bytes;
 			}
+			else
+			{
+				const uint64_t row_el = base_el + (uint64_t)(b - 1) * band + (uint32_t)(j * hw);
+				const int shr = (int)(row_el & 7);
+				src = p.stream + (row_el - shr) + (c0 - 8 + x0);
+				bytes = (uint32_t)(((col_end - x0 + shr) + 7) & ~7) * 2;
+			}
+			const uint32_t total = __reduce_add_sync((1u << UT_STEP) - 1u, bytes);
+			if (lane == 0)
+				mbar_expect_tx(&bars[buf], total);
+			__syncwarp((1u << UT_STEP) - 1u);
+			bulk_g2s(dst, src, bytes, &bars[buf]);
 		}
 	};
 	static_assert(UT_THREADS / 32 == 4, "one issuing warp per band");
@@ -326,15 +356,17 @@ __global__ void __launch_bounds__(UT_THREADS, 6) k_unlift_strip(const UnstripPar
 	const bool right_side = tid >= 64;
 	const int vt = tid & 63;
 	const int lo_band = right_side ? 2 : 0, hi_band = right_side ? 3 : 1;   // (LL, C) or (B, D)
-	const int hp_word = 2 + vt + (sh >> 1);                                 // word of the pair in a shifted subband row
+	const int hp_word = 2 + vt + (sh >> 1);                                 // ALIGNED: word of the pair in a shifted subband row
 	const bool odd_shift = (sh & 1) != 0;
+	// not ALIGNED: shift of row j of a band = (band_sh + j * hwm) & 7
+	const int hi_sh0 = (int)((base_el + (uint64_t)(hi_band - 1) * band) & 7);
+	const int lo_sh0 = right_side ? (int)((base_el + (uint64_t)(lo_band - 1) * band) & 7) : 0;
 	const int qhi = q << 16;
 	UnstripV<WL> vs;
 	vs.init();
 
 	const int j_first = i_begin - LAT, j_last = i_end + LAT;
 	issue(j_first, 0);
-	__syncthreads(); // tail fills of the first buffer
 
 	int buf = 0;
 	uint32_t phase = 0;
@@ -353,19 +385,40 @@ __global__ void __launch_bounds__(UT_THREADS, 6) k_unlift_strip(const UnstripPar
 			uint32_t* vb = reinterpret_cast<uint32_t*>(VBs) + tid;
 			const bool interior = (js - LAT > 0) && (js + UT_STEP <= hh);
 
-			auto vstep = [&](auto edge_tag, auto quant_tag) {
+			auto vstep = [&](auto edge_tag, auto quant_tag, auto aligned_tag) {
 				constexpr bool EDGE = decltype(edge_tag)::value;
 				constexpr bool QUANT = decltype(quant_tag)::value;
+				constexpr bool ALIGNED = decltype(aligned_tag)::value;
 #pragma unroll
 				for (int k = 0; k < UT_STEP; k++)
 				{
-					// odd_shift is uniform per CTA
-					uint32_t wh = phi[k * (UT_SP / 2)];
-					if (odd_shift)
-						wh = __funnelshift_r(wh, phi[k * (UT_SP / 2) + 1], 16);
-					uint32_t wl = plo[k * (UT_SP / 2)];
-					if (odd_shift && right_side)
-						wl = __funnelshift_r(wl, plo[k * (UT_SP / 2) + 1], 16);
+					uint32_t wh, wl;
+					if (ALIGNED)
+					{
+						// odd_shift is uniform per CTA
+						wh = phi[k * (UT_SP / 2)];
+						if (odd_shift)
+							wh = __funnelshift_r(wh, phi[k * (UT_SP / 2) + 1], 16);
+						wl = plo[k * (UT_SP / 2)];
+						if (odd_shift && right_side)
+							wl = __funnelshift_r(wl, plo[k * (UT_SP / 2) + 1], 16);
+					}
+					else
+					{
+						// the row's own shift: rows of a level whose width is no multiple of 8 start anywhere
+						const int j = EDGE ? min(max(js + k, 0), hh - 1) : js + k;
+						const int s_hi = (hi_sh0 + j * hwm) & 7;
+						const uint32_t* ph = sb + ((hi_band * UT_STEP + k) * (UT_SP / 2) + 2 + vt) + (s_hi >> 1);
+						wh = __funnelshift_r(ph[0], ph[1], (s_hi & 1) << 4);
+						if (right_side)
+						{
+							const int s_lo = (lo_sh0 + j * hwm) & 7;
+							const uint32_t* pl = sb + ((lo_band * UT_STEP + k) * (UT_SP / 2) + 2 + vt) + (s_lo >> 1);
+							wl = __funnelshift_r(pl[0], pl[1], (s_lo & 1) << 4);
+						}
+						else
+							wl = plo[k * (UT_SP / 2)];
+					}
 					if (QUANT)
 					{
 						// lifting.c:30-40: all three highpass subbands; LL is never quantised.
@@ -380,11 +433,17 @@ __global__ void __launch_bounds__(UT_THREADS, 6) k_unlift_strip(const UnstripPar
 					vb[(2 * k + 1) * (UT_VP / 2)] = odd;
 				}
 			};
+			auto vstep_q = [&](auto edge_tag, auto quant_tag) {
+				if (aligned)
+					vstep(edge_tag, quant_tag, std::true_type{});
+				else
+					vstep(edge_tag, quant_tag, std::false_type{});
+			};
 			auto vstep_e = [&](auto edge_tag) {
 				if (q > 1)
-					vstep(edge_tag, std::true_type{});
+					vstep_q(edge_tag, std::true_type{});
 				else
-					vstep(edge_tag, std::false_type{});
+					vstep_q(edge_tag, std::false_type{});
 			};
 			if (interior)
 				vstep_e(std::false_type{});
@@ -420,7 +479,10 @@ __global__ void __launch_bounds__(UT_THREADS, 6) k_unlift_strip(const UnstripPar
 				unstrip_hpass<WL>(lw, gw, c0 + a == 0, hw - (c0 + a), w);
 				uint4* dst = reinterpret_cast<uint4*>(out + (uint64_t)oy * p.out_rs + 2 * (c0 + a));
 				dst[0] = make_uint4(w[0], w[1], w[2], w[3]);
-				dst[1] = make_uint4(w[4], w[5], w[6], w[7]);
+				// the last chunk of a row may end inside its first eight samples: the other eight would land beyond the
+				// row's padding, on the next row
+				if (2 * (c0 + a) + 8 < (int)p.tw)
+					dst[1] = make_uint4(w[4], w[5], w[6], w[7]);
 			}
 		}
 		// No barrier here: the next step's V pass writes the other VB buffer. S[buf] is reloaded by the issue() of
@@ -433,9 +495,12 @@ __global__ void __launch_bounds__(UT_THREADS, 6) k_unlift_strip(const UnstripPar
 	}
 }
 
+// Any level from 32 x 8 coefficients whose planes have 16-byte aligned rows. An odd output width (tw = 2 hw - 1) has its
+// dropped last sample written into the row's padding, which must be there (out_rs >= 2 hw). Subband copies may read up
+// to 15 elements beyond a row's end: the caller's stream buffer carries that slack after its last element.
 static inline bool unlift_strip_eligible(const UnliftParams& p)
 {
-	return p.wrap == AKOD_WRAP_CLAMP && (p.hw % 8) == 0 && p.tw == 2 * p.hw && p.hw >= 32 && p.hh >= 8 &&
+	return p.wrap == AKOD_WRAP_CLAMP && (p.tw == 2 * p.hw || p.tw + 1 == 2 * p.hw) && p.out_rs >= 2 * p.hw && p.hw >= 32 && p.hh >= 8 &&
 	       (p.out_rs % 8) == 0 && (p.out_ps % 8) == 0 && (p.out_is % 8) == 0 && ((uintptr_t)p.out % 16) == 0 &&
 	       (p.ll_rs % 8) == 0 && (p.ll_ps % 8) == 0 && (p.ll_is % 8) == 0 && ((uintptr_t)p.ll % 16) == 0 &&
 	       (p.stream_is % 8) == 0 && ((uintptr_t)p.stream % 16) == 0 && p.off_c[0] >= 16 &&
