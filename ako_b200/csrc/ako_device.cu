@@ -685,6 +685,18 @@ static inline uint32_t akod_pad8(uint32_t v)
 	return (v + 7u) & ~7u;
 }
 
+// Does the single-launch tail kernel (one CTA per plane, lift_small.cuh) take the pyramid from this level down? It is
+// there for the latency of a lone image's small levels; a batch of many planes (tiles of a large image, many images)
+// has the parallelism for the strip kernels, which run several times faster per sample, down to their smallest level.
+static inline bool akod_small_from(const akodPlan* plan, uint32_t l, uint32_t n_members)
+{
+	const akodLevel* L = &plan->level[l];
+	if (!small_eligible(L->cw, L->ch, plan->levels - l))
+		return false;
+	const bool strip_size = plan->wrap == AKOD_WRAP_CLAMP && L->cw >= 64 && L->ch >= 16;
+	return !(strip_size && (uint64_t)n_members * plan->channels >= 128);
+}
+
 // u8: when not NULL, level 0 may read the interleaved RGBA8 image itself (the colour/format pass fused into the
 // lifting kernel); *fused tells whether it did -- if not, the caller's planes must hold the formatted image.
 struct LiftRgba
@@ -717,7 +729,7 @@ static int lift_pyramid(akodContext* c, const akodPlan* plan, int16_t* d_planes,
 	for (uint32_t l = 0; l < plan->levels; l++)
 	{
 		const akodLevel* L = &plan->level[l];
-		if (!no_small && small_eligible(L->cw, L->ch, plan->levels - l))
+		if (!no_small && akod_small_from(plan, l, n))
 			return launch_small(c, plan, l, true, src, src_rs, src_ps, src_is, d_stream, stream_is, n);
 		LiftParams p;
 		memset(&p, 0, sizeof(p));
@@ -894,7 +906,7 @@ extern "C" int akod_unlift(akodContext* c, const akodPlan* plan, const int16_t* 
 	uint32_t l_top = plan->levels; // levels l_top .. levels-1 are done by the small kernel
 	if (!no_small)
 		for (uint32_t l = 0; l < plan->levels; l++)
-			if (small_eligible(plan->level[l].cw, plan->level[l].ch, plan->levels - l))
+			if (akod_small_from(plan, l, n))
 			{
 				l_top = l;
 				break;

@@ -65,6 +65,27 @@ LIFT_SHAPES = [(64, 64, 4), (65, 63, 3), (33, 47, 1), (16, 17, 2), (3, 3, 4), (5
                (248, 33, 1), (968, 72, 1)]
 
 
+@pytest.mark.parametrize("wavelet", [W_DD137, W_CDF53, W_HAAR])
+def test_strip_kernels_any_width(orc, ctx, wavelet):
+    """The strip kernels at every residue of the width: 34 consecutive widths (coefficient columns 65 .. 82: every
+    position of the right edge inside a 16-column chunk of the forward H pass and an 8-column chunk of the inverse one,
+    every row misalignment of the subbands), two strips, several row splits, both directions against the oracle."""
+    rs = np.random.RandomState(500 + wavelet)
+    for w in list(range(130, 164)) + [263, 519, 1031]:
+        h = 40 + (w % 5)
+        for ch, (q, g) in [(1, (0, 0)), (2, (7, 9))]:
+            planes = rs.randint(-300, 600, size=(ch, h, w)).astype(np.int16)
+            n = orc.orc_tile_data_size(w, h) * ch // 2
+            want = np.zeros(n, np.int16)
+            os_ = OS(wavelet=wavelet, wrap=0, q=q, g=g)
+            orc.orc_lift(C.byref(os_), ch, w, h, P(planes.copy(), i16p), P(want, i16p))
+            s = S(wavelet=wavelet, wrap=0, q=q, g=g)
+            assert np.array_equal(want, ctx.lift(planes, s)), (w, h, ch, q)
+            back_want = np.zeros((ch, h, w), np.int16)
+            orc.orc_unlift(C.byref(os_), ch, w, h, P(want.copy(), i16p), P(back_want, i16p))
+            assert np.array_equal(back_want, ctx.unlift(want, s, ch, w, h)), (w, h, ch, q)
+
+
 @pytest.mark.parametrize("wrap", [0, 1, 2, 3])
 @pytest.mark.parametrize("wavelet", [W_DD137, W_CDF53, W_HAAR])
 def test_lift_unlift_stage(orc, ctx, wavelet, wrap):
@@ -218,6 +239,18 @@ def test_end_to_end_shapes(orc, shape):
             if q == 0 and g == 0 and blob is not None:
                 out, st, _ = ako_b200.decode(blob)
                 assert np.array_equal(out, img)
+
+
+@pytest.mark.parametrize("shape", [(1921, 1081, 4), (1000, 1000, 3), (777, 555, 2), (2050, 300, 4), (1028, 516, 4)],
+                         ids=lambda s: "x".join(map(str, s)))
+def test_end_to_end_odd_sizes(orc, shape):
+    """Sizes off the multiples of 8 at the scale where the strip kernels carry every level (several strips and row
+    splits per level, odd widths and heights down the pyramid), all wavelets, lossless and quantised."""
+    w, h, ch = shape
+    img = ol.synth(orc, w, h, 3 + w)[..., :ch].copy()
+    for wavelet in (W_DD137, W_CDF53, W_HAAR):
+        for q, g in [(0, 0), (16, 16)]:
+            _e2e(orc, img, wavelet=wavelet, q=q, g=g)
 
 
 def test_end_to_end_options(orc):
