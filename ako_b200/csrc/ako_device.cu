@@ -1216,10 +1216,10 @@ extern "C" int akod_kagari_decode(akodContext* c, uint64_t n_values, const uint8
 		const uint32_t gx = (uint32_t)((pieces_max + 7) / 8 < want ? (pieces_max + 7) / 8 : want);
 		const dim3 gridf(gx ? gx : 1, n_images);
 		AKOD_LAUNCH(c, "kagari_dec_fill", k_kt_fill, gridf, 256, 0, big_list, big_count, big_cap, d_out, out_stride, info,
-		            n_values, d_result);
+		            n_values, d_size, d_result);
 	}
-	// Streams that did not self-synchronise within KD_MAX_RUNS (adversarial input) are decoded by one thread
-	// on the device; a no-op for every other image.
+	// Blocks the parallel decoder does not accept (broken input, or no fixed point within KD_MAX_RUNS) are decoded by
+	// one thread on the device exactly as the reference would; a no-op for every well-formed block.
 	AKOD_LAUNCH(c, "kagari_dec_rescue", k_kd_sequential, n_images, 32, 0, d_in, d_off, d_size, n_values, d_out, out_stride,
 	            d_result, (const KdImage*)info, 1);
 	return AKOD_OK;

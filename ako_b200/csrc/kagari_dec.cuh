@@ -19,36 +19,66 @@
 //         R  : this token IS the RLE count        : -> A
 //     Functions on 4 states compose associatively, so a scan classifies every token; carrying, per entry
 //     state, the number of values a span of tokens expands to gives every token its output position too.
+//     The scan runs inside ONE kernel (k_kd_decode): spans per thread while walking, a block scan, a decoupled
+//     look-back between CTAs.
 //
-// A token expands to one value, or to (u-1) copies of the value before it. Long runs are filled
-// cooperatively by the whole CTA with 128-bit stores.
+// A token expands to one value, or to (u-1) copies of the value before it. Long runs are filled cooperatively
+// with 128-bit stores.
 //
-// Result per block: bytes consumed = ceil(end of last codeword / 8) when exactly n values came out, else 0.
-// (The reference reports what its 64-bit accumulator happened to have fetched, kagari.c:365; for every
-// well-formed block both equal block_size. Blocks with trailing garbage are rejected here.)
+// Result per block: the block's size when exactly n values came out of a chain that ends in the block's last byte
+// (then the reference reports the whole block consumed). Every other block -- broken input -- is decoded again by
+// k_kd_sequential, the reference's own algorithm (64-bit accumulator, refill policy, codewords of up to 27 leading
+// zeros, the bytes its read-ahead has fetched as the result): status and values are the reference's on any bytes.
 #pragma once
 
 #include "common.cuh"
 
 // ------------------------------------------------------------------------------------------------
-// sequential decoder, one thread per block: the simple device implementation the parallel decoder is
-// validated against (AKO_B200_SEQ_DECODE=1 selects it)
-
-__device__ __forceinline__ uint32_t kd_peek32_bytes(const uint8_t* __restrict__ in, uint64_t size, uint64_t pos)
-{
-	const uint64_t byte = pos >> 3;
-	uint64_t acc = 0;
-#pragma unroll
-	for (int i = 0; i < 5; i++)
-	{
-		const uint64_t b = byte + i;
-		acc = (acc << 8) | (uint64_t)((b < size) ? in[b] : 0);
-	}
-	return (uint32_t)(acc >> (8 - (pos & 7)));
-}
+// sequential decoder, one thread per block: akoKagariDecode / akoEliasDecodeStep as they are (kagari.c:119-163,
+// :301-366), 64-bit accumulator and refill policy included, so that it answers exactly what the reference answers on
+// ANY bytes: codewords of 16 to 27 leading zeros are taken (value truncated to 16 bits), and the bytes it reports
+// consumed are the bytes its accumulator has fetched, read-ahead included. The parallel decoder hands every block it
+// does not accept to this kernel (k_kt_fill's verdict): well-formed blocks never come here, broken ones get the
+// reference's status and pixels. AKO_B200_SEQ_DECODE=1 sends everything here (the device implementation the parallel
+// decoder is validated against).
 
 struct KdImage;
-__device__ __forceinline__ bool kd_needs_rescue(const KdImage* info, uint32_t img);
+__device__ __forceinline__ bool kd_wants_sequential(const KdImage* info, uint32_t img);
+
+struct KdAcc
+{
+	const uint8_t* cur;
+	const uint8_t* end;
+	uint64_t acc;
+	int usage;
+};
+
+// akoEliasDecodeStep; *bits = 0 on failure
+__device__ __forceinline__ uint32_t kd_reference_step(KdAcc& r, int* bits)
+{
+	*bits = 0;
+	if (r.acc == 0 || r.usage < 32)
+	{
+		while (r.usage < 56 && r.cur < r.end)
+		{
+			r.usage += 8;
+			r.acc |= (uint64_t)(*r.cur) << (64 - r.usage);
+			r.cur++;
+		}
+		if (r.acc == 0)
+			return 0;
+	}
+	const uint32_t top = (uint32_t)(r.acc >> 32);
+	const int z = top ? __clz(top) : 32;
+	const int total = 2 * z + 1;
+	if (total > r.usage)
+		return 0;
+	*bits = total;
+	const uint32_t v = (uint32_t)(r.acc >> (64 - total)) & 0xFFFFu;
+	r.acc <<= total;
+	r.usage -= total;
+	return v;
+}
 
 __global__ void k_kd_sequential(const uint8_t* __restrict__ in_base, const uint64_t* __restrict__ in_off,
                                 const uint64_t* __restrict__ in_size, uint64_t n, int16_t* __restrict__ out_base,
@@ -57,45 +87,38 @@ __global__ void k_kd_sequential(const uint8_t* __restrict__ in_base, const uint6
 	const uint32_t img = blockIdx.x;
 	if (threadIdx.x != 0)
 		return;
-	if (rescue && !kd_needs_rescue(info, img))
+	if (rescue && !kd_wants_sequential(info, img))
 		return;
 	const uint8_t* in = in_base + in_off[img];
 	const uint64_t size = in_size[img];
 	int16_t* out = out_base + out_stride * img;
-	const uint64_t total_bits = size * 8;
+	KdAcc r;
+	r.cur = in;
+	r.end = in + size;
+	r.acc = 0;
+	r.usage = 0;
 
-	uint64_t pos = 0, produced = 0;
+	uint64_t produced = 0;
 	int cn = 0;
 	int16_t prev = 0;
 	bool ok = size > 0 && n > 0;
-
 	while (ok && produced < n)
 	{
-		uint32_t w = kd_peek32_bytes(in, size, pos);
-		int z = w ? __clz(w) : 32;
-		if (z > 15 || pos + 2 * z + 1 > total_bits)
+		int bits;
+		const uint32_t u = (kd_reference_step(r, &bits) - 1u) & 0xFFFFu;
+		if (bits == 0)
 		{
 			ok = false;
 			break;
 		}
-		uint32_t u = ((w >> (31 - 2 * z)) - 1) & 0xFFFFu;
-		pos += 2 * z + 1;
 		const int16_t v = (int16_t)((u >> 1) ^ (0u - (u & 1))); // kagari.c:175-178
 		out[produced++] = v;
 		if (produced > 1 && v == prev)
 		{
 			if (++cn == 2)
 			{
-				w = kd_peek32_bytes(in, size, pos);
-				z = w ? __clz(w) : 32;
-				if (z > 15 || pos + 2 * z + 1 > total_bits)
-				{
-					ok = false;
-					break;
-				}
-				const uint32_t len = ((w >> (31 - 2 * z)) - 1) & 0xFFFFu;
-				pos += 2 * z + 1;
-				if (produced + len > n)
+				const uint32_t len = (kd_reference_step(r, &bits) - 1u) & 0xFFFFu;
+				if (bits == 0 || produced + len > n)
 				{
 					ok = false;
 					break;
@@ -111,7 +134,7 @@ __global__ void k_kd_sequential(const uint8_t* __restrict__ in_base, const uint6
 			cn = 0;
 		}
 	}
-	result[img] = ok ? ((pos + 7) >> 3) : 0;
+	result[img] = ok ? (uint64_t)(r.cur - in) : 0;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -132,12 +155,17 @@ struct KdImage
 	uint64_t stop_pos;     // bit position right after the last codeword
 	uint64_t tokens;       // number of codewords
 	uint64_t outputs;      // values they expand to
-	uint64_t overflow;     // token buffer too small / inconsistent
+	uint64_t sequential;   // the parallel decoder does not accept the block: the sequential kernel decides
 };
 
 __device__ __forceinline__ bool kd_needs_rescue(const KdImage* info, uint32_t img)
 {
 	return info[img].changed[KD_MAX_RUNS - 1] != 0;
+}
+
+__device__ __forceinline__ bool kd_wants_sequential(const KdImage* info, uint32_t img)
+{
+	return info[img].sequential != 0;
 }
 
 __global__ void k_kd_init(KdImage* info, uint32_t n)
@@ -150,7 +178,7 @@ __global__ void k_kd_init(KdImage* info, uint32_t n)
 	info[i].stop_pos = KD_STOP64;
 	info[i].tokens = 0;
 	info[i].outputs = 0;
-	info[i].overflow = 0;
+	info[i].sequential = 0;
 }
 
 struct KdSubState
@@ -1179,18 +1207,24 @@ __global__ void __launch_bounds__(KD_THREADS, KF_CTAS)
 	}
 }
 
-// the big runs, one warp per piece, spread over the whole GPU; the first thread of each image also gives the verdict:
-// bytes consumed = ceil(end of the last codeword / 8) when exactly n values came out, else 0
+// the big runs, one warp per piece, spread over the whole GPU; the first thread of each image also gives the verdict.
+// A well-formed block expands to exactly n values and ends in the last byte of the block: then the reference reports
+// the whole block consumed. Everything else (no fixed point of the boundary search, a chain that stops early or on a
+// codeword of more than 15 leading zeros, trailing bytes, too few or too many values) is left to the sequential
+// kernel, which answers as the reference does.
 __global__ void __launch_bounds__(256)
     k_kt_fill(const KtRun* __restrict__ big_list, const uint32_t* __restrict__ big_count, uint32_t big_cap,
-              int16_t* __restrict__ out_base, uint64_t out_stride, const KdImage* __restrict__ info, uint64_t n_values,
-              uint64_t* __restrict__ result)
+              int16_t* __restrict__ out_base, uint64_t out_stride, KdImage* __restrict__ info, uint64_t n_values,
+              const uint64_t* __restrict__ in_size, uint64_t* __restrict__ result)
 {
 	const uint32_t img = blockIdx.y;
 	if (blockIdx.x == 0 && threadIdx.x == 0)
 	{
-		const bool ok = info[img].outputs == n_values && !kd_needs_rescue(info, img) && info[img].stop_pos != KD_STOP64;
-		result[img] = ok ? ((info[img].stop_pos + 7) >> 3) : 0;
+		const uint64_t size = in_size[img];
+		const bool ok = info[img].outputs == n_values && !kd_needs_rescue(info, img) && info[img].stop_pos != KD_STOP64 &&
+		                ((info[img].stop_pos + 7) >> 3) == size;
+		result[img] = ok ? size : 0;
+		info[img].sequential = ok ? 0 : 1;
 	}
 	const uint32_t n = min(big_count[img], big_cap);
 	const uint32_t warps = gridDim.x * (blockDim.x >> 5);

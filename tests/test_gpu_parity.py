@@ -214,6 +214,50 @@ def test_kagari_decode_rejects_broken(ctx):
     assert used == 0
 
 
+def _orc_kagari_decode(orc, data, n):
+    data = np.ascontiguousarray(data, dtype=np.uint8)
+    out = np.zeros(n, np.int16)
+    used = orc.orc_kagari_decode(n, len(data), P(data, u8p), P(out, i16p))
+    return used, out
+
+
+def test_kagari_decode_answers_like_the_reference_on_any_bytes(orc, ctx):
+    """What the parallel decoder does not accept goes to a kernel that IS the reference's decoder (64-bit accumulator,
+    refill policy, kagari.c:119-163): blocks with trailing bytes (the reference reports the bytes its read-ahead has
+    fetched, so some are accepted), codewords of 16..27 leading zeros (accepted, value truncated to 16 bits), random
+    bytes, truncated blocks. Consumed bytes and -- whenever the block is accepted -- the values are the oracle's."""
+    rs = np.random.RandomState(77)
+    cases = []
+    for trial in range(24):
+        n = int(rs.randint(20, 6000))
+        v = (rs.randint(-40, 41, size=n) * (rs.rand(n) < 0.4)).astype(np.int16)
+        good = ctx.kagari_encode(v, cap=4 * n + 64)
+        for tail in (0, 1, 2, 3, 5, 6, 7, 9):
+            extra = rs.randint(0, 256, size=tail).astype(np.uint8) if trial % 2 else np.zeros(tail, np.uint8)
+            cases.append((np.concatenate([good, extra]), n))
+        cases.append((good[:len(good) - 1 - trial % 4], n))
+        cases.append((good, n + 1 + trial))      # asks for more values than the block holds
+        cases.append((good, max(1, n - 1 - trial)))  # ... and for fewer
+    for trial in range(60):
+        # long zero spans between set bits: codewords with many leading zeros
+        size = int(rs.randint(8, 400))
+        raw = (rs.randint(0, 256, size=size) * (rs.rand(size) < 0.25)).astype(np.uint8)
+        cases.append((raw, int(rs.randint(1, 200))))
+    # 17 zeros, a one, 17 more bits: a codeword of 35 bits whose value is truncated to 16 bits
+    bits = "0" * 17 + "1" + "01100110011001101" + "1" * 11
+    raw = np.frombuffer(int(bits, 2).to_bytes(len(bits) // 8 + 1, "big")[-(len(bits) + 7) // 8:], dtype=np.uint8)
+    cases.append((np.concatenate([raw, np.full(8, 0xFF, np.uint8)]), 4))
+    accepted = 0
+    for data, n in cases:
+        want_used, want = _orc_kagari_decode(orc, data, n)
+        used, got = ctx.kagari_decode(data, n)
+        assert used == want_used, (len(data), n, used, want_used)
+        if want_used:
+            accepted += 1
+            assert np.array_equal(got, want), (len(data), n)
+    assert accepted >= 40
+
+
 # ------------------------------------------------------------------ whole codec through akoEncodeExt / akoDecodeExt
 
 def _e2e(orc, img, **kw):
