@@ -26,6 +26,7 @@ struct akoB200Context
 	struct akoSettings plan_settings[4];
 	int plan_valid[4];
 	int plan_next;
+	int mail_pending; /* an upload kernel may still be reading the pinned mailbox (see upload_words) */
 };
 
 /* ------------------------------------------------------------------------------------------------ */
@@ -695,12 +696,13 @@ static enum akoStatus upload_words(akoB200Context* ctx, uint64_t* d_dst, const u
 	for (size_t o = 0; o < words && st == AKO_OK; o += MAILBOX_WORDS)
 	{
 		const size_t m = (words - o < MAILBOX_WORDS) ? words - o : MAILBOX_WORDS;
-		if (o != 0)
-			st = from_dev(akod_sync(ctx->dev)); /* previous chunk still in flight */
+		if (o != 0 || ctx->mail_pending)
+			st = from_dev(akod_sync(ctx->dev)); /* the previous chunk, or an earlier upload that no read-back has followed */
 		if (st == AKO_OK)
 		{
 			memcpy(mail, src + o, sizeof(uint64_t) * m);
 			st = from_dev(akod_copy_words(ctx->dev, d_dst + o, mail, m)); /* a kernel reads the pinned mailbox */
+			ctx->mail_pending = 1;
 		}
 	}
 	return st;
@@ -716,6 +718,7 @@ static enum akoStatus download_words(akoB200Context* ctx, uint64_t* dst, const u
 		st = from_dev(akod_copy_words(ctx->dev, mail, d_src + o, m)); /* a kernel writes the pinned mailbox */
 		if (st == AKO_OK)
 			st = from_dev(akod_sync(ctx->dev));
+		ctx->mail_pending = 0;
 		if (st == AKO_OK)
 			memcpy(dst + o, mail, sizeof(uint64_t) * m);
 	}
