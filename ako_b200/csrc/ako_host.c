@@ -1320,7 +1320,7 @@ AKO_API size_t akoB200EncodeDevice(akoB200Context* ctx, const struct akoSettings
 }
 
 /* ---- one tiled image over several GPUs: tiles are independent blocks (encode.c:115-205,
- * decode.c:113-230), so the tile rows are cut into one band per device of $AKO_CUDA_DEVICES. A band is encoded or
+ * decode.c:113-230), so the tile rows are cut into bands, a few per device of $AKO_CUDA_DEVICES. A band is encoded or
  * decoded as the image it is (same width, same tiles_dimension: its tiles have the sizes they have in the whole
  * image, and a tile's block does not depend on where the tile lies); the host concatenates the bands' blocks in raster
  * order behind the one head, or cuts the blob at the block heads it has walked. Events are tile-ordered callbacks
@@ -1353,11 +1353,20 @@ static int bands_wanted(const struct akoCallbacks* cb, const struct akoSettings*
 	const size_t td = s->tiles_dimension;
 	if (td == 0 || (cb != NULL && cb->events != NULL) || w * h < env_size("AKO_B200_BANDS_MIN_PIXELS", BANDS_MIN_PIXELS, 1, (size_t)1 << 40))
 		return 0;
-	const int nd = env_devices(devices);
+	/* Several bands per device: each band has its own pooled context and stream, so one band's copies overlap
+	 * another band's kernels -- on a single device too (a 16384 x 16384 image is a gigabyte each way). */
+	int listed[MAX_DEVICES];
+	const int nd = env_devices(listed);
+	const size_t per = env_size("AKO_B200_BANDS_PER_DEVICE", nd == 1 ? 4 : 2, 1, MAX_DEVICES);
 	const size_t rows = (h / td) + (h % td != 0);
-	if (nd < 2 || rows < 2)
+	size_t nb = (size_t)nd * per;
+	nb = (nb > MAX_DEVICES) ? MAX_DEVICES : nb;
+	nb = (nb > rows) ? rows : nb;
+	if (nb < 2)
 		return 0;
-	return (rows < (size_t)nd) ? (int)rows : nd;
+	for (size_t k = 0; k < nb; k++)
+		devices[k] = listed[k % (size_t)nd];
+	return (int)nb;
 }
 
 static void bands_cut(struct band_job* jobs, int nb, const int* devices, size_t w, size_t h, size_t td)

@@ -146,7 +146,9 @@ constexpr int KD_CTA_BITS = KD_SUB_BITS * KD_THREADS;      // 32768 bits = 4 KiB
 constexpr int KD_CTA_WORDS = KD_CTA_BITS / 32;
 constexpr uint32_t KD_STOP = 0xFFFFFFFFu;                  // "the chain ended before this point"
 constexpr uint64_t KD_STOP64 = ~(uint64_t)0;
-constexpr int KD_MAX_RUNS = 6;                             // CTA-level synchronisation runs (later ones are no-ops once stable)
+constexpr int KD_MAX_RUNS = 4;                             // CTA-level synchronisation runs: 0 speculates, 1 starts every chunk where its
+                                                           // predecessor ended, 2 proves it (3: one more round); a stream that has not
+                                                           // settled by then goes to the sequential kernel
 
 // per-image bookkeeping, device resident
 struct KdImage
@@ -608,7 +610,7 @@ struct KtRun
 	int16_t value;
 };
 
-constexpr uint32_t KT_BIG = 2048;   // runs at least this long leave the CTA: they go to a list that k_kt_fill spreads over the GPU
+constexpr uint32_t KT_BIG = 2048;   // (512 and 256 measured slower: the decode pass fills such runs faster than the list round trip) runs at least this long leave the CTA: they go to a list that k_kt_fill spreads over the GPU
 constexpr uint32_t KT_PIECE = 4096; // ... in pieces of at most this many values (one warp each)
 
 // ------------------------------------------------------------------------------------------------
@@ -1122,9 +1124,9 @@ __global__ void __launch_bounds__(KD_THREADS, KF_CTAS)
 					const bool fits = pos + count <= n_values;
 					if (staged || fits)
 					{
-						if (count >= KT_BIG)
+						if (count >= KT_BIG && !staged)
 						{
-							// (never in a staged warp: its values would not fit KF_WIN, so 'fits' holds here)
+							// (a staged warp fills its runs in shared memory whatever their length: they fit KF_WIN)
 							const uint32_t pieces = (count + KT_PIECE - 1) / KT_PIECE;
 							const uint32_t first = atomicAdd(&big_count[img], pieces);
 							for (uint32_t k = 0; k < pieces; k++)

@@ -947,7 +947,8 @@ def secondary_tiled(env, world, size=16384, tiles=512):
     e1, d1, blob1, dig1 = best(3)
     px = w * h
     res = {"workload": f"DD137 -q16 -g16 tiles_dimension={tiles}: akoEncodeExt / akoDecodeExt of one synthetic {w}x{h} RGBA8 "
-                       "image, page-locked host buffers, wall time of the call",
+                       "image, page-locked host buffers, wall time of the call (the library cuts the tile rows into bands: four "
+                       "streams on one device, so copies overlap kernels; two bands per device over several)",
            "blob_bytes": int(blob1.size),
            "one_device": {"encode_ms": round(e1, 2), "decode_ms": round(d1, 2),
                           "encode_MPix_s": round(px / e1 / 1e3, 1), "decode_MPix_s": round(px / d1 / 1e3, 1)}}
