@@ -101,6 +101,53 @@ __global__ void __launch_bounds__(256) kmix(uint32_t* out, uint32_t seed, long l
 		cycles[blockIdx.x] = t1 - t0;
 }
 
+// two ops interleaved on independent chains: do they share a pipe (rate of one) or not (rate of both)?
+template <int A, int B>
+__global__ void __launch_bounds__(256) kmix2(uint32_t* out, uint32_t seed, long long* cycles)
+{
+	uint32_t a[CHAINS];
+#pragma unroll
+	for (int i = 0; i < CHAINS; i++)
+		a[i] = seed * (threadIdx.x + 1) + i;
+	const uint32_t b = seed | 3;
+	long long t0 = clock64();
+#pragma unroll 16
+	for (int it = 0; it < ITERS; it++)
+	{
+#pragma unroll
+		for (int i = 0; i < CHAINS; i += 2)
+		{
+			a[i] = op<A>(a[i], b);
+			a[i + 1] = op<B>(a[i + 1], b);
+		}
+	}
+	long long t1 = clock64();
+	uint32_t s = 0;
+#pragma unroll
+	for (int i = 0; i < CHAINS; i++)
+		s ^= a[i];
+	out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+	if (threadIdx.x == 0)
+		cycles[blockIdx.x] = t1 - t0;
+}
+
+template <int A, int B>
+void run2(const char* name, uint32_t* d_out, long long* d_cyc)
+{
+	const int blocks = 148 * 4, threads = 256;
+	kmix2<A, B><<<blocks, threads>>>(d_out, 12345, d_cyc);
+	cudaDeviceSynchronize();
+	kmix2<A, B><<<blocks, threads>>>(d_out, 12345, d_cyc);
+	cudaDeviceSynchronize();
+	long long h[148 * 4];
+	cudaMemcpy(h, d_cyc, sizeof(h), cudaMemcpyDeviceToHost);
+	double avg = 0;
+	for (int i = 0; i < blocks; i++)
+		avg += (double)h[i];
+	avg /= blocks;
+	printf("%-28s %8.1f thread-ops/clk/SM   (%.0f cycles)\n", name, 4.0 * threads * ITERS * CHAINS / avg, avg);
+}
+
 template <int OP>
 void run(const char* name, uint32_t* d_out, long long* d_cyc)
 {
@@ -171,5 +218,11 @@ int main()
 		avg /= blocks;
 		printf("%-28s %8.1f thread-ops/clk/SM   (%.0f cycles)\n", "PRMT+IMAD interleaved", 4.0 * threads * ITERS * CHAINS / avg, avg);
 	}
+	run2<2, 4>("IDP.2A + PRMT", d_out, d_cyc);
+	run2<2, 0>("IDP.2A + IMAD", d_out, d_cyc);
+	run2<4, 7>("PRMT + LOP3", d_out, d_cyc);
+	run2<5, 0>("shr+add + IMAD", d_out, d_cyc);
+	run2<6, 0>("SHF + IMAD", d_out, d_cyc);
+	run2<9, 4>("add.s32 + PRMT", d_out, d_cyc);
 	return 0;
 }
