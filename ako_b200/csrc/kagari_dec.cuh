@@ -155,7 +155,6 @@ struct KdImage
 {
 	uint64_t changed[8];   // per sync run: number of CTAs whose end moved
 	uint64_t stop_pos;     // bit position right after the last codeword
-	uint64_t tokens;       // number of codewords
 	uint64_t outputs;      // values they expand to
 	uint64_t sequential;   // the parallel decoder does not accept the block: the sequential kernel decides
 };
@@ -178,7 +177,6 @@ __global__ void k_kd_init(KdImage* info, uint32_t n)
 	for (int r = 0; r < 8; r++)
 		info[i].changed[r] = 0;
 	info[i].stop_pos = KD_STOP64;
-	info[i].tokens = 0;
 	info[i].outputs = 0;
 	info[i].sequential = 0;
 }
@@ -214,11 +212,6 @@ __device__ __forceinline__ void kd_stage_bits(uint32_t* sm, const uint8_t* __res
 		}
 		sm[i] = w;
 	}
-}
-
-__device__ __forceinline__ uint32_t kd_peek(const uint32_t* sm, uint32_t pos)
-{
-	return __funnelshift_l(sm[(pos >> 5) + 1], sm[pos >> 5], pos & 31);
 }
 
 // walks codewords from 'start' (relative to the CTA) until the first boundary >= limit.
@@ -418,13 +411,7 @@ __global__ void __launch_bounds__(KD_THREADS)
 // ------------------------------------------------------------------------------------------------
 // phase 2: classification + expansion
 
-constexpr int KT_THREADS = 256;
-constexpr int KT_ITEMS = 8;                     // tokens per thread in the expand pass: its loop body is large, 16 unrolled copies
-                                                // were 80 KB of code and a fifth of its stall samples were instruction fetch
-constexpr int KT_BLOCK = KT_THREADS * KT_ITEMS; // tokens per CTA (2048), the unit pass A and B describe
-constexpr int KT_SPAN_ITEMS = 16;               // the span pass has a small body: more tokens per thread, fewer scan steps
-constexpr int KT_SPAN_THREADS = KT_BLOCK / KT_SPAN_ITEMS;
-constexpr int KT_LONG = 16;                     // runs at least this long are filled by the whole CTA
+constexpr int KT_LONG = 16;                     // runs at least this long are filled by the whole warp
 
 enum : uint32_t
 {
@@ -544,32 +531,6 @@ __device__ __forceinline__ KtSpan kt_warp_excl_scan(const KtSpan& v, KtSpan* tot
 	for (int s = 0; s < 4; s++)
 		total->out[s] = __shfl_sync(AKOD_FULL_MASK, incl.out[s], 31);
 	return excl;
-}
-
-// Block-wide exclusive scan of spans. sm must hold 33 KtSpan. Returns the span of everything before this thread;
-// *total = span of the whole CTA.
-__device__ __forceinline__ KtSpan kt_block_excl_scan(KtSpan v, KtSpan* sm, KtSpan* total)
-{
-	const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
-	KtSpan warp_total;
-	const KtSpan excl = kt_warp_excl_scan(v, &warp_total);
-	if (lane == 0)
-		sm[wid] = warp_total;
-	__syncthreads();
-	if (wid == 0)
-	{
-		const KtSpan w = (lane < nw) ? sm[lane] : kt_identity();
-		KtSpan all;
-		const KtSpan we = kt_warp_excl_scan(w, &all, nw);
-		sm[lane] = we;
-		if (lane == 0)
-			sm[32] = all;
-	}
-	__syncthreads();
-	const KtSpan r = kt_compose(sm[wid], excl);
-	*total = sm[32];
-	__syncthreads();
-	return r;
 }
 
 __device__ __forceinline__ int16_t kt_value(uint32_t u)
