@@ -571,7 +571,7 @@ __device__ __forceinline__ void kg_emitters(const KgChunk& c, const KgMasks& m, 
 
 __device__ __forceinline__ uint32_t kg_payload_len(uint32_t p)
 {
-	return p ? 2u * (31u - (uint32_t)__clz(p)) + 1u : 1u;
+	return 63u - 2u * (uint32_t)__clz(p | 1u); // 2 * floor(log2 p) + 1; the degenerate p == 0 is one bit
 }
 
 // pass 2: bits emitted by each block (+ the bit string itself into the block's slot when it fits).
@@ -580,7 +580,8 @@ __device__ __forceinline__ uint32_t kg_payload_len(uint32_t p)
 // pass has no __syncthreads and no shared-memory scans at all -- only ballots and shuffles. With one CTA per block the
 // pass was bound by the latency chain of a short-lived CTA (summary words -> values -> three barriers) and by the
 // 300 000 CTAs per step that only find out that their block lies inside a run. The values of step i+1 are fetched
-// before step i is worked on.
+// before step i is worked on. Every lane assembles the bit string of its own eight values in a 64-bit register and ORs
+// it into the warp's bit buffer (see the step body).
 constexpr int KGL_WARPS = KG_THREADS / 32;
 constexpr int KGL_BLOCKS_PER_WARP = 4; // at most: the launcher takes fewer when the batch is too small to fill the GPU so
 constexpr int KGL_STEPS = KG_BLOCK / (32 * KG_ITEMS); // 8
@@ -639,12 +640,37 @@ __device__ __forceinline__ KgChunk kg_chunk_from(const KgFetch& f, uint64_t n, u
 	return c;
 }
 
+// The codes of a lane's own emitters in stream order, straight from its registers (value j first, then the length of
+// the run that ends at j): the general sink of a lane whose bit string does not fit 64 bits. PUT(payload, length).
+template <typename PUT>
+__device__ __forceinline__ void kg_lane_codes(const KgChunk& c, const KgMasks& m, PUT put)
+{
+	const uint4 q = *reinterpret_cast<const uint4*>(c.v);
+	const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+	for (int j = 0; j < KG_ITEMS; j++)
+	{
+		if (m.V & (1u << j))
+		{
+			const int a = (j & 1) ? ((int)w[j >> 1] >> 16) : (int)(short)w[j >> 1];
+			const uint32_t p = ((uint32_t)((a << 1) ^ (a >> 15)) + 1u) & 0xFFFFu;
+			put(p, kg_payload_len(p));
+		}
+		if (m.R & (1u << j))
+		{
+			const uint32_t before = c.start_mask & ((2u << j) - 1u);
+			const uint32_t cj = before ? (uint32_t)j - (31u - (uint32_t)__clz(before)) : m.c0 + (uint32_t)j;
+			put(cj - 1u, kg_payload_len(cj - 1u)); // cj >= 2
+		}
+	}
+}
+
 // one block by one warp; returns the block's bit count. WHOLE = false: the last, partial block of a stream, whose
 // chunks come through the general loader (kept out of line: it is one block per stream and would only cost the
 // common path registers)
 template <bool WHOLE>
 __device__ __forceinline__ uint32_t kgl_block_body(const int16_t* __restrict__ in, uint64_t n, uint64_t first, uint32_t carry_start,
-                                                   uint32_t* bitbuf, uint16_t* list, KgFetch f, int lane)
+                                                   uint32_t* bitbuf, KgFetch f, int lane)
 {
 	uint32_t run_carry = carry_start; // (index + 1) of the last run start before the current step
 	uint32_t bitpos = 0;
@@ -666,72 +692,100 @@ __device__ __forceinline__ uint32_t kgl_block_body(const int16_t* __restrict__ i
 		if (any)
 			run_carry = warp_last;
 
-		// ---- the step's emitters, compacted into the warp's list in stream order
+		// ---- the step's emitters. Every lane codes its own: its whole bit string is assembled in a 64-bit register in
+		// ONE unrolled, branch-free pass over its eight values (a run length follows its value only where some lane of
+		// the warp has one at that position), and after the warp scan of the lengths it is placed with at most three
+		// atomicOr. (Round 1 compacted the emitters of a step into a list and dealt them over the lanes again: balanced,
+		// but twice through shared memory, with divergent loops on both sides -- 2.5 x the instructions on lossless
+		// content and still behind on sparse content.) A lane whose string is longer than 64 bits, a counter overflow
+		// in reach or the partial chunk at the end of the stream take the general sink.
 		const KgMasks m = kg_masks(c, base, run_start);
-		uint32_t cnt;
-		if (m.slow)
-		{
-			cnt = 0;
-			kg_emitters(c, m, n, base, run_start, [&](uint32_t) { cnt++; });
-		}
-		else
-			cnt = __popc(m.V) + __popc(m.R);
-		if (__ballot_sync(AKOD_FULL_MASK, cnt != 0) == 0)
+		if (__ballot_sync(AKOD_FULL_MASK, m.slow || (m.V | m.R) != 0) == 0)
 			continue;
-		const uint32_t incl_cnt = warp_incl_sum(cnt);
-		const uint32_t emitters = __shfl_sync(AKOD_FULL_MASK, incl_cnt, 31);
-		if (cnt)
-		{
-			uint32_t at = incl_cnt - cnt;
-			kg_emitters(c, m, n, base, run_start, [&](uint32_t p) { list[at++] = (uint16_t)p; });
-		}
-		__syncwarp();
-
-		// ---- lane l takes the entries [l * per, (l + 1) * per): lengths, a warp scan, then the codes
-		const uint32_t per = (emitters + 31) >> 5;
-		const uint32_t e0 = min((uint32_t)lane * per, emitters), e1 = min(e0 + per, emitters);
+		uint64_t acc = 0;
 		uint32_t bits = 0;
-		for (uint32_t i = e0; i < e1; i++)
-			bits += kg_payload_len(list[i]);
+		{
+			const uint4 q = *reinterpret_cast<const uint4*>(c.v);
+			const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+			const uint32_t V = m.slow ? 0u : m.V, R = m.slow ? 0u : m.R;
+#pragma unroll
+			for (int j = 0; j < KG_ITEMS; j++)
+			{
+				const int a = (j & 1) ? ((int)w[j >> 1] >> 16) : (int)(short)w[j >> 1];
+				const uint32_t vb = (V >> j) & 1u;
+				const uint32_t pv = (((uint32_t)((a << 1) ^ (a >> 15)) + 1u) & 0xFFFFu) & (0u - vb);
+				const uint32_t lv = kg_payload_len(pv) & (0u - vb);
+				acc = (acc << lv) | pv;
+				bits += lv;
+				if (__any_sync(AKOD_FULL_MASK, (R >> j) & 1u))
+				{
+					const uint32_t rb = (R >> j) & 1u;
+					const uint32_t before = c.start_mask & ((2u << j) - 1u);
+					const uint32_t cj = before ? (uint32_t)j - (31u - (uint32_t)__clz(before)) : m.c0 + (uint32_t)j;
+					const uint32_t pr = (cj - 1u) & (0u - rb);
+					const uint32_t lr = kg_payload_len(pr) & (0u - rb);
+					acc = (acc << lr) | pr;
+					bits += lr;
+				}
+			}
+		}
+		if (m.slow)
+			kg_emitters(c, m, n, base, run_start, [&](uint32_t p) { bits += kg_payload_len(p); });
 		const uint32_t incl = warp_incl_sum(bits);
 		const uint32_t step_total = __shfl_sync(AKOD_FULL_MASK, incl, 31);
 		overflow = overflow || (bitpos + step_total > KG_SLOT_BITS);
 		if (bits && !overflow)
 		{
-			KgSink sink;
-			sink.open(bitbuf, bitpos + incl - bits);
-			for (uint32_t i = e0; i < e1; i++)
+			const uint32_t pos = bitpos + incl - bits;
+			if (bits <= 64u && !m.slow)
 			{
-				const uint32_t p = list[i];
-				sink.put(p, kg_payload_len(p));
+				// MSB-first: the string's first bit is bit (31 - pos % 32) of word pos / 32
+				const uint64_t x = acc << (64u - bits);
+				const uint32_t xh = (uint32_t)(x >> 32), xl = (uint32_t)x, sh = pos & 31u;
+				uint32_t* const at = bitbuf + (pos >> 5);
+				const uint32_t w0 = xh >> sh, w1 = __funnelshift_r(xl, xh, sh), w2 = sh ? (xl << (32u - sh)) : 0u;
+				atomicOr(at, w0);
+				if (w1)
+					atomicOr(at + 1, w1);
+				if (w2)
+					atomicOr(at + 2, w2);
 			}
-			sink.close();
+			else
+			{
+				KgSink sink;
+				sink.open(bitbuf, pos);
+				if (m.slow)
+					kg_emitters(c, m, n, base, run_start, [&](uint32_t p) { sink.put(p, kg_payload_len(p)); });
+				else
+					kg_lane_codes(c, m, [&](uint32_t p, uint32_t len) { sink.put(p, len); });
+				sink.close();
+			}
 		}
 		bitpos += step_total;
-		__syncwarp(); // the list is rewritten by the next step
 	}
 	return bitpos;
 }
 
 __device__ __noinline__ uint32_t kgl_block_tail(const int16_t* __restrict__ in, uint64_t n, uint64_t first, uint32_t carry_start,
-                                                uint32_t* bitbuf, uint16_t* list, int lane)
+                                                uint32_t* bitbuf, int lane)
 {
 	KgFetch f;
 	f.q = make_uint4(0, 0, 0, 0);
 	f.before = f.after = 0;
-	return kgl_block_body<false>(in, n, first, carry_start, bitbuf, list, f, lane);
+	return kgl_block_body<false>(in, n, first, carry_start, bitbuf, f, lane);
 }
 
-__global__ void __launch_bounds__(KG_THREADS, 5)
+#ifndef KGL_CTAS
+#define KGL_CTAS 5
+#endif
+__global__ void __launch_bounds__(KG_THREADS, KGL_CTAS)
     k_kg_lengths(const int16_t* __restrict__ in, uint64_t in_stride, uint64_t n, const uint32_t* __restrict__ blk_carry,
                  uint32_t* __restrict__ blk_bits, uint32_t nblocks, uint32_t* __restrict__ slots,
                  const uint32_t* __restrict__ blk_own, const uint8_t* __restrict__ blk_first, uint32_t blocks_per_warp)
 {
 	__shared__ uint32_t bitbuf_all[KGL_WARPS][KG_SLOT_WORDS + 2];
-	__shared__ uint16_t list_all[KGL_WARPS][2 * 32 * KG_ITEMS]; // at most two codes per value
 	const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
 	uint32_t* const bitbuf = bitbuf_all[wid];
-	uint16_t* const list = list_all[wid];
 	const uint64_t row = (uint64_t)nblocks * blockIdx.y;
 	in += in_stride * blockIdx.y;
 	for (uint32_t i = lane; i < KG_SLOT_WORDS + 2; i += 32)
@@ -769,8 +823,8 @@ __global__ void __launch_bounds__(KG_THREADS, 5)
 				continue;
 			}
 		}
-		const uint32_t bitpos = whole ? kgl_block_body<true>(in, n, first, carry_start, bitbuf, list, f, lane)
-		                              : kgl_block_tail(in, n, first, carry_start, bitbuf, list, lane);
+		const uint32_t bitpos = whole ? kgl_block_body<true>(in, n, first, carry_start, bitbuf, f, lane)
+		                              : kgl_block_tail(in, n, first, carry_start, bitbuf, lane);
 		if (lane == 0)
 			blk_bits[bi] = bitpos;
 		__syncwarp();
