@@ -708,6 +708,7 @@ __device__ __forceinline__ uint32_t kgl_block_body(const int16_t* __restrict__ i
 			const uint4 q = *reinterpret_cast<const uint4*>(c.v);
 			const uint32_t w[4] = {q.x, q.y, q.z, q.w};
 			const uint32_t V = m.slow ? 0u : m.V, R = m.slow ? 0u : m.R;
+			const uint32_t any_r = __reduce_or_sync(AKOD_FULL_MASK, R); // positions where some lane ends a run
 #pragma unroll
 			for (int j = 0; j < KG_ITEMS; j++)
 			{
@@ -717,7 +718,7 @@ __device__ __forceinline__ uint32_t kgl_block_body(const int16_t* __restrict__ i
 				const uint32_t lv = kg_payload_len(pv) & (0u - vb);
 				acc = (acc << lv) | pv;
 				bits += lv;
-				if (__any_sync(AKOD_FULL_MASK, (R >> j) & 1u))
+				if (any_r & (1u << j))
 				{
 					const uint32_t rb = (R >> j) & 1u;
 					const uint32_t before = c.start_mask & ((2u << j) - 1u);
