@@ -151,14 +151,22 @@ int png_min_read(const char* path, uint8_t** out_pixels, size_t* out_w, size_t* 
 		goto done;
 	}
 
-	const size_t row = w * channels;
-	uLongf raw_size = (uLongf)((row + 1) * h);
-	if ((raw = malloc(raw_size)) == NULL || (pixels = malloc(row * h)) == NULL)
+	/* sizes from an untrusted IHDR: refuse what would wrap (w = h = 2^31 ...) before anything is allocated */
+	size_t row, raw_bytes, image_bytes;
+	if (w == 0 || h == 0 || __builtin_mul_overflow(w, channels, &row) || row > ((size_t)1 << 40) ||
+	    __builtin_mul_overflow(row + 1, h, &raw_bytes) || __builtin_mul_overflow(row, h, &image_bytes) ||
+	    raw_bytes > ((size_t)1 << 40))
+	{
+		fail(err, err_len, "image dimensions out of range");
+		goto done;
+	}
+	uLongf raw_size = (uLongf)raw_bytes;
+	if ((raw = malloc(raw_size)) == NULL || (pixels = malloc(image_bytes)) == NULL)
 	{
 		fail(err, err_len, "out of memory");
 		goto done;
 	}
-	if (uncompress(raw, &raw_size, idat, (uLong)idat_size) != Z_OK || raw_size != (uLongf)((row + 1) * h))
+	if (uncompress(raw, &raw_size, idat, (uLong)idat_size) != Z_OK || raw_size != (uLongf)raw_bytes)
 	{
 		fail(err, err_len, "corrupted image data");
 		goto done;
