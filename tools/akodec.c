@@ -136,7 +136,20 @@ int main(int argc, const char* argv[])
 		printf("Input data: %zu channels, %zux%zu px, wavelet: %i, color: %i, wrap: %i, compression: %i\n", channels, w, h,
 		       (int)settings.wavelet, (int)settings.color, (int)settings.wrap, (int)settings.compression);
 
-	const uint32_t input_checksum = checksum ? (uint32_t)adler32(1L, image, (uInt)(w * h * channels)) : 0;
+	/* adler32 takes a 32-bit length: images of 4 GiB and more go in pieces */
+	uint32_t input_checksum = 0;
+	if (checksum)
+	{
+		uLong a = adler32(0L, Z_NULL, 0);
+		for (size_t left = w * h * channels, at = 0; left > 0;)
+		{
+			const size_t piece = (left > ((size_t)1 << 30)) ? ((size_t)1 << 30) : left;
+			a = adler32(a, image + at, (uInt)piece);
+			at += piece;
+			left -= piece;
+		}
+		input_checksum = (uint32_t)a;
+	}
 
 	if (verbose)
 		printf("Encoding...\n");
