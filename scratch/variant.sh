@@ -8,4 +8,5 @@ mkdir -p build
   -I../../include -I. "$@" -c ako_device.cu -o build/ako_device_$NAME.o
 [ -f build/ako_host.o ] || make build/ako_host.o
 /usr/local/cuda/bin/nvcc -gencode arch=compute_100a,code=sm_100a -shared -o ../../scratch/lib_$NAME.so build/ako_device_$NAME.o build/ako_host.o -lpthread -lm
+rm -f build/ako_device_$NAME.o
 echo scratch/lib_$NAME.so
