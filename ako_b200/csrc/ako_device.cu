@@ -439,6 +439,10 @@ extern "C" int akod_format_forward(akodContext* c, int discard, int color, uint3
 	const uint32_t pitch = (b && b->planes_pitch) ? b->planes_pitch : w;
 	const bool fast = channels == 4 && (w % 8) == 0 && (pitch % 8) == 0 && (in_stride_px % 4) == 0 && ((uintptr_t)d_in % 16) == 0 &&
 	                  ((uintptr_t)d_planes % 16) == 0 && (in_is % 16) == 0 && (pl_is % 8) == 0 && fmt_tiles_aligned(ft);
+	// RGB8: 8 pixels are 24 bytes, 8-byte aligned when every row and member starts on a multiple of 8 pixels
+	const bool fast3 = channels == 3 && (w % 8) == 0 && (pitch % 8) == 0 && (in_stride_px % 8) == 0 && ((uintptr_t)d_in % 8) == 0 &&
+	                   ((uintptr_t)d_planes % 16) == 0 && (in_is % 8) == 0 && (pl_is % 8) == 0 &&
+	                   (ft.n_real == 0 || ((ft.step % 8) == 0 && (ft.x0 % 8) == 0));
 	AKOD_BYTES(c, (uint64_t)3 * w * h * channels * n); // u8 in, int16 out
 	// the members of a batch ride in gridDim.y; a member of few pixels gets a grid of few CTAs
 	const unsigned per_sm = n >= 64 ? 1 : 8;
@@ -447,6 +451,12 @@ extern "C" int akod_format_forward(akodContext* c, int discard, int color, uint3
 		const dim3 grid(akod_stream_grid(c, (uint64_t)(w / 8) * h, 256, per_sm), n);
 		AKOD_LAUNCH(c, "format_fwd_rgba8x8", k_format_fwd_rgba8x8, grid, 256, 0, d_in, d_planes, w, h, in_stride_px, color,
 		            discard, in_is, pl_is, ft, pitch);
+	}
+	else if (fast3)
+	{
+		const dim3 grid(akod_stream_grid(c, (uint64_t)(w / 8) * h, 256, per_sm), n);
+		AKOD_LAUNCH(c, "format_fwd_rgb8x8", k_format_fwd_rgb8x8, grid, 256, 0, d_in, d_planes, w, h, in_stride_px, color, in_is,
+		            pl_is, ft, pitch);
 	}
 	else
 	{
@@ -467,6 +477,9 @@ extern "C" int akod_format_inverse(akodContext* c, int color, uint32_t channels,
 	const uint32_t pitch = (b && b->planes_pitch) ? b->planes_pitch : w;
 	const bool fast = channels == 4 && (w % 8) == 0 && (pitch % 8) == 0 && (out_stride_px % 4) == 0 && ((uintptr_t)d_out % 16) == 0 &&
 	                  ((uintptr_t)d_planes % 16) == 0 && (out_is % 16) == 0 && (pl_is % 8) == 0 && fmt_tiles_aligned(ft);
+	const bool fast3 = channels == 3 && (w % 8) == 0 && (pitch % 8) == 0 && (out_stride_px % 8) == 0 && ((uintptr_t)d_out % 8) == 0 &&
+	                   ((uintptr_t)d_planes % 16) == 0 && (out_is % 8) == 0 && (pl_is % 8) == 0 &&
+	                   (ft.n_real == 0 || ((ft.step % 8) == 0 && (ft.x0 % 8) == 0));
 	AKOD_BYTES(c, (uint64_t)3 * w * h * channels * n); // int16 in, u8 out
 	const unsigned per_sm = n >= 64 ? 1 : 8;
 	if (fast)
@@ -474,6 +487,12 @@ extern "C" int akod_format_inverse(akodContext* c, int color, uint32_t channels,
 		const dim3 grid(akod_stream_grid(c, (uint64_t)(w / 8) * h, 256, per_sm), n);
 		AKOD_LAUNCH(c, "format_inv_rgba8x8", k_format_inv_rgba8x8, grid, 256, 0, d_planes, d_out, w, h, out_stride_px, color,
 		            pl_is, out_is, ft, pitch);
+	}
+	else if (fast3)
+	{
+		const dim3 grid(akod_stream_grid(c, (uint64_t)(w / 8) * h, 256, per_sm), n);
+		AKOD_LAUNCH(c, "format_inv_rgb8x8", k_format_inv_rgb8x8, grid, 256, 0, d_planes, d_out, w, h, out_stride_px, color, pl_is,
+		            out_is, ft, pitch);
 	}
 	else
 	{

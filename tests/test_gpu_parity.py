@@ -43,7 +43,8 @@ def OS(**kw):
 @pytest.mark.parametrize("color", [C_YCOCG, C_SUBG, C_NONE, C_YCOCG_Q])
 def test_format_stage(orc, ctx, color):
     rs = np.random.RandomState(color)
-    for (w, h, ch) in [(16, 9, 4), (64, 33, 4), (7, 5, 3), (9, 4, 1), (8, 8, 2), (5, 5, 6), (24, 3, 16)]:
+    for (w, h, ch) in [(16, 9, 4), (64, 33, 4), (7, 5, 3), (9, 4, 1), (8, 8, 2), (5, 5, 6), (24, 3, 16), (64, 33, 3), (24, 9, 3),
+                       (200, 17, 3)]:
         for discard in (0, 1):
             img = noise_image(w, h, ch, 3 + w)
             img[rs.rand(h, w) < 0.3, ch - 1] = 0
