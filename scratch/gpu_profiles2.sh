@@ -9,7 +9,7 @@ summarise() { # $1 = report path without extension
 }
 CMD="python bench.py --steps 1 --warmup 3 --skip-cpu --secondaries none"
 $CMD > $O/${TAG}_plain_c2.log 2>&1 || exit 1
-ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $O/${TAG}_c2_launches.csv $CMD > /dev/null 2>&1
+ncu --metrics gpu__time_duration.sum --clock-control none -k regex:^k_ -c 400 --csv --log-file $O/${TAG}_c2_launches.csv $CMD > /dev/null 2>&1
 for K in k_lift_strip4 k_unlift_strip k_kg_lengths k_kd_decode k_kd_sync k_kt_fill; do
   ncu --set full --clock-control none --import-source on -k regex:$K -s 0 -c 1 -f -o $O/${TAG}_c2_$K $CMD > /dev/null 2>&1
   summarise $O/${TAG}_c2_$K
