@@ -966,7 +966,7 @@ def secondary_tiled(env, world, size=16384, tiles=512):
             res["all_devices"] = {"devices": world, "encode_ms": round(eN, 2), "decode_ms": round(dN, 2),
                                   "encode_MPix_s": round(px / eN / 1e3, 1), "decode_MPix_s": round(px / dN / 1e3, 1),
                                   "same_bytes_as_one_device": bool(np.array_equal(blob1, blobN) and dig1 == digN),
-                                  "how": "bands of tile rows, one per device of AKO_CUDA_DEVICES, blocks concatenated "
+                                  "how": "bands of tile rows, two per device of AKO_CUDA_DEVICES, blocks concatenated "
                                          "in raster order by the host"}
         finally:
             os.environ.pop("AKO_CUDA_DEVICES", None)
