@@ -341,6 +341,16 @@ def test_end_to_end_tiles(orc, tiles):
             _e2e(orc, img, wavelet=wavelet, tiles=tiles, q=16, g=4)
 
 
+def test_end_to_end_rgb_tiles(orc):
+    """3-channel images whose tiles start on multiples of 8 pixels take the 8-pixels-per-thread RGB8 format kernels with
+    the tile addressing (full tiles, right / bottom / corner tiles of another shape)."""
+    for (w, h, tiles) in [(256, 192, 64), (200, 136, 64), (520, 264, 128)]:
+        img = ol.synth(orc, w, h, 5 + w)[..., :3].copy()
+        for wavelet in (W_DD137, W_CDF53):
+            _e2e(orc, img, wavelet=wavelet, tiles=tiles, q=0)
+            _e2e(orc, img, wavelet=wavelet, tiles=tiles, q=12, g=4, color=C_SUBG)
+
+
 def test_more_tiles_than_a_grid_dimension(orc):
     """2048 x 2056 with tiles_dimension = 8 is 65 792 tiles (a grid dimension holds 65 535); all four tile shape
     groups with every wavelet at a smaller size, through events (tile by tile) and without (one pass per shape)."""
