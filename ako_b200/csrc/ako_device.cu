@@ -699,6 +699,17 @@ static int launch_small(akodContext* c, const akodPlan* plan, uint32_t l0, bool 
 	return AKOD_OK;
 }
 
+// The wrap mode a level's kernels are given. The four modes only differ in what an out-of-range tap reads
+// (oracle/ako_oracle.c s_map, pinned against wavelet-*.c): Haar has no such tap, and for CDF 5/3 MIRROR maps indices
+// like CLAMP (its two tap substitutions exist only in DD 13/7, wavelet-dd137.c:123, :164). Those levels take the
+// CLAMP kernels -- which include the strip kernels -- with identical results.
+static inline int akod_level_wrap(int level_wavelet, int wrap)
+{
+	if (level_wavelet == AKOD_HAAR || (level_wavelet == AKOD_CDF53 && wrap == AKOD_WRAP_MIRROR))
+		return AKOD_WRAP_CLAMP;
+	return wrap;
+}
+
 static inline uint32_t akod_pad8(uint32_t v)
 {
 	return (v + 7u) & ~7u;
@@ -760,7 +771,7 @@ static int lift_pyramid(akodContext* c, const akodPlan* plan, int16_t* d_planes,
 		p.ch = L->ch;
 		p.tw = L->tw;
 		p.th = L->th;
-		p.wrap = plan->wrap;
+		p.wrap = akod_level_wrap(L->wavelet, plan->wrap);
 		p.channels = plan->channels;
 		p.stream = d_stream;
 		p.stream_is = stream_is;
@@ -949,7 +960,7 @@ extern "C" int akod_unlift(akodContext* c, const akodPlan* plan, const int16_t* 
 		p.hh = L->th;
 		p.tw = L->cw;
 		p.th = L->ch;
-		p.wrap = plan->wrap;
+		p.wrap = akod_level_wrap(L->wavelet, plan->wrap);
 		p.channels = plan->channels;
 		p.stream = d_stream;
 		p.stream_is = stream_is;
