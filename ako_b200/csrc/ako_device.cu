@@ -516,6 +516,48 @@ static int launch_lift_level(akodContext* c, const LiftParams& p, uint32_t n_ima
 	return AKOD_OK;
 }
 
+// A level with a wrap mode other than CLAMP on the strip kernels: the strip kernel does the plane as CLAMP, the general
+// kernel then does the tiles along the plane's edge again with the real wrap mode (lift_tile). Worth it while those are
+// at most half of the tiles (the general kernel takes about three times as long per tile). w, h = the level's size in
+// coefficients.
+struct FrameGeom
+{
+	uint32_t nx, ny, rc, br, tiles;
+};
+
+static inline FrameGeom frame_geom(uint32_t w, uint32_t h)
+{
+	FrameGeom f;
+	f.nx = (w + LIFT_TW - 1) / LIFT_TW;
+	f.ny = (h + LIFT_TH - 1) / LIFT_TH;
+	f.rc = (w - (f.nx - 1) * LIFT_TW < FRAME_REACH) ? 2 : 1;
+	f.br = (h - (f.ny - 1) * LIFT_TH < FRAME_REACH) ? 2 : 1;
+	f.tiles = lift_frame_tiles(f.nx, f.ny, f.rc, f.br);
+	return f;
+}
+
+static inline bool frame_worth(uint32_t w, uint32_t h)
+{
+	const FrameGeom f = frame_geom(w, h);
+	return f.tiles != 0 && 2 * (uint64_t)f.tiles <= (uint64_t)f.nx * f.ny;
+}
+
+template <int WL>
+static int launch_lift_frame(akodContext* c, const LiftParams& p_in, uint32_t n_images)
+{
+	LiftParams p = p_in;
+	const FrameGeom f = frame_geom(p.tw, p.th);
+	p.frame_nx = f.nx;
+	p.frame_ny = f.ny;
+	p.frame_rc = f.rc;
+	p.frame_br = f.br;
+	const dim3 grid(f.tiles, 1, p.channels * n_images);
+	static const char* const names[3] = {"lift_frame_dd137", "lift_frame_cdf53", "lift_frame_haar"};
+	AKOD_BYTES(c, (uint64_t)16 * LIFT_TW * LIFT_TH * f.tiles * p.channels * n_images);
+	AKOD_LAUNCH(c, names[WL], k_lift_level<WL>, grid, LIFT_THREADS, lift_smem_bytes<WL>(), p);
+	return AKOD_OK;
+}
+
 // strip kernel: pick the rows-per-CTA so that the grid fills the machine a few times over while the
 // warm-up rows (2*LAT per CTA) stay a small fraction
 // Rows per CTA for the strip kernels. A CTA marches 8k - 2*LAT output rows after 2*LAT warm-up rows, so larger k
@@ -640,6 +682,22 @@ static int launch_unlift_level(akodContext* c, const UnliftParams& p, uint32_t n
 	return AKOD_OK;
 }
 
+template <int WL>
+static int launch_unlift_frame(akodContext* c, const UnliftParams& p_in, uint32_t n_images)
+{
+	UnliftParams p = p_in;
+	const FrameGeom f = frame_geom(p.hw, p.hh);
+	p.frame_nx = f.nx;
+	p.frame_ny = f.ny;
+	p.frame_rc = f.rc;
+	p.frame_br = f.br;
+	const dim3 grid(f.tiles, 1, p.channels * n_images);
+	static const char* const names[3] = {"unlift_frame_dd137", "unlift_frame_cdf53", "unlift_frame_haar"};
+	AKOD_BYTES(c, (uint64_t)16 * LIFT_TW * LIFT_TH * f.tiles * p.channels * n_images);
+	AKOD_LAUNCH(c, names[WL], k_unlift_level<WL>, grid, LIFT_THREADS, unlift_smem_bytes<WL>(), p);
+	return AKOD_OK;
+}
+
 // the tail of the pyramid (levels l0 .. levels-1) in one launch; see lift_small.cuh
 static int launch_small(akodContext* c, const akodPlan* plan, uint32_t l0, bool forward, int16_t* planes, uint32_t planes_rs,
                         uint64_t planes_ps, uint64_t planes_is, int16_t* stream, uint64_t stream_is, uint32_t n_images)
@@ -708,6 +766,13 @@ static inline int akod_level_wrap(int level_wavelet, int wrap)
 	if (level_wavelet == AKOD_HAAR || (level_wavelet == AKOD_CDF53 && wrap == AKOD_WRAP_MIRROR))
 		return AKOD_WRAP_CLAMP;
 	return wrap;
+}
+
+template <class P>
+static inline P as_clamp(P p)
+{
+	p.wrap = AKOD_WRAP_CLAMP;
+	return p;
 }
 
 static inline uint32_t akod_pad8(uint32_t v)
@@ -805,6 +870,7 @@ static int lift_pyramid(akodContext* c, const akodPlan* plan, int16_t* d_planes,
 		int rc;
 		static const bool no_strip = getenv("AKO_B200_NO_STRIP") != nullptr;
 		static const bool no_fuse = getenv("AKO_B200_NO_FUSE") != nullptr;
+		static const bool no_frame = getenv("AKO_B200_NO_FRAME") != nullptr;
 		if (l == 0 && fused)
 		{
 			*fused = u8 != nullptr && !no_strip && !no_fuse &&
@@ -829,6 +895,17 @@ static int lift_pyramid(akodContext* c, const akodPlan* plan, int16_t* d_planes,
 				rc = launch_lift_strip<AKOD_CDF53>(c, p, n);
 			else
 				rc = launch_lift_strip<AKOD_HAAR>(c, p, n);
+		}
+		else if (!no_strip && !no_frame && p.wrap != AKOD_WRAP_CLAMP && lift_strip_eligible(as_clamp(p)) &&
+		         frame_worth(p.tw, p.th))
+		{
+			// (Haar never gets here: akod_level_wrap)
+			if (L->wavelet == AKOD_DD137)
+				rc = launch_lift_strip<AKOD_DD137>(c, as_clamp(p), n);
+			else
+				rc = launch_lift_strip<AKOD_CDF53>(c, as_clamp(p), n);
+			if (rc == AKOD_OK)
+				rc = (L->wavelet == AKOD_DD137) ? launch_lift_frame<AKOD_DD137>(c, p, n) : launch_lift_frame<AKOD_CDF53>(c, p, n);
 		}
 		else if (L->wavelet == AKOD_DD137)
 			rc = launch_lift_level<AKOD_DD137>(c, p, n);
@@ -988,15 +1065,21 @@ extern "C" int akod_unlift(akodContext* c, const akodPlan* plan, const int16_t* 
 			p.off_c[ch] = L->off_c[ch];
 		int rc;
 		static const bool no_strip = getenv("AKO_B200_NO_STRIP") != nullptr;
-		const bool v2 = !no_strip && unlift_strip_eligible(p), v1 = !no_strip && !v2 && unlift_strip_v1_eligible(p);
+		static const bool no_frame = getenv("AKO_B200_NO_FRAME") != nullptr;
+		const bool framed = !no_strip && !no_frame && p.wrap != AKOD_WRAP_CLAMP &&
+		                    frame_worth(p.hw, p.hh);
+		const UnliftParams ps = framed ? as_clamp(p) : p; // what the strip kernels are asked
+		const bool v2 = !no_strip && unlift_strip_eligible(ps), v1 = !no_strip && !v2 && unlift_strip_v1_eligible(ps);
 		if (v2 || v1)
 		{
 			if (L->wavelet == AKOD_DD137)
-				rc = launch_unlift_strip<AKOD_DD137>(c, p, n, v1);
+				rc = launch_unlift_strip<AKOD_DD137>(c, ps, n, v1);
 			else if (L->wavelet == AKOD_CDF53)
-				rc = launch_unlift_strip<AKOD_CDF53>(c, p, n, v1);
+				rc = launch_unlift_strip<AKOD_CDF53>(c, ps, n, v1);
 			else
-				rc = launch_unlift_strip<AKOD_HAAR>(c, p, n, v1);
+				rc = launch_unlift_strip<AKOD_HAAR>(c, ps, n, v1);
+			if (rc == AKOD_OK && framed)
+				rc = (L->wavelet == AKOD_DD137) ? launch_unlift_frame<AKOD_DD137>(c, p, n) : launch_unlift_frame<AKOD_CDF53>(c, p, n);
 		}
 		else if (L->wavelet == AKOD_DD137)
 			rc = launch_unlift_level<AKOD_DD137>(c, p, n);

@@ -50,6 +50,46 @@ struct LiftGeom
 	static constexpr int EH = LIFT_TH + EOFF + EEXT;
 };
 
+// Which tile a CTA works on. Plain launch: (blockIdx.x, blockIdx.y). Frame launch (frame_nx, frame_ny = tiles across /
+// down, both != 0): blockIdx.x counts the tiles that touch the plane's edge -- the top row, the bottom row(s), then the
+// left tile and the right tile(s) of every row between -- and nothing else. The wrap modes differ only in what a tap
+// beyond the edge reads, i.e. in coefficients within three positions of the edge (DD 13/7: H(c) reads E(c-1..c+2), L(c)
+// reads H(c-2..c+1); the inverse likewise); a level with another wrap mode than CLAMP is done by the CLAMP strip kernel
+// and then has its frame of edge tiles computed again by this kernel with the real wrap mode. Where the last tile
+// column / row is thinner than FRAME_REACH coefficients the one before it belongs to the frame too (frame_rc / frame_br = 2).
+constexpr uint32_t FRAME_REACH = 6;
+
+__device__ __forceinline__ void lift_tile(uint32_t nx, uint32_t ny, uint32_t rc, uint32_t br, int& tx, int& ty)
+{
+	if (nx == 0)
+	{
+		tx = (int)blockIdx.x;
+		ty = (int)blockIdx.y;
+		return;
+	}
+	uint32_t i = blockIdx.x;
+	const uint32_t full_rows = nx * (1 + br);
+	if (i < full_rows)
+	{
+		const uint32_t r = i / nx;
+		tx = (int)(i - r * nx);
+		ty = (r == 0) ? 0 : (int)(ny - br + (r - 1));
+		return;
+	}
+	i -= full_rows;
+	const uint32_t per = 1 + rc, r = i / per, k = i - r * per;
+	ty = 1 + (int)r;
+	tx = (k == 0) ? 0 : (int)(nx - rc + (k - 1));
+}
+
+// tiles in the frame; 0 when the plane is too small to have an inside
+static inline uint32_t lift_frame_tiles(uint32_t nx, uint32_t ny, uint32_t rc, uint32_t br)
+{
+	if (nx < rc + 2 || ny < br + 2)
+		return 0;
+	return nx * (1 + br) + (ny - 1 - br) * (1 + rc);
+}
+
 // wrap mode as an index map; -1 means "the tap reads zero"
 __device__ __forceinline__ int wrap_map(int v, int t, int wrap)
 {
@@ -125,6 +165,7 @@ struct LiftParams
 	uint64_t stream_is;
 	uint32_t cw, ch, tw, th;
 	int wrap;
+	uint32_t frame_nx, frame_ny, frame_rc, frame_br; // k_lift_level only: frame_nx != 0 => the grid is the frame of edge tiles (see lift_tile)
 	uint32_t channels;
 	uint64_t off_c[AKOD_MAX_CHANNELS];
 	int16_t q[AKOD_MAX_CHANNELS];
@@ -160,7 +201,9 @@ __global__ void __launch_bounds__(LIFT_THREADS) k_lift_level(const LiftParams p)
 	int16_t* LB = HB + XH * G::HBW;     // XH x TW   horizontal lowpass
 	int16_t* HV = X;                    // HVH x 2TW vertical highpass of [LB | HB]
 
-	const int c0 = blockIdx.x * TW, r0 = blockIdx.y * TH;
+	int tile_x, tile_y;
+	lift_tile(p.frame_nx, p.frame_ny, p.frame_rc, p.frame_br, tile_x, tile_y);
+	const int c0 = tile_x * TW, r0 = tile_y * TH;
 	const uint32_t img = blockIdx.z / p.channels, chn = blockIdx.z - img * p.channels;
 	const int tw = (int)p.tw, th = (int)p.th, wrap = p.wrap;
 	const int16_t* in = p.in + p.in_is * img + p.in_ps * chn;
@@ -273,7 +316,7 @@ __global__ void __launch_bounds__(LIFT_THREADS) k_lift_level(const LiftParams p)
 	const uint32_t magic = p.qmagic[chn];
 
 	// akoLiftHead{q} sits right before the C subband (lifting.c:266-267)
-	if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0)
+	if (tile_x == 0 && tile_y == 0 && threadIdx.x == 0)
 		out_c[-1] = (int16_t)q;
 
 	for (int i = threadIdx.x; i < TH * 2 * TW; i += LIFT_THREADS)
@@ -333,6 +376,7 @@ struct UnliftParams
 	uint64_t out_ps, out_is;
 	uint32_t hw, hh, tw, th;
 	int wrap;
+	uint32_t frame_nx, frame_ny, frame_rc, frame_br; // k_unlift_level only: frame_nx != 0 => the grid is the frame of edge tiles (see lift_tile)
 	uint32_t channels;
 	uint64_t off_c[AKOD_MAX_CHANNELS];
 };
@@ -353,7 +397,9 @@ __global__ void __launch_bounds__(LIFT_THREADS) k_unlift_level(const UnliftParam
 	int16_t* OV = EV + 2 * G::EH * NS; // 2 x TH x NS : odd rows
 	int16_t* EHb = A0;              // 2TH x EW : horizontally reconstructed even samples (reuses A*)
 
-	const int c0 = blockIdx.x * TW, r0 = blockIdx.y * TH;
+	int tile_x, tile_y;
+	lift_tile(p.frame_nx, p.frame_ny, p.frame_rc, p.frame_br, tile_x, tile_y);
+	const int c0 = tile_x * TW, r0 = tile_y * TH;
 	const uint32_t img = blockIdx.z / p.channels, chn = blockIdx.z - img * p.channels;
 	const int hw = (int)p.hw, hh = (int)p.hh, wrap = p.wrap;
 	const uint64_t band = (uint64_t)p.hw * p.hh;

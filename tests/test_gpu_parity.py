@@ -113,6 +113,37 @@ def test_lift_unlift_stage(orc, ctx, wavelet, wrap):
                 assert np.array_equal(back, planes)
 
 
+@pytest.mark.parametrize("wrap", [1, 2, 3])
+@pytest.mark.parametrize("wavelet", [W_DD137, W_CDF53])
+def test_wrap_modes_strip_plus_frame(orc, ctx, wavelet, wrap):
+    """MIRROR / REPEAT / ZERO at sizes where a level is done by the CLAMP strip kernel and then has the tiles along its
+    edge computed again with the real wrap mode (ako_device.cu frame_worth): last tile column / row thinner than the
+    reach of the edge taps (two columns / rows of tiles in the frame), odd sizes, several channels."""
+    rs = np.random.RandomState(700 + wavelet * 4 + wrap)
+    for (w, h, ch) in [(1500, 1200, 2), (1290, 1034, 1), (1026, 2100, 1), (1281, 1027, 1), (2064, 1100, 3)]:
+        for q, g in [(0, 0), (7, 9)]:
+            planes = rs.randint(-300, 600, size=(ch, h, w)).astype(np.int16)
+            n = orc.orc_tile_data_size(w, h) * ch // 2
+            want = np.zeros(n, np.int16)
+            tmp = planes.copy()
+            os_ = OS(wavelet=wavelet, wrap=wrap, q=q, g=g)
+            orc.orc_lift(C.byref(os_), ch, w, h, P(tmp, i16p), P(want, i16p))
+            s = S(wavelet=wavelet, wrap=wrap, q=q, g=g)
+            got = ctx.lift(planes, s)
+            assert np.array_equal(want, got), (w, h, ch, q, g, int(np.argmax(want != got)))
+            back_want = np.zeros((ch, h, w), np.int16)
+            st = want.copy()
+            orc.orc_unlift(C.byref(os_), ch, w, h, P(st, i16p), P(back_want, i16p))
+            back = ctx.unlift(want, s, ch, w, h)
+            assert np.array_equal(back_want, back), (w, h, ch, q, g)
+            if q == 0 and g == 0:
+                assert np.array_equal(back, planes)
+    # and through the whole codec
+    img = ol.synth(orc, 1290, 1034, 77)
+    _e2e(orc, img, wavelet=wavelet, wrap=wrap, q=0)
+    _e2e(orc, img, wavelet=wavelet, wrap=wrap, q=12, g=5)
+
+
 def _runs_vector(rs, n, zero_heavy):
     out = []
     while len(out) < n:
