@@ -979,6 +979,9 @@ SHAPES = {
     "rgb_1000x1000": (1000, 1000, 3, 0, 16, 0, 0, 64),
     "rgba_1921x1081": (1921, 1081, 4, 0, 16, 0, 0, 32),
     "rgba_8192x8192_tiles256": (8192, 8192, 4, 0, 16, 0, 256, 1),
+    # another wrap mode than CLAMP: strip kernels + the frame of edge tiles again (9th field = wrap)
+    "rgba_2048x2048_wrap_mirror": (2048, 2048, 4, 0, 16, 0, 0, 16, 1),
+    "rgba_2048x2048_wrap_repeat": (2048, 2048, 4, 0, 16, 0, 0, 16, 2),
 }
 
 
@@ -989,22 +992,23 @@ def secondary_shapes(env, steps):
     from ako_b200.synth import synth_rgba8_torch
     dev = f"cuda:{local}"
     res = {}
-    for name, (w, h, ch, wavelet, q, g, tiles, B) in SHAPES.items():
+    for name, spec in SHAPES.items():
+        (w, h, ch, wavelet, q, g, tiles, B), wrap = spec[:8], (spec[8] if len(spec) > 8 else 0)
         P = B if tiles else _pool_images(w * h * ch, B)
         distinct = min(P, 4)
         base = synth_rgba8_torch(w, h, [40 + i for i in range(distinct)], device=dev)[..., :ch].contiguous()
         pool = base.repeat((P + distinct - 1) // distinct, 1, 1, 1)[:P].contiguous()
-        s = ako.default_settings(wavelet=wavelet, quantization=q, gate=g, tiles_dimension=tiles)
+        s = ako.default_settings(wavelet=wavelet, quantization=q, gate=g, tiles_dimension=tiles, wrap=wrap)
         dc = DeviceCodec(torch, ako, ctx, local, w, h, ch, s, B, pool)
         try:
-            exact = dc.gate(env["ol"], env["orc"], dict(wavelet=wavelet, q=q, g=g, tiles=tiles))
+            exact = dc.gate(env["ol"], env["orc"], dict(wavelet=wavelet, q=q, g=g, tiles=tiles, wrap=wrap))
         except RuntimeError as e:
             res[name] = {"error": str(e)}
             continue
         for i in range(2):
             dc.step(i)
         ms = _events_ms(torch, stream, dc.step, steps)
-        res[name] = {"images_per_step": B, "channels": ch, "tiles_dimension": tiles, "bit_exact_vs_oracle": exact,
+        res[name] = {"images_per_step": B, "channels": ch, "tiles_dimension": tiles, "wrap": wrap, "bit_exact_vs_oracle": exact,
                      "ms_per_step": round(ms, 4), "MPix_s": round(w * h * B / ms / 1e3, 1),
                      "ns_per_pixel": round(ms * 1e6 / (w * h * B), 5)}
         del dc, pool, base
