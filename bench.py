@@ -978,6 +978,7 @@ SHAPES = {
     "aligned_rgba_1024x1024": (1024, 1024, 4, 0, 16, 0, 0, 64),
     "rgb_1000x1000": (1000, 1000, 3, 0, 16, 0, 0, 64),
     "rgba_1921x1081": (1921, 1081, 4, 0, 16, 0, 0, 32),
+    "rgba_8192x8192": (8192, 8192, 4, 0, 16, 0, 0, 1),  # the same image untiled, next to the tiled line
     "rgba_8192x8192_tiles256": (8192, 8192, 4, 0, 16, 0, 256, 1),
     # another wrap mode than CLAMP: strip kernels + the frame of edge tiles again (9th field = wrap)
     "rgba_2048x2048_wrap_mirror": (2048, 2048, 4, 0, 16, 0, 0, 16, 1),
@@ -1010,13 +1011,20 @@ def secondary_shapes(env, steps):
         ms = _events_ms(torch, stream, dc.step, steps)
         res[name] = {"images_per_step": B, "channels": ch, "tiles_dimension": tiles, "wrap": wrap, "bit_exact_vs_oracle": exact,
                      "ms_per_step": round(ms, 4), "MPix_s": round(w * h * B / ms / 1e3, 1),
-                     "ns_per_pixel": round(ms * 1e6 / (w * h * B), 5)}
+                     "ns_per_pixel": round(ms * 1e6 / (w * h * B), 5),
+                     "blob_bytes_per_pixel": round(float(sum(dc.sizes)) / (w * h * B), 4)}
         del dc, pool, base
         torch.cuda.empty_cache()
     ref_ns = res["aligned_rgba_1024x1024"].get("ns_per_pixel")
     for name, r in res.items():
         if ref_ns and "ns_per_pixel" in r:
             r["per_pixel_time_vs_aligned_rgba"] = round(r["ns_per_pixel"] / ref_ns, 3)
+    # tiles are read against the same image untiled -- and against blob_bytes_per_pixel: a 256-pixel tile has 7 lifting
+    # levels where the whole image has 12, the quantiser schedule follows the level count (quantization.c), and the
+    # tiled blob comes out 40 x the untiled one; the entropy coder's share of the step grows with it
+    big, tiled = res.get("rgba_8192x8192", {}), res.get("rgba_8192x8192_tiles256", {})
+    if "ns_per_pixel" in big and "ns_per_pixel" in tiled:
+        tiled["per_pixel_time_vs_same_image_untiled"] = round(tiled["ns_per_pixel"] / big["ns_per_pixel"], 3)
     return res
 
 

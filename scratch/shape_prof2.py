@@ -6,7 +6,7 @@ sys.path.insert(0, R); sys.path.insert(0, os.path.join(R, "tests"))
 import ako_b200, bench
 from ako_b200.synth import synth_rgba8_torch
 name = sys.argv[1]
-w, h, ch, wavelet, q, g, tiles, B = bench.SHAPES[name]
+w, h, ch, wavelet, q, g, tiles, B = bench.SHAPES[name][:8]
 ctx = ako_b200.Context(0)
 imgs = synth_rgba8_torch(w, h, list(range(B)), device="cuda")[..., :ch].contiguous()
 s = ako_b200.default_settings(wavelet=wavelet, quantization=q, gate=g, tiles_dimension=tiles)
@@ -21,6 +21,8 @@ def once():
     done2, st2 = ctx.decode_batch_device(B, blobs.data_ptr(), stride, sz, out.data_ptr(), w * h * ch)
     assert done2 == B
 for _ in range(2): once()
+_d, _st, _sz = ctx.encode_batch_device(s, ch, w, h, B, imgs.data_ptr(), w * h * ch, blobs.data_ptr(), stride)
+print("compressed bytes per pixel", round(float(np.sum(_sz)) / (w * h * B), 4), "largest blob", int(np.max(_sz)))
 ctx.sync()
 ctx.profile_reset(); ctx.profile(True); once(); ctx.sync()
 prof = ctx.profile_get(); ctx.profile(False)
