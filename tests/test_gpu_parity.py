@@ -142,6 +142,10 @@ def test_wrap_modes_strip_plus_frame(orc, ctx, wavelet, wrap):
     img = ol.synth(orc, 1290, 1034, 77)
     _e2e(orc, img, wavelet=wavelet, wrap=wrap, q=0)
     _e2e(orc, img, wavelet=wavelet, wrap=wrap, q=12, g=5)
+    if wavelet == W_DD137:
+        # tiles large enough to have a frame of their own, as batch members (four tile shapes). Encoder only: the
+        # reference's reader refuses tiles above 512 (AKO_INVALID_FLAGS), and so do the oracle and this library.
+        _e2e(orc, ol.synth(orc, 3100, 2900, 78), wavelet=wavelet, wrap=wrap, q=12, g=5, tiles=2048)
 
 
 def _runs_vector(rs, n, zero_heavy):
@@ -299,8 +303,12 @@ def _e2e(orc, img, **kw):
     assert want == got, kw
     if want is None:
         return None
-    want_px, _ = ol.orc_decode(orc, want)
+    want_px, dst = ol.orc_decode(orc, want)
     got_px, st, s = ako_b200.decode(want)
+    if want_px is None:
+        # (tiles of 1024 and up encode, but their tile code sets a flag bit the reference's reader refuses, head.c:124)
+        assert st == dst and got_px is None, (kw, st, dst)
+        return want
     assert st == 0 and np.array_equal(want_px, got_px), kw
     return want
 
