@@ -517,44 +517,30 @@ static int launch_lift_level(akodContext* c, const LiftParams& p, uint32_t n_ima
 }
 
 // A level with a wrap mode other than CLAMP on the strip kernels: the strip kernel does the plane as CLAMP, the general
-// kernel then does the tiles along the plane's edge again with the real wrap mode (lift_tile). Worth it while those are
-// at most half of the tiles (the general kernel takes about three times as long per tile). w, h = the level's size in
-// coefficients.
-struct FrameGeom
-{
-	uint32_t nx, ny, rc, br, tiles;
-};
-
-static inline FrameGeom frame_geom(uint32_t w, uint32_t h)
-{
-	FrameGeom f;
-	f.nx = (w + LIFT_TW - 1) / LIFT_TW;
-	f.ny = (h + LIFT_TH - 1) / LIFT_TH;
-	f.rc = (w - (f.nx - 1) * LIFT_TW < FRAME_REACH) ? 2 : 1;
-	f.br = (h - (f.ny - 1) * LIFT_TH < FRAME_REACH) ? 2 : 1;
-	f.tiles = lift_frame_tiles(f.nx, f.ny, f.rc, f.br);
-	return f;
-}
-
+// kernel then does the FRAME_BAND rows / columns along the plane's edge again with the real wrap mode, as thin tiles
+// (lift_tile_origin). Worth it from a few tiles each way (w, h = the level's size in coefficients): against the general
+// kernel alone (about five strip kernels' time per coefficient) the strip pass costs w h, the frame about 5 x 8 x 2 (1.6 w +
+// 2.2 h) with its halos.
 static inline bool frame_worth(uint32_t w, uint32_t h)
 {
-	const FrameGeom f = frame_geom(w, h);
-	return f.tiles != 0 && 2 * (uint64_t)f.tiles <= (uint64_t)f.nx * f.ny;
+	return w >= 2 * LIFT_TW && h >= 2 * LIFT_TH;
 }
 
 template <int WL>
 static int launch_lift_frame(akodContext* c, const LiftParams& p_in, uint32_t n_images)
 {
 	LiftParams p = p_in;
-	const FrameGeom f = frame_geom(p.tw, p.th);
-	p.frame_nx = f.nx;
-	p.frame_ny = f.ny;
-	p.frame_rc = f.rc;
-	p.frame_br = f.br;
-	const dim3 grid(f.tiles, 1, p.channels * n_images);
 	static const char* const names[3] = {"lift_frame_dd137", "lift_frame_cdf53", "lift_frame_haar"};
-	AKOD_BYTES(c, (uint64_t)16 * LIFT_TW * LIFT_TH * f.tiles * p.channels * n_images);
-	AKOD_LAUNCH(c, names[WL], k_lift_level<WL>, grid, LIFT_THREADS, lift_smem_bytes<WL>(), p);
+	p.frame = FRAME_ROWS;
+	const dim3 grid_r((p.tw + LIFT_TW - 1) / LIFT_TW, 2, p.channels * n_images);
+	AKOD_BYTES(c, (uint64_t)4 * 4 * LIFT_TW * FRAME_BAND * grid_r.x * grid_r.y * grid_r.z);
+	AKOD_LAUNCH(c, names[WL], (k_lift_level<WL, LIFT_TW, FRAME_BAND>), grid_r, LIFT_THREADS,
+	            (lift_smem_bytes<WL, LIFT_TW, FRAME_BAND>()), p);
+	p.frame = FRAME_COLS;
+	const dim3 grid_c(2, (p.th + LIFT_TH - 1) / LIFT_TH, p.channels * n_images);
+	AKOD_BYTES(c, (uint64_t)4 * 4 * FRAME_BAND * LIFT_TH * grid_c.x * grid_c.y * grid_c.z);
+	AKOD_LAUNCH(c, names[WL], (k_lift_level<WL, FRAME_BAND, LIFT_TH>), grid_c, LIFT_THREADS,
+	            (lift_smem_bytes<WL, FRAME_BAND, LIFT_TH>()), p);
 	return AKOD_OK;
 }
 
@@ -686,15 +672,17 @@ template <int WL>
 static int launch_unlift_frame(akodContext* c, const UnliftParams& p_in, uint32_t n_images)
 {
 	UnliftParams p = p_in;
-	const FrameGeom f = frame_geom(p.hw, p.hh);
-	p.frame_nx = f.nx;
-	p.frame_ny = f.ny;
-	p.frame_rc = f.rc;
-	p.frame_br = f.br;
-	const dim3 grid(f.tiles, 1, p.channels * n_images);
 	static const char* const names[3] = {"unlift_frame_dd137", "unlift_frame_cdf53", "unlift_frame_haar"};
-	AKOD_BYTES(c, (uint64_t)16 * LIFT_TW * LIFT_TH * f.tiles * p.channels * n_images);
-	AKOD_LAUNCH(c, names[WL], k_unlift_level<WL>, grid, LIFT_THREADS, unlift_smem_bytes<WL>(), p);
+	p.frame = FRAME_ROWS;
+	const dim3 grid_r((p.hw + LIFT_TW - 1) / LIFT_TW, 2, p.channels * n_images);
+	AKOD_BYTES(c, (uint64_t)4 * 4 * LIFT_TW * FRAME_BAND * grid_r.x * grid_r.y * grid_r.z);
+	AKOD_LAUNCH(c, names[WL], (k_unlift_level<WL, LIFT_TW, FRAME_BAND>), grid_r, LIFT_THREADS,
+	            (unlift_smem_bytes<WL, LIFT_TW, FRAME_BAND>()), p);
+	p.frame = FRAME_COLS;
+	const dim3 grid_c(2, (p.hh + LIFT_TH - 1) / LIFT_TH, p.channels * n_images);
+	AKOD_BYTES(c, (uint64_t)4 * 4 * FRAME_BAND * LIFT_TH * grid_c.x * grid_c.y * grid_c.z);
+	AKOD_LAUNCH(c, names[WL], (k_unlift_level<WL, FRAME_BAND, LIFT_TH>), grid_c, LIFT_THREADS,
+	            (unlift_smem_bytes<WL, FRAME_BAND, LIFT_TH>()), p);
 	return AKOD_OK;
 }
 
@@ -871,21 +859,35 @@ static int lift_pyramid(akodContext* c, const akodPlan* plan, int16_t* d_planes,
 		static const bool no_strip = getenv("AKO_B200_NO_STRIP") != nullptr;
 		static const bool no_fuse = getenv("AKO_B200_NO_FUSE") != nullptr;
 		static const bool no_frame = getenv("AKO_B200_NO_FRAME") != nullptr;
+		// another wrap mode than CLAMP: the strip kernels as CLAMP, then the frame of edge tiles again (launch_lift_frame)
+		const bool framed = !no_strip && !no_frame && p.wrap != AKOD_WRAP_CLAMP && frame_worth(p.tw, p.th);
+		const LiftParams ps = framed ? as_clamp(p) : p; // what the strip kernels are asked
 		if (l == 0 && fused)
 		{
 			*fused = u8 != nullptr && !no_strip && !no_fuse &&
-			         lift_strip4_eligible(p, u8->rgba, u8->rgba_is, u8->rgba_rs);
+			         lift_strip4_eligible(ps, u8->rgba, u8->rgba_is, u8->rgba_rs);
 			if (probe_only)
 				return AKOD_OK;
 		}
 		if (l == 0 && fused && *fused)
 		{
 			if (L->wavelet == AKOD_DD137)
-				rc = launch_lift_strip4<AKOD_DD137>(c, p, n, u8->rgba, u8->rgba_is, u8->rgba_rs, u8->color, u8->discard);
+				rc = launch_lift_strip4<AKOD_DD137>(c, ps, n, u8->rgba, u8->rgba_is, u8->rgba_rs, u8->color, u8->discard);
 			else if (L->wavelet == AKOD_CDF53)
-				rc = launch_lift_strip4<AKOD_CDF53>(c, p, n, u8->rgba, u8->rgba_is, u8->rgba_rs, u8->color, u8->discard);
+				rc = launch_lift_strip4<AKOD_CDF53>(c, ps, n, u8->rgba, u8->rgba_is, u8->rgba_rs, u8->color, u8->discard);
 			else
-				rc = launch_lift_strip4<AKOD_HAAR>(c, p, n, u8->rgba, u8->rgba_is, u8->rgba_rs, u8->color, u8->discard);
+				rc = launch_lift_strip4<AKOD_HAAR>(c, ps, n, u8->rgba, u8->rgba_is, u8->rgba_rs, u8->color, u8->discard);
+			if (rc == AKOD_OK && framed)
+			{
+				// the planes were never written: the frame converts the pixels it needs itself
+				LiftParams pf = p;
+				pf.rgba = u8->rgba;
+				pf.rgba_is = u8->rgba_is;
+				pf.rgba_rs = u8->rgba_rs;
+				pf.rgba_color = u8->color;
+				pf.rgba_discard = u8->discard;
+				rc = (L->wavelet == AKOD_DD137) ? launch_lift_frame<AKOD_DD137>(c, pf, n) : launch_lift_frame<AKOD_CDF53>(c, pf, n);
+			}
 		}
 		else if (!no_strip && lift_strip_eligible(p))
 		{
@@ -896,14 +898,13 @@ static int lift_pyramid(akodContext* c, const akodPlan* plan, int16_t* d_planes,
 			else
 				rc = launch_lift_strip<AKOD_HAAR>(c, p, n);
 		}
-		else if (!no_strip && !no_frame && p.wrap != AKOD_WRAP_CLAMP && lift_strip_eligible(as_clamp(p)) &&
-		         frame_worth(p.tw, p.th))
+		else if (framed && lift_strip_eligible(ps))
 		{
 			// (Haar never gets here: akod_level_wrap)
 			if (L->wavelet == AKOD_DD137)
-				rc = launch_lift_strip<AKOD_DD137>(c, as_clamp(p), n);
+				rc = launch_lift_strip<AKOD_DD137>(c, ps, n);
 			else
-				rc = launch_lift_strip<AKOD_CDF53>(c, as_clamp(p), n);
+				rc = launch_lift_strip<AKOD_CDF53>(c, ps, n);
 			if (rc == AKOD_OK)
 				rc = (L->wavelet == AKOD_DD137) ? launch_lift_frame<AKOD_DD137>(c, p, n) : launch_lift_frame<AKOD_CDF53>(c, p, n);
 		}

@@ -24,6 +24,7 @@
 #pragma once
 
 #include "common.cuh"
+#include "format.cuh"
 
 #define AKOD_WRAP_CLAMP 0
 #define AKOD_WRAP_MIRROR 1
@@ -34,7 +35,7 @@ constexpr int LIFT_TW = 64; // coefficients per tile row (per subband)
 constexpr int LIFT_TH = 32; // coefficient rows per tile
 constexpr int LIFT_THREADS = 256;
 
-template <int WL>
+template <int WL, int TW_ = LIFT_TW, int TH_ = LIFT_TH>
 struct LiftGeom
 {
 	static constexpr int HALO = (WL == AKOD_DD137) ? 3 : (WL == AKOD_CDF53) ? 1 : 0; // coefficient slots each side
@@ -42,52 +43,34 @@ struct LiftGeom
 	static constexpr int HEXT = (WL == AKOD_DD137) ? 1 : 0;                           // ... and right of it
 	static constexpr int EOFF = (WL == AKOD_DD137) ? 1 : 0;                           // inverse: evens left of tile
 	static constexpr int EEXT = (WL == AKOD_DD137) ? 2 : (WL == AKOD_CDF53) ? 1 : 0;  // ... and right of it
-	static constexpr int NS = LIFT_TW + 2 * HALO;
-	static constexpr int MS = LIFT_TH + 2 * HALO;
-	static constexpr int HBW = LIFT_TW + HOFF + HEXT;
-	static constexpr int HVH = LIFT_TH + HOFF + HEXT;
-	static constexpr int EW = LIFT_TW + EOFF + EEXT;
-	static constexpr int EH = LIFT_TH + EOFF + EEXT;
+	static constexpr int NS = TW_ + 2 * HALO;
+	static constexpr int MS = TH_ + 2 * HALO;
+	static constexpr int HBW = TW_ + HOFF + HEXT;
+	static constexpr int HVH = TH_ + HOFF + HEXT;
+	static constexpr int EW = TW_ + EOFF + EEXT;
+	static constexpr int EH = TH_ + EOFF + EEXT;
 };
 
-// Which tile a CTA works on. Plain launch: (blockIdx.x, blockIdx.y). Frame launch (frame_nx, frame_ny = tiles across /
-// down, both != 0): blockIdx.x counts the tiles that touch the plane's edge -- the top row, the bottom row(s), then the
-// left tile and the right tile(s) of every row between -- and nothing else. The wrap modes differ only in what a tap
-// beyond the edge reads, i.e. in coefficients within three positions of the edge (DD 13/7: H(c) reads E(c-1..c+2), L(c)
-// reads H(c-2..c+1); the inverse likewise); a level with another wrap mode than CLAMP is done by the CLAMP strip kernel
-// and then has its frame of edge tiles computed again by this kernel with the real wrap mode. Where the last tile
-// column / row is thinner than FRAME_REACH coefficients the one before it belongs to the frame too (frame_rc / frame_br = 2).
-constexpr uint32_t FRAME_REACH = 6;
+// Where a CTA's tile starts. Plain launch (frame == 0): tile (blockIdx.x, blockIdx.y) of the grid of TW x TH tiles.
+// The wrap modes differ only in what a tap beyond the plane's edge reads, i.e. in coefficients within three positions
+// of the edge (DD 13/7: H(c) reads E(c-1..c+2), L(c) reads H(c-2..c+1); the inverse likewise). A level with another
+// wrap mode than CLAMP is therefore done by the CLAMP strip kernel and then has its FRAME computed again by these
+// kernels with the real wrap mode, as two launches of thin tiles anchored to the edges:
+//   FRAME_ROWS  tiles of LIFT_TW x FRAME_BAND, grid (tiles across, 2): the top and the bottom FRAME_BAND rows
+//   FRAME_COLS  tiles of FRAME_BAND x LIFT_TH, grid (2, tiles down):   the left and the right FRAME_BAND columns
+// (w, h = the level's size in coefficients; the corners are computed twice, to the same values).
+constexpr int FRAME_ROWS = 1, FRAME_COLS = 2;
+constexpr int FRAME_BAND = 8;
 
-__device__ __forceinline__ void lift_tile(uint32_t nx, uint32_t ny, uint32_t rc, uint32_t br, int& tx, int& ty)
+template <int TW, int TH>
+__device__ __forceinline__ void lift_tile_origin(int frame, int w, int h, int& c0, int& r0)
 {
-	if (nx == 0)
-	{
-		tx = (int)blockIdx.x;
-		ty = (int)blockIdx.y;
-		return;
-	}
-	uint32_t i = blockIdx.x;
-	const uint32_t full_rows = nx * (1 + br);
-	if (i < full_rows)
-	{
-		const uint32_t r = i / nx;
-		tx = (int)(i - r * nx);
-		ty = (r == 0) ? 0 : (int)(ny - br + (r - 1));
-		return;
-	}
-	i -= full_rows;
-	const uint32_t per = 1 + rc, r = i / per, k = i - r * per;
-	ty = 1 + (int)r;
-	tx = (k == 0) ? 0 : (int)(nx - rc + (k - 1));
-}
-
-// tiles in the frame; 0 when the plane is too small to have an inside
-static inline uint32_t lift_frame_tiles(uint32_t nx, uint32_t ny, uint32_t rc, uint32_t br)
-{
-	if (nx < rc + 2 || ny < br + 2)
-		return 0;
-	return nx * (1 + br) + (ny - 1 - br) * (1 + rc);
+	c0 = (int)blockIdx.x * TW;
+	r0 = (int)blockIdx.y * TH;
+	if (frame == FRAME_ROWS && blockIdx.y != 0)
+		r0 = max(h - TH, 0);
+	if (frame == FRAME_COLS && blockIdx.x != 0)
+		c0 = max(w - TW, 0);
 }
 
 // wrap mode as an index map; -1 means "the tap reads zero"
@@ -165,7 +148,12 @@ struct LiftParams
 	uint64_t stream_is;
 	uint32_t cw, ch, tw, th;
 	int wrap;
-	uint32_t frame_nx, frame_ny, frame_rc, frame_br; // k_lift_level only: frame_nx != 0 => the grid is the frame of edge tiles (see lift_tile)
+	int frame; // k_lift_level only: 0, FRAME_ROWS or FRAME_COLS (see lift_tile_origin)
+	// k_lift_level only: != nullptr => level 0 of a 4-channel image read from the interleaved RGBA8 image itself (the
+	// frame of a level whose inside the fused strip kernel did, lift_strip4.cuh); 'in' is unused then
+	const uint8_t* rgba;
+	uint64_t rgba_is, rgba_rs; // bytes between images / rows
+	int rgba_color, rgba_discard;
 	uint32_t channels;
 	uint64_t off_c[AKOD_MAX_CHANNELS];
 	int16_t q[AKOD_MAX_CHANNELS];
@@ -188,11 +176,10 @@ __device__ __forceinline__ int16_t gate_quantize(int v, int q, int g, uint32_t m
 	return (int16_t)(v < 0 ? -d : d);
 }
 
-template <int WL>
+template <int WL, int TW = LIFT_TW, int TH = LIFT_TH>
 __global__ void __launch_bounds__(LIFT_THREADS) k_lift_level(const LiftParams p)
 {
-	using G = LiftGeom<WL>;
-	constexpr int TW = LIFT_TW, TH = LIFT_TH;
+	using G = LiftGeom<WL, TW, TH>;
 	constexpr int XW = 2 * G::NS, XH = 2 * G::MS;
 
 	extern __shared__ int16_t smem[];
@@ -201,11 +188,10 @@ __global__ void __launch_bounds__(LIFT_THREADS) k_lift_level(const LiftParams p)
 	int16_t* LB = HB + XH * G::HBW;     // XH x TW   horizontal lowpass
 	int16_t* HV = X;                    // HVH x 2TW vertical highpass of [LB | HB]
 
-	int tile_x, tile_y;
-	lift_tile(p.frame_nx, p.frame_ny, p.frame_rc, p.frame_br, tile_x, tile_y);
-	const int c0 = tile_x * TW, r0 = tile_y * TH;
 	const uint32_t img = blockIdx.z / p.channels, chn = blockIdx.z - img * p.channels;
 	const int tw = (int)p.tw, th = (int)p.th, wrap = p.wrap;
+	int c0, r0;
+	lift_tile_origin<TW, TH>(p.frame, tw, th, c0, r0);
 	const int16_t* in = p.in + p.in_is * img + p.in_ps * chn;
 
 	// ---- stage the tile: slot (sy,sx) <-> virtual coefficient (vr,vc) + parity; wrap applied here
@@ -219,7 +205,20 @@ __global__ void __launch_bounds__(LIFT_THREADS) k_lift_level(const LiftParams p)
 		{
 			const uint32_t y = min((uint32_t)(2 * mr + (sy & 1)), p.ch - 1); // odd height: duplicate last row
 			const uint32_t x = min((uint32_t)(2 * mc + (sx & 1)), p.cw - 1); // odd width: duplicate last column
-			v = __ldg(in + (uint64_t)y * p.in_rs + x);
+			if (p.rgba != nullptr)
+			{
+				// format.c:33-51, :64-135 for this one sample (k_format_fwd_rgba8x8 does the same for whole rows)
+				const uint32_t px = __ldg(reinterpret_cast<const uint32_t*>(p.rgba + p.rgba_is * img + (uint64_t)y * p.rgba_rs) + x);
+				int r = px & 255, g = (px >> 8) & 255, bl = (px >> 16) & 255;
+				const int al = px >> 24;
+				if (p.rgba_discard && al == 0)
+					r = g = bl = 0;
+				int16_t c0v, c1v, c2v;
+				color_forward(p.rgba_color, r, g, bl, c0v, c1v, c2v);
+				v = (chn == 0) ? c0v : (chn == 1) ? c1v : (chn == 2) ? c2v : (int16_t)al;
+			}
+			else
+				v = __ldg(in + (uint64_t)y * p.in_rs + x);
 		}
 		X[i] = v;
 	}
@@ -316,7 +315,7 @@ __global__ void __launch_bounds__(LIFT_THREADS) k_lift_level(const LiftParams p)
 	const uint32_t magic = p.qmagic[chn];
 
 	// akoLiftHead{q} sits right before the C subband (lifting.c:266-267)
-	if (tile_x == 0 && tile_y == 0 && threadIdx.x == 0)
+	if (c0 == 0 && r0 == 0 && threadIdx.x == 0)
 		out_c[-1] = (int16_t)q;
 
 	for (int i = threadIdx.x; i < TH * 2 * TW; i += LIFT_THREADS)
@@ -354,11 +353,11 @@ __global__ void __launch_bounds__(LIFT_THREADS) k_lift_level(const LiftParams p)
 	}
 }
 
-template <int WL>
+template <int WL, int TW = LIFT_TW, int TH = LIFT_TH>
 constexpr size_t lift_smem_bytes()
 {
-	using G = LiftGeom<WL>;
-	return sizeof(int16_t) * ((size_t)(2 * G::MS) * (2 * G::NS) + (size_t)(2 * G::MS) * G::HBW + (size_t)(2 * G::MS) * LIFT_TW);
+	using G = LiftGeom<WL, TW, TH>;
+	return sizeof(int16_t) * ((size_t)(2 * G::MS) * (2 * G::NS) + (size_t)(2 * G::MS) * G::HBW + (size_t)(2 * G::MS) * TW);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -376,16 +375,15 @@ struct UnliftParams
 	uint64_t out_ps, out_is;
 	uint32_t hw, hh, tw, th;
 	int wrap;
-	uint32_t frame_nx, frame_ny, frame_rc, frame_br; // k_unlift_level only: frame_nx != 0 => the grid is the frame of edge tiles (see lift_tile)
+	int frame; // k_unlift_level only: 0, FRAME_ROWS or FRAME_COLS (see lift_tile_origin)
 	uint32_t channels;
 	uint64_t off_c[AKOD_MAX_CHANNELS];
 };
 
-template <int WL>
+template <int WL, int TW = LIFT_TW, int TH = LIFT_TH>
 __global__ void __launch_bounds__(LIFT_THREADS) k_unlift_level(const UnliftParams p)
 {
-	using G = LiftGeom<WL>;
-	constexpr int TW = LIFT_TW, TH = LIFT_TH;
+	using G = LiftGeom<WL, TW, TH>;
 	constexpr int NS = G::NS, MS = G::MS;
 
 	extern __shared__ int16_t smem[];
@@ -397,11 +395,10 @@ __global__ void __launch_bounds__(LIFT_THREADS) k_unlift_level(const UnliftParam
 	int16_t* OV = EV + 2 * G::EH * NS; // 2 x TH x NS : odd rows
 	int16_t* EHb = A0;              // 2TH x EW : horizontally reconstructed even samples (reuses A*)
 
-	int tile_x, tile_y;
-	lift_tile(p.frame_nx, p.frame_ny, p.frame_rc, p.frame_br, tile_x, tile_y);
-	const int c0 = tile_x * TW, r0 = tile_y * TH;
 	const uint32_t img = blockIdx.z / p.channels, chn = blockIdx.z - img * p.channels;
 	const int hw = (int)p.hw, hh = (int)p.hh, wrap = p.wrap;
+	int c0, r0;
+	lift_tile_origin<TW, TH>(p.frame, hw, hh, c0, r0);
 	const uint64_t band = (uint64_t)p.hw * p.hh;
 	const int16_t* in_ll = p.ll + p.ll_is * img + p.ll_ps * chn;
 	const int16_t* in_c = p.stream + p.stream_is * img + p.off_c[chn];
@@ -556,9 +553,9 @@ __global__ void __launch_bounds__(LIFT_THREADS) k_unlift_level(const UnliftParam
 	}
 }
 
-template <int WL>
+template <int WL, int TW = LIFT_TW, int TH = LIFT_TH>
 constexpr size_t unlift_smem_bytes()
 {
-	using G = LiftGeom<WL>;
-	return sizeof(int16_t) * ((size_t)4 * G::MS * G::NS + (size_t)2 * G::EH * G::NS + (size_t)2 * LIFT_TH * G::NS);
+	using G = LiftGeom<WL, TW, TH>;
+	return sizeof(int16_t) * ((size_t)4 * G::MS * G::NS + (size_t)2 * G::EH * G::NS + (size_t)2 * TH * G::NS);
 }

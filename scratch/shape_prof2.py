@@ -7,9 +7,10 @@ import ako_b200, bench
 from ako_b200.synth import synth_rgba8_torch
 name = sys.argv[1]
 w, h, ch, wavelet, q, g, tiles, B = bench.SHAPES[name][:8]
+wrap = bench.SHAPES[name][8] if len(bench.SHAPES[name]) > 8 else 0
 ctx = ako_b200.Context(0)
 imgs = synth_rgba8_torch(w, h, list(range(B)), device="cuda")[..., :ch].contiguous()
-s = ako_b200.default_settings(wavelet=wavelet, quantization=q, gate=g, tiles_dimension=tiles)
+s = ako_b200.default_settings(wavelet=wavelet, quantization=q, gate=g, tiles_dimension=tiles, wrap=wrap)
 bound = ctx.encode_bound(s, ch, w, h)
 stride = (bound + 255) & ~255
 blobs = torch.empty(B * stride, dtype=torch.uint8, device="cuda")

@@ -142,6 +142,14 @@ def test_wrap_modes_strip_plus_frame(orc, ctx, wavelet, wrap):
     img = ol.synth(orc, 1290, 1034, 77)
     _e2e(orc, img, wavelet=wavelet, wrap=wrap, q=0)
     _e2e(orc, img, wavelet=wavelet, wrap=wrap, q=12, g=5)
+    # level 0 fused with the RGBA8 read (width a multiple of 4): the frame converts the pixels it needs itself
+    img = ol.synth(orc, 1296, 1040, 79)
+    img[:40, :, 3] = 0
+    img[:, -30:, 3] = 0
+    img[500:520, 600:640, 3] = 0
+    for color in (C_YCOCG, C_SUBG, C_NONE):
+        _e2e(orc, img, wavelet=wavelet, wrap=wrap, color=color, discard=1, q=8, g=2)
+    _e2e(orc, img, wavelet=wavelet, wrap=wrap, q=0)
     if wavelet == W_DD137:
         # tiles large enough to have a frame of their own, as batch members (four tile shapes). Encoder only: the
         # reference's reader refuses tiles above 512 (AKO_INVALID_FLAGS), and so do the oracle and this library.
