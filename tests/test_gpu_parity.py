@@ -585,6 +585,7 @@ RATIO_CASES = [  # (w, h, seed, ratio, settings) -- the CPU twin of this list pi
     (200, 160, 14, 1, dict(wavelet=0, q=40, g=5)),
     (200, 160, 14, 0, dict(wavelet=0, q=12, g=0)),
     (128, 128, 15, 12, dict(wavelet=0, color=1, g=0)),
+    (1296, 1040, 16, 15, dict(wavelet=0, wrap=2, g=4)),  # REPEAT at a size where levels are strip + frame on the GPU
     (1632, 2464, 2, 25, dict(wavelet=0, g=16)),  # configs[1] shape
 ]
 

@@ -336,6 +336,7 @@ RATIO_CASES = [  # (w, h, seed, ratio, settings)
     (200, 160, 14, 1, dict(wavelet=0, q=40, g=5)),  # ratio 1 = lossless
     (200, 160, 14, 0, dict(wavelet=0, q=12, g=0)),  # ratio 0 = one plain pass
     (128, 128, 15, 12, dict(wavelet=0, color=1, g=0)),
+    (1296, 1040, 16, 15, dict(wavelet=0, wrap=2, g=4)),  # REPEAT at a size where levels are strip + frame on the GPU
 ]
 
 
