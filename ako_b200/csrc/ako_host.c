@@ -2243,6 +2243,31 @@ static enum akoStatus walk_blocks_device(akoB200Context* ctx, const uint8_t* d_b
 	return AKO_OK;
 }
 
+/* The 16-byte head of a device-resident blob and, in the same read-back, the size field of its first block (bytes
+ * 16..19; *first = 0 when the blob ends before it). An untiled image has no other block: its block walk is then done
+ * (first_block), which saves a lone image one kernel and one round trip. */
+static enum akoStatus fetch_head(akoB200Context* ctx, const void* d_in, size_t input_size, uint8_t head[16], uint64_t* first)
+{
+	uint8_t* mail = akod_mailbox(ctx->dev);
+	const size_t n = (input_size >= 20) ? 20 : 16;
+	enum akoStatus st;
+	if ((st = from_dev(akod_d2h(ctx->dev, mail, d_in, n))) != AKO_OK || (st = from_dev(akod_sync(ctx->dev))) != AKO_OK)
+		return st;
+	memcpy(head, mail, 16);
+	*first = (n == 20) ? (uint64_t)load_le32(mail + 16) : 0;
+	return AKO_OK;
+}
+
+/* what k_walk_blocks answers for the only block of an untiled blob (decode.c:150-158) */
+static enum akoStatus first_block(uint64_t first, size_t input_size, uint64_t* off, uint64_t* size)
+{
+	if (first == 0 || 20 + first > input_size)
+		return AKO_BROKEN_INPUT;
+	*off = 20;
+	*size = first;
+	return AKO_OK;
+}
+
 AKO_API enum akoStatus akoB200DecodeDevice(akoB200Context* ctx, size_t input_size, const void* d_in, const void* head16,
                                            void* d_out, size_t out_capacity, struct akoSettings* out_s,
                                            size_t* out_channels, size_t* out_w, size_t* out_h)
@@ -2258,15 +2283,11 @@ AKO_API enum akoStatus akoB200DecodeDevice(akoB200Context* ctx, size_t input_siz
 		return AKO_INVALID_INPUT;
 	if (input_size < 16)
 		return AKO_BROKEN_INPUT;
+	uint64_t first = 0;
 	if (head16 != NULL)
 		memcpy(head, head16, 16);
-	else
-	{
-		uint8_t* mail = akod_mailbox(ctx->dev);
-		if ((st = from_dev(akod_d2h(ctx->dev, mail, d_in, 16))) != AKO_OK || (st = from_dev(akod_sync(ctx->dev))) != AKO_OK)
-			return st;
-		memcpy(head, mail, 16);
-	}
+	else if ((st = fetch_head(ctx, d_in, input_size, head, &first)) != AKO_OK)
+		return st;
 	if ((st = head_read(head, &channels, &w, &h, &s)) != AKO_OK)
 		return st;
 	if (s.wavelet == AKO_WAVELET_NONE && s.compression != AKO_COMPRESSION_NONE)
@@ -2277,7 +2298,10 @@ AKO_API enum akoStatus akoB200DecodeDevice(akoB200Context* ctx, size_t input_siz
 	const size_t tiles = tiles_count(w, h, s.tiles_dimension);
 	if ((blk = malloc(sizeof(uint64_t) * tiles * 2)) == NULL)
 		return AKO_NO_ENOUGH_MEMORY;
-	st = walk_blocks_device(ctx, d_in, input_size, &s, channels, w, h, blk, blk + tiles);
+	if (head16 == NULL && tiles == 1 && s.compression != AKO_COMPRESSION_NONE)
+		st = first_block(first, input_size, blk, blk + 1);
+	else
+		st = walk_blocks_device(ctx, d_in, input_size, &s, channels, w, h, blk, blk + tiles);
 	if (st == AKO_OK)
 		st = decode_core(ctx, NULL, &s, channels, w, h, 1, d_in, 0, blk, blk + tiles, d_out, 0, &ok);
 	free(blk);
@@ -2312,18 +2336,17 @@ AKO_API size_t akoB200DecodeBatchDevice(akoB200Context* ctx, size_t n_images, co
 		st = AKO_INVALID_INPUT;
 		goto done;
 	}
+	uint64_t first = 0;
 	{
 		/* header of blob 0 defines the batch's shape */
-		uint8_t* mail = akod_mailbox(ctx->dev);
 		if (in_sizes[0] < 16)
 		{
 			st = AKO_BROKEN_INPUT;
 			goto done;
 		}
-		if ((st = from_dev(akod_d2h(ctx->dev, mail, d_in, 16))) != AKO_OK || (st = from_dev(akod_sync(ctx->dev))) != AKO_OK)
-			goto done;
 		uint8_t head[16];
-		memcpy(head, mail, 16);
+		if ((st = fetch_head(ctx, d_in, in_sizes[0], head, &first)) != AKO_OK)
+			goto done;
 		if ((st = head_read(head, &channels, &w, &h, &s)) != AKO_OK)
 			goto done;
 	}
@@ -2352,6 +2375,8 @@ AKO_API size_t akoB200DecodeBatchDevice(akoB200Context* ctx, size_t n_images, co
 			st = walk_blocks_device(ctx, (const uint8_t*)d_in + in_stride * i, in_sizes[i], &s, channels, w, h,
 			                        off + tiles * i, size + tiles * i);
 	}
+	else if (n_images == 1 && tiles == 1)
+		st = first_block(first, in_sizes[0], off, size); /* one untiled image: the head's read-back held its block walk */
 	else
 	{
 		/* one kernel walks the block heads of every blob, one read-back brings offsets and sizes home */

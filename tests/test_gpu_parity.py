@@ -536,6 +536,24 @@ def test_device_resident_and_batch(orc, ctx):
     st, dims, s2 = ctx.decode_device(sizes[2], d_out + 2 * stride, d_px, w * h * ch)
     assert st == 0 and dims == (ch, w, h)
     assert np.array_equal(ctx.to_host(d_px, (h, w, ch), np.uint8), px[2])
+    # a batch of one untiled image: its block walk rides on the head's read-back (ako_host.c first_block)
+    done, st = ctx.decode_batch_device(1, d_out + 3 * stride, stride, sizes[3:4], d_px, w * h * ch)
+    assert done == 1 and st == 0
+    assert np.array_equal(ctx.to_host(d_px, (h, w, ch), np.uint8), px[3])
+    # ... and answers like the block walk for a blob cut short or with a forged / zero block size
+    for cut in (17, 20, sizes[3] - 1):
+        done, st = ctx.decode_batch_device(1, d_out + 3 * stride, stride, [cut], d_px, w * h * ch)
+        assert done == 0 and st == ol.orc_decode(orc, want[3][:cut])[1] == 15, (cut, st)
+        st, dims, _ = ctx.decode_device(cut, d_out + 3 * stride, d_px, w * h * ch)
+        assert st == 15, (cut, st)
+    bad = np.frombuffer(want[3], np.uint8).copy()
+    bad[16:20] = 0
+    d_bad = ctx.to_device(bad)
+    done, st = ctx.decode_batch_device(1, d_bad, stride, [len(bad)], d_px, w * h * ch)
+    assert done == 0 and st == ol.orc_decode(orc, bad.tobytes())[1] == 15
+    st, dims, _ = ctx.decode_device(len(bad), d_bad, d_px, w * h * ch)
+    assert st == 15
+    ctx.free(d_bad)
     assert ctx.launch_count() > 0
     for p in (d_in, d_out, d_px):
         ctx.free(p)
